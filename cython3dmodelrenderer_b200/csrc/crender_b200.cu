@@ -1,0 +1,1242 @@
+// crender_b200.cu -- B200 (sm_100a) implementation of the Version C rendering hot path of
+// oKatanaaa/Cython3DModelRenderer, behind the C ABI in include/crender_b200.h.
+//
+// Reference being replaced ("pyx" = crender/cy/pixel_buffer_filler/advanced_pixel_buffer_filler.pyx,
+// "mu" = crender/cy/pixel_buffer_filler/math_utils.pyx):
+//   pyx:106-130  project_on_screen_multithread          -> k_setup (phase 1: transform + projection)
+//   pyx:202-211  back-face cull, pixel rectangle         -> k_setup (phase 2: setup, cull, bbox, tile counts)
+//   pyx:213-224  per-pixel barycentrics, depth, z-test   -> k_raster (shared-memory tile, 64-bit packed-key min)
+//   pyx:226-242  attribute interpolation + buffer writes -> k_raster (deferred shading of the winning triangle)
+//
+// Design: the reference walks triangles and fights over pixels with per-pixel locks; here the
+// screen is cut into TW x TH tiles, every tile is owned by exactly one CTA, visibility is resolved inside shared
+// memory with a deterministic min over key = (orderable depth bits << 32 | ~triangle index), and only the winner
+// of each pixel is shaded and written -- once, with full 128-byte lines.  Results equal the reference's
+// n_threads=1 output bit for bit; all arithmetic is IEEE binary32, one rounding per operation (this file MUST be
+// compiled with -fmad=false; divisions and square roots are the correctly rounded defaults).
+//
+// Not a port: nothing here mirrors the reference's loop structure, locking or memory layout.
+
+#include <cuda_runtime.h>
+
+#include <climits>
+#include <cmath>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "crender_b200.h"
+
+// ------------------------------------------------------------------------------------------------------------
+// constants
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int TW = 32;          // tile width in pixels  (one 128-byte line of z, three of colour / normals)
+constexpr int TH = 32;          // tile height in pixels
+constexpr int NT = 256;         // threads per CTA in every kernel
+constexpr int CH = 256;         // triangles staged in shared memory per pass of the tile rasterizer (== NT)
+constexpr int KEY_STRIDE = TW + 1;  // padded key row: rows of one column land in different banks
+constexpr unsigned long long KEY_EMPTY = 0xFFFFFFFFFFFFFFFFull;
+constexpr float Z_INIT = 1e6f;  // pyx:67
+constexpr float REJ_EPS = 1e-6f;      // fast-reject guard band on barycentric numerators (see tri_fast_setup)
+constexpr float L3_MIN = 1e-30f, L3_MAX = 1e30f;
+constexpr int MAX_DIM = 65535;  // bbox corners are packed in 16 bits
+
+static_assert(CH == NT, "one staged triangle per thread");
+static_assert(TW == 32, "a tile row is one warp wide");
+
+struct ProjC {
+    float p[16];   // row-major 4x4, proj_mat of pyx:85-90
+    float xs, ys;  // (float)(w/2.0), (float)(h/2.0)  pyx:109
+};
+
+struct Frame {
+    ProjC proj;
+    int W, H;            // full image size
+    int row0, row1;      // rows owned by this filler (band); buffers hold rows [row0,row1)
+    int tilesX, tilesY, nTiles;
+    long long T;         // triangles per view
+    int nViews;
+    unsigned flags;
+    // inputs
+    const float *v, *c, *n;     // [T,3,3]
+    const float *views;         // [nViews,16] or nullptr
+    // scratch
+    float4 *rec0, *rec1, *rec2; // [nViews*T] screen-space triangle records (SoA of float4)
+    unsigned *count;            // [nViews*nTiles] triangles per tile (zero between frames)
+    unsigned *offset;           // [nViews*nTiles] start of the tile's list
+    unsigned *cursor;           // [nViews*nTiles] fill cursor
+    unsigned *list;             // [pairCap] triangle indices, tile by tile
+    unsigned long long *total;  // [0] pairs of this frame, [1] sticky max of overflowing totals
+    long long pairCap;
+    // outputs (per view slab stride = rows*W (z) or rows*W*3)
+    float *z, *color, *normals;
+    unsigned char *color_u8;
+    long long slabPixels;       // rows*W
+    float light[3];
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// device arithmetic shared by every path.  Operation order restates the reference exactly.
+// ------------------------------------------------------------------------------------------------------------
+
+// pyx:116-130.  Source and destination alias in the reference (project_on_screen_multithread(triangles, triangles)),
+// so column j sees the components columns < j already overwrote; restated literally (matters for inf/NaN inputs).
+__device__ __forceinline__ void project_vertex(const ProjC &P, float &x, float &y, float &z)
+{
+    const float z0 = z;
+    float X = ((x * P.p[0] + y * P.p[4]) + z * P.p[8]) + P.p[12];
+    float Y = ((X * P.p[1] + y * P.p[5]) + z * P.p[9]) + P.p[13];
+    float Z = ((X * P.p[2] + Y * P.p[6]) + z * P.p[10]) + P.p[14];
+    X = X / z0;
+    Y = Y / z0;
+    Z = Z / z0;
+    X = X + 1.0f;
+    Y = Y + 1.0f;
+    x = X * P.xs;
+    y = Y * P.ys;
+    z = Z;
+}
+
+// Batched views: v' = R (v - p) + q, evaluated ((r0*d0 + r1*d1) + r2*d2) + q   (crender_b200.h, crb_render_views)
+__device__ __forceinline__ void view_point(const float *M, float &x, float &y, float &z)
+{
+    const float dx = x - M[9], dy = y - M[10], dz = z - M[11];
+    x = ((M[0] * dx + M[1] * dy) + M[2] * dz) + M[12];
+    y = ((M[3] * dx + M[4] * dy) + M[5] * dz) + M[13];
+    z = ((M[6] * dx + M[7] * dy) + M[8] * dz) + M[14];
+}
+__device__ __forceinline__ void view_normal(const float *M, float &x, float &y, float &z)
+{
+    const float nx = x, ny = y, nz = z;
+    x = (M[0] * nx + M[1] * ny) + M[2] * nz;
+    y = (M[3] * nx + M[4] * ny) + M[5] * nz;
+    z = (M[6] * nx + M[7] * ny) + M[8] * nz;
+}
+
+// (int)ceil(x) as the reference binary performs it (pyx:165-166): x86-64 cvttsd2si yields INT_MIN for anything
+// outside int range (the C cast is undefined there); CUDA's cvt would saturate instead, so the range test is explicit.
+__device__ __forceinline__ int ceil_to_int_ref(float x)
+{
+    const float c = ceilf(x);
+    if (!(c >= -2147483648.0f && c < 2147483648.0f)) return INT_MIN;
+    return (int)c;
+}
+__device__ __forceinline__ int clipi(int a, int lo, int hi) { return a < lo ? lo : (a > hi ? hi : a); }
+
+// Depth -> 32-bit key whose unsigned order equals the float order the reference's `new_z > z_buffer` uses.
+// -0.0 is folded onto +0.0 first (they compare equal in the reference, so the triangle index must break the tie).
+__device__ __forceinline__ unsigned depth_key(float z)
+{
+    unsigned b = __float_as_uint(z);
+    if (b == 0x80000000u) b = 0u;
+    return b ^ ((b & 0x80000000u) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ unsigned long long pack_key(float z, unsigned tri)
+{
+    return ((unsigned long long)depth_key(z) << 32) | (unsigned long long)(~tri);
+}
+
+// mu:5-34, all three coordinates of one pixel, plain restatement (used by shading and by the atomic path).
+struct Tri9 {
+    float x0, y0, x1, y1, x2, y2, z0, z1, z2;
+};
+__device__ __forceinline__ void barycentric(const Tri9 &t, float px, float py, float &b1, float &b2, float &b3)
+{
+    const float l01 = t.x1 - t.x2, l02 = t.y1 - t.y2;
+    const float l03 = l01 * (t.y0 - t.y2) - l02 * (t.x0 - t.x2);
+    const float l11 = t.x2 - t.x0, l12 = t.y2 - t.y0;
+    const float l13 = l11 * (t.y1 - t.y0) - l12 * (t.x1 - t.x0);
+    const float l21 = t.x0 - t.x1, l22 = t.y0 - t.y1;
+    const float l23 = l21 * (t.y2 - t.y1) - l22 * (t.x2 - t.x1);
+    b1 = (l01 * (py - t.y2) - l02 * (px - t.x2)) / l03;
+    b2 = (l11 * (py - t.y0) - l12 * (px - t.x0)) / l13;
+    b3 = (l21 * (py - t.y1) - l22 * (px - t.x1)) / l23;
+}
+
+__device__ __forceinline__ Tri9 load_tri9(const Frame &F, long long ridx)
+{
+    const float4 a = F.rec0[ridx], b = F.rec1[ridx], c = F.rec2[ridx];
+    Tri9 t;
+    t.x0 = a.x; t.y0 = a.y; t.x1 = a.z; t.y1 = a.w;
+    t.x2 = b.x; t.y2 = b.y; t.z0 = b.z; t.z1 = b.w;
+    t.z2 = c.x;
+    return t;
+}
+
+// pyx:219-242 for the pixel's winning triangle: depth, colour, normal (left-associated sums).  Returns false if the
+// fragment would not have been drawn (some barycentric < 0, NaN depth) -- cannot happen for a key that won, kept as a
+// guard.  `M` (may be nullptr) is the view matrix applied to the normals.
+__device__ __forceinline__ bool shade_fragment(const Frame &F, const Tri9 &t, long long tri, const float *M, float px,
+                                               float py, float &z, float c[3], float n[3])
+{
+    float b1, b2, b3;
+    barycentric(t, px, py, b1, b2, b3);
+    if (b1 < 0.0f || b2 < 0.0f || b3 < 0.0f) return false;
+    z = (t.z0 * b1 + t.z1 * b2) + t.z2 * b3;
+    if (z != z) return false;
+    const float *cc = F.c + tri * 9, *nn = F.n + tri * 9;
+    float m[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) m[k] = __ldg(nn + k);
+    if (M) {
+        view_normal(M, m[0], m[1], m[2]);
+        view_normal(M, m[3], m[4], m[5]);
+        view_normal(M, m[6], m[7], m[8]);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        n[k] = (m[k] * b1 + m[3 + k] * b2) + m[6 + k] * b3;
+        c[k] = (__ldg(cc + k) * b1 + __ldg(cc + 3 + k) * b2) + __ldg(cc + 6 + k) * b3;
+    }
+    if (F.flags & CRB_GURO) {  // guro_illumination.py:23-27 (float32, left-to-right sums)
+        const float dot = (n[0] * F.light[0] + n[1] * F.light[1]) + n[2] * F.light[2];
+        const float nrm = sqrtf((n[0] * n[0] + n[1] * n[1]) + n[2] * n[2]);
+        float s = dot / (nrm + 1e-6f);
+        if (s < 0.0f) s = 0.0f;
+        if (s > 1.0f) s = 1.0f;
+        c[0] *= s; c[1] *= s; c[2] *= s;
+    }
+    return true;
+}
+
+// run.py:26 .astype('uint8'): C truncation toward zero, then the low 8 bits.
+__device__ __forceinline__ unsigned char to_u8(float c) { return (unsigned char)(int)c; }
+
+// ------------------------------------------------------------------------------------------------------------
+// K1+K2: vertex transform + projection, triangle setup, cull, bbox, per-tile counts
+// ------------------------------------------------------------------------------------------------------------
+
+// Coalesced, float4-vectorised staging of a CTA's contiguous run of [.,3,3] floats into shared memory.
+__device__ __forceinline__ void stage_floats(const float *__restrict__ g, long long first, long long count, float *s)
+{
+    const float *src = g + first;
+    if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+        const long long n4 = count >> 2;
+        const float4 *s4 = reinterpret_cast<const float4 *>(src);
+        for (long long i = threadIdx.x; i < n4; i += NT) reinterpret_cast<float4 *>(s)[i] = __ldg(s4 + i);
+        for (long long i = (n4 << 2) + threadIdx.x; i < count; i += NT) s[i] = __ldg(src + i);
+    } else {
+        for (long long i = threadIdx.x; i < count; i += NT) s[i] = __ldg(src + i);
+    }
+}
+
+__device__ __forceinline__ void tile_span(const Frame &F, unsigned bx, unsigned by, int &tx0, int &tx1, int &ty0, int &ty1)
+{
+    const int xl = bx & 0xFFFF, xr = bx >> 16, yt = by & 0xFFFF, yb = by >> 16;
+    tx0 = xl / TW;
+    tx1 = (xr - 1) / TW;
+    ty0 = (yt - F.row0) / TH;
+    ty1 = (yb - 1 - F.row0) / TH;
+}
+
+__global__ void __launch_bounds__(NT) k_setup(const Frame F)
+{
+    __shared__ __align__(16) float sv[NT * 9];
+    __shared__ __align__(16) float sn[NT * 9];
+    __shared__ float sM[16];
+    const int view = blockIdx.y;
+    const long long first = (long long)blockIdx.x * NT;
+    const long long cnt = min((long long)NT, F.T - first);
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) F.total[0] = 0ull;  // k_alloc (next launch) accumulates
+    stage_floats(F.v, first * 9, cnt * 9, sv);
+    stage_floats(F.n, first * 9, cnt * 9, sn);
+    if (F.views && threadIdx.x < 16) sM[threadIdx.x] = F.views[view * 16 + threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x >= cnt) return;
+    const long long tri = first + threadIdx.x;
+    const long long ridx = (long long)view * F.T + tri;
+
+    float x[3], y[3], z[3], nz[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        x[k] = sv[threadIdx.x * 9 + k * 3 + 0];
+        y[k] = sv[threadIdx.x * 9 + k * 3 + 1];
+        z[k] = sv[threadIdx.x * 9 + k * 3 + 2];
+        nz[k] = sn[threadIdx.x * 9 + k * 3 + 2];
+        if (F.views) {
+            view_point(sM, x[k], y[k], z[k]);
+            const float nx = sn[threadIdx.x * 9 + k * 3 + 0], ny = sn[threadIdx.x * 9 + k * 3 + 1];
+            nz[k] = (sM[6] * nx + sM[7] * ny) + sM[8] * nz[k];
+        }
+        project_vertex(F.proj, x[k], y[k], z[k]);
+    }
+
+    // pyx:202-204: (n0z + n1z + n2z)/3 >= 0 in double -- only the sign of the float sum matters (NaN: not culled)
+    const float nsum = (nz[0] + nz[1]) + nz[2];
+    bool drawn = !(nsum >= 0.0f);
+
+    // pyx:132-175: running min from (w,h), running max from 0; NaN never wins a comparison
+    float fxl = (float)F.W, fxr = 0.0f, fyt = (float)F.H, fyb = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (x[k] < fxl) fxl = x[k];
+        if (x[k] > fxr) fxr = x[k];
+        if (y[k] < fyt) fyt = y[k];
+        if (y[k] > fyb) fyb = y[k];
+    }
+    int xl = clipi(ceil_to_int_ref(fxl), 0, F.W), xr = clipi(ceil_to_int_ref(fxr), 0, F.W);
+    int yt = clipi(ceil_to_int_ref(fyt), 0, F.H), yb = clipi(ceil_to_int_ref(fyb), 0, F.H);
+    yt = max(yt, F.row0);  // band sharding: rows outside [row0,row1) belong to another filler
+    yb = min(yb, F.row1);
+    drawn = drawn && (xl < xr) && (yt < yb);  // pyx:209-211 and the empty range() cases
+    const unsigned bx = drawn ? ((unsigned)xl | ((unsigned)xr << 16)) : 0u;
+    const unsigned by = drawn ? ((unsigned)yt | ((unsigned)yb << 16)) : 0u;
+
+    F.rec2[ridx] = make_float4(z[2], __uint_as_float(bx), __uint_as_float(by), 0.0f);
+    if (!drawn) return;
+    F.rec0[ridx] = make_float4(x[0], y[0], x[1], y[1]);
+    F.rec1[ridx] = make_float4(x[2], y[2], z[0], z[1]);
+    if (F.flags & CRB_PATH_ATOMIC) return;
+
+    int tx0, tx1, ty0, ty1;
+    tile_span(F, bx, by, tx0, tx1, ty0, ty1);
+    unsigned *cnt_view = F.count + (long long)view * F.nTiles;
+    for (int ty = ty0; ty <= ty1; ++ty)
+        for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(cnt_view + ty * F.tilesX + tx, 1u);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K2b: list space for every tile.  Block-wide exclusive scan (warp shuffles) of the tile counts, one bump
+// allocation per CTA.  List order in memory is irrelevant: the packed key makes the result order-independent.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned *warp_sums, unsigned &block_total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    unsigned base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) {
+        const unsigned s = warp_sums[w];
+        if (w < wid) base += s;
+        tot += s;
+    }
+    block_total = tot;
+    __syncthreads();
+    return base + inc - v;
+}
+
+__global__ void __launch_bounds__(NT) k_alloc(const Frame F)
+{
+    __shared__ unsigned warp_sums[NT / 32];
+    __shared__ unsigned long long block_base;
+    const long long i = (long long)blockIdx.x * NT + threadIdx.x;
+    const long long nAll = (long long)F.nViews * F.nTiles;
+    const unsigned c = (i < nAll) ? F.count[i] : 0u;
+    unsigned tot;
+    const unsigned excl = block_exclusive_scan(c, warp_sums, tot);
+    if (threadIdx.x == 0) block_base = tot ? atomicAdd(F.total, (unsigned long long)tot) : 0ull;
+    __syncthreads();
+    if (i < nAll) {
+        const unsigned long long o = block_base + excl;
+        F.offset[i] = (unsigned)(o > 0xFFFFFFFFull ? 0xFFFFFFFFull : o);
+        F.cursor[i] = 0u;
+    }
+}
+
+// K2c: scatter triangle indices into the tile lists.
+__global__ void __launch_bounds__(NT) k_fill(const Frame F)
+{
+    if (*F.total > (unsigned long long)F.pairCap) return;  // overflow: frame is skipped, host is told via crb_status
+    const int view = blockIdx.y;
+    const long long tri = (long long)blockIdx.x * NT + threadIdx.x;
+    if (tri >= F.T) return;
+    const float4 r2 = F.rec2[(long long)view * F.T + tri];
+    const unsigned bx = __float_as_uint(r2.y), by = __float_as_uint(r2.z);
+    if ((bx >> 16) == 0) return;  // not drawn (x_right >= 1 for every drawn triangle)
+    int tx0, tx1, ty0, ty1;
+    tile_span(F, bx, by, tx0, tx1, ty0, ty1);
+    const long long vb = (long long)view * F.nTiles;
+    for (int ty = ty0; ty <= ty1; ++ty)
+        for (int tx = tx0; tx <= tx1; ++tx) {
+            const long long t = vb + ty * F.tilesX + tx;
+            const unsigned pos = atomicAdd(F.cursor + t, 1u);
+            F.list[F.offset[t] + pos] = (unsigned)tri;
+        }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K3+K4: tile rasterizer + deferred shading
+// ------------------------------------------------------------------------------------------------------------
+
+// shared-memory 64-bit min.  There is no native 64-bit ATOMS.MIN; most fragments lose the depth test and leave after
+// the plain load, winners pay one CAS (retry only when two lanes hit the same pixel in the same instant).
+__device__ __forceinline__ void smem_key_min(unsigned long long *p, unsigned long long key)
+{
+    unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(p);
+    while (key < cur) {
+        const unsigned long long old = atomicCAS(p, cur, key);
+        if (old == cur) break;
+        cur = old;
+    }
+}
+
+struct __align__(16) TileSmem {
+    unsigned long long keys[TH * KEY_STRIDE];
+    union {
+        struct {
+            float4 s0[CH];  // x0 y0 x1 y1
+            float4 s1[CH];  // x2 y2 z0 z1
+            float4 s2[CH];  // z2 l03' l13' l23'   (l' = sign-normalised denominators, see below)
+            uint4 s3[CH];   // bx by tri flags
+            unsigned rowStart[CH + 1];
+        } st;
+        struct {
+            float col[TH * TW * 3];
+            float nrm[TH * TW * 3];
+        } out;
+    } u;
+    unsigned warp_sums[NT / 32];
+};
+
+// Writes one tile of cleared pixels (fresh-filler values) -- the whole frame's "memset" is fused here.
+__device__ __forceinline__ void write_clear_tile(const Frame &F, int view, int x0, int yl0, int tw, int th)
+{
+    const long long slab = (long long)view * F.slabPixels;
+    const bool vec = (tw == TW) && ((F.W & 3) == 0);
+    if (vec) {
+        if (F.z) {
+            for (int i = threadIdx.x; i < th * (TW / 4); i += NT) {
+                const int r = i / (TW / 4), q = i % (TW / 4);
+                reinterpret_cast<float4 *>(F.z + slab + (long long)(yl0 + r) * F.W + x0)[q] =
+                    make_float4(Z_INIT, Z_INIT, Z_INIT, Z_INIT);
+            }
+        }
+        for (int i = threadIdx.x; i < th * (TW * 3 / 4); i += NT) {
+            const int r = i / (TW * 3 / 4), q = i % (TW * 3 / 4);
+            const long long o = (slab + (long long)(yl0 + r) * F.W + x0) * 3;
+            if (F.color) reinterpret_cast<float4 *>(F.color + o)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (F.normals) reinterpret_cast<float4 *>(F.normals + o)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    } else {
+        for (int i = threadIdx.x; i < th * tw; i += NT) {
+            const int r = i / tw, xx = i % tw;
+            const long long p = slab + (long long)(yl0 + r) * F.W + x0 + xx;
+            if (F.z) F.z[p] = Z_INIT;
+            if (F.color) { F.color[p * 3] = 0.f; F.color[p * 3 + 1] = 0.f; F.color[p * 3 + 2] = 0.f; }
+            if (F.normals) { F.normals[p * 3] = 0.f; F.normals[p * 3 + 1] = 0.f; F.normals[p * 3 + 2] = 0.f; }
+        }
+    }
+    if (F.color_u8) {
+        const int rows = F.row1 - F.row0;
+        for (int i = threadIdx.x; i < th * tw * 3; i += NT) {
+            const int r = i / (tw * 3), xx = i % (tw * 3);
+            F.color_u8[((long long)view * F.slabPixels + (long long)(rows - 1 - (yl0 + r)) * F.W + x0) * 3 + xx] = 0;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(NT) k_raster(const Frame F)
+{
+    __shared__ TileSmem S;
+    const int view = blockIdx.y;
+    const int tile = blockIdx.x;
+    const long long tIdx = (long long)view * F.nTiles + tile;
+    const int tx = tile % F.tilesX, ty = tile / F.tilesX;
+    const int x0 = tx * TW, yl0 = ty * TH;       // yl0: row inside the band's buffers
+    const int y0 = F.row0 + yl0;                  // absolute image row
+    const int tw = min(TW, F.W - x0), th = min(TH, F.row1 - y0);
+    const bool clear = (F.flags & CRB_CLEAR_FIRST) != 0;
+    const bool overflow = *F.total > (unsigned long long)F.pairCap;
+
+    __shared__ unsigned s_n;
+    if (threadIdx.x == 0) {
+        s_n = F.count[tIdx];
+        F.count[tIdx] = 0u;  // self-cleaning: the next frame's k_setup starts from zero
+    }
+    __syncthreads();
+    const unsigned n = s_n;
+    if (overflow) {
+        if (tIdx == 0 && threadIdx.x == 0) atomicMax(F.total + 1, *F.total);
+        return;
+    }
+    if (n == 0) {
+        if (clear) write_clear_tile(F, view, x0, yl0, tw, th);
+        return;
+    }
+    const unsigned off = F.offset[tIdx];
+    for (int i = threadIdx.x; i < TH * KEY_STRIDE; i += NT) S.keys[i] = KEY_EMPTY;
+
+    // ---- visibility: every (triangle,row) of the tile is one work item -------------------------------------
+    for (unsigned base = 0; base < n; base += CH) {
+        const unsigned m = min((unsigned)CH, n - base);
+        __syncthreads();  // keys initialised / previous pass finished with the staging area
+        unsigned rows = 0;
+        if (threadIdx.x < m) {
+            const unsigned tri = F.list[off + base + threadIdx.x];
+            const long long ridx = (long long)view * F.T + tri;
+            const float4 a = F.rec0[ridx], b = F.rec1[ridx], c = F.rec2[ridx];
+            const unsigned bx = __float_as_uint(c.y), by = __float_as_uint(c.z);
+            // denominators of mu:12-21
+            const float l01 = a.z - b.x, l02 = a.w - b.y;
+            const float l03 = l01 * (a.y - b.y) - l02 * (a.x - b.x);
+            const float l11 = b.x - a.x, l12 = b.y - a.y;
+            const float l13 = l11 * (a.w - a.y) - l12 * (a.z - a.x);
+            const float l21 = a.x - a.z, l22 = a.y - a.w;
+            const float l23 = l21 * (b.y - a.w) - l22 * (b.x - a.z);
+            // Fast rejection (SURVEY 7, K3 obligation).  num/l3 is bit-identical to (-num)/(-l3), and negation commutes
+            // with every rounding that produced num, so each coordinate is evaluated with l3' = |l3| (edge vector negated
+            // when l3 < 0).  For L3_MIN <= l3' <= L3_MAX a numerator <= -REJ_EPS then gives a quotient that is a negative
+            // NON-ZERO float (|q| >= 1e-36), i.e. exactly the reference's `bar < 0` -- no division needed.  Everything else
+            // (denominator zero / tiny / huge / non-finite, numerator inside the guard band or NaN) takes the exact
+            // division path.  flags bit k: negate coordinate k; bit 4+k: coordinate k may use the fast rejection.
+            unsigned fl = 0;
+            float d1 = l03, d2 = l13, d3 = l23;
+            if (fabsf(l03) >= L3_MIN && fabsf(l03) <= L3_MAX) { fl |= 16u; if (l03 < 0.f) { fl |= 1u; d1 = -l03; } }
+            if (fabsf(l13) >= L3_MIN && fabsf(l13) <= L3_MAX) { fl |= 32u; if (l13 < 0.f) { fl |= 2u; d2 = -l13; } }
+            if (fabsf(l23) >= L3_MIN && fabsf(l23) <= L3_MAX) { fl |= 64u; if (l23 < 0.f) { fl |= 4u; d3 = -l23; } }
+            S.u.st.s0[threadIdx.x] = a;
+            S.u.st.s1[threadIdx.x] = b;
+            S.u.st.s2[threadIdx.x] = make_float4(c.x, d1, d2, d3);
+            S.u.st.s3[threadIdx.x] = make_uint4(bx, by, tri, fl);
+            const int yt = max((int)(by & 0xFFFF), y0), yb = min((int)(by >> 16), y0 + th);
+            rows = (unsigned)max(yb - yt, 0);
+        }
+        unsigned totalRows;
+        const unsigned start = block_exclusive_scan(rows, S.warp_sums, totalRows);
+        if (threadIdx.x < m) S.u.st.rowStart[threadIdx.x] = start;
+        __syncthreads();
+
+        for (unsigned r = threadIdx.x; r < totalRows; r += NT) {
+            unsigned lo = 0, hi = m;
+            while (hi - lo > 1) {
+                const unsigned mid = (lo + hi) >> 1;
+                if (S.u.st.rowStart[mid] <= r) lo = mid; else hi = mid;
+            }
+            const float4 a = S.u.st.s0[lo], b = S.u.st.s1[lo], c = S.u.st.s2[lo];
+            const uint4 d = S.u.st.s3[lo];
+            const int y = max((int)(d.y & 0xFFFF), y0) + (int)(r - S.u.st.rowStart[lo]);
+            const int xa = max((int)(d.x & 0xFFFF), x0), xb = min((int)(d.x >> 16), x0 + tw);
+            const unsigned s1 = (d.w & 1u) << 31, s2 = (d.w & 2u) << 30, s3 = (d.w & 4u) << 29;
+            // edge vectors, sign-normalised (exact negation: flip the sign bit)
+            const float l01 = __uint_as_float(__float_as_uint(a.z - b.x) ^ s1), l02 = __uint_as_float(__float_as_uint(a.w - b.y) ^ s1);
+            const float l11 = __uint_as_float(__float_as_uint(b.x - a.x) ^ s2), l12 = __uint_as_float(__float_as_uint(b.y - a.y) ^ s2);
+            const float l21 = __uint_as_float(__float_as_uint(a.x - a.z) ^ s3), l22 = __uint_as_float(__float_as_uint(a.y - a.w) ^ s3);
+            const float thr1 = (d.w & 16u) ? -REJ_EPS : -INFINITY;
+            const float thr2 = (d.w & 32u) ? -REJ_EPS : -INFINITY;
+            const float thr3 = (d.w & 64u) ? -REJ_EPS : -INFINITY;
+            const float py = (float)y;
+            const float A1 = l01 * (py - b.y), A2 = l11 * (py - a.y), A3 = l21 * (py - a.w);
+            // pass 1: cheap rejection over the row -> candidate mask
+            unsigned mask = 0;
+            for (int x = xa; x < xb; ++x) {
+                const float px = (float)x;
+                const float n1 = A1 - l02 * (px - b.x);
+                const float n2 = A2 - l12 * (px - a.x);
+                const float n3 = A3 - l22 * (px - a.z);
+                if (!(n1 < thr1 || n2 < thr2 || n3 < thr3)) mask |= 1u << (x - x0);
+            }
+            // pass 2: exact barycentrics, depth, key for the survivors
+            unsigned long long *krow = S.keys + (y - y0) * KEY_STRIDE;
+            while (mask) {
+                const int bit = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const float px = (float)(x0 + bit);
+                const float b1 = (A1 - l02 * (px - b.x)) / c.y;
+                const float b2 = (A2 - l12 * (px - a.x)) / c.z;
+                const float b3 = (A3 - l22 * (px - a.z)) / c.w;
+                if (b1 < 0.0f || b2 < 0.0f || b3 < 0.0f) continue;      // pyx:216
+                const float z = (b.z * b1 + b.w * b2) + c.x * b3;        // pyx:219
+                if (z != z) continue;                                    // pyx:220 rejects NaN only
+                smem_key_min(krow + bit, pack_key(z, d.z));
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- deferred shading of the winners, staged so that every global store is a full 16-byte vector -------
+    const float *M = F.views ? F.views + view * 16 : nullptr;
+    const long long slab = (long long)view * F.slabPixels;
+    const bool vec = clear && (tw == TW) && ((F.W & 3) == 0);
+    for (int p = threadIdx.x; p < TH * TW; p += NT) {
+        const int yy = p / TW, xx = p % TW;
+        if (yy >= th || xx >= tw) continue;
+        const unsigned long long key = S.keys[yy * KEY_STRIDE + xx];
+        float z = Z_INIT, c[3] = {0.f, 0.f, 0.f}, nn[3] = {0.f, 0.f, 0.f};
+        bool write = clear;
+        const long long pix = slab + (long long)(yl0 + yy) * F.W + x0 + xx;
+        if (key != KEY_EMPTY) {
+            const unsigned tri = ~(unsigned)(key & 0xFFFFFFFFull);
+            const Tri9 t = load_tri9(F, (long long)view * F.T + tri);
+            float fz, fc[3], fn[3];
+            if (shade_fragment(F, t, tri, M, (float)(x0 + xx), (float)(y0 + yy), fz, fc, fn)) {
+                const float zold = clear ? Z_INIT : F.z[pix];
+                if (!(fz > zold)) {  // pyx:223: drawn unless new_z > z_buffer (equal depth overwrites)
+                    z = fz; c[0] = fc[0]; c[1] = fc[1]; c[2] = fc[2]; nn[0] = fn[0]; nn[1] = fn[1]; nn[2] = fn[2];
+                    write = true;
+                }
+            }
+        }
+        if (vec) {
+            S.u.out.col[p * 3] = c[0]; S.u.out.col[p * 3 + 1] = c[1]; S.u.out.col[p * 3 + 2] = c[2];
+            S.u.out.nrm[p * 3] = nn[0]; S.u.out.nrm[p * 3 + 1] = nn[1]; S.u.out.nrm[p * 3 + 2] = nn[2];
+            if (F.z) F.z[pix] = z;
+        } else if (write) {
+            if (F.z) F.z[pix] = z;
+            if (F.color) { F.color[pix * 3] = c[0]; F.color[pix * 3 + 1] = c[1]; F.color[pix * 3 + 2] = c[2]; }
+            if (F.normals) { F.normals[pix * 3] = nn[0]; F.normals[pix * 3 + 1] = nn[1]; F.normals[pix * 3 + 2] = nn[2]; }
+        }
+        if (F.color_u8 && write) {
+            const int rows = F.row1 - F.row0;
+            unsigned char *o = F.color_u8 + (slab + (long long)(rows - 1 - (yl0 + yy)) * F.W + x0 + xx) * 3;
+            o[0] = to_u8(c[0]); o[1] = to_u8(c[1]); o[2] = to_u8(c[2]);
+        }
+    }
+    if (vec) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < th * (TW * 3 / 4); i += NT) {
+            const int r = i / (TW * 3 / 4), q = i % (TW * 3 / 4);
+            const long long o = (slab + (long long)(yl0 + r) * F.W + x0) * 3;
+            if (F.color) reinterpret_cast<float4 *>(F.color + o)[q] = reinterpret_cast<const float4 *>(S.u.out.col + r * TW * 3)[q];
+            if (F.normals) reinterpret_cast<float4 *>(F.normals + o)[q] = reinterpret_cast<const float4 *>(S.u.out.nrm + r * TW * 3)[q];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Differential path (CRB_PATH_ATOMIC): one warp per triangle, global 64-bit atomicMin, then a per-pixel shade.
+// Same records, same arithmetic, no binning, no shared memory -- an independent check of the tiled path.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) k_raster_atomic(const Frame F, unsigned long long *keybuf)
+{
+    const long long tri = ((long long)blockIdx.x * NT + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (tri >= F.T) return;
+    const float4 r2 = F.rec2[tri];
+    const unsigned bx = __float_as_uint(r2.y), by = __float_as_uint(r2.z);
+    if ((bx >> 16) == 0) return;
+    const Tri9 t = load_tri9(F, tri);
+    const int xl = bx & 0xFFFF, xr = bx >> 16, yt = by & 0xFFFF, yb = by >> 16;
+    const int bw = xr - xl;
+    const long long area = (long long)bw * (yb - yt);
+    for (long long i = lane; i < area; i += 32) {
+        const int x = xl + (int)(i % bw), y = yt + (int)(i / bw);
+        float b1, b2, b3;
+        barycentric(t, (float)x, (float)y, b1, b2, b3);
+        if (b1 < 0.0f || b2 < 0.0f || b3 < 0.0f) continue;
+        const float z = (t.z0 * b1 + t.z1 * b2) + t.z2 * b3;
+        if (z != z) continue;
+        atomicMin(keybuf + (long long)(y - F.row0) * F.W + x, pack_key(z, (unsigned)tri));
+    }
+}
+
+__global__ void __launch_bounds__(NT) k_shade_atomic(const Frame F, unsigned long long *keybuf)
+{
+    const long long pix = (long long)blockIdx.x * NT + threadIdx.x;
+    if (pix >= F.slabPixels) return;
+    const unsigned long long key = keybuf[pix];
+    const bool clear = (F.flags & CRB_CLEAR_FIRST) != 0;
+    float z = Z_INIT, c[3] = {0.f, 0.f, 0.f}, nn[3] = {0.f, 0.f, 0.f};
+    bool write = clear;
+    if (key != KEY_EMPTY) {
+        keybuf[pix] = KEY_EMPTY;
+        const unsigned tri = ~(unsigned)(key & 0xFFFFFFFFull);
+        const Tri9 t = load_tri9(F, tri);
+        const int y = F.row0 + (int)(pix / F.W), x = (int)(pix % F.W);
+        float fz, fc[3], fn[3];
+        if (shade_fragment(F, t, tri, nullptr, (float)x, (float)y, fz, fc, fn)) {
+            const float zold = clear ? Z_INIT : F.z[pix];
+            if (!(fz > zold)) {
+                z = fz; c[0] = fc[0]; c[1] = fc[1]; c[2] = fc[2]; nn[0] = fn[0]; nn[1] = fn[1]; nn[2] = fn[2];
+                write = true;
+            }
+        }
+    }
+    if (!write) return;
+    F.z[pix] = z;
+    F.color[pix * 3] = c[0]; F.color[pix * 3 + 1] = c[1]; F.color[pix * 3 + 2] = c[2];
+    F.normals[pix * 3] = nn[0]; F.normals[pix * 3 + 1] = nn[1]; F.normals[pix * 3 + 2] = nn[2];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// small kernels: fills, post-passes, view export
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) k_fill_u64(unsigned long long *p, long long n, unsigned long long v)
+{
+    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) p[i] = v;
+}
+__global__ void __launch_bounds__(NT) k_fill_u32(unsigned *p, long long n, unsigned v)
+{
+    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) p[i] = v;
+}
+
+// pyx:65-67
+__global__ void __launch_bounds__(NT) k_init_buffers(float *z, float *color, float *normals, long long pixels)
+{
+    const long long stride = (long long)gridDim.x * NT;
+    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < pixels * 3; i += stride) {
+        color[i] = 0.0f;
+        normals[i] = 0.0f;
+        if (i < pixels) z[i] = Z_INIT;
+    }
+}
+
+// guro_illumination.py:20-27 over the whole buffer, in place
+__global__ void __launch_bounds__(NT) k_guro(float *color, const float *normals, long long pixels, float l0, float l1, float l2)
+{
+    const long long stride = (long long)gridDim.x * NT;
+    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < pixels; i += stride) {
+        const float n0 = normals[i * 3], n1 = normals[i * 3 + 1], n2 = normals[i * 3 + 2];
+        const float dot = (n0 * l0 + n1 * l1) + n2 * l2;
+        const float nrm = sqrtf((n0 * n0 + n1 * n1) + n2 * n2);
+        float s = dot / (nrm + 1e-6f);
+        if (s < 0.0f) s = 0.0f;
+        if (s > 1.0f) s = 1.0f;
+        color[i * 3] *= s; color[i * 3 + 1] *= s; color[i * 3 + 2] *= s;
+    }
+}
+
+// run.py:26
+__global__ void __launch_bounds__(NT) k_color_u8_flipped(const float *color, unsigned char *out, int rows, int W)
+{
+    const long long n = (long long)rows * W * 3, stride = (long long)gridDim.x * NT;
+    const long long rowElems = (long long)W * 3;
+    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += stride) {
+        const long long r = i / rowElems, e = i % rowElems;
+        out[(rows - 1 - r) * rowElems + e] = to_u8(color[i]);
+    }
+}
+
+__global__ void __launch_bounds__(NT) k_transform_view(const float *v, const float *n, long long nVerts, const float *view,
+                                                       float *vo, float *no)
+{
+    __shared__ float M[16];
+    if (threadIdx.x < 16) M[threadIdx.x] = view[threadIdx.x];
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * NT + threadIdx.x;
+    if (i >= nVerts) return;
+    float x = v[i * 3], y = v[i * 3 + 1], z = v[i * 3 + 2];
+    view_point(M, x, y, z);
+    vo[i * 3] = x; vo[i * 3 + 1] = y; vo[i * 3 + 2] = z;
+    x = n[i * 3]; y = n[i * 3 + 1]; z = n[i * 3 + 2];
+    view_normal(M, x, y, z);
+    no[i * 3] = x; no[i * 3 + 1] = y; no[i * 3 + 2] = z;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess) return fail(CRB_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));     \
+    } while (0)
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace
+
+struct crb_filler {
+    int h, w, device;
+    int row0, row1;
+    float fov, z_near, z_far;
+    ProjC proj;
+    // outputs
+    float *z, *color, *normals;
+    bool own_buffers;
+    // workspace
+    void *ws;
+    size_t ws_bytes;
+    bool own_ws;
+    long long maxT;
+    int maxViews;
+    long long pairCap;
+    float4 *rec0, *rec1, *rec2;
+    unsigned *count, *offset, *cursor, *list;
+    unsigned long long *total;
+    float *stage_v, *stage_c, *stage_n;  // device staging for host-pointer calls
+    // differential path scratch (library-owned, lazily allocated)
+    unsigned long long *keybuf;
+    long long keybuf_pixels;
+    long long launches;
+};
+
+namespace {
+
+struct WsLayout {
+    size_t rec0, rec1, rec2, count, offset, cursor, list, total, sv, sc, sn, bytes;
+};
+
+long long default_pair_cap(const crb_filler *f, long long T, int views)
+{
+    const long long tiles = (long long)((f->w + TW - 1) / TW) * ((f->row1 - f->row0 + TH - 1) / TH);
+    long long cap = 4 * T * views + tiles * views + 65536;
+    return cap;
+}
+
+WsLayout ws_layout(const crb_filler *f, long long T, int views, long long pairCap)
+{
+    WsLayout L;
+    const long long tiles = (long long)((f->w + TW - 1) / TW) * ((f->row1 - f->row0 + TH - 1) / TH);
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 256); return at; };
+    const size_t recs = (size_t)(T > 0 ? T : 1) * views;
+    L.rec0 = take(recs * sizeof(float4));
+    L.rec1 = take(recs * sizeof(float4));
+    L.rec2 = take(recs * sizeof(float4));
+    L.count = take((size_t)tiles * views * 4);
+    L.offset = take((size_t)tiles * views * 4);
+    L.cursor = take((size_t)tiles * views * 4);
+    L.list = take((size_t)pairCap * 4);
+    L.total = take(64);
+    L.sv = take((size_t)(T > 0 ? T : 1) * 36);
+    L.sc = take((size_t)(T > 0 ? T : 1) * 36);
+    L.sn = take((size_t)(T > 0 ? T : 1) * 36);
+    L.bytes = o;
+    return L;
+}
+
+int check_filler(const crb_filler *f)
+{
+    if (!f) return fail(CRB_ERR_INVALID, "filler is NULL");
+    return CRB_OK;
+}
+
+int host_projection(int h, int w, float fov, float z_near, float z_far, ProjC *P)
+{
+    if (w == 0) return fail(CRB_ERR_ZERODIV, "division by zero");  // pyx:59 h / w
+    const float a = (float)((double)h / (double)w);
+    const double ang = (((double)fov / 2.0) / 180.0) * 3.141592653589793;  // pyx:55, np.pi
+    const float fl = (float)(1.0 / tan(ang));
+    const float d = z_far - z_near;
+    if (d == 0.0f || a == 0.0f) return fail(CRB_ERR_ZERODIV, "float division");  // pyx:84, pyx:86
+    const float q = z_far / d;
+    memset(P->p, 0, sizeof(P->p));
+    P->p[0] = fl / a;
+    P->p[5] = fl;
+    P->p[10] = q;
+    P->p[11] = 1.0f;
+    P->p[14] = (-z_near) * q;
+    P->xs = (float)((double)w / 2.0);
+    P->ys = (float)((double)h / 2.0);
+    return CRB_OK;
+}
+
+void fill_frame(const crb_filler *f, Frame *F)
+{
+    memset(F, 0, sizeof(*F));
+    F->proj = f->proj;
+    F->W = f->w;
+    F->H = f->h;
+    F->row0 = f->row0;
+    F->row1 = f->row1;
+    F->tilesX = (f->w + TW - 1) / TW;
+    F->tilesY = (f->row1 - f->row0 + TH - 1) / TH;
+    F->nTiles = F->tilesX * F->tilesY;
+    F->rec0 = f->rec0; F->rec1 = f->rec1; F->rec2 = f->rec2;
+    F->count = f->count; F->offset = f->offset; F->cursor = f->cursor; F->list = f->list;
+    F->total = f->total;
+    F->pairCap = f->pairCap;
+    F->slabPixels = (long long)(f->row1 - f->row0) * f->w;
+}
+
+int launch_check(crb_filler *f, const char *name)
+{
+    f->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(CRB_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e));
+    return CRB_OK;
+}
+
+// project/setup/count -> alloc -> fill -> raster+shade for up to maxViews views
+int run_tiled(crb_filler *f, Frame &F, cudaStream_t st)
+{
+    int rc;
+    const unsigned gT = (unsigned)((F.T + NT - 1) / NT);
+    if (F.T > 0) {
+        k_setup<<<dim3(gT, F.nViews), NT, 0, st>>>(F);
+        if ((rc = launch_check(f, "k_setup"))) return rc;
+    } else {
+        CU(cudaMemsetAsync(f->total, 0, 8, st));
+    }
+    const long long nAll = (long long)F.nViews * F.nTiles;
+    k_alloc<<<(unsigned)((nAll + NT - 1) / NT), NT, 0, st>>>(F);
+    if ((rc = launch_check(f, "k_alloc"))) return rc;
+    if (F.T > 0) {
+        k_fill<<<dim3(gT, F.nViews), NT, 0, st>>>(F);
+        if ((rc = launch_check(f, "k_fill"))) return rc;
+    }
+    k_raster<<<dim3(F.nTiles, F.nViews), NT, 0, st>>>(F);
+    return launch_check(f, "k_raster");
+}
+
+int run_atomic(crb_filler *f, Frame &F, cudaStream_t st)
+{
+    int rc;
+    if (F.nViews != 1 || F.views) return fail(CRB_ERR_INVALID, "CRB_PATH_ATOMIC supports single-view renders only");
+    if (!F.z || !F.color || !F.normals) return fail(CRB_ERR_STATE, "CRB_PATH_ATOMIC needs all three buffers");
+    if (f->keybuf_pixels < F.slabPixels) {
+        if (f->keybuf) cudaFree(f->keybuf);
+        f->keybuf = nullptr;
+        CU(cudaMalloc(&f->keybuf, (size_t)F.slabPixels * 8));
+        f->keybuf_pixels = F.slabPixels;
+        k_fill_u64<<<1184, NT, 0, st>>>(f->keybuf, F.slabPixels, KEY_EMPTY);
+        if ((rc = launch_check(f, "k_fill_u64"))) return rc;
+    }
+    if (F.T > 0) {
+        k_setup<<<dim3((unsigned)((F.T + NT - 1) / NT), 1), NT, 0, st>>>(F);
+        if ((rc = launch_check(f, "k_setup"))) return rc;
+        k_raster_atomic<<<(unsigned)((F.T * 32 + NT - 1) / NT), NT, 0, st>>>(F, f->keybuf);
+        if ((rc = launch_check(f, "k_raster_atomic"))) return rc;
+    }
+    k_shade_atomic<<<(unsigned)((F.slabPixels + NT - 1) / NT), NT, 0, st>>>(F, f->keybuf);
+    return launch_check(f, "k_shade_atomic");
+}
+
+int bind_ws_pointers(crb_filler *f, void *ws, size_t bytes, long long T, int views, long long pairCap, cudaStream_t st)
+{
+    if (views < 1) views = 1;
+    if (T < 0) return fail(CRB_ERR_INVALID, "max_triangles < 0");
+    if (pairCap <= 0) pairCap = default_pair_cap(f, T, views);
+    if (pairCap > 0xFFFFFFF0ll) return fail(CRB_ERR_INVALID, "pair capacity exceeds 32-bit list offsets");
+    const WsLayout L = ws_layout(f, T, views, pairCap);
+    if (!ws || bytes < L.bytes) return fail(CRB_ERR_INVALID, "workspace too small: %zu < %zu", bytes, L.bytes);
+    if (reinterpret_cast<uintptr_t>(ws) & 255u) return fail(CRB_ERR_INVALID, "workspace must be 256-byte aligned");
+    char *b = (char *)ws;
+    f->ws = ws; f->ws_bytes = bytes;
+    f->maxT = T; f->maxViews = views; f->pairCap = pairCap;
+    f->rec0 = (float4 *)(b + L.rec0); f->rec1 = (float4 *)(b + L.rec1); f->rec2 = (float4 *)(b + L.rec2);
+    f->count = (unsigned *)(b + L.count); f->offset = (unsigned *)(b + L.offset); f->cursor = (unsigned *)(b + L.cursor);
+    f->list = (unsigned *)(b + L.list);
+    f->total = (unsigned long long *)(b + L.total);
+    f->stage_v = (float *)(b + L.sv); f->stage_c = (float *)(b + L.sc); f->stage_n = (float *)(b + L.sn);
+    CU(cudaMemsetAsync(b + L.count, 0, L.offset - L.count, st));  // tile counts start at zero, k_raster keeps them so
+    CU(cudaMemsetAsync(b + L.total, 0, 64, st));
+    return CRB_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int crb_version(void) { return CRB_VERSION; }
+const char *crb_last_error(void) { return g_err; }
+
+int crb_device_count(int *count)
+{
+    if (!count) return fail(CRB_ERR_INVALID, "count is NULL");
+    CU(cudaGetDeviceCount(count));
+    return CRB_OK;
+}
+
+int crb_projection(int h, int w, float fov, float z_near, float z_far, float proj[16])
+{
+    if (!proj) return fail(CRB_ERR_INVALID, "proj is NULL");
+    ProjC P;
+    int rc = host_projection(h, w, fov, z_near, z_far, &P);
+    if (rc) return rc;
+    memcpy(proj, P.p, sizeof(P.p));
+    return CRB_OK;
+}
+
+int crb_create(int h, int w, float fov, float z_near, float z_far, int device, crb_filler **out)
+{
+    if (!out) return fail(CRB_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (h < 0 || w < 0 || h > MAX_DIM || w > MAX_DIM) return fail(CRB_ERR_INVALID, "resolution %dx%d outside [0,%d]", h, w, MAX_DIM);
+    ProjC P;
+    int rc = host_projection(h, w, fov, z_near, z_far, &P);
+    if (rc) return rc;
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(CRB_ERR_INVALID, "device %d not in [0,%d)", device, ndev);
+    crb_filler *f = new (std::nothrow) crb_filler();
+    if (!f) return fail(CRB_ERR_INVALID, "out of host memory");
+    memset(f, 0, sizeof(*f));
+    f->h = h; f->w = w; f->device = device;
+    f->row0 = 0; f->row1 = h;
+    f->fov = fov; f->z_near = z_near; f->z_far = z_far;
+    f->proj = P;
+    *out = f;
+    return CRB_OK;
+}
+
+void crb_destroy(crb_filler *f)
+{
+    if (!f) return;
+    cudaSetDevice(f->device);
+    if (f->own_buffers) { cudaFree(f->z); cudaFree(f->color); cudaFree(f->normals); }
+    if (f->own_ws) cudaFree(f->ws);
+    if (f->keybuf) cudaFree(f->keybuf);
+    delete f;
+}
+
+int crb_get_size(const crb_filler *f, int *h, int *w)
+{
+    if (check_filler(f)) return CRB_ERR_INVALID;
+    if (h) *h = f->h;
+    if (w) *w = f->w;
+    return CRB_OK;
+}
+
+int crb_get_projection(const crb_filler *f, float proj[16])
+{
+    if (check_filler(f) || !proj) return fail(CRB_ERR_INVALID, "NULL argument");
+    memcpy(proj, f->proj.p, sizeof(f->proj.p));
+    return CRB_OK;
+}
+
+int crb_set_band(crb_filler *f, int row0, int row1)
+{
+    if (check_filler(f)) return CRB_ERR_INVALID;
+    if (row0 < 0 || row1 > f->h || row0 > row1) return fail(CRB_ERR_INVALID, "band [%d,%d) outside [0,%d)", row0, row1, f->h);
+    if (f->ws || f->z) return fail(CRB_ERR_STATE, "set the band before binding buffers / workspace");
+    f->row0 = row0; f->row1 = row1;
+    return CRB_OK;
+}
+
+int crb_bind_buffers(crb_filler *f, float *z, float *color, float *normals)
+{
+    if (check_filler(f)) return CRB_ERR_INVALID;
+    if (f->own_buffers) return fail(CRB_ERR_STATE, "buffers are library-owned");
+    if ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(color) | reinterpret_cast<uintptr_t>(normals)) & 15u)
+        return fail(CRB_ERR_INVALID, "buffers must be 16-byte aligned");
+    f->z = z; f->color = color; f->normals = normals;
+    return CRB_OK;
+}
+
+size_t crb_workspace_bytes(const crb_filler *f, int64_t max_triangles, int max_views, int64_t pair_capacity)
+{
+    if (!f || max_triangles < 0) return 0;
+    if (max_views < 1) max_views = 1;
+    if (pair_capacity <= 0) pair_capacity = default_pair_cap(f, max_triangles, max_views);
+    return ws_layout(f, max_triangles, max_views, pair_capacity).bytes;
+}
+
+int crb_bind_workspace(crb_filler *f, void *workspace, size_t bytes, int64_t max_triangles, int max_views,
+                       int64_t pair_capacity, void *stream)
+{
+    if (check_filler(f)) return CRB_ERR_INVALID;
+    if (f->own_ws) return fail(CRB_ERR_STATE, "workspace is library-owned");
+    CU(cudaSetDevice(f->device));
+    return bind_ws_pointers(f, workspace, bytes, max_triangles, max_views, pair_capacity, (cudaStream_t)stream);
+}
+
+int crb_alloc_owned(crb_filler *f, int64_t max_triangles, int max_views, int64_t pair_capacity)
+{
+    if (check_filler(f)) return CRB_ERR_INVALID;
+    CU(cudaSetDevice(f->device));
+    const size_t px = (size_t)(f->row1 - f->row0) * f->w;
+    if (!f->z && !f->own_buffers) {
+        CU(cudaMalloc(&f->z, (px ? px : 1) * 4));
+        CU(cudaMalloc(&f->color, (px ? px : 1) * 12));
+        CU(cudaMalloc(&f->normals, (px ? px : 1) * 12));
+        f->own_buffers = true;
+        int rc = crb_init_buffers(f, nullptr);
+        if (rc) return rc;
+    }
+    if (f->own_ws) { cudaFree(f->ws); f->ws = nullptr; f->own_ws = false; }
+    if (max_views < 1) max_views = 1;
+    if (pair_capacity <= 0) pair_capacity = default_pair_cap(f, max_triangles, max_views);
+    const size_t bytes = ws_layout(f, max_triangles, max_views, pair_capacity).bytes;
+    void *ws = nullptr;
+    CU(cudaMalloc(&ws, bytes));
+    int rc = bind_ws_pointers(f, ws, bytes, max_triangles, max_views, pair_capacity, nullptr);
+    if (rc) { cudaFree(ws); f->ws = nullptr; return rc; }
+    f->own_ws = true;
+    return CRB_OK;
+}
+
+int crb_device_buffers(const crb_filler *f, float **z, float **color, float **normals)
+{
+    if (check_filler(f)) return CRB_ERR_INVALID;
+    if (z) *z = f->z;
+    if (color) *color = f->color;
+    if (normals) *normals = f->normals;
+    return CRB_OK;
+}
+
+int crb_init_buffers(crb_filler *f, void *stream)
+{
+    if (check_filler(f)) return CRB_ERR_INVALID;
+    if (!f->z || !f->color || !f->normals) return fail(CRB_ERR_STATE, "buffers not bound");
+    CU(cudaSetDevice(f->device));
+    const long long px = (long long)(f->row1 - f->row0) * f->w;
+    if (px == 0) return CRB_OK;
+    k_init_buffers<<<1184, NT, 0, (cudaStream_t)stream>>>(f->z, f->color, f->normals, px);
+    return launch_check(f, "k_init_buffers");
+}
+
+int crb_render(crb_filler *f, const float *v, const float *c, const float *n, int64_t T, unsigned flags, void *stream)
+{
+    if (check_filler(f)) return CRB_ERR_INVALID;
+    if (T < 0) return fail(CRB_ERR_INVALID, "T < 0");
+    if (T > 0 && (!v || !c || !n)) return fail(CRB_ERR_INVALID, "NULL triangle array");
+    if (!f->z || !f->color || !f->normals) return fail(CRB_ERR_STATE, "buffers not bound");
+    if (!f->ws) return fail(CRB_ERR_STATE, "workspace not bound");
+    if (T > f->maxT) return fail(CRB_ERR_STATE, "T=%lld exceeds the workspace's max_triangles=%lld", (long long)T, f->maxT);
+    if (T > 0xFFFFFFF0ll) return fail(CRB_ERR_INVALID, "T exceeds 32-bit triangle indices");
+    CU(cudaSetDevice(f->device));
+    if ((long long)(f->row1 - f->row0) * f->w == 0) return CRB_OK;
+    Frame F;
+    fill_frame(f, &F);
+    F.T = T; F.nViews = 1; F.flags = flags & (CRB_CLEAR_FIRST | CRB_PATH_ATOMIC);
+    F.v = v; F.c = c; F.n = n;
+    F.z = f->z; F.color = f->color; F.normals = f->normals;
+    return (flags & CRB_PATH_ATOMIC) ? run_atomic(f, F, (cudaStream_t)stream) : run_tiled(f, F, (cudaStream_t)stream);
+}
+
+int crb_render_host(crb_filler *f, const float *v, const float *c, const float *n, int64_t T, unsigned flags,
+                    unsigned download_mask, float *z_out, float *color_out, float *normals_out, void *stream)
+{
+    if (check_filler(f)) return CRB_ERR_INVALID;
+    if (!f->ws) return fail(CRB_ERR_STATE, "workspace not bound");
+    if (T < 0 || T > f->maxT) return fail(CRB_ERR_STATE, "T=%lld outside the workspace's [0,%lld]", (long long)T, f->maxT);
+    if (T > 0 && (!v || !c || !n)) return fail(CRB_ERR_INVALID, "NULL triangle array");
+    CU(cudaSetDevice(f->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (T > 0) {
+        CU(cudaMemcpyAsync(f->stage_v, v, (size_t)T * 36, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(f->stage_c, c, (size_t)T * 36, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(f->stage_n, n, (size_t)T * 36, cudaMemcpyHostToDevice, st));
+    }
+    int rc = crb_render(f, f->stage_v, f->stage_c, f->stage_n, T, flags, stream);
+    if (rc) return rc;
+    rc = crb_download(f, download_mask, z_out, color_out, normals_out, stream);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(st));
+    return CRB_OK;
+}
+
+int crb_render_views(crb_filler *f, const float *v, const float *c, const float *n, int64_t T, const float *views,
+                     int n_views, float *z_out, float *color_out, float *normals_out, uint8_t *color_u8_out,
+                     unsigned flags, const float light[3], void *stream)
+{
+    if (check_filler(f)) return CRB_ERR_INVALID;
+    if (T < 0 || n_views < 0) return fail(CRB_ERR_INVALID, "negative size");
+    if (T > 0 && (!v || !c || !n)) return fail(CRB_ERR_INVALID, "NULL triangle array");
+    if (n_views > 0 && !views) return fail(CRB_ERR_INVALID, "views is NULL");
+    if (!f->ws) return fail(CRB_ERR_STATE, "workspace not bound");
+    if (T > f->maxT) return fail(CRB_ERR_STATE, "T=%lld exceeds the workspace's max_triangles=%lld", (long long)T, f->maxT);
+    if (flags & CRB_PATH_ATOMIC) return fail(CRB_ERR_INVALID, "CRB_PATH_ATOMIC supports single-view renders only");
+    if ((flags & CRB_GURO) && !light) return fail(CRB_ERR_INVALID, "CRB_GURO needs a light direction");
+    if ((reinterpret_cast<uintptr_t>(z_out) | reinterpret_cast<uintptr_t>(color_out) | reinterpret_cast<uintptr_t>(normals_out)) & 15u)
+        return fail(CRB_ERR_INVALID, "output slabs must be 16-byte aligned");
+    CU(cudaSetDevice(f->device));
+    const long long slab = (long long)(f->row1 - f->row0) * f->w;
+    if (slab == 0) return CRB_OK;
+    for (int v0 = 0; v0 < n_views; v0 += f->maxViews) {
+        Frame F;
+        fill_frame(f, &F);
+        F.T = T; F.nViews = (n_views - v0 < f->maxViews) ? n_views - v0 : f->maxViews;
+        F.flags = (flags & CRB_GURO) | CRB_CLEAR_FIRST;
+        F.v = v; F.c = c; F.n = n;
+        F.views = views + (size_t)v0 * 16;
+        F.z = z_out ? z_out + (size_t)v0 * slab : nullptr;
+        F.color = color_out ? color_out + (size_t)v0 * slab * 3 : nullptr;
+        F.normals = normals_out ? normals_out + (size_t)v0 * slab * 3 : nullptr;
+        F.color_u8 = color_u8_out ? color_u8_out + (size_t)v0 * slab * 3 : nullptr;
+        if (light) { F.light[0] = light[0]; F.light[1] = light[1]; F.light[2] = light[2]; }
+        int rc = run_tiled(f, F, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return CRB_OK;
+}
+
+int crb_transform_view(crb_filler *f, const float *v, const float *n, int64_t T, const float *view, float *v_out,
+                       float *n_out, void *stream)
+{
+    if (check_filler(f)) return CRB_ERR_INVALID;
+    if (T < 0 || !view || (T > 0 && (!v || !n || !v_out || !n_out))) return fail(CRB_ERR_INVALID, "bad argument");
+    CU(cudaSetDevice(f->device));
+    if (T == 0) return CRB_OK;
+    k_transform_view<<<(unsigned)((T * 3 + NT - 1) / NT), NT, 0, (cudaStream_t)stream>>>(v, n, T * 3, view, v_out, n_out);
+    return launch_check(f, "k_transform_view");
+}
+
+int crb_guro(crb_filler *f, const float light[3], void *stream)
+{
+    if (check_filler(f) || !light) return fail(CRB_ERR_INVALID, "NULL argument");
+    if (!f->color || !f->normals) return fail(CRB_ERR_STATE, "buffers not bound");
+    CU(cudaSetDevice(f->device));
+    const long long px = (long long)(f->row1 - f->row0) * f->w;
+    if (px == 0) return CRB_OK;
+    k_guro<<<1184, NT, 0, (cudaStream_t)stream>>>(f->color, f->normals, px, light[0], light[1], light[2]);
+    return launch_check(f, "k_guro");
+}
+
+int crb_color_u8_flipped(crb_filler *f, uint8_t *out_u8, void *stream)
+{
+    if (check_filler(f) || !out_u8) return fail(CRB_ERR_INVALID, "NULL argument");
+    if (!f->color) return fail(CRB_ERR_STATE, "buffers not bound");
+    CU(cudaSetDevice(f->device));
+    if ((long long)(f->row1 - f->row0) * f->w == 0) return CRB_OK;
+    k_color_u8_flipped<<<1184, NT, 0, (cudaStream_t)stream>>>(f->color, out_u8, f->row1 - f->row0, f->w);
+    return launch_check(f, "k_color_u8_flipped");
+}
+
+int crb_download(crb_filler *f, unsigned mask, float *z_host, float *color_host, float *normals_host, void *stream)
+{
+    if (check_filler(f)) return CRB_ERR_INVALID;
+    if (!f->z || !f->color || !f->normals) return fail(CRB_ERR_STATE, "buffers not bound");
+    CU(cudaSetDevice(f->device));
+    const size_t px = (size_t)(f->row1 - f->row0) * f->w;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (px == 0) return CRB_OK;
+    if ((mask & CRB_BUF_Z) && z_host) CU(cudaMemcpyAsync(z_host, f->z, px * 4, cudaMemcpyDeviceToHost, st));
+    if ((mask & CRB_BUF_COLOR) && color_host) CU(cudaMemcpyAsync(color_host, f->color, px * 12, cudaMemcpyDeviceToHost, st));
+    if ((mask & CRB_BUF_NORMALS) && normals_host) CU(cudaMemcpyAsync(normals_host, f->normals, px * 12, cudaMemcpyDeviceToHost, st));
+    return CRB_OK;
+}
+
+int crb_upload(crb_filler *f, unsigned mask, const float *z_host, const float *color_host, const float *normals_host,
+               void *stream)
+{
+    if (check_filler(f)) return CRB_ERR_INVALID;
+    if (!f->z || !f->color || !f->normals) return fail(CRB_ERR_STATE, "buffers not bound");
+    CU(cudaSetDevice(f->device));
+    const size_t px = (size_t)(f->row1 - f->row0) * f->w;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (px == 0) return CRB_OK;
+    if ((mask & CRB_BUF_Z) && z_host) CU(cudaMemcpyAsync(f->z, z_host, px * 4, cudaMemcpyHostToDevice, st));
+    if ((mask & CRB_BUF_COLOR) && color_host) CU(cudaMemcpyAsync(f->color, color_host, px * 12, cudaMemcpyHostToDevice, st));
+    if ((mask & CRB_BUF_NORMALS) && normals_host) CU(cudaMemcpyAsync(f->normals, normals_host, px * 12, cudaMemcpyHostToDevice, st));
+    return CRB_OK;
+}
+
+int crb_status(crb_filler *f, int64_t *pairs_needed, int64_t *pair_capacity, void *stream)
+{
+    if (check_filler(f)) return CRB_ERR_INVALID;
+    if (!f->ws) return fail(CRB_ERR_STATE, "workspace not bound");
+    CU(cudaSetDevice(f->device));
+    unsigned long long t[2] = {0, 0};
+    CU(cudaMemcpyAsync(t, f->total, 16, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    if (pair_capacity) *pair_capacity = f->pairCap;
+    if (t[1] > (unsigned long long)f->pairCap) {
+        if (pairs_needed) *pairs_needed = (int64_t)t[1];
+        CU(cudaMemsetAsync(f->total + 1, 0, 8, (cudaStream_t)stream));
+        return fail(CRB_ERR_OVERFLOW, "frame needs %llu (triangle,tile) pairs, workspace holds %lld; frame not drawn", t[1],
+                    f->pairCap);
+    }
+    if (pairs_needed) *pairs_needed = (int64_t)t[0];
+    return CRB_OK;
+}
+
+int64_t crb_launch_count(const crb_filler *f) { return f ? f->launches : 0; }
+
+}  // extern "C"

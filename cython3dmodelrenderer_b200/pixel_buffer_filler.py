@@ -1,0 +1,269 @@
+"""Drop-in `AdvancedPixelBufferFiller` backed by libcrender_b200.so (hand-written sm_100a CUDA).
+
+Mirrors the reference extension type
+(crender/cy/pixel_buffer_filler/advanced_pixel_buffer_filler.pyx:20-253): same constructor, `get_size`,
+`render_model`, `get_normals_buffer`, `get_color_buffer`, `get_z_buffer`, same errors, same persistent
+(compositing) buffers, same live-view contract for the returned arrays.  PyTorch only owns memory
+(device buffers, workspace, pinned host mirrors) and supplies the stream; all work happens behind the
+C ABI (include/crender_b200.h).  There is no CPU fallback.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+
+
+def _require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("cython3dmodelrenderer_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch
+
+
+def _check_tri_array(a, name):
+    """Same acceptance rules as the reference's `float[:, :, :]` memoryviews (pyx:94-96)."""
+    if a is None:
+        # `model._colors_by_triangles.copy()` on an untextured model (pyx:95)
+        raise AttributeError("'NoneType' object has no attribute 'copy'")
+    a = np.asarray(a)
+    if a.dtype != np.float32:
+        got = {"float64": "double", "int32": "int", "int64": "long", "float16": "npy_half",
+               "uint8": "unsigned char"}.get(a.dtype.name, a.dtype.name)
+        raise ValueError(f"Buffer dtype mismatch, expected 'float' but got '{got}'")
+    if a.ndim != 3:
+        raise ValueError(f"Buffer has wrong number of dimensions (expected 3, got {a.ndim})")
+    if a.shape[1:] != (3, 3):
+        raise ValueError(f"{name}: expected shape [T,3,3], got {tuple(a.shape)}")
+    return a
+
+
+class AdvancedPixelBufferFiller:
+    """B200 implementation of the Version C filler.  `n_threads` is accepted and ignored.
+
+    Extra keyword (not in the reference): `device` -- CUDA device index (default: torch's current device),
+    `band=(row0,row1)` -- own only those rows of the h x w image (screen-band sharding).
+    """
+
+    def __init__(self, h, w, fov=90.0, z_near=0.1, z_far=1000.0, n_threads=1, device=None, band=None):
+        torch = _require_cuda()
+        self._torch = torch
+        self._L = _lib.load_library()
+        self.h, self.w = int(h), int(w)   # pyx:40-41 `<int>h`
+        self.n_threads = n_threads
+        self._device = torch.cuda.current_device() if device is None else int(device)
+        self._dev = torch.device("cuda", self._device)
+        handle = ctypes.c_void_p()
+        check(self._L.crb_create(self.h, self.w, float(fov), float(z_near), float(z_far), self._device,
+                                 ctypes.byref(handle)))
+        self._handle = handle
+        self.row0, self.row1 = (0, self.h) if band is None else (int(band[0]), int(band[1]))
+        if band is not None:
+            check(self._L.crb_set_band(self._handle, self.row0, self.row1))
+        rows = self.row1 - self.row0
+        with torch.cuda.device(self._dev):
+            # pyx:65-67: normals 0, colour 0, z = 1e6
+            self._z = torch.empty((rows, self.w), dtype=torch.float32, device=self._dev)
+            self._color = torch.empty((rows, self.w, 3), dtype=torch.float32, device=self._dev)
+            self._normals = torch.empty((rows, self.w, 3), dtype=torch.float32, device=self._dev)
+            check(self._L.crb_bind_buffers(self._handle, self._z.data_ptr(), self._color.data_ptr(),
+                                           self._normals.data_ptr()))
+            check(self._L.crb_init_buffers(self._handle, self._stream()))
+        self._ws = None
+        self._ws_T = -1
+        self._ws_views = 1
+        self._pair_cap = 0
+        self._stage = None            # pinned host staging for the three input arrays
+        self._host = {}               # name -> pinned torch tensor (host mirror); numpy views in _host_np
+        self._host_np = {}
+        self._stale = {"z": True, "color": True, "normals": True}   # device newer than host mirror
+        self._exposed = set()         # mirrors handed to the caller (may have been written through)
+        self._pending_clear = False
+
+    # ------------------------------------------------------------------------------------------------ plumbing
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None):
+                self._L.crb_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+    def _stream(self):
+        return ctypes.c_void_p(self._torch.cuda.current_stream(self._dev).cuda_stream)
+
+    def _ensure_workspace(self, T, views=1, pair_cap=0):
+        if self._ws is not None and T <= self._ws_T and views <= self._ws_views and pair_cap <= self._pair_cap:
+            return
+        torch = self._torch
+        T = max(int(T), self._ws_T, 1)
+        views = max(int(views), self._ws_views)
+        pair_cap = max(int(pair_cap), self._pair_cap if pair_cap else 0)
+        torch.cuda.current_stream(self._dev).synchronize()
+        nbytes = self._L.crb_workspace_bytes(self._handle, T, views, pair_cap)
+        with torch.cuda.device(self._dev):
+            ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=self._dev)
+        ptr = (ws.data_ptr() + 255) // 256 * 256
+        check(self._L.crb_bind_workspace(self._handle, ptr, nbytes, T, views, pair_cap, self._stream()))
+        self._ws, self._ws_T, self._ws_views = ws, T, views
+        cap = ctypes.c_int64()
+        need = ctypes.c_int64()
+        check(self._L.crb_status(self._handle, ctypes.byref(need), ctypes.byref(cap), self._stream()))
+        self._pair_cap = cap.value
+
+    def _mirror(self, name):
+        if name not in self._host:
+            src = {"z": self._z, "color": self._color, "normals": self._normals}[name]
+            t = self._torch.empty(src.shape, dtype=self._torch.float32, pin_memory=True)
+            self._host[name] = t
+            self._host_np[name] = t.numpy()
+        return self._host[name]
+
+    def _push_exposed(self):
+        """Live-view contract (pyx:246-253 return views of the filler's own memory): whatever the caller wrote
+        through a returned array is part of the buffers the next render composites into."""
+        if not self._exposed:
+            return
+        mask, ptrs = 0, {"z": None, "color": None, "normals": None}
+        for name, bit in (("z", _lib.CRB_BUF_Z), ("color", _lib.CRB_BUF_COLOR), ("normals", _lib.CRB_BUF_NORMALS)):
+            if name in self._exposed and not self._stale[name]:
+                mask |= bit
+                ptrs[name] = self._host[name].data_ptr()
+        if mask:
+            check(self._L.crb_upload(self._handle, mask, ptrs["z"], ptrs["color"], ptrs["normals"], self._stream()))
+
+    def _materialize_clear(self):
+        if self._pending_clear:          # clear() with no render since: materialise the fresh-filler state
+            check(self._L.crb_init_buffers(self._handle, self._stream()))
+            self._pending_clear = False
+
+    def _get(self, name, bit):
+        t = self._mirror(name)
+        self._materialize_clear()
+        if self._stale[name]:
+            args = {"z": None, "color": None, "normals": None}
+            args[name] = t.data_ptr()
+            check(self._L.crb_download(self._handle, bit, args["z"], args["color"], args["normals"], self._stream()))
+            self._torch.cuda.current_stream(self._dev).synchronize()
+            self._stale[name] = False
+        self._exposed.add(name)
+        return self._host_np[name]
+
+    # ---------------------------------------------------------------------------------------- reference API
+    def get_size(self):
+        """pyx:80-81"""
+        return self.h, self.w
+
+    def render_model(self, model):
+        """pyx:92-104.  Reads model._vertices_by_triangles / _colors_by_triangles / _normals_by_triangles
+        ([T,3,3] float32), never mutates them, composites into the persistent buffers."""
+        v = _check_tri_array(getattr(model, "_vertices_by_triangles"), "vertices")
+        c = _check_tri_array(getattr(model, "_colors_by_triangles"), "colors")
+        n = _check_tri_array(getattr(model, "_normals_by_triangles"), "normals")
+        if not (v.shape[0] == c.shape[0] == n.shape[0]):
+            raise IndexError("Out of bounds on buffer access (axis 0)")   # what the bounds-checked memoryviews raise
+        self.render_arrays(v, c, n)
+
+    def get_normals_buffer(self):
+        """pyx:246-247 -- live float32 [h,w,3] view (same array object on every call)."""
+        return self._get("normals", _lib.CRB_BUF_NORMALS)
+
+    def get_color_buffer(self):
+        """pyx:249-250"""
+        return self._get("color", _lib.CRB_BUF_COLOR)
+
+    def get_z_buffer(self):
+        """pyx:252-253"""
+        return self._get("z", _lib.CRB_BUF_Z)
+
+    # ---------------------------------------------------------------------------------------- extensions
+    def clear(self):
+        """Fresh-filler state (pyx:65-67).  The reference has no reset (a new filler per frame is its idiom,
+        run.py:21); here the clear is fused into the next frame's tile pass instead of a separate memset."""
+        self._pending_clear = True
+        for name in self._stale:
+            self._stale[name] = True
+        self._exposed.clear()   # arrays handed out earlier are detached until fetched again
+
+    def render_arrays(self, v, c, n, path="tiled", check_status=True):
+        """Render [T,3,3] float32 arrays.  numpy inputs are staged through pinned memory and copied H2D;
+        torch CUDA tensors are used in place (device-resident inputs)."""
+        torch = self._torch
+        flags = _lib.CRB_PATH_ATOMIC if path == "atomic" else 0
+        on_device = all(isinstance(a, torch.Tensor) for a in (v, c, n))
+        if on_device:
+            for a in (v, c, n):
+                if a.dtype != torch.float32 or a.dim() != 3 or tuple(a.shape[1:]) != (3, 3) or not a.is_cuda:
+                    raise ValueError("device inputs must be CUDA float32 tensors of shape [T,3,3]")
+            v, c, n = v.contiguous(), c.contiguous(), n.contiguous()
+            T = v.shape[0]
+        else:
+            v, c, n = (np.asarray(a) for a in (v, c, n))
+            T = v.shape[0]
+            if T and bool((v[:, :, 2] == 0).any()):
+                # pyx:122 `buff / z` with Cython's division check: a vertex at z == 0 raises upstream
+                raise ZeroDivisionError("float division")
+        if self._pending_clear:
+            flags |= _lib.CRB_CLEAR_FIRST
+        else:
+            self._push_exposed()
+        self._ensure_workspace(T)
+        while True:
+            if on_device:
+                check(self._L.crb_render(self._handle, v.data_ptr(), c.data_ptr(), n.data_ptr(), T, flags,
+                                         self._stream()))
+            else:
+                if self._stage is None or self._stage.shape[1] < T:
+                    self._stage = torch.empty((3, max(T, 1), 3, 3), dtype=torch.float32, pin_memory=True)
+                    self._stage_np = self._stage.numpy()
+                s = self._stage_np
+                s[0, :T] = v
+                s[1, :T] = c
+                s[2, :T] = n
+                st = self._stage
+                check(self._L.crb_render_host(self._handle, st[0].data_ptr(), st[1].data_ptr(), st[2].data_ptr(), T,
+                                              flags, 0, None, None, None, self._stream()))
+            if not check_status:
+                break
+            need, cap = ctypes.c_int64(), ctypes.c_int64()
+            rc = self._L.crb_status(self._handle, ctypes.byref(need), ctypes.byref(cap), self._stream())
+            if rc == _lib.CRB_ERR_OVERFLOW:
+                # the frame was not drawn; give the pair list the room it asked for and draw it again
+                self._ensure_workspace(T, self._ws_views, int(need.value * 1.25) + 1024)
+                continue
+            check(rc)
+            break
+        self._pending_clear = False
+        for name in self._stale:
+            self._stale[name] = True
+        # arrays already handed out are live views upstream: keep them current
+        for name, bit in (("z", _lib.CRB_BUF_Z), ("color", _lib.CRB_BUF_COLOR), ("normals", _lib.CRB_BUF_NORMALS)):
+            if name in self._exposed:
+                self._get(name, bit)
+
+    def device_buffers(self):
+        """(z, color, normals) torch CUDA tensors -- the device-resident truth (no copy)."""
+        self._materialize_clear()
+        self._push_exposed()
+        return self._z, self._color, self._normals
+
+    def illuminate_guro(self, light_direction):
+        """GuroIllumination.draw_illumination on the device buffers, in place (guro_illumination.py:20-27)."""
+        self._materialize_clear()
+        self._push_exposed()
+        arr = (ctypes.c_float * 3)(*[float(x) for x in light_direction])
+        check(self._L.crb_guro(self._handle, arr, self._stream()))
+        self._stale["color"] = True
+
+    def color_u8_flipped(self):
+        """run.py:26 `image[::-1].astype('uint8')` computed on device; returns a torch CUDA uint8 tensor."""
+        self._materialize_clear()
+        self._push_exposed()
+        out = self._torch.empty((self.row1 - self.row0, self.w, 3), dtype=self._torch.uint8, device=self._dev)
+        check(self._L.crb_color_u8_flipped(self._handle, out.data_ptr(), self._stream()))
+        return out
+
+    @property
+    def launch_count(self):
+        return int(self._L.crb_launch_count(self._handle))

@@ -1,0 +1,162 @@
+/*
+ * crender_b200.h -- C ABI of libcrender_b200.so: the B200 (sm_100a) implementation of the Version C
+ * rendering hot path of oKatanaaa/Cython3DModelRenderer.
+ *
+ * The reference has no C ABI: its boundary is the Cython extension type `AdvancedPixelBufferFiller`
+ * (crender/cy/pixel_buffer_filler/advanced_pixel_buffer_filler.pyx:20), whose `cdef` methods are not
+ * callable from outside.  Each entry point below names the reference lines it stands in for ("pyx" is that
+ * file).  A maintainer binds these from the .pyx (`cdef extern from "crender_b200.h"`) or, as this repo
+ * does, from Python with ctypes -- both are shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is either a HOST pointer or a DEVICE pointer as documented;
+ *   - every function returns CRB_OK (0) or a negative CRB_ERR_* code; crb_last_error() gives the text of the
+ *     calling thread's most recent failure;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Calls are asynchronous
+ *     with respect to the host unless the name says "host" or "sync";
+ *   - a filler is not re-entrant (same as the reference object), different fillers are independent.
+ *   - triangle arrays are [T,3,3] float32, C-contiguous: (triangle, vertex, xyz | BGR | normal xyz), exactly
+ *     `model._vertices_by_triangles/_colors_by_triangles/_normals_by_triangles` (pyx:94-96).
+ *   - output buffers: z [h,w] f32, colour [h,w,3] f32, normals [h,w,3] f32, row-major, y-up (pyx:65-67).
+ */
+#ifndef CRENDER_B200_H
+#define CRENDER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define CRB_VERSION 100
+
+#define CRB_OK 0
+#define CRB_ERR_INVALID (-1)   /* bad argument (NULL, negative size, unsupported resolution) */
+#define CRB_ERR_CUDA (-2)      /* a CUDA runtime call or kernel launch failed                */
+#define CRB_ERR_ZERODIV (-3)   /* where the reference raises ZeroDivisionError (pyx:59,84,86) */
+#define CRB_ERR_STATE (-4)     /* buffers / workspace not bound                              */
+#define CRB_ERR_OVERFLOW (-5)  /* triangle-tile pair list exceeded the workspace; see crb_status */
+
+/* crb_render* flags */
+#define CRB_CLEAR_FIRST 1u     /* fresh-filler semantics (z=1e6, colour=normals=0, pyx:65-67) fused into the frame */
+#define CRB_PATH_ATOMIC 2u     /* differential path: per-triangle raster with global 64-bit atomicMin + deferred
+                                  shading (no binning).  Same results; kept for cross-checking the tiled path. */
+#define CRB_GURO 4u            /* N1: fuse GuroIllumination (guro_illumination.py:20-27) into the shading pass   */
+
+/* which-buffer masks for crb_download / crb_render_host */
+#define CRB_BUF_Z 1u
+#define CRB_BUF_COLOR 2u
+#define CRB_BUF_NORMALS 4u
+#define CRB_BUF_ALL 7u
+
+typedef struct crb_filler crb_filler;
+
+/* ---- library ------------------------------------------------------------------------------------------- */
+int crb_version(void);
+const char *crb_last_error(void);
+int crb_device_count(int *count);
+
+/* ---- constructor pieces: pyx:39-77 (__cinit__) and pyx:83-90 (_init_projection_matrix) ------------------- */
+
+/* Host only.  proj = row-major 4x4 float32 identical to the reference's proj_mat:
+ * f = (float)(1/tan(fov/2/180*pi)) in double on the float fov, a = (float)(h/w), q = z_far/(z_far-z_near),
+ * P00 = f/a, P11 = f, P22 = q, P23 = 1, P32 = -z_near*q (all float).  CRB_ERR_ZERODIV where the reference
+ * raises (w == 0, h == 0, z_far == z_near). */
+int crb_projection(int h, int w, float fov, float z_near, float z_far, float proj[16]);
+
+/* Creates a filler bound to CUDA device `device`.  No buffers are allocated yet: bind caller-owned device
+ * memory with crb_bind_buffers / crb_bind_workspace, or let the library own them (crb_alloc_owned). */
+int crb_create(int h, int w, float fov, float z_near, float z_far, int device, crb_filler **out);
+void crb_destroy(crb_filler *f);
+
+int crb_get_size(const crb_filler *f, int *h, int *w);        /* pyx:80-81 get_size */
+int crb_get_projection(const crb_filler *f, float proj[16]);  /* the cdef attribute proj_mat */
+
+/* Restrict the filler to rows [row0,row1) of the h x w image (screen-tile-band sharding).  The bound
+ * buffers then hold only those rows ([row1-row0, w, ...]).  Per-pixel arithmetic does not depend on the band, so the
+ * concatenated bands equal the full-frame result bit for bit.  Default band is [0,h). */
+int crb_set_band(crb_filler *f, int row0, int row1);
+
+/* ---- memory ------------------------------------------------------------------------------------------------ */
+
+/* Device pointers to caller-owned buffers (e.g. torch tensors): z [rows,w], color [rows,w,3], normals [rows,w,3]. */
+int crb_bind_buffers(crb_filler *f, float *z, float *color, float *normals);
+
+/* Scratch needed to render up to max_triangles triangles in up to max_views simultaneous views with room for
+ * pair_capacity (triangle,tile) pairs (0 = default heuristic). */
+size_t crb_workspace_bytes(const crb_filler *f, int64_t max_triangles, int max_views, int64_t pair_capacity);
+int crb_bind_workspace(crb_filler *f, void *workspace, size_t bytes, int64_t max_triangles, int max_views,
+                       int64_t pair_capacity, void *stream);
+
+/* Library-owned alternative (cudaMalloc): output buffers + workspace.  For hosts without a device allocator. */
+int crb_alloc_owned(crb_filler *f, int64_t max_triangles, int max_views, int64_t pair_capacity);
+int crb_device_buffers(const crb_filler *f, float **z, float **color, float **normals);
+
+/* z = 1e6, colour = 0, normals = 0 (pyx:65-67), asynchronous on `stream`. */
+int crb_init_buffers(crb_filler *f, void *stream);
+
+/* ---- render_model: pyx:92-104 -> project (pyx:106-130) + cull/bbox/raster/z-test/writes (pyx:177-244) ------- */
+
+/* v, c, n: DEVICE pointers, [T,3,3] f32.  Composites into the bound buffers exactly like successive
+ * render_model calls on one reference filler (n_threads=1 order: min depth wins, equal depth -> higher triangle
+ * index / later call wins).  Inputs are never written. */
+int crb_render(crb_filler *f, const float *v, const float *c, const float *n, int64_t T, unsigned flags,
+               void *stream);
+
+/* Same, all pointers HOST memory (pinned recommended): H2D of the three arrays, render, D2H of the buffers named in
+ * `download_mask` (CRB_BUF_*; NULL pointers allowed for buffers not requested), then a stream synchronize.  This is
+ * the call that replaces the body of render_model for a host-resident caller. */
+int crb_render_host(crb_filler *f, const float *v, const float *c, const float *n, int64_t T, unsigned flags,
+                    unsigned download_mask, float *z_out, float *color_out, float *normals_out, void *stream);
+
+/* Batched views (config C5; the reference has no camera stage -- views are made by mutating the model on the host,
+ * crender/cy/data_structures/model.py:238-256).  views: DEVICE [n_views,16] f32 = {R (9, row-major), p (3), q (3), pad}:
+ *   v' = R (v - p) + q,   n' = R n     evaluated per component as ((r0*d0 + r1*d1) + r2*d2) + q, float32, no FMA.
+ * Each view is rendered with fresh-filler semantics into its own slab of z_out [n_views,rows,w], color_out /
+ * normals_out [n_views,rows,w,3] (DEVICE).  Any of the three output pointers may be NULL (buffer not wanted).
+ * color_u8_out, if not NULL, additionally receives run.py:26's output stage on device: [n_views,rows,w,3] uint8,
+ * rows flipped (image[::-1]) and truncated like .astype('uint8'). */
+int crb_render_views(crb_filler *f, const float *v, const float *c, const float *n, int64_t T, const float *views,
+                     int n_views, float *z_out, float *color_out, float *normals_out, uint8_t *color_u8_out,
+                     unsigned flags, const float light[3], void *stream);
+
+/* Writes the camera-space arrays a view produces ([T,3,3] each, DEVICE) -- what the reference would be handed as
+ * model._vertices_by_triangles / _normals_by_triangles for that view.  Used to feed the oracle in parity tests. */
+int crb_transform_view(crb_filler *f, const float *v, const float *n, int64_t T, const float *view /* device [16] */,
+                       float *v_out, float *n_out, void *stream);
+
+/* ---- N1 / N3 post-passes on the bound buffers --------------------------------------------------------------- */
+
+/* GuroIllumination.draw_illumination on the bound colour/normal buffers, in place (guro_illumination.py:20-27).
+ * light = the already negated + normalised direction the reference keeps in self.light_direction. */
+int crb_guro(crb_filler *f, const float light[3], void *stream);
+
+/* run.py:26: image[::-1].astype('uint8') of the colour buffer -> out_u8 DEVICE [rows,w,3]. */
+int crb_color_u8_flipped(crb_filler *f, uint8_t *out_u8, void *stream);
+
+/* ---- transfers and status ------------------------------------------------------------------------------------- */
+int crb_download(crb_filler *f, unsigned mask, float *z_host, float *color_host, float *normals_host, void *stream);
+int crb_upload(crb_filler *f, unsigned mask, const float *z_host, const float *color_host, const float *normals_host,
+               void *stream);
+
+/* Synchronises `stream` and reports the last frame's bookkeeping: pairs_needed = (triangle,tile) pairs the frame
+ * produced; if it exceeded the workspace's pair capacity the frame was NOT drawn (buffers untouched) and the return
+ * value is CRB_ERR_OVERFLOW -- re-bind a workspace with pair_capacity >= pairs_needed and render again. */
+int crb_status(crb_filler *f, int64_t *pairs_needed, int64_t *pair_capacity, void *stream);
+
+/* Number of kernel launches issued by this filler since creation (bench.py's gpu_launches). */
+int64_t crb_launch_count(const crb_filler *f);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRENDER_B200_H */

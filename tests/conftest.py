@@ -1,0 +1,65 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "ref: needs the reference's own Cython build in oracle/_ref")
+
+
+class TriModel:
+    """Duck-typed stand-in for crender.cy.data_structures.Model: render_model only reads these three attributes."""
+
+    def __init__(self, v, c, n):
+        self._vertices_by_triangles = v
+        self._colors_by_triangles = c
+        self._normals_by_triangles = n
+
+
+def load_indexed(name):
+    d = np.load(os.path.join(GOLDEN, name + "_fit.npz"))
+    v = np.ascontiguousarray(d["vertices"][d["tri_v"]])
+    n = np.ascontiguousarray(d["normals"][d["tri_n"]])
+    c = np.ascontiguousarray(d["colors"].astype(np.float32)[d["tri_vt"]])
+    return TriModel(v, c, n)
+
+
+def random_scene(seed, T=None, span=1.0):
+    """SURVEY 8d property-test scenes: mixed sizes, depths 0.2..5, some behind the camera, some snapped to a grid."""
+    rng = np.random.default_rng(seed)
+    T = int(rng.integers(1, 400)) if T is None else T
+    ctr = rng.uniform(-span, span, (T, 1, 3)).astype(np.float32)
+    ctr[..., 2] = rng.uniform(0.2, 5, (T, 1))
+    ext = np.exp(rng.uniform(np.log(0.002), np.log(1.0), (T, 1, 1))).astype(np.float32)
+    v = (ctr + rng.uniform(-1, 1, (T, 3, 3)).astype(np.float32) * ext).astype(np.float32)
+    if seed % 5 == 0:
+        v[..., 2] -= np.float32(1.0)
+    if seed % 7 == 0:
+        v = (np.round(v * 8) / 8).astype(np.float32)
+    v[v[..., 2] == 0] += np.float32(0.01)
+    n = rng.standard_normal((T, 3, 3)).astype(np.float32)
+    c = (rng.random((T, 3, 3)) * 255).astype(np.float32)
+    return TriModel(v, c, n)
+
+
+def bits_equal(a, b):
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    return a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.fixture(scope="session")
+def trex():
+    return load_indexed("trex")
+
+
+@pytest.fixture(scope="session")
+def bunny():
+    return load_indexed("bunny")

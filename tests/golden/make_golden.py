@@ -1,0 +1,102 @@
+"""Generate the committed golden fixtures from the reference's own code.
+
+Run in the build container only (needs /root/reference, via the oracle/_ref build made by
+oracle/build_ref.py).  The GPU box has neither; the tests there read the files written here.
+
+Outputs (tests/golden/):
+  trex_fit.npz    -- T-Rex after the README flow (run.py:29-39): indexed arrays from which the three
+                     [T,3,3] float32 inputs of render_model are rebuilt bit-exactly (v = vertices[tri_v], ...)
+  bunny_fit.npz   -- bunny.obj + igor_texture.png after fit_model (SURVEY.md section 8d, config C2/C3 substitute)
+  checksums.json  -- sha256 of the reference's z / colour / normal buffers (n_threads=1) for a list of
+                     (model, h, w, fov) cases, plus the projection-matrix known answers
+  trex_128.npz    -- full reference output buffers for T-Rex at 128x128 (small enough to commit)
+"""
+import hashlib
+import io
+import json
+import os
+import sys
+import contextlib
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.path.join(ROOT, "oracle", "_ref")
+sys.path.insert(0, ROOT)
+from oracle import build_ref  # noqa: E402
+
+build_ref.build()
+sys.path.insert(0, REF)
+import numpy as np  # noqa: E402
+from crender.cy.data_structures import Model  # noqa: E402
+from crender.cy.pixel_buffer_filler import AdvancedPixelBufferFiller  # noqa: E402
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def fit_model(m):  # run.py:30-33
+    m.shift(-m.get_mean_vertex())
+    m.scale(1 / m.get_max_span())
+    m.shift(shift=[0, 0, 1])
+
+
+def indexed(m):
+    d = dict(vertices=m._vertices, normals=m._normals, tri_v=m._triangles_vertices.astype(np.int32),
+             tri_n=np.asarray(m._triangles_normals, dtype=np.int32),
+             colors=m._colors.astype(np.uint8), tri_vt=m._triangles_texture_coords.astype(np.int32))
+    assert np.array_equal(d["colors"].astype(np.float32), m._colors)
+    assert np.array_equal(d["vertices"][d["tri_v"]].view("u4"), m._vertices_by_triangles.view("u4"))
+    assert np.array_equal(d["normals"][d["tri_n"]].view("u4"), m._normals_by_triangles.view("u4"))
+    assert np.array_equal(d["colors"].astype(np.float32)[d["tri_vt"]], m._colors_by_triangles)
+    return d
+
+
+def render(m, h, w, fov, **kw):
+    f = AdvancedPixelBufferFiller(h, w, fov=fov, n_threads=1, **kw)
+    f.render_model(m)
+    return f.get_z_buffer(), f.get_color_buffer(), f.get_normals_buffer()
+
+
+def main():
+    os.chdir(REF)
+    trex = Model.read_model("objects/T-Rex.obj")
+    trex.rotate([-90, 180, 0])
+    trex.rotate([10, -80, 0])
+    fit_model(trex)
+    bunny = Model.read_model("objects/bunny.obj", external_texture_filename="objects/igor_texture.png")
+    fit_model(bunny)
+    np.savez_compressed(os.path.join(HERE, "trex_fit.npz"), **indexed(trex))
+    np.savez_compressed(os.path.join(HERE, "bunny_fit.npz"), **indexed(bunny))
+
+    cases = {}
+    models = {"trex": trex, "bunny": bunny}
+    for name, h, w, fov in [("trex", 1024, 1024, 45.0), ("trex", 512, 512, 90.0), ("trex", 333, 777, 60.0),
+                            ("trex", 128, 128, 45.0), ("trex", 2048, 2048, 45.0),
+                            ("bunny", 1024, 1024, 45.0), ("bunny", 2048, 2048, 45.0), ("bunny", 4096, 4096, 45.0),
+                            ("bunny", 500, 300, 30.0)]:
+        m = models[name]
+        z, c, n = render(m, h, w, fov)
+        cases[f"{name}_{h}x{w}_fov{fov:g}"] = dict(
+            model=name, h=h, w=w, fov=fov, z=sha(z), color=sha(c), normals=sha(n),
+            covered=int((z < 1e5).sum()), T=int(m._vertices_by_triangles.shape[0]))
+        if (name, h) == ("trex", 128):
+            np.savez_compressed(os.path.join(HERE, "trex_128.npz"), z=z, color=c, normals=n)
+    # compositing: bunny drawn over T-Rex in one filler (buffers persist, pyx:65-67 + no reset)
+    f = AdvancedPixelBufferFiller(640, 480, fov=50.0, n_threads=1)
+    f.render_model(trex)
+    f.render_model(bunny)
+    cases["trex_then_bunny_640x480_fov50"] = dict(
+        model="trex+bunny", h=640, w=480, fov=50.0, z=sha(f.get_z_buffer()), color=sha(f.get_color_buffer()),
+        normals=sha(f.get_normals_buffer()), covered=int((f.get_z_buffer() < 1e5).sum()))
+    inputs = {k: dict(v=sha(m._vertices_by_triangles), c=sha(m._colors_by_triangles), n=sha(m._normals_by_triangles))
+              for k, m in models.items()}
+    with open(os.path.join(HERE, "checksums.json"), "w") as fo:
+        json.dump(dict(generator="tests/golden/make_golden.py (reference Cython build, n_threads=1)",
+                       numpy=np.__version__, inputs=inputs, cases=cases), fo, indent=1, sort_keys=True)
+    print(json.dumps(cases, indent=1))
+
+
+if __name__ == "__main__":
+    with contextlib.redirect_stderr(io.StringIO()):
+        main()

@@ -1,0 +1,86 @@
+"""C-ABI surface (CPU only): the library loads without a GPU, exports every symbol include/crender_b200.h
+declares, and its host-only entry points behave like the reference constructor."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from cython3dmodelrenderer_b200 import _lib
+
+
+@pytest.fixture(scope="module")
+def lib():
+    _lib.build()
+    return _lib.load_library()
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "crender_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(crb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_all_exported_and_bound(lib):
+    names = declared_symbols()
+    assert len(names) >= 20
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in crender_b200.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes prototype"
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_version_and_error_text(lib):
+    assert lib.crb_version() == 100
+    P = (ctypes.c_float * 16)()
+    assert lib.crb_projection(8, 0, 45.0, 0.1, 1000.0, P) == _lib.CRB_ERR_ZERODIV
+    assert b"division" in lib.crb_last_error()
+    assert lib.crb_projection(8, 8, 45.0, 1.0, 1.0, P) == _lib.CRB_ERR_ZERODIV
+    assert lib.crb_projection(8, 8, 45.0, 0.1, 1000.0, None) == _lib.CRB_ERR_INVALID
+
+
+def test_projection_matches_oracle_and_known_answer(lib):
+    from oracle import oracle as O
+    P = _lib.projection_matrix(1024, 1024, 45.0)
+    assert float(P[0, 0]).hex() == "0x1.3504f40000000p+1"
+    assert float(P[3, 2]).hex() == "-0x1.99a4160000000p-4"
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        h, w = int(rng.integers(1, 5000)), int(rng.integers(1, 5000))
+        fov, zn = float(rng.uniform(1, 179)), float(rng.uniform(0.001, 2))
+        zf = zn + float(rng.uniform(0.5, 5000))
+        assert np.array_equal(_lib.projection_matrix(h, w, fov, zn, zf).view(np.uint32),
+                              O.projection_matrix(h, w, fov, zn, zf).view(np.uint32))
+    with pytest.raises(ZeroDivisionError):
+        _lib.projection_matrix(8, 0)
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from cython3dmodelrenderer_b200 import AdvancedPixelBufferFiller
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        AdvancedPixelBufferFiller(16, 16)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "cython3dmodelrenderer_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cuh")):
+                text = open(os.path.join(root, f)).read()
+                assert "oracle" not in text.replace("the oracle in parity tests", ""), f"{f} mentions the oracle"
+
+
+def test_input_validation_matches_reference_messages():
+    from cython3dmodelrenderer_b200.pixel_buffer_filler import _check_tri_array
+    with pytest.raises(ValueError, match="Buffer dtype mismatch, expected 'float' but got 'double'"):
+        _check_tri_array(np.zeros((2, 3, 3)), "v")
+    with pytest.raises(AttributeError, match="'NoneType' object has no attribute 'copy'"):
+        _check_tri_array(None, "c")
+    with pytest.raises(ValueError, match="wrong number of dimensions"):
+        _check_tri_array(np.zeros((2, 9), np.float32), "v")
+    assert _check_tri_array(np.zeros((2, 3, 3), np.float32), "v").shape == (2, 3, 3)

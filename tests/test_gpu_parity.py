@@ -1,0 +1,256 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the reference's golden vectors.  GPU only.
+Bar: bit-exact z, colour and normals (integer/bit compare of the float32 buffers)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, TriModel, bits_equal, random_scene
+
+pytestmark = pytest.mark.gpu
+CHECKS = json.load(open(os.path.join(GOLDEN, "checksums.json")))
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def Filler():
+    from cython3dmodelrenderer_b200 import AdvancedPixelBufferFiller
+    return AdvancedPixelBufferFiller
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle
+    return oracle
+
+
+def buffers(f):
+    return f.get_z_buffer().copy(), f.get_color_buffer().copy(), f.get_normals_buffer().copy()
+
+
+def assert_same(got, want, what=""):
+    for name, g, w in zip(("z", "color", "normals"), got, want):
+        if not bits_equal(g, w):
+            bad = np.argwhere(g.view(np.uint32) != w.view(np.uint32))
+            raise AssertionError(f"{what}: {name} differs at {len(bad)} words, first {bad[:5].tolist()}: "
+                                 f"got {g[tuple(bad[0])]!r} want {w[tuple(bad[0])]!r}")
+
+
+@pytest.mark.parametrize("path", ["tiled", "atomic"])
+@pytest.mark.parametrize("seed", range(30))
+def test_random_scenes_bit_exact(seed, path, Filler, O):
+    rng = np.random.default_rng(1000 + seed)
+    h, w, fov = int(rng.integers(8, 200)), int(rng.integers(8, 200)), float(rng.uniform(20, 120))
+    m = random_scene(seed)
+    g, o = Filler(h, w, fov=fov), O.OracleFiller(h, w, fov=fov)
+    for _ in range(2 if seed % 3 == 0 else 1):
+        g.render_arrays(m._vertices_by_triangles, m._colors_by_triangles, m._normals_by_triangles, path=path)
+        o.render_model(m)
+    assert_same(buffers(g), buffers(o), f"seed {seed} {h}x{w} {path}")
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_dense_scenes_bit_exact(seed, Filler, O):
+    """Many triangles per tile (several staging passes of the tile rasterizer) and large triangles (many tiles)."""
+    m = random_scene(100 + seed, T=6000, span=0.6)
+    h, w = (257, 391) if seed % 2 else (512, 512)
+    g, o = Filler(h, w, fov=70.0), O.OracleFiller(h, w, fov=70.0)
+    g.render_model(m)
+    o.render_model(m)
+    assert_same(buffers(g), buffers(o), f"dense seed {seed}")
+
+
+@pytest.mark.parametrize("case", ["trex_1024x1024_fov45", "trex_512x512_fov90", "trex_333x777_fov60",
+                                  "trex_2048x2048_fov45", "bunny_1024x1024_fov45", "bunny_500x300_fov30",
+                                  "bunny_4096x4096_fov45"])
+def test_reference_golden_checksums(case, Filler, trex, bunny):
+    info = CHECKS["cases"][case]
+    m = {"trex": trex, "bunny": bunny}[info["model"]]
+    f = Filler(info["h"], info["w"], fov=info["fov"], n_threads=8)
+    f.render_model(m)
+    z, c, n = f.get_z_buffer(), f.get_color_buffer(), f.get_normals_buffer()
+    assert int((z < 1e5).sum()) == info["covered"]
+    assert (sha(z), sha(c), sha(n)) == (info["z"], info["color"], info["normals"])
+
+
+def test_trex_128_full_arrays(Filler, trex):
+    g = np.load(os.path.join(GOLDEN, "trex_128.npz"))
+    f = Filler(128, 128, fov=45.0)
+    f.render_model(trex)
+    assert_same(buffers(f), (g["z"], g["color"], g["normals"]), "trex 128")
+
+
+def test_compositing_two_models_matches_reference(Filler, trex, bunny):
+    info = CHECKS["cases"]["trex_then_bunny_640x480_fov50"]
+    f = Filler(640, 480, fov=50.0)
+    f.render_model(trex)
+    f.render_model(bunny)
+    assert (sha(f.get_z_buffer()), sha(f.get_color_buffer()), sha(f.get_normals_buffer())) == \
+        (info["z"], info["color"], info["normals"])
+
+
+def _tri(vs, nz=-1.0, col=100.0):
+    v = np.asarray(vs, dtype=np.float32).reshape(-1, 3, 3)
+    n = np.zeros_like(v)
+    n[..., 2] = nz
+    c = np.full_like(v, col)
+    return v, c, n
+
+
+KATS = {
+    # two triangles sharing the diagonal of a square: inclusive edges, both rasterize the shared pixels
+    "shared_edge": _tri([[[-0.5, -0.5, 1], [0.5, -0.5, 1], [0.5, 0.5, 1]], [[-0.5, -0.5, 1], [0.5, 0.5, 1], [-0.5, 0.5, 1]]]),
+    # identical geometry twice: exact depth tie -> the higher triangle index must win
+    "exact_tie": _tri([[[-0.5, -0.5, 1], [0.5, -0.5, 1], [0.0, 0.5, 1]]] * 2),
+    "off_screen": _tri([[[5, 5, 1], [6, 5, 1], [5, 6, 1]]]),
+    "zero_area": _tri([[[-0.5, -0.5, 1], [0.0, 0.0, 1], [0.5, 0.5, 1]]]),
+    "behind_camera": _tri([[[-0.5, -0.5, -1], [0.5, -0.5, -1], [0.0, 0.5, -1]]]),
+    "straddles_camera_plane": _tri([[[-0.5, -0.5, -0.3], [0.5, -0.5, 0.7], [0.0, 0.5, 1.0]]]),
+    "back_facing": _tri([[[-0.5, -0.5, 1], [0.5, -0.5, 1], [0.0, 0.5, 1]]], nz=1.0),
+    "zero_normal_sum_is_culled": _tri([[[-0.5, -0.5, 1], [0.5, -0.5, 1], [0.0, 0.5, 1]]], nz=0.0),
+    "huge": _tri([[[-300, -300, 1], [300, -300, 1], [0.0, 300, 1]]]),
+    "out_of_int_range": _tri([[[-3e9, -0.5, 1.0], [3e9, 0.5, 1.0], [0.0, 4e9, 1.0]],
+                              [[-0.4, -0.4, 1.5], [0.4, -0.4, 1.5], [0.0, 0.4, 1.5]]]),
+    "inf_vertex": _tri([[[-0.5, -0.5, 1], [np.inf, -0.5, 1], [0.0, 0.5, 1]], [[-0.4, -0.4, 1.5], [0.4, -0.4, 1.5], [0.0, 0.4, 1.5]]]),
+    "nan_vertex": _tri([[[-0.5, np.nan, 1], [0.5, -0.5, 1], [0.0, 0.5, 1]], [[-0.4, -0.4, 1.5], [0.4, -0.4, 1.5], [0.0, 0.4, 1.5]]]),
+    "negative_zero_depth_tie": _tri([[[-0.5, -0.5, 1], [0.5, -0.5, 1], [0.0, 0.5, 1]]]),
+}
+KATS["exact_tie"][1][1] = 200.0   # second copy has another colour so the winner is visible
+KATS["exact_tie"][1][0] = 50.0
+
+
+@pytest.mark.parametrize("path", ["tiled", "atomic"])
+@pytest.mark.parametrize("name", sorted(KATS))
+@pytest.mark.parametrize("size", [(64, 64), (50, 70)])
+def test_known_answer_cases(name, size, path, Filler, O):
+    v, c, n = KATS[name]
+    h, w = size
+    # vertices on pixel centres: fov 90, square image -> x_screen = (x/z + 1) * w/2 lands on integers for these inputs
+    g, o = Filler(h, w, fov=90.0), O.OracleFiller(h, w, fov=90.0)
+    g.render_arrays(v, c, n, path=path)
+    o.render_arrays(v, c, n)
+    assert_same(buffers(g), buffers(o), name)
+    if name == "exact_tie":
+        z, col, _ = buffers(g)
+        assert set(np.unique(col[z < 1e5])) == {200.0}
+    if name in ("off_screen", "back_facing", "zero_normal_sum_is_culled"):
+        assert (g.get_z_buffer() == np.float32(1e6)).all()
+
+
+def test_empty_model_and_single_triangle(Filler, O):
+    f = Filler(33, 17, fov=60.0)
+    e = np.zeros((0, 3, 3), np.float32)
+    f.render_arrays(e, e, e)
+    assert (f.get_z_buffer() == np.float32(1e6)).all() and not f.get_color_buffer().any()
+    v, c, n = KATS["shared_edge"]
+    o = O.OracleFiller(33, 17, fov=60.0)
+    f.render_arrays(v[:1], c[:1], n[:1])
+    o.render_arrays(v[:1], c[:1], n[:1])
+    assert_same(buffers(f), buffers(o), "single")
+
+
+def test_clear_is_fused_and_equals_fresh_filler(Filler, O, trex):
+    f = Filler(200, 300, fov=45.0)
+    m = random_scene(3)
+    f.render_model(m)
+    f.clear()
+    f.render_model(trex)
+    o = O.OracleFiller(200, 300, fov=45.0)
+    o.render_model(trex)
+    assert_same(buffers(f), buffers(o), "clear+render")
+    f.clear()
+    assert (f.get_z_buffer() == np.float32(1e6)).all() and not f.get_normals_buffer().any()
+
+
+def test_pair_list_overflow_is_detected_and_retried(Filler, O):
+    # a few hundred full-screen triangles at 512x512: far more (triangle,tile) pairs than the default workspace holds
+    T = 600
+    v = np.tile(np.array([[[-30, -30, 1.0], [30, -30, 1.0], [0.0, 30, 1.0]]], np.float32), (T, 1, 1))
+    v[:, :, 2] += np.linspace(0, 0.5, T, dtype=np.float32)[:, None]
+    n = -np.ones((T, 3, 3), np.float32)
+    c = np.random.default_rng(0).random((T, 3, 3)).astype(np.float32) * 255
+    f, o = Filler(512, 512, fov=90.0), O.OracleFiller(512, 512, fov=90.0)
+    f.render_arrays(v, c, n)
+    o.render_arrays(v, c, n)
+    assert_same(buffers(f), buffers(o), "overflow retry")
+
+
+def test_api_contract_matches_reference(Filler, trex):
+    f = Filler(64, 48, fov=45.0, z_near=0.1, z_far=1000.0, n_threads=8)
+    assert f.get_size() == (64, 48)
+    z = f.get_z_buffer()
+    assert z.dtype == np.float32 and z.shape == (64, 48) and (z == np.float32(1e6)).all()
+    assert f.get_color_buffer().shape == (64, 48, 3) and f.get_normals_buffer().shape == (64, 48, 3)
+    # live views: same memory on every call, writable, and later renders show through the array already held
+    c1 = f.get_color_buffer()
+    assert c1 is f.get_color_buffer() and c1.flags.writeable
+    v0 = trex._vertices_by_triangles.copy()
+    f.render_model(trex)
+    assert np.array_equal(v0, trex._vertices_by_triangles)          # the model is never mutated
+    assert c1.any() and (z < 1e5).any()
+    with pytest.raises(ValueError, match="expected 'float' but got 'double'"):
+        f.render_model(TriModel(v0.astype(np.float64), trex._colors_by_triangles, trex._normals_by_triangles))
+    with pytest.raises(AttributeError):
+        f.render_model(TriModel(v0, None, trex._normals_by_triangles))
+    bad = v0.copy()
+    bad[7, 1, 2] = 0.0
+    with pytest.raises(ZeroDivisionError):
+        f.render_model(TriModel(bad, trex._colors_by_triangles, trex._normals_by_triangles))
+
+
+def test_host_writes_through_live_views_persist(Filler, O, trex):
+    """Renderer.render's pattern (crender/cy/renderer.py:47-49): illumination mutates the colour view in place, the
+    next get_color_buffer() shows it, and a later render composites over the mutated buffers."""
+    f, o = Filler(96, 96, fov=45.0), O.OracleFiller(96, 96, fov=45.0)
+    f.render_model(trex)
+    o.render_model(trex)
+    for x in (f, o):
+        x.get_color_buffer()[...] *= np.float32(0.5)
+        x.get_z_buffer()[:10] = np.float32(-5.0)     # nothing can be drawn in front of these rows any more
+    assert bits_equal(f.get_color_buffer(), o.get_color_buffer())
+    m = random_scene(11)
+    f.render_model(m)
+    o.render_model(m)
+    assert_same(buffers(f), buffers(o), "after host writes")
+
+
+def test_device_resident_inputs(Filler, O, trex):
+    import torch
+    f, o = Filler(256, 256, fov=45.0), O.OracleFiller(256, 256, fov=45.0)
+    dv, dc, dn = (torch.from_numpy(a).cuda() for a in
+                  (trex._vertices_by_triangles, trex._colors_by_triangles, trex._normals_by_triangles))
+    f.render_arrays(dv, dc, dn)
+    o.render_model(trex)
+    assert_same(buffers(f), buffers(o), "device inputs")
+    assert f.launch_count >= 4
+
+
+def test_band_sharded_fillers_concatenate_to_full_frame(Filler, O, trex):
+    h, w = 300, 260
+    o = O.OracleFiller(h, w, fov=45.0)
+    o.render_model(trex)
+    parts = []
+    for r0, r1 in [(0, 70), (70, 75), (75, 201), (201, 300)]:
+        f = Filler(h, w, fov=45.0, band=(r0, r1))
+        f.render_model(trex)
+        parts.append(buffers(f))
+    got = tuple(np.concatenate([p[i] for p in parts], axis=0) for i in range(3))
+    assert_same(got, buffers(o), "bands")
+
+
+def test_guro_on_device_and_u8_output(Filler, O, trex):
+    f, o = Filler(200, 200, fov=45.0), O.OracleFiller(200, 200, fov=45.0)
+    f.render_model(trex)
+    o.render_model(trex)
+    light = -np.asarray([0, 0, 1], dtype="float32")
+    light = light / np.linalg.norm(light)
+    f.illuminate_guro(light)
+    O.guro(o.get_color_buffer(), o.get_normals_buffer(), [0, 0, 1])
+    assert bits_equal(f.get_color_buffer(), o.get_color_buffer())
+    u8 = f.color_u8_flipped().cpu().numpy()
+    assert np.array_equal(u8, o.get_color_buffer()[::-1].astype("uint8"))   # run.py:26
