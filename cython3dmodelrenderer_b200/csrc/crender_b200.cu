@@ -44,6 +44,7 @@ constexpr float Z_INIT = 1e6f;  // pyx:67
 constexpr float REJ_EPS = 1e-6f;      // fast-reject guard band on barycentric numerators (see tri_fast_setup)
 constexpr float L3_MIN = 1e-30f, L3_MAX = 1e30f;
 constexpr int MAX_DIM = 65535;  // bbox corners are packed in 16 bits
+constexpr int PROF_MAX = 8192;  // k_raster launches that can be timed between two crb_profile_read calls
 
 static_assert(CH == NT, "one staged triangle per thread");
 static_assert(TW == 32, "a tile row is one warp wide");
@@ -770,6 +771,10 @@ struct crb_filler {
     unsigned long long *keybuf;
     long long keybuf_pixels;
     long long launches;
+    // optional timing of the dominant kernel (k_raster) with CUDA events on the launching stream
+    bool prof_on;
+    int prof_n;
+    cudaEvent_t *prof_ev;  // 2 * PROF_MAX events, created on first use
 };
 
 namespace {
@@ -877,8 +882,15 @@ int run_tiled(crb_filler *f, Frame &F, cudaStream_t st)
         k_fill<<<dim3(gT, F.nViews), NT, 0, st>>>(F);
         if ((rc = launch_check(f, "k_fill"))) return rc;
     }
+    const bool prof = f->prof_on && f->prof_n < PROF_MAX;
+    if (prof) CU(cudaEventRecord(f->prof_ev[2 * f->prof_n], st));
     k_raster<<<dim3(F.nTiles, F.nViews), NT, 0, st>>>(F);
-    return launch_check(f, "k_raster");
+    if ((rc = launch_check(f, "k_raster"))) return rc;
+    if (prof) {
+        CU(cudaEventRecord(f->prof_ev[2 * f->prof_n + 1], st));
+        f->prof_n++;
+    }
+    return CRB_OK;
 }
 
 int run_atomic(crb_filler *f, Frame &F, cudaStream_t st)
@@ -982,6 +994,10 @@ void crb_destroy(crb_filler *f)
     if (f->own_buffers) { cudaFree(f->z); cudaFree(f->color); cudaFree(f->normals); }
     if (f->own_ws) cudaFree(f->ws);
     if (f->keybuf) cudaFree(f->keybuf);
+    if (f->prof_ev) {
+        for (int i = 0; i < 2 * PROF_MAX; ++i) cudaEventDestroy(f->prof_ev[i]);
+        delete[] f->prof_ev;
+    }
     delete f;
 }
 
@@ -1238,5 +1254,36 @@ int crb_status(crb_filler *f, int64_t *pairs_needed, int64_t *pair_capacity, voi
 }
 
 int64_t crb_launch_count(const crb_filler *f) { return f ? f->launches : 0; }
+
+int crb_profile(crb_filler *f, int enable)
+{
+    if (check_filler(f)) return CRB_ERR_INVALID;
+    CU(cudaSetDevice(f->device));
+    if (enable && !f->prof_ev) {
+        f->prof_ev = new (std::nothrow) cudaEvent_t[2 * PROF_MAX];
+        if (!f->prof_ev) return fail(CRB_ERR_INVALID, "out of host memory");
+        for (int i = 0; i < 2 * PROF_MAX; ++i) CU(cudaEventCreate(&f->prof_ev[i]));
+    }
+    f->prof_on = enable != 0;
+    f->prof_n = 0;
+    return CRB_OK;
+}
+
+int crb_profile_read(crb_filler *f, int *launches, double *total_ms)
+{
+    if (check_filler(f)) return CRB_ERR_INVALID;
+    CU(cudaSetDevice(f->device));
+    double tot = 0.0;
+    for (int i = 0; i < f->prof_n; ++i) {
+        float ms = 0.f;
+        CU(cudaEventSynchronize(f->prof_ev[2 * i + 1]));
+        CU(cudaEventElapsedTime(&ms, f->prof_ev[2 * i], f->prof_ev[2 * i + 1]));
+        tot += ms;
+    }
+    if (launches) *launches = f->prof_n;
+    if (total_ms) *total_ms = tot;
+    f->prof_n = 0;
+    return CRB_OK;
+}
 
 }  // extern "C"

@@ -264,6 +264,86 @@ class AdvancedPixelBufferFiller:
         check(self._L.crb_color_u8_flipped(self._handle, out.data_ptr(), self._stream()))
         return out
 
+    def render_views(self, v, c, n, views, z_out=None, color_out=None, normals_out=None, color_u8_out=None,
+                     want=("z", "color", "normals"), guro_light=None, chunk=32, check_status=True):
+        """Batched multi-view render (config C5): every view gets fresh-filler buffers in its own slab.
+
+        v, c, n: torch CUDA float32 [T,3,3] (device-resident base mesh);  views: [V,16] float32 (numpy or CUDA tensor,
+        see views.py).  Outputs are torch CUDA tensors [V,rows,w(,3)], allocated here unless passed in; `want` selects
+        which float32 buffers are produced, `color_u8_out=True` (or a tensor) adds run.py:26's flipped uint8 image.
+        `guro_light` = raw light direction (as given to GuroIllumination) fuses the illumination into the shading pass.
+        Returns a dict of the produced tensors."""
+        torch = self._torch
+        for a in (v, c, n):
+            if not isinstance(a, torch.Tensor) or not a.is_cuda or a.dtype != torch.float32 or tuple(a.shape[1:]) != (3, 3):
+                raise ValueError("render_views needs CUDA float32 tensors of shape [T,3,3]")
+        v, c, n = v.contiguous(), c.contiguous(), n.contiguous()
+        T = v.shape[0]
+        if not isinstance(views, torch.Tensor):
+            views = torch.from_numpy(np.ascontiguousarray(views, dtype=np.float32)).to(self._dev)
+        views = views.contiguous()
+        V = views.shape[0]
+        rows = self.row1 - self.row0
+        out = {}
+
+        def slab(name, given, shape, dtype):
+            if given is None and name not in want:
+                return None
+            t = given if isinstance(given, torch.Tensor) else torch.empty(shape, dtype=dtype, device=self._dev)
+            assert t.is_cuda and t.is_contiguous() and tuple(t.shape) == shape and t.dtype == dtype
+            out[name] = t
+            return t
+
+        z_out = slab("z", z_out, (V, rows, self.w), torch.float32)
+        color_out = slab("color", color_out, (V, rows, self.w, 3), torch.float32)
+        normals_out = slab("normals", normals_out, (V, rows, self.w, 3), torch.float32)
+        if color_u8_out is True:
+            color_u8_out = torch.empty((V, rows, self.w, 3), dtype=torch.uint8, device=self._dev)
+        if color_u8_out is not None:
+            out["color_u8"] = color_u8_out
+        flags, light = 0, None
+        if guro_light is not None:
+            # GuroIllumination.__init__ (guro_illumination.py:17-18): negate, then normalise, in float32
+            l = -np.asarray(guro_light, dtype="float32")
+            l = l / np.linalg.norm(l)
+            light = (ctypes.c_float * 3)(*[float(x) for x in l])
+            flags |= _lib.CRB_GURO
+        self._ensure_workspace(T, views=min(int(chunk), max(V, 1)))
+        ptr = lambda t: None if t is None else t.data_ptr()
+        while True:
+            check(self._L.crb_render_views(self._handle, v.data_ptr(), c.data_ptr(), n.data_ptr(), T, views.data_ptr(), V,
+                                           ptr(z_out), ptr(color_out), ptr(normals_out), ptr(color_u8_out), flags, light,
+                                           self._stream()))
+            if not check_status:
+                break
+            need, cap = ctypes.c_int64(), ctypes.c_int64()
+            rc = self._L.crb_status(self._handle, ctypes.byref(need), ctypes.byref(cap), self._stream())
+            if rc == _lib.CRB_ERR_OVERFLOW:
+                self._ensure_workspace(T, self._ws_views, int(need.value * 1.25) + 1024)
+                continue
+            check(rc)
+            break
+        return out
+
+    def transform_view(self, v, n, view):
+        """The camera-space [T,3,3] arrays one view produces (what the reference would be handed for that view)."""
+        torch = self._torch
+        if not isinstance(view, torch.Tensor):
+            view = torch.from_numpy(np.ascontiguousarray(view, dtype=np.float32).ravel()).to(self._dev)
+        vo, no = torch.empty_like(v), torch.empty_like(n)
+        check(self._L.crb_transform_view(self._handle, v.data_ptr(), n.data_ptr(), v.shape[0], view.data_ptr(),
+                                         vo.data_ptr(), no.data_ptr(), self._stream()))
+        return vo, no
+
+    def profile(self, enable=True):
+        check(self._L.crb_profile(self._handle, int(bool(enable))))
+
+    def profile_read(self):
+        """(launches, total_ms) of the tile rasterizer kernel since the last read (CUDA events on the render stream)."""
+        n, ms = ctypes.c_int(), ctypes.c_double()
+        check(self._L.crb_profile_read(self._handle, ctypes.byref(n), ctypes.byref(ms)))
+        return n.value, ms.value
+
     @property
     def launch_count(self):
         return int(self._L.crb_launch_count(self._handle))

@@ -152,6 +152,12 @@ int crb_status(crb_filler *f, int64_t *pairs_needed, int64_t *pair_capacity, voi
 /* Number of kernel launches issued by this filler since creation (bench.py's gpu_launches). */
 int64_t crb_launch_count(const crb_filler *f);
 
+/* Measurement aid: while enabled, every launch of the dominant kernel (the tile rasterizer + shader, k_raster) is
+ * bracketed by CUDA events on the launching stream.  crb_profile_read waits for them and returns how many launches
+ * were timed since the last read and their summed device time.  Not usable inside CUDA-graph capture. */
+int crb_profile(crb_filler *f, int enable);
+int crb_profile_read(crb_filler *f, int *launches, double *total_ms);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -137,7 +137,7 @@ def test_known_answer_cases(name, size, path, Filler, O):
     assert_same(buffers(g), buffers(o), name)
     if name == "exact_tie":
         z, col, _ = buffers(g)
-        assert set(np.unique(col[z < 1e5])) == {200.0}
+        assert (z < 1e5).any() and (col[z < 1e5] > 150.0).all()   # the later copy (colour 200) wins
     if name in ("off_screen", "back_facing", "zero_normal_sum_is_culled"):
         assert (g.get_z_buffer() == np.float32(1e6)).all()
 
@@ -254,3 +254,44 @@ def test_guro_on_device_and_u8_output(Filler, O, trex):
     assert bits_equal(f.get_color_buffer(), o.get_color_buffer())
     u8 = f.color_u8_flipped().cpu().numpy()
     assert np.array_equal(u8, o.get_color_buffer()[::-1].astype("uint8"))   # run.py:26
+
+
+def test_batched_views_match_oracle_on_transformed_arrays(Filler, O, trex):
+    """C5 parity: per view, the oracle is fed the camera-space arrays the view transform produces."""
+    import torch
+    from cython3dmodelrenderer_b200 import views as VW
+    h, w = 160, 192
+    f = Filler(h, w, fov=45.0)
+    dv, dc, dn = (torch.from_numpy(a).cuda() for a in
+                  (trex._vertices_by_triangles, trex._colors_by_triangles, trex._normals_by_triangles))
+    V = 11
+    views = VW.orbit_views(V)
+    out = f.render_views(dv, dc, dn, views, chunk=4, color_u8_out=True)   # 3 chunks: 4 + 4 + 3
+    for k in range(V):
+        vk, nk = VW.transform_arrays_host(views[k], trex._vertices_by_triangles, trex._normals_by_triangles)
+        gv, gn = f.transform_view(dv, dn, views[k])
+        assert bits_equal(gv.cpu().numpy(), vk) and bits_equal(gn.cpu().numpy(), nk)
+        o = O.OracleFiller(h, w, fov=45.0)
+        o.render_arrays(vk, trex._colors_by_triangles, nk)
+        got = (out["z"][k].cpu().numpy(), out["color"][k].cpu().numpy(), out["normals"][k].cpu().numpy())
+        assert_same(got, buffers(o), f"view {k}")
+        assert np.array_equal(out["color_u8"][k].cpu().numpy(), o.get_color_buffer()[::-1].astype("uint8"))
+    assert len({sha(out["z"][k].cpu().numpy()) for k in range(V)}) == V   # the views really differ
+
+
+def test_batched_views_fused_guro_and_colour_only(Filler, O, trex):
+    import torch
+    from cython3dmodelrenderer_b200 import views as VW
+    h, w = 128, 128
+    f = Filler(h, w, fov=45.0)
+    dv, dc, dn = (torch.from_numpy(a).cuda() for a in
+                  (trex._vertices_by_triangles, trex._colors_by_triangles, trex._normals_by_triangles))
+    views = VW.orbit_views(16, first=3, count=3)
+    out = f.render_views(dv, dc, dn, views, want=("color",), guro_light=[0, 0, 1])
+    assert set(out) == {"color"}
+    for k in range(3):
+        vk, nk = VW.transform_arrays_host(views[k], trex._vertices_by_triangles, trex._normals_by_triangles)
+        o = O.OracleFiller(h, w, fov=45.0)
+        o.render_arrays(vk, trex._colors_by_triangles, nk)
+        O.guro(o.get_color_buffer(), o.get_normals_buffer(), [0, 0, 1])
+        assert bits_equal(out["color"][k].cpu().numpy(), o.get_color_buffer())
