@@ -67,6 +67,7 @@ struct Frame {
     const float *views;         // [nViews,16] or nullptr
     // scratch
     float4 *rec0, *rec1, *rec2; // [nViews*T] screen-space triangle records (SoA of float4)
+    float4 *nrec0, *nrec1;      // [nViews*T] view-space vertex normals n0 n1 n2.xy (n2.z rides in rec2.w); batched views only
     unsigned *count;            // [nViews*nTiles] triangles per tile (zero between frames)
     unsigned *offset;           // [nViews*nTiles] start of the tile's list
     unsigned *cursor;           // [nViews*nTiles] fill cursor
@@ -171,8 +172,8 @@ __device__ __forceinline__ Tri9 load_tri9(const Frame &F, long long ridx)
 // pyx:219-242 for the pixel's winning triangle: depth, colour, normal (left-associated sums).  Returns false if the
 // fragment would not have been drawn (some barycentric < 0, NaN depth) -- cannot happen for a key that won, kept as a
 // guard.  `M` (may be nullptr) is the view matrix applied to the normals.
-__device__ __forceinline__ bool shade_fragment(const Frame &F, const Tri9 &t, long long tri, const float *M, float px,
-                                               float py, float &z, float c[3], float n[3])
+__device__ __forceinline__ bool shade_fragment(const Frame &F, const Tri9 &t, long long tri, long long ridx, const float *M,
+                                               float px, float py, float &z, float c[3], float n[3])
 {
     float b1, b2, b3;
     barycentric(t, px, py, b1, b2, b3);
@@ -181,12 +182,13 @@ __device__ __forceinline__ bool shade_fragment(const Frame &F, const Tri9 &t, lo
     if (z != z) return false;
     const float *cc = F.c + tri * 9, *nn = F.n + tri * 9;
     float m[9];
+    if (M) {  // batched views: k_setup already rotated this triangle's normals into the view (nrec)
+        const float4 q0 = F.nrec0[ridx], q1 = F.nrec1[ridx];
+        m[0] = q0.x; m[1] = q0.y; m[2] = q0.z; m[3] = q0.w; m[4] = q1.x; m[5] = q1.y; m[6] = q1.z; m[7] = q1.w;
+        m[8] = F.rec2[ridx].w;
+    } else {
 #pragma unroll
-    for (int k = 0; k < 9; ++k) m[k] = __ldg(nn + k);
-    if (M) {
-        view_normal(M, m[0], m[1], m[2]);
-        view_normal(M, m[3], m[4], m[5]);
-        view_normal(M, m[6], m[7], m[8]);
+        for (int k = 0; k < 9; ++k) m[k] = __ldg(nn + k);
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -202,6 +204,19 @@ __device__ __forceinline__ bool shade_fragment(const Frame &F, const Tri9 &t, lo
         c[0] *= s; c[1] *= s; c[2] *= s;
     }
     return true;
+}
+
+// Colour of a pixel no triangle covers.  Plain renders: 0 (pyx:66).  With the fused Guro pass the reference still runs
+// draw_illumination over the whole buffer: normal (0,0,0) gives shadow = clip(0*l/(0+1e-6)) whose SIGN follows the light
+// (e.g. -0.0 for the default light), and 0 * -0.0 = -0.0 is what lands in the buffer -- reproduced for bit parity.
+__device__ __forceinline__ float background_color(const Frame &F)
+{
+    if (!(F.flags & CRB_GURO)) return 0.0f;
+    const float dot = (0.0f * F.light[0] + 0.0f * F.light[1]) + 0.0f * F.light[2];
+    float s = dot / (sqrtf(0.0f) + 1e-6f);
+    if (s < 0.0f) s = 0.0f;
+    if (s > 1.0f) s = 1.0f;
+    return 0.0f * s;
 }
 
 // run.py:26 .astype('uint8'): C truncation toward zero, then the low 8 bits.
@@ -251,17 +266,18 @@ __global__ void __launch_bounds__(NT) k_setup(const Frame F)
     const long long tri = first + threadIdx.x;
     const long long ridx = (long long)view * F.T + tri;
 
-    float x[3], y[3], z[3], nz[3];
+    float x[3], y[3], z[3], nx[3], ny[3], nz[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         x[k] = sv[threadIdx.x * 9 + k * 3 + 0];
         y[k] = sv[threadIdx.x * 9 + k * 3 + 1];
         z[k] = sv[threadIdx.x * 9 + k * 3 + 2];
+        nx[k] = sn[threadIdx.x * 9 + k * 3 + 0];
+        ny[k] = sn[threadIdx.x * 9 + k * 3 + 1];
         nz[k] = sn[threadIdx.x * 9 + k * 3 + 2];
         if (F.views) {
             view_point(sM, x[k], y[k], z[k]);
-            const float nx = sn[threadIdx.x * 9 + k * 3 + 0], ny = sn[threadIdx.x * 9 + k * 3 + 1];
-            nz[k] = (sM[6] * nx + sM[7] * ny) + sM[8] * nz[k];
+            view_normal(sM, nx[k], ny[k], nz[k]);
         }
         project_vertex(F.proj, x[k], y[k], z[k]);
     }
@@ -287,10 +303,14 @@ __global__ void __launch_bounds__(NT) k_setup(const Frame F)
     const unsigned bx = drawn ? ((unsigned)xl | ((unsigned)xr << 16)) : 0u;
     const unsigned by = drawn ? ((unsigned)yt | ((unsigned)yb << 16)) : 0u;
 
-    F.rec2[ridx] = make_float4(z[2], __uint_as_float(bx), __uint_as_float(by), 0.0f);
+    F.rec2[ridx] = make_float4(z[2], __uint_as_float(bx), __uint_as_float(by), nz[2]);
     if (!drawn) return;
     F.rec0[ridx] = make_float4(x[0], y[0], x[1], y[1]);
     F.rec1[ridx] = make_float4(x[2], y[2], z[0], z[1]);
+    if (F.views) {
+        F.nrec0[ridx] = make_float4(nx[0], ny[0], nz[0], nx[1]);
+        F.nrec1[ridx] = make_float4(ny[1], nz[1], nx[2], ny[2]);
+    }
     if (F.flags & CRB_PATH_ATOMIC) return;
 
     int tx0, tx1, ty0, ty1;
@@ -388,9 +408,10 @@ struct __align__(16) TileSmem {
         struct {
             float4 s0[CH];  // x0 y0 x1 y1
             float4 s1[CH];  // x2 y2 z0 z1
-            float4 s2[CH];  // z2 l03' l13' l23'   (l' = sign-normalised denominators, see below)
+            float4 s2[CH];  // z2 d1 d2 d3   (d = sign-normalised denominators l03' l13' l23', see stage_pair)
             uint4 s3[CH];   // bx by tri flags
-            unsigned rowStart[CH + 1];
+            unsigned rowStart[CH];
+            unsigned char owner[CH * TH];  // row work item -> staged triangle
         } st;
         struct {
             float col[TH * TW * 3];
@@ -398,43 +419,103 @@ struct __align__(16) TileSmem {
         } out;
     } u;
     unsigned warp_sums[NT / 32];
+    unsigned n;
 };
+
+// flags of a staged triangle: bit k (k=0..2) -> barycentric k is evaluated with negated edge vector and denominator;
+// bit 4+k -> barycentric k may use the division-free rejection; bit 8 -> row spans may be bounded analytically.
+constexpr unsigned FL_SPAN = 256u;
+constexpr float SPAN_COORD_MAX = 262144.0f;  // 2^18: beyond this the float span bounds lose sub-pixel accuracy
 
 // Writes one tile of cleared pixels (fresh-filler values) -- the whole frame's "memset" is fused here.
 __device__ __forceinline__ void write_clear_tile(const Frame &F, int view, int x0, int yl0, int tw, int th)
 {
     const long long slab = (long long)view * F.slabPixels;
     const bool vec = (tw == TW) && ((F.W & 3) == 0);
+    const float bg = background_color(F);
     if (vec) {
-        if (F.z) {
-            for (int i = threadIdx.x; i < th * (TW / 4); i += NT) {
-                const int r = i / (TW / 4), q = i % (TW / 4);
-                reinterpret_cast<float4 *>(F.z + slab + (long long)(yl0 + r) * F.W + x0)[q] =
-                    make_float4(Z_INIT, Z_INIT, Z_INIT, Z_INIT);
+        // thread -> (row = tid/8 (+32 per pass), 16-byte column q = tid%8 (+8, +16)): shifts only, 128-byte runs
+        const int q = threadIdx.x & 7;
+        for (int r = threadIdx.x >> 3; r < th; r += NT / 8) {
+            const long long rowpix = slab + (long long)(yl0 + r) * F.W + x0;
+            if (F.z) reinterpret_cast<float4 *>(F.z + rowpix)[q] = make_float4(Z_INIT, Z_INIT, Z_INIT, Z_INIT);
+            if (F.color) {
+                float4 *o = reinterpret_cast<float4 *>(F.color + rowpix * 3);
+                o[q] = make_float4(bg, bg, bg, bg); o[q + 8] = make_float4(bg, bg, bg, bg); o[q + 16] = make_float4(bg, bg, bg, bg);
             }
-        }
-        for (int i = threadIdx.x; i < th * (TW * 3 / 4); i += NT) {
-            const int r = i / (TW * 3 / 4), q = i % (TW * 3 / 4);
-            const long long o = (slab + (long long)(yl0 + r) * F.W + x0) * 3;
-            if (F.color) reinterpret_cast<float4 *>(F.color + o)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (F.normals) reinterpret_cast<float4 *>(F.normals + o)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (F.normals) {
+                float4 *o = reinterpret_cast<float4 *>(F.normals + rowpix * 3);
+                o[q] = make_float4(0.f, 0.f, 0.f, 0.f); o[q + 8] = make_float4(0.f, 0.f, 0.f, 0.f); o[q + 16] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
     } else {
         for (int i = threadIdx.x; i < th * tw; i += NT) {
             const int r = i / tw, xx = i % tw;
             const long long p = slab + (long long)(yl0 + r) * F.W + x0 + xx;
             if (F.z) F.z[p] = Z_INIT;
-            if (F.color) { F.color[p * 3] = 0.f; F.color[p * 3 + 1] = 0.f; F.color[p * 3 + 2] = 0.f; }
+            if (F.color) { F.color[p * 3] = bg; F.color[p * 3 + 1] = bg; F.color[p * 3 + 2] = bg; }
             if (F.normals) { F.normals[p * 3] = 0.f; F.normals[p * 3 + 1] = 0.f; F.normals[p * 3 + 2] = 0.f; }
         }
     }
     if (F.color_u8) {
         const int rows = F.row1 - F.row0;
+        const unsigned char b8 = to_u8(bg);
         for (int i = threadIdx.x; i < th * tw * 3; i += NT) {
             const int r = i / (tw * 3), xx = i % (tw * 3);
-            F.color_u8[((long long)view * F.slabPixels + (long long)(rows - 1 - (yl0 + r)) * F.W + x0) * 3 + xx] = 0;
+            F.color_u8[((long long)view * F.slabPixels + (long long)(rows - 1 - (yl0 + r)) * F.W + x0) * 3 + xx] = b8;
         }
     }
+}
+
+// One staged triangle: everything a row work item needs, computed once per (triangle, tile).
+__device__ __forceinline__ unsigned stage_pair(TileSmem &S, int slot, const float4 a, const float4 b, const float4 c, unsigned tri,
+                                               int y0, int th)
+{
+    const unsigned bx = __float_as_uint(c.y), by = __float_as_uint(c.z);
+    // denominators of mu:12-21
+    const float l01 = a.z - b.x, l02 = a.w - b.y;
+    const float l03 = l01 * (a.y - b.y) - l02 * (a.x - b.x);
+    const float l11 = b.x - a.x, l12 = b.y - a.y;
+    const float l13 = l11 * (a.w - a.y) - l12 * (a.z - a.x);
+    const float l21 = a.x - a.z, l22 = a.y - a.w;
+    const float l23 = l21 * (b.y - a.w) - l22 * (b.x - a.z);
+    // Division-free rejection (SURVEY 7, K3 obligation).  num/l3 is bit-identical to (-num)/(-l3), and negation commutes
+    // with every rounding that produced num, so each coordinate is evaluated with l3' = |l3| (edge vector negated when
+    // l3 < 0).  For L3_MIN <= l3' <= L3_MAX a numerator <= -REJ_EPS then gives a quotient that is a negative NON-ZERO
+    // float (|q| >= 1e-36), i.e. exactly the reference's `bar < 0` -- no division needed.  Everything else (denominator
+    // zero / tiny / huge / non-finite, numerator inside the guard band or NaN) takes the exact division path.
+    unsigned fl = 0;
+    float d1 = l03, d2 = l13, d3 = l23;
+    if (fabsf(l03) >= L3_MIN && fabsf(l03) <= L3_MAX) { fl |= 16u; if (l03 < 0.f) { fl |= 1u; d1 = -l03; } }
+    if (fabsf(l13) >= L3_MIN && fabsf(l13) <= L3_MAX) { fl |= 32u; if (l13 < 0.f) { fl |= 2u; d2 = -l13; } }
+    if (fabsf(l23) >= L3_MIN && fabsf(l23) <= L3_MAX) { fl |= 64u; if (l23 < 0.f) { fl |= 4u; d3 = -l23; } }
+    const float cmax = fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))), fmaxf(fabsf(b.x), fabsf(b.y)));
+    if ((fl & 112u) == 112u && cmax <= SPAN_COORD_MAX) fl |= FL_SPAN;  // (NaN coordinates fail the comparison)
+    S.u.st.s0[slot] = a;
+    S.u.st.s1[slot] = b;
+    S.u.st.s2[slot] = make_float4(c.x, d1, d2, d3);
+    S.u.st.s3[slot] = make_uint4(bx, by, tri, fl);
+    const int yt = max((int)(by & 0xFFFF), y0), yb = min((int)(by >> 16), y0 + th);
+    return (unsigned)max(yb - yt, 0);
+}
+
+// Conservative bound of the pixels of one row that can pass `bar_k >= 0`, for one barycentric.
+// Reference (mu:34): num = fl(fl(l1*fl(py-a)) - fl(l2*fl(px-b))), inside <=> !(num/l3 < 0).  With the sign-normalised
+// (l1', l2', d' > 0) form, inside => num' >= -REJ_EPS (stage_pair).  num' differs from the real-valued
+// E(x) = A - l2'*(x-b) by at most 3*2^-24*(|A| + |l2'|*|x-b|); M below is > 16x that bound plus the guard band, so
+// E(x) < -M proves the reference rejects the pixel.  E is linear in x: the admissible x form a half line whose end is
+// b + (A+M)/l2'.  The end is computed with an approximate reciprocal and widened by one pixel; coordinates are limited
+// to 2^18 (FL_SPAN) so that the float evaluation of the end is accurate to < 1/4 pixel wherever it lies on the screen.
+__device__ __forceinline__ void span_bound(float A, float l2, float b, float wmax, float &lo, float &hi)
+{
+    const float M = 3.814697e-6f * (fabsf(A) + fabsf(l2) * wmax) + 1e-5f;   // 2^-18 * magnitude + guard
+    if (l2 == 0.0f) {
+        if (A < -M) { lo = 1e30f; hi = -1e30f; }   // the whole row is outside this edge
+        return;
+    }
+    const float e = b + __fdividef(A + M, l2);
+    if (l2 > 0.0f) hi = fminf(hi, e + 1.0f);       // x <= e   (fminf/fmaxf ignore a NaN e: no tightening)
+    else lo = fmaxf(lo, e - 1.0f);                 // x >= e
 }
 
 __global__ void __launch_bounds__(NT) k_raster(const Frame F)
@@ -450,13 +531,12 @@ __global__ void __launch_bounds__(NT) k_raster(const Frame F)
     const bool clear = (F.flags & CRB_CLEAR_FIRST) != 0;
     const bool overflow = *F.total > (unsigned long long)F.pairCap;
 
-    __shared__ unsigned s_n;
     if (threadIdx.x == 0) {
-        s_n = F.count[tIdx];
+        S.n = F.count[tIdx];
         F.count[tIdx] = 0u;  // self-cleaning: the next frame's k_setup starts from zero
     }
     __syncthreads();
-    const unsigned n = s_n;
+    const unsigned n = S.n;
     if (overflow) {
         if (tIdx == 0 && threadIdx.x == 0) atomicMax(F.total + 1, *F.total);
         return;
@@ -476,48 +556,22 @@ __global__ void __launch_bounds__(NT) k_raster(const Frame F)
         if (threadIdx.x < m) {
             const unsigned tri = F.list[off + base + threadIdx.x];
             const long long ridx = (long long)view * F.T + tri;
-            const float4 a = F.rec0[ridx], b = F.rec1[ridx], c = F.rec2[ridx];
-            const unsigned bx = __float_as_uint(c.y), by = __float_as_uint(c.z);
-            // denominators of mu:12-21
-            const float l01 = a.z - b.x, l02 = a.w - b.y;
-            const float l03 = l01 * (a.y - b.y) - l02 * (a.x - b.x);
-            const float l11 = b.x - a.x, l12 = b.y - a.y;
-            const float l13 = l11 * (a.w - a.y) - l12 * (a.z - a.x);
-            const float l21 = a.x - a.z, l22 = a.y - a.w;
-            const float l23 = l21 * (b.y - a.w) - l22 * (b.x - a.z);
-            // Fast rejection (SURVEY 7, K3 obligation).  num/l3 is bit-identical to (-num)/(-l3), and negation commutes
-            // with every rounding that produced num, so each coordinate is evaluated with l3' = |l3| (edge vector negated
-            // when l3 < 0).  For L3_MIN <= l3' <= L3_MAX a numerator <= -REJ_EPS then gives a quotient that is a negative
-            // NON-ZERO float (|q| >= 1e-36), i.e. exactly the reference's `bar < 0` -- no division needed.  Everything else
-            // (denominator zero / tiny / huge / non-finite, numerator inside the guard band or NaN) takes the exact
-            // division path.  flags bit k: negate coordinate k; bit 4+k: coordinate k may use the fast rejection.
-            unsigned fl = 0;
-            float d1 = l03, d2 = l13, d3 = l23;
-            if (fabsf(l03) >= L3_MIN && fabsf(l03) <= L3_MAX) { fl |= 16u; if (l03 < 0.f) { fl |= 1u; d1 = -l03; } }
-            if (fabsf(l13) >= L3_MIN && fabsf(l13) <= L3_MAX) { fl |= 32u; if (l13 < 0.f) { fl |= 2u; d2 = -l13; } }
-            if (fabsf(l23) >= L3_MIN && fabsf(l23) <= L3_MAX) { fl |= 64u; if (l23 < 0.f) { fl |= 4u; d3 = -l23; } }
-            S.u.st.s0[threadIdx.x] = a;
-            S.u.st.s1[threadIdx.x] = b;
-            S.u.st.s2[threadIdx.x] = make_float4(c.x, d1, d2, d3);
-            S.u.st.s3[threadIdx.x] = make_uint4(bx, by, tri, fl);
-            const int yt = max((int)(by & 0xFFFF), y0), yb = min((int)(by >> 16), y0 + th);
-            rows = (unsigned)max(yb - yt, 0);
+            rows = stage_pair(S, threadIdx.x, F.rec0[ridx], F.rec1[ridx], F.rec2[ridx], tri, y0, th);
         }
         unsigned totalRows;
         const unsigned start = block_exclusive_scan(rows, S.warp_sums, totalRows);
-        if (threadIdx.x < m) S.u.st.rowStart[threadIdx.x] = start;
+        if (threadIdx.x < m) {
+            S.u.st.rowStart[threadIdx.x] = start;
+            for (unsigned j = 0; j < rows; ++j) S.u.st.owner[start + j] = (unsigned char)threadIdx.x;
+        }
         __syncthreads();
 
         for (unsigned r = threadIdx.x; r < totalRows; r += NT) {
-            unsigned lo = 0, hi = m;
-            while (hi - lo > 1) {
-                const unsigned mid = (lo + hi) >> 1;
-                if (S.u.st.rowStart[mid] <= r) lo = mid; else hi = mid;
-            }
-            const float4 a = S.u.st.s0[lo], b = S.u.st.s1[lo], c = S.u.st.s2[lo];
-            const uint4 d = S.u.st.s3[lo];
-            const int y = max((int)(d.y & 0xFFFF), y0) + (int)(r - S.u.st.rowStart[lo]);
-            const int xa = max((int)(d.x & 0xFFFF), x0), xb = min((int)(d.x >> 16), x0 + tw);
+            const unsigned o = S.u.st.owner[r];
+            const float4 a = S.u.st.s0[o], b = S.u.st.s1[o], c = S.u.st.s2[o];
+            const uint4 d = S.u.st.s3[o];
+            const int y = max((int)(d.y & 0xFFFF), y0) + (int)(r - S.u.st.rowStart[o]);
+            int xa = max((int)(d.x & 0xFFFF), x0), xb = min((int)(d.x >> 16), x0 + tw);
             const unsigned s1 = (d.w & 1u) << 31, s2 = (d.w & 2u) << 30, s3 = (d.w & 4u) << 29;
             // edge vectors, sign-normalised (exact negation: flip the sign bit)
             const float l01 = __uint_as_float(__float_as_uint(a.z - b.x) ^ s1), l02 = __uint_as_float(__float_as_uint(a.w - b.y) ^ s1);
@@ -528,28 +582,29 @@ __global__ void __launch_bounds__(NT) k_raster(const Frame F)
             const float thr3 = (d.w & 64u) ? -REJ_EPS : -INFINITY;
             const float py = (float)y;
             const float A1 = l01 * (py - b.y), A2 = l11 * (py - a.y), A3 = l21 * (py - a.w);
-            // pass 1: cheap rejection over the row -> candidate mask
-            unsigned mask = 0;
+            if (d.w & FL_SPAN) {
+                // analytic, conservative span of this row: replaces a per-pixel rejection loop
+                float lo = (float)xa, hi = (float)(xb - 1);
+                const float fa = lo, fb = hi;
+                span_bound(A1, l02, b.x, fmaxf(fabsf(fa - b.x), fabsf(fb - b.x)), lo, hi);
+                span_bound(A2, l12, a.x, fmaxf(fabsf(fa - a.x), fabsf(fb - a.x)), lo, hi);
+                span_bound(A3, l22, a.z, fmaxf(fabsf(fa - a.z), fabsf(fb - a.z)), lo, hi);
+                if (!(lo <= hi)) continue;
+                xa = max(xa, (int)ceilf(lo));      // lo, hi lie within [xa-2, xb+1]: the conversions are exact
+                xb = min(xb, (int)floorf(hi) + 1);
+            }
+            unsigned long long *krow = S.keys + (y - y0) * KEY_STRIDE - x0;
             for (int x = xa; x < xb; ++x) {
                 const float px = (float)x;
                 const float n1 = A1 - l02 * (px - b.x);
                 const float n2 = A2 - l12 * (px - a.x);
                 const float n3 = A3 - l22 * (px - a.z);
-                if (!(n1 < thr1 || n2 < thr2 || n3 < thr3)) mask |= 1u << (x - x0);
-            }
-            // pass 2: exact barycentrics, depth, key for the survivors
-            unsigned long long *krow = S.keys + (y - y0) * KEY_STRIDE;
-            while (mask) {
-                const int bit = __ffs(mask) - 1;
-                mask &= mask - 1;
-                const float px = (float)(x0 + bit);
-                const float b1 = (A1 - l02 * (px - b.x)) / c.y;
-                const float b2 = (A2 - l12 * (px - a.x)) / c.z;
-                const float b3 = (A3 - l22 * (px - a.z)) / c.w;
+                if (n1 < thr1 || n2 < thr2 || n3 < thr3) continue;      // certainly bar < 0 (see stage_pair)
+                const float b1 = n1 / c.y, b2 = n2 / c.z, b3 = n3 / c.w;
                 if (b1 < 0.0f || b2 < 0.0f || b3 < 0.0f) continue;      // pyx:216
                 const float z = (b.z * b1 + b.w * b2) + c.x * b3;        // pyx:219
                 if (z != z) continue;                                    // pyx:220 rejects NaN only
-                smem_key_min(krow + bit, pack_key(z, d.z));
+                smem_key_min(krow + x, pack_key(z, d.z));
             }
         }
     }
@@ -559,18 +614,20 @@ __global__ void __launch_bounds__(NT) k_raster(const Frame F)
     const float *M = F.views ? F.views + view * 16 : nullptr;
     const long long slab = (long long)view * F.slabPixels;
     const bool vec = clear && (tw == TW) && ((F.W & 3) == 0);
+    const float bg = background_color(F);
     for (int p = threadIdx.x; p < TH * TW; p += NT) {
         const int yy = p / TW, xx = p % TW;
         if (yy >= th || xx >= tw) continue;
         const unsigned long long key = S.keys[yy * KEY_STRIDE + xx];
-        float z = Z_INIT, c[3] = {0.f, 0.f, 0.f}, nn[3] = {0.f, 0.f, 0.f};
+        float z = Z_INIT, c[3] = {bg, bg, bg}, nn[3] = {0.f, 0.f, 0.f};
         bool write = clear;
         const long long pix = slab + (long long)(yl0 + yy) * F.W + x0 + xx;
         if (key != KEY_EMPTY) {
             const unsigned tri = ~(unsigned)(key & 0xFFFFFFFFull);
-            const Tri9 t = load_tri9(F, (long long)view * F.T + tri);
+            const long long ridx = (long long)view * F.T + tri;
+            const Tri9 t = load_tri9(F, ridx);
             float fz, fc[3], fn[3];
-            if (shade_fragment(F, t, tri, M, (float)(x0 + xx), (float)(y0 + yy), fz, fc, fn)) {
+            if (shade_fragment(F, t, tri, ridx, M, (float)(x0 + xx), (float)(y0 + yy), fz, fc, fn)) {
                 const float zold = clear ? Z_INIT : F.z[pix];
                 if (!(fz > zold)) {  // pyx:223: drawn unless new_z > z_buffer (equal depth overwrites)
                     z = fz; c[0] = fc[0]; c[1] = fc[1]; c[2] = fc[2]; nn[0] = fn[0]; nn[1] = fn[1]; nn[2] = fn[2];
@@ -595,11 +652,19 @@ __global__ void __launch_bounds__(NT) k_raster(const Frame F)
     }
     if (vec) {
         __syncthreads();
-        for (int i = threadIdx.x; i < th * (TW * 3 / 4); i += NT) {
-            const int r = i / (TW * 3 / 4), q = i % (TW * 3 / 4);
+        const int q = threadIdx.x & 7;
+        for (int r = threadIdx.x >> 3; r < th; r += NT / 8) {
             const long long o = (slab + (long long)(yl0 + r) * F.W + x0) * 3;
-            if (F.color) reinterpret_cast<float4 *>(F.color + o)[q] = reinterpret_cast<const float4 *>(S.u.out.col + r * TW * 3)[q];
-            if (F.normals) reinterpret_cast<float4 *>(F.normals + o)[q] = reinterpret_cast<const float4 *>(S.u.out.nrm + r * TW * 3)[q];
+            if (F.color) {
+                float4 *g = reinterpret_cast<float4 *>(F.color + o);
+                const float4 *s = reinterpret_cast<const float4 *>(S.u.out.col + r * TW * 3);
+                g[q] = s[q]; g[q + 8] = s[q + 8]; g[q + 16] = s[q + 16];
+            }
+            if (F.normals) {
+                float4 *g = reinterpret_cast<float4 *>(F.normals + o);
+                const float4 *s = reinterpret_cast<const float4 *>(S.u.out.nrm + r * TW * 3);
+                g[q] = s[q]; g[q + 8] = s[q + 8]; g[q + 16] = s[q + 16];
+            }
         }
     }
 }
@@ -645,7 +710,7 @@ __global__ void __launch_bounds__(NT) k_shade_atomic(const Frame F, unsigned lon
         const Tri9 t = load_tri9(F, tri);
         const int y = F.row0 + (int)(pix / F.W), x = (int)(pix % F.W);
         float fz, fc[3], fn[3];
-        if (shade_fragment(F, t, tri, nullptr, (float)x, (float)y, fz, fc, fn)) {
+        if (shade_fragment(F, t, tri, tri, nullptr, (float)x, (float)y, fz, fc, fn)) {
             const float zold = clear ? Z_INIT : F.z[pix];
             if (!(fz > zold)) {
                 z = fz; c[0] = fc[0]; c[1] = fc[1]; c[2] = fc[2]; nn[0] = fn[0]; nn[1] = fn[1]; nn[2] = fn[2];
@@ -763,7 +828,7 @@ struct crb_filler {
     long long maxT;
     int maxViews;
     long long pairCap;
-    float4 *rec0, *rec1, *rec2;
+    float4 *rec0, *rec1, *rec2, *nrec0, *nrec1;
     unsigned *count, *offset, *cursor, *list;
     unsigned long long *total;
     float *stage_v, *stage_c, *stage_n;  // device staging for host-pointer calls
@@ -780,7 +845,7 @@ struct crb_filler {
 namespace {
 
 struct WsLayout {
-    size_t rec0, rec1, rec2, count, offset, cursor, list, total, sv, sc, sn, bytes;
+    size_t rec0, rec1, rec2, nrec0, nrec1, count, offset, cursor, list, total, sv, sc, sn, bytes;
 };
 
 long long default_pair_cap(const crb_filler *f, long long T, int views)
@@ -800,6 +865,8 @@ WsLayout ws_layout(const crb_filler *f, long long T, int views, long long pairCa
     L.rec0 = take(recs * sizeof(float4));
     L.rec1 = take(recs * sizeof(float4));
     L.rec2 = take(recs * sizeof(float4));
+    L.nrec0 = take(recs * sizeof(float4));
+    L.nrec1 = take(recs * sizeof(float4));
     L.count = take((size_t)tiles * views * 4);
     L.offset = take((size_t)tiles * views * 4);
     L.cursor = take((size_t)tiles * views * 4);
@@ -849,7 +916,7 @@ void fill_frame(const crb_filler *f, Frame *F)
     F->tilesX = (f->w + TW - 1) / TW;
     F->tilesY = (f->row1 - f->row0 + TH - 1) / TH;
     F->nTiles = F->tilesX * F->tilesY;
-    F->rec0 = f->rec0; F->rec1 = f->rec1; F->rec2 = f->rec2;
+    F->rec0 = f->rec0; F->rec1 = f->rec1; F->rec2 = f->rec2; F->nrec0 = f->nrec0; F->nrec1 = f->nrec1;
     F->count = f->count; F->offset = f->offset; F->cursor = f->cursor; F->list = f->list;
     F->total = f->total;
     F->pairCap = f->pairCap;
@@ -929,6 +996,7 @@ int bind_ws_pointers(crb_filler *f, void *ws, size_t bytes, long long T, int vie
     f->ws = ws; f->ws_bytes = bytes;
     f->maxT = T; f->maxViews = views; f->pairCap = pairCap;
     f->rec0 = (float4 *)(b + L.rec0); f->rec1 = (float4 *)(b + L.rec1); f->rec2 = (float4 *)(b + L.rec2);
+    f->nrec0 = (float4 *)(b + L.nrec0); f->nrec1 = (float4 *)(b + L.nrec1);
     f->count = (unsigned *)(b + L.count); f->offset = (unsigned *)(b + L.offset); f->cursor = (unsigned *)(b + L.cursor);
     f->list = (unsigned *)(b + L.list);
     f->total = (unsigned long long *)(b + L.total);
