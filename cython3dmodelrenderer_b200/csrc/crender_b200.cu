@@ -71,7 +71,8 @@ struct Frame {
     unsigned *count;            // [nViews*nTiles] triangles per tile (zero between frames)
     unsigned *offset;           // [nViews*nTiles] start of the tile's list
     unsigned *cursor;           // [nViews*nTiles] fill cursor
-    unsigned *list;             // [pairCap] triangle indices, tile by tile
+    float4 *ls0, *ls1, *ls2;    // [pairCap] staged triangle setups, tile by tile: (x0 y0 x1 y1) (x2 y2 z0 z1) (z2 d1 d2 d3)
+    uint4 *ls3;                 // [pairCap] (bbox x, bbox y, triangle index, flags)
     unsigned long long *total;  // [0] pairs of this frame, [1] sticky max of overflowing totals
     long long pairCap;
     // outputs (per view slab stride = rows*W (z) or rows*W*3)
@@ -366,23 +367,52 @@ __global__ void __launch_bounds__(NT) k_alloc(const Frame F)
 }
 
 // K2c: scatter triangle indices into the tile lists.
+// flags of a staged triangle: bit k (k=0..2) -> barycentric k is evaluated with negated edge vector and denominator;
+// bit 4+k -> barycentric k may use the division-free rejection; bit 8 -> row spans may be bounded analytically.
+constexpr unsigned FL_SPAN = 256u;
+constexpr float SPAN_COORD_MAX = 262144.0f;  // 2^18: beyond this the float span bounds lose sub-pixel accuracy
+
 __global__ void __launch_bounds__(NT) k_fill(const Frame F)
 {
     if (*F.total > (unsigned long long)F.pairCap) return;  // overflow: frame is skipped, host is told via crb_status
     const int view = blockIdx.y;
     const long long tri = (long long)blockIdx.x * NT + threadIdx.x;
     if (tri >= F.T) return;
-    const float4 r2 = F.rec2[(long long)view * F.T + tri];
-    const unsigned bx = __float_as_uint(r2.y), by = __float_as_uint(r2.z);
+    const long long ridx = (long long)view * F.T + tri;
+    const float4 c = F.rec2[ridx];
+    const unsigned bx = __float_as_uint(c.y), by = __float_as_uint(c.z);
     if ((bx >> 16) == 0) return;  // not drawn (x_right >= 1 for every drawn triangle)
+    const float4 a = F.rec0[ridx], b = F.rec1[ridx];
+    // denominators of mu:12-21
+    const float l01 = a.z - b.x, l02 = a.w - b.y;
+    const float l03 = l01 * (a.y - b.y) - l02 * (a.x - b.x);
+    const float l11 = b.x - a.x, l12 = b.y - a.y;
+    const float l13 = l11 * (a.w - a.y) - l12 * (a.z - a.x);
+    const float l21 = a.x - a.z, l22 = a.y - a.w;
+    const float l23 = l21 * (b.y - a.w) - l22 * (b.x - a.z);
+    // Division-free rejection (SURVEY 7, K3 obligation).  num/l3 is bit-identical to (-num)/(-l3), and negation commutes
+    // with every rounding that produced num, so each coordinate is evaluated with l3' = |l3| (edge vector negated when
+    // l3 < 0).  For L3_MIN <= l3' <= L3_MAX a numerator <= -REJ_EPS then gives a quotient that is a negative NON-ZERO
+    // float (|q| >= 1e-36), i.e. exactly the reference's `bar < 0` -- no division needed.  Everything else (denominator
+    // zero / tiny / huge / non-finite, numerator inside the guard band or NaN) takes the exact division path.
+    unsigned fl = 0;
+    float d1 = l03, d2 = l13, d3 = l23;
+    if (fabsf(l03) >= L3_MIN && fabsf(l03) <= L3_MAX) { fl |= 16u; if (l03 < 0.f) { fl |= 1u; d1 = -l03; } }
+    if (fabsf(l13) >= L3_MIN && fabsf(l13) <= L3_MAX) { fl |= 32u; if (l13 < 0.f) { fl |= 2u; d2 = -l13; } }
+    if (fabsf(l23) >= L3_MIN && fabsf(l23) <= L3_MAX) { fl |= 64u; if (l23 < 0.f) { fl |= 4u; d3 = -l23; } }
+    const float cmax = fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))), fmaxf(fabsf(b.x), fabsf(b.y)));
+    if ((fl & 112u) == 112u && cmax <= SPAN_COORD_MAX) fl |= FL_SPAN;  // (NaN coordinates fail the comparison)
+    const float4 s2 = make_float4(c.x, d1, d2, d3);
+    const uint4 s3 = make_uint4(bx, by, (unsigned)tri, fl);
+
     int tx0, tx1, ty0, ty1;
     tile_span(F, bx, by, tx0, tx1, ty0, ty1);
     const long long vb = (long long)view * F.nTiles;
     for (int ty = ty0; ty <= ty1; ++ty)
         for (int tx = tx0; tx <= tx1; ++tx) {
             const long long t = vb + ty * F.tilesX + tx;
-            const unsigned pos = atomicAdd(F.cursor + t, 1u);
-            F.list[F.offset[t] + pos] = (unsigned)tri;
+            const unsigned at = F.offset[t] + atomicAdd(F.cursor + t, 1u);
+            F.ls0[at] = a; F.ls1[at] = b; F.ls2[at] = s2; F.ls3[at] = s3;
         }
 }
 
@@ -408,7 +438,7 @@ struct __align__(16) TileSmem {
         struct {
             float4 s0[CH];  // x0 y0 x1 y1
             float4 s1[CH];  // x2 y2 z0 z1
-            float4 s2[CH];  // z2 d1 d2 d3   (d = sign-normalised denominators l03' l13' l23', see stage_pair)
+            float4 s2[CH];  // z2 d1 d2 d3   (d = sign-normalised denominators l03' l13' l23', see k_fill)
             uint4 s3[CH];   // bx by tri flags
             unsigned rowStart[CH];
             unsigned char owner[CH * TH];  // row work item -> staged triangle
@@ -419,13 +449,8 @@ struct __align__(16) TileSmem {
         } out;
     } u;
     unsigned warp_sums[NT / 32];
-    unsigned n;
+    unsigned n[2], off[2];   // double-buffered bookkeeping of the current / prefetched tile
 };
-
-// flags of a staged triangle: bit k (k=0..2) -> barycentric k is evaluated with negated edge vector and denominator;
-// bit 4+k -> barycentric k may use the division-free rejection; bit 8 -> row spans may be bounded analytically.
-constexpr unsigned FL_SPAN = 256u;
-constexpr float SPAN_COORD_MAX = 262144.0f;  // 2^18: beyond this the float span bounds lose sub-pixel accuracy
 
 // Writes one tile of cleared pixels (fresh-filler values) -- the whole frame's "memset" is fused here.
 __device__ __forceinline__ void write_clear_tile(const Frame &F, int view, int x0, int yl0, int tw, int th)
@@ -467,41 +492,9 @@ __device__ __forceinline__ void write_clear_tile(const Frame &F, int view, int x
     }
 }
 
-// One staged triangle: everything a row work item needs, computed once per (triangle, tile).
-__device__ __forceinline__ unsigned stage_pair(TileSmem &S, int slot, const float4 a, const float4 b, const float4 c, unsigned tri,
-                                               int y0, int th)
-{
-    const unsigned bx = __float_as_uint(c.y), by = __float_as_uint(c.z);
-    // denominators of mu:12-21
-    const float l01 = a.z - b.x, l02 = a.w - b.y;
-    const float l03 = l01 * (a.y - b.y) - l02 * (a.x - b.x);
-    const float l11 = b.x - a.x, l12 = b.y - a.y;
-    const float l13 = l11 * (a.w - a.y) - l12 * (a.z - a.x);
-    const float l21 = a.x - a.z, l22 = a.y - a.w;
-    const float l23 = l21 * (b.y - a.w) - l22 * (b.x - a.z);
-    // Division-free rejection (SURVEY 7, K3 obligation).  num/l3 is bit-identical to (-num)/(-l3), and negation commutes
-    // with every rounding that produced num, so each coordinate is evaluated with l3' = |l3| (edge vector negated when
-    // l3 < 0).  For L3_MIN <= l3' <= L3_MAX a numerator <= -REJ_EPS then gives a quotient that is a negative NON-ZERO
-    // float (|q| >= 1e-36), i.e. exactly the reference's `bar < 0` -- no division needed.  Everything else (denominator
-    // zero / tiny / huge / non-finite, numerator inside the guard band or NaN) takes the exact division path.
-    unsigned fl = 0;
-    float d1 = l03, d2 = l13, d3 = l23;
-    if (fabsf(l03) >= L3_MIN && fabsf(l03) <= L3_MAX) { fl |= 16u; if (l03 < 0.f) { fl |= 1u; d1 = -l03; } }
-    if (fabsf(l13) >= L3_MIN && fabsf(l13) <= L3_MAX) { fl |= 32u; if (l13 < 0.f) { fl |= 2u; d2 = -l13; } }
-    if (fabsf(l23) >= L3_MIN && fabsf(l23) <= L3_MAX) { fl |= 64u; if (l23 < 0.f) { fl |= 4u; d3 = -l23; } }
-    const float cmax = fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))), fmaxf(fabsf(b.x), fabsf(b.y)));
-    if ((fl & 112u) == 112u && cmax <= SPAN_COORD_MAX) fl |= FL_SPAN;  // (NaN coordinates fail the comparison)
-    S.u.st.s0[slot] = a;
-    S.u.st.s1[slot] = b;
-    S.u.st.s2[slot] = make_float4(c.x, d1, d2, d3);
-    S.u.st.s3[slot] = make_uint4(bx, by, tri, fl);
-    const int yt = max((int)(by & 0xFFFF), y0), yb = min((int)(by >> 16), y0 + th);
-    return (unsigned)max(yb - yt, 0);
-}
-
 // Conservative bound of the pixels of one row that can pass `bar_k >= 0`, for one barycentric.
 // Reference (mu:34): num = fl(fl(l1*fl(py-a)) - fl(l2*fl(px-b))), inside <=> !(num/l3 < 0).  With the sign-normalised
-// (l1', l2', d' > 0) form, inside => num' >= -REJ_EPS (stage_pair).  num' differs from the real-valued
+// (l1', l2', d' > 0) form, inside => num' >= -REJ_EPS (k_fill).  num' differs from the real-valued
 // E(x) = A - l2'*(x-b) by at most 3*2^-24*(|A| + |l2'|*|x-b|); M below is > 16x that bound plus the guard band, so
 // E(x) < -M proves the reference rejects the pixel.  E is linear in x: the admissible x form a half line whose end is
 // b + (A+M)/l2'.  The end is computed with an approximate reciprocal and widened by one pixel; coordinates are limited
@@ -518,34 +511,45 @@ __device__ __forceinline__ void span_bound(float A, float l2, float b, float wma
     else lo = fmaxf(lo, e - 1.0f);                 // x >= e
 }
 
+// Persistent: gridDim.x CTAs walk the (view, tile) space with stride gridDim.x; the next tile's triangle count and list
+// offset are fetched while the current tile is processed, so neither CTA launch cost nor that dependent load sits on the
+// critical path of the 70 % of tiles that are empty and only need their fused clear.
 __global__ void __launch_bounds__(NT) k_raster(const Frame F)
 {
     __shared__ TileSmem S;
-    const int view = blockIdx.y;
-    const int tile = blockIdx.x;
-    const long long tIdx = (long long)view * F.nTiles + tile;
+    const long long nAll = (long long)F.nViews * F.nTiles;
+    const bool clear = (F.flags & CRB_CLEAR_FIRST) != 0;
+    const bool overflow = *F.total > (unsigned long long)F.pairCap;
+    if (overflow) {   // frame skipped (host is told via crb_status); tile counts must still return to zero
+        for (long long t = (long long)blockIdx.x * NT + threadIdx.x; t < nAll; t += (long long)gridDim.x * NT) F.count[t] = 0u;
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(F.total + 1, *F.total);
+        return;
+    }
+    if (threadIdx.x == 0) {
+        const long long t = blockIdx.x;
+        S.n[0] = (t < nAll) ? F.count[t] : 0u;
+        S.off[0] = (t < nAll) ? F.offset[t] : 0u;
+    }
+    __syncthreads();
+
+    int cur = 0;
+    for (long long tIdx = blockIdx.x; tIdx < nAll; tIdx += gridDim.x, cur ^= 1) {
+    const unsigned n = S.n[cur], off = S.off[cur];
+    unsigned n_next = 0, off_next = 0;
+    if (threadIdx.x == 0) {   // prefetch the next tile's bookkeeping; consumed after this tile is done
+        const long long t = tIdx + gridDim.x;
+        if (t < nAll) { n_next = F.count[t]; off_next = F.offset[t]; }
+        if (n) F.count[tIdx] = 0u;  // self-cleaning: the next frame's k_setup starts from zero
+    }
+    const int view = (int)(tIdx / F.nTiles), tile = (int)(tIdx % F.nTiles);
     const int tx = tile % F.tilesX, ty = tile / F.tilesX;
     const int x0 = tx * TW, yl0 = ty * TH;       // yl0: row inside the band's buffers
     const int y0 = F.row0 + yl0;                  // absolute image row
     const int tw = min(TW, F.W - x0), th = min(TH, F.row1 - y0);
-    const bool clear = (F.flags & CRB_CLEAR_FIRST) != 0;
-    const bool overflow = *F.total > (unsigned long long)F.pairCap;
 
-    if (threadIdx.x == 0) {
-        S.n = F.count[tIdx];
-        F.count[tIdx] = 0u;  // self-cleaning: the next frame's k_setup starts from zero
-    }
-    __syncthreads();
-    const unsigned n = S.n;
-    if (overflow) {
-        if (tIdx == 0 && threadIdx.x == 0) atomicMax(F.total + 1, *F.total);
-        return;
-    }
-    if (n == 0) {
+    if (n == 0 || (F.flags & 0x10000u)) {
         if (clear) write_clear_tile(F, view, x0, yl0, tw, th);
-        return;
-    }
-    const unsigned off = F.offset[tIdx];
+    } else {
     for (int i = threadIdx.x; i < TH * KEY_STRIDE; i += NT) S.keys[i] = KEY_EMPTY;
 
     // ---- visibility: every (triangle,row) of the tile is one work item -------------------------------------
@@ -553,59 +557,103 @@ __global__ void __launch_bounds__(NT) k_raster(const Frame F)
         const unsigned m = min((unsigned)CH, n - base);
         __syncthreads();  // keys initialised / previous pass finished with the staging area
         unsigned rows = 0;
-        if (threadIdx.x < m) {
-            const unsigned tri = F.list[off + base + threadIdx.x];
-            const long long ridx = (long long)view * F.T + tri;
-            rows = stage_pair(S, threadIdx.x, F.rec0[ridx], F.rec1[ridx], F.rec2[ridx], tri, y0, th);
+        if (threadIdx.x < m) {   // coalesced copy of the setups k_fill prepared for this tile
+            const unsigned at = off + base + threadIdx.x;
+            const uint4 d = F.ls3[at];
+            S.u.st.s0[threadIdx.x] = F.ls0[at];
+            S.u.st.s1[threadIdx.x] = F.ls1[at];
+            S.u.st.s2[threadIdx.x] = F.ls2[at];
+            S.u.st.s3[threadIdx.x] = d;
+            const int yt = max((int)(d.y & 0xFFFF), y0), yb = min((int)(d.y >> 16), y0 + th);
+            rows = (unsigned)max(yb - yt, 0);
         }
         unsigned totalRows;
         const unsigned start = block_exclusive_scan(rows, S.warp_sums, totalRows);
+        if (F.flags & 0x40000u) totalRows = 0;
         if (threadIdx.x < m) {
             S.u.st.rowStart[threadIdx.x] = start;
             for (unsigned j = 0; j < rows; ++j) S.u.st.owner[start + j] = (unsigned char)threadIdx.x;
         }
         __syncthreads();
 
-        for (unsigned r = threadIdx.x; r < totalRows; r += NT) {
-            const unsigned o = S.u.st.owner[r];
-            const float4 a = S.u.st.s0[o], b = S.u.st.s1[o], c = S.u.st.s2[o];
-            const uint4 d = S.u.st.s3[o];
-            const int y = max((int)(d.y & 0xFFFF), y0) + (int)(r - S.u.st.rowStart[o]);
-            int xa = max((int)(d.x & 0xFFFF), x0), xb = min((int)(d.x >> 16), x0 + tw);
-            const unsigned s1 = (d.w & 1u) << 31, s2 = (d.w & 2u) << 30, s3 = (d.w & 4u) << 29;
-            // edge vectors, sign-normalised (exact negation: flip the sign bit)
-            const float l01 = __uint_as_float(__float_as_uint(a.z - b.x) ^ s1), l02 = __uint_as_float(__float_as_uint(a.w - b.y) ^ s1);
-            const float l11 = __uint_as_float(__float_as_uint(b.x - a.x) ^ s2), l12 = __uint_as_float(__float_as_uint(b.y - a.y) ^ s2);
-            const float l21 = __uint_as_float(__float_as_uint(a.x - a.z) ^ s3), l22 = __uint_as_float(__float_as_uint(a.y - a.w) ^ s3);
-            const float thr1 = (d.w & 16u) ? -REJ_EPS : -INFINITY;
-            const float thr2 = (d.w & 32u) ? -REJ_EPS : -INFINITY;
-            const float thr3 = (d.w & 64u) ? -REJ_EPS : -INFINITY;
-            const float py = (float)y;
-            const float A1 = l01 * (py - b.y), A2 = l11 * (py - a.y), A3 = l21 * (py - a.w);
-            if (d.w & FL_SPAN) {
-                // analytic, conservative span of this row: replaces a per-pixel rejection loop
-                float lo = (float)xa, hi = (float)(xb - 1);
-                const float fa = lo, fb = hi;
-                span_bound(A1, l02, b.x, fmaxf(fabsf(fa - b.x), fabsf(fb - b.x)), lo, hi);
-                span_bound(A2, l12, a.x, fmaxf(fabsf(fa - a.x), fabsf(fb - a.x)), lo, hi);
-                span_bound(A3, l22, a.z, fmaxf(fabsf(fa - a.z), fabsf(fb - a.z)), lo, hi);
-                if (!(lo <= hi)) continue;
-                xa = max(xa, (int)ceilf(lo));      // lo, hi lie within [xa-2, xb+1]: the conversions are exact
-                xb = min(xb, (int)floorf(hi) + 1);
+        // Row work items, 32 per warp per trip.  Trip counts are warp-uniform and the body is predicated, so the warp
+        // stays converged (a per-thread `for (r = tid; ...)` with early `continue`s lets lanes drift apart under
+        // independent thread scheduling: measured 7.5 active lanes per instruction).
+        const unsigned lane = threadIdx.x & 31u;
+        for (unsigned rb = threadIdx.x & ~31u; rb < totalRows; rb += NT) {
+            const unsigned r = rb + lane;
+            const bool active = r < totalRows;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, c = a;
+            float l02 = 0.f, l12 = 0.f, l22 = 0.f, A1 = 0.f, A2 = 0.f, A3 = 0.f;
+            float thr1 = 0.f, thr2 = 0.f, thr3 = 0.f;
+            unsigned tri = 0;
+            int xa = 0, xb = 0, y = y0;
+            if (active) {
+                const unsigned o = S.u.st.owner[r];
+                a = S.u.st.s0[o]; b = S.u.st.s1[o]; c = S.u.st.s2[o];
+                const uint4 d = S.u.st.s3[o];
+                tri = d.z;
+                y = max((int)(d.y & 0xFFFF), y0) + (int)(r - S.u.st.rowStart[o]);
+                xa = max((int)(d.x & 0xFFFF), x0);
+                xb = min((int)(d.x >> 16), x0 + tw);
+                const unsigned s1 = (d.w & 1u) << 31, s2 = (d.w & 2u) << 30, s3 = (d.w & 4u) << 29;
+                // edge vectors, sign-normalised (exact negation: flip the sign bit)
+                const float l01 = __uint_as_float(__float_as_uint(a.z - b.x) ^ s1);
+                const float l11 = __uint_as_float(__float_as_uint(b.x - a.x) ^ s2);
+                const float l21 = __uint_as_float(__float_as_uint(a.x - a.z) ^ s3);
+                l02 = __uint_as_float(__float_as_uint(a.w - b.y) ^ s1);
+                l12 = __uint_as_float(__float_as_uint(b.y - a.y) ^ s2);
+                l22 = __uint_as_float(__float_as_uint(a.y - a.w) ^ s3);
+                thr1 = (d.w & 16u) ? -REJ_EPS : -INFINITY;
+                thr2 = (d.w & 32u) ? -REJ_EPS : -INFINITY;
+                thr3 = (d.w & 64u) ? -REJ_EPS : -INFINITY;
+                const float py = (float)y;
+                A1 = l01 * (py - b.y); A2 = l11 * (py - a.y); A3 = l21 * (py - a.w);
+                if (d.w & FL_SPAN) {
+                    // analytic, conservative span of this row: replaces a per-pixel rejection loop over the bbox row
+                    float lo = (float)xa, hi = (float)(xb - 1);
+                    const float fa = lo, fb = hi;
+                    span_bound(A1, l02, b.x, fmaxf(fabsf(fa - b.x), fabsf(fb - b.x)), lo, hi);
+                    span_bound(A2, l12, a.x, fmaxf(fabsf(fa - a.x), fabsf(fb - a.x)), lo, hi);
+                    span_bound(A3, l22, a.z, fmaxf(fabsf(fa - a.z), fabsf(fb - a.z)), lo, hi);
+                    if (lo <= hi) {
+                        xa = max(xa, (int)ceilf(lo));      // lo, hi lie within [xa-2, xb+1]: the conversions are exact
+                        xb = min(xb, (int)floorf(hi) + 1);
+                    } else {
+                        xb = xa;
+                    }
+                }
             }
-            unsigned long long *krow = S.keys + (y - y0) * KEY_STRIDE - x0;
-            for (int x = xa; x < xb; ++x) {
-                const float px = (float)x;
+            // pass 1 (cheap, predicated): numerators over the span -> mask of pixels that need the exact path
+            const int len = max(xb - xa, 0);
+            const int maxlen = __reduce_max_sync(0xFFFFFFFFu, len);
+            unsigned mask = 0;
+            for (int i = 0; i < maxlen; ++i) {
+                const float px = (float)(xa + i);
                 const float n1 = A1 - l02 * (px - b.x);
                 const float n2 = A2 - l12 * (px - a.x);
                 const float n3 = A3 - l22 * (px - a.z);
-                if (n1 < thr1 || n2 < thr2 || n3 < thr3) continue;      // certainly bar < 0 (see stage_pair)
-                const float b1 = n1 / c.y, b2 = n2 / c.z, b3 = n3 / c.w;
-                if (b1 < 0.0f || b2 < 0.0f || b3 < 0.0f) continue;      // pyx:216
-                const float z = (b.z * b1 + b.w * b2) + c.x * b3;        // pyx:219
-                if (z != z) continue;                                    // pyx:220 rejects NaN only
-                smem_key_min(krow + x, pack_key(z, d.z));
+                const bool keep = (i < len) && !(n1 < thr1 || n2 < thr2 || n3 < thr3);   // else: certainly bar < 0
+                mask |= (keep ? 1u : 0u) << ((xa + i - x0) & 31);
             }
+            // pass 2 (exact): divisions, depth, key -- one surviving pixel per lane per trip
+            const int maxcnt = __reduce_max_sync(0xFFFFFFFFu, __popc(mask));
+            unsigned long long *krow = S.keys + (y - y0) * KEY_STRIDE;
+            for (int j = 0; j < maxcnt; ++j) {
+                if (mask) {
+                    const int bit = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const float px = (float)(x0 + bit);
+                    const float b1 = (A1 - l02 * (px - b.x)) / c.y;
+                    const float b2 = (A2 - l12 * (px - a.x)) / c.z;
+                    const float b3 = (A3 - l22 * (px - a.z)) / c.w;
+                    if (!(b1 < 0.0f || b2 < 0.0f || b3 < 0.0f)) {              // pyx:216
+                        const float z = (b.z * b1 + b.w * b2) + c.x * b3;          // pyx:219
+                        if (z == z) smem_key_min(krow + bit, pack_key(z, tri));    // pyx:220 rejects NaN only
+                    }
+                }
+            }
+            __syncwarp();
         }
     }
     __syncthreads();
@@ -622,7 +670,7 @@ __global__ void __launch_bounds__(NT) k_raster(const Frame F)
         float z = Z_INIT, c[3] = {bg, bg, bg}, nn[3] = {0.f, 0.f, 0.f};
         bool write = clear;
         const long long pix = slab + (long long)(yl0 + yy) * F.W + x0 + xx;
-        if (key != KEY_EMPTY) {
+        if (key != KEY_EMPTY && !(F.flags & 0x20000u)) {
             const unsigned tri = ~(unsigned)(key & 0xFFFFFFFFull);
             const long long ridx = (long long)view * F.T + tri;
             const Tri9 t = load_tri9(F, ridx);
@@ -657,16 +705,20 @@ __global__ void __launch_bounds__(NT) k_raster(const Frame F)
             const long long o = (slab + (long long)(yl0 + r) * F.W + x0) * 3;
             if (F.color) {
                 float4 *g = reinterpret_cast<float4 *>(F.color + o);
-                const float4 *s = reinterpret_cast<const float4 *>(S.u.out.col + r * TW * 3);
-                g[q] = s[q]; g[q + 8] = s[q + 8]; g[q + 16] = s[q + 16];
+                const float4 *sc = reinterpret_cast<const float4 *>(S.u.out.col + r * TW * 3);
+                g[q] = sc[q]; g[q + 8] = sc[q + 8]; g[q + 16] = sc[q + 16];
             }
             if (F.normals) {
                 float4 *g = reinterpret_cast<float4 *>(F.normals + o);
-                const float4 *s = reinterpret_cast<const float4 *>(S.u.out.nrm + r * TW * 3);
-                g[q] = s[q]; g[q + 8] = s[q + 8]; g[q + 16] = s[q + 16];
+                const float4 *sn = reinterpret_cast<const float4 *>(S.u.out.nrm + r * TW * 3);
+                g[q] = sn[q]; g[q + 8] = sn[q + 8]; g[q + 16] = sn[q + 16];
             }
         }
     }
+    }  // busy tile
+    if (threadIdx.x == 0) { S.n[cur ^ 1] = n_next; S.off[cur ^ 1] = off_next; }
+    __syncthreads();  // publishes the prefetched bookkeeping; shared memory is free for the next tile
+    }  // tile loop
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -829,7 +881,9 @@ struct crb_filler {
     int maxViews;
     long long pairCap;
     float4 *rec0, *rec1, *rec2, *nrec0, *nrec1;
-    unsigned *count, *offset, *cursor, *list;
+    unsigned *count, *offset, *cursor;
+    float4 *ls0, *ls1, *ls2;
+    uint4 *ls3;
     unsigned long long *total;
     float *stage_v, *stage_c, *stage_n;  // device staging for host-pointer calls
     // differential path scratch (library-owned, lazily allocated)
@@ -837,6 +891,7 @@ struct crb_filler {
     long long keybuf_pixels;
     long long launches;
     // optional timing of the dominant kernel (k_raster) with CUDA events on the launching stream
+    int raster_ctas;       // persistent grid of k_raster: SM count x resident CTAs per SM
     bool prof_on;
     int prof_n;
     cudaEvent_t *prof_ev;  // 2 * PROF_MAX events, created on first use
@@ -845,7 +900,7 @@ struct crb_filler {
 namespace {
 
 struct WsLayout {
-    size_t rec0, rec1, rec2, nrec0, nrec1, count, offset, cursor, list, total, sv, sc, sn, bytes;
+    size_t rec0, rec1, rec2, nrec0, nrec1, count, offset, cursor, ls0, ls1, ls2, ls3, total, sv, sc, sn, bytes;
 };
 
 long long default_pair_cap(const crb_filler *f, long long T, int views)
@@ -870,7 +925,10 @@ WsLayout ws_layout(const crb_filler *f, long long T, int views, long long pairCa
     L.count = take((size_t)tiles * views * 4);
     L.offset = take((size_t)tiles * views * 4);
     L.cursor = take((size_t)tiles * views * 4);
-    L.list = take((size_t)pairCap * 4);
+    L.ls0 = take((size_t)pairCap * 16);
+    L.ls1 = take((size_t)pairCap * 16);
+    L.ls2 = take((size_t)pairCap * 16);
+    L.ls3 = take((size_t)pairCap * 16);
     L.total = take(64);
     L.sv = take((size_t)(T > 0 ? T : 1) * 36);
     L.sc = take((size_t)(T > 0 ? T : 1) * 36);
@@ -917,7 +975,8 @@ void fill_frame(const crb_filler *f, Frame *F)
     F->tilesY = (f->row1 - f->row0 + TH - 1) / TH;
     F->nTiles = F->tilesX * F->tilesY;
     F->rec0 = f->rec0; F->rec1 = f->rec1; F->rec2 = f->rec2; F->nrec0 = f->nrec0; F->nrec1 = f->nrec1;
-    F->count = f->count; F->offset = f->offset; F->cursor = f->cursor; F->list = f->list;
+    F->count = f->count; F->offset = f->offset; F->cursor = f->cursor;
+    F->ls0 = f->ls0; F->ls1 = f->ls1; F->ls2 = f->ls2; F->ls3 = f->ls3;
     F->total = f->total;
     F->pairCap = f->pairCap;
     F->slabPixels = (long long)(f->row1 - f->row0) * f->w;
@@ -951,7 +1010,9 @@ int run_tiled(crb_filler *f, Frame &F, cudaStream_t st)
     }
     const bool prof = f->prof_on && f->prof_n < PROF_MAX;
     if (prof) CU(cudaEventRecord(f->prof_ev[2 * f->prof_n], st));
-    k_raster<<<dim3(F.nTiles, F.nViews), NT, 0, st>>>(F);
+    const long long nAllTiles = (long long)F.nTiles * F.nViews;
+    const unsigned gR = (unsigned)(nAllTiles < f->raster_ctas ? nAllTiles : f->raster_ctas);
+    k_raster<<<gR, NT, 0, st>>>(F);
     if ((rc = launch_check(f, "k_raster"))) return rc;
     if (prof) {
         CU(cudaEventRecord(f->prof_ev[2 * f->prof_n + 1], st));
@@ -998,7 +1059,7 @@ int bind_ws_pointers(crb_filler *f, void *ws, size_t bytes, long long T, int vie
     f->rec0 = (float4 *)(b + L.rec0); f->rec1 = (float4 *)(b + L.rec1); f->rec2 = (float4 *)(b + L.rec2);
     f->nrec0 = (float4 *)(b + L.nrec0); f->nrec1 = (float4 *)(b + L.nrec1);
     f->count = (unsigned *)(b + L.count); f->offset = (unsigned *)(b + L.offset); f->cursor = (unsigned *)(b + L.cursor);
-    f->list = (unsigned *)(b + L.list);
+    f->ls0 = (float4 *)(b + L.ls0); f->ls1 = (float4 *)(b + L.ls1); f->ls2 = (float4 *)(b + L.ls2); f->ls3 = (uint4 *)(b + L.ls3);
     f->total = (unsigned long long *)(b + L.total);
     f->stage_v = (float *)(b + L.sv); f->stage_c = (float *)(b + L.sc); f->stage_n = (float *)(b + L.sn);
     CU(cudaMemsetAsync(b + L.count, 0, L.offset - L.count, st));  // tile counts start at zero, k_raster keeps them so
@@ -1051,6 +1112,14 @@ int crb_create(int h, int w, float fov, float z_near, float z_far, int device, c
     f->row0 = 0; f->row1 = h;
     f->fov = fov; f->z_near = z_near; f->z_far = z_far;
     f->proj = P;
+    {
+        cudaDeviceProp prop;
+        int per_sm = 0;
+        CU(cudaSetDevice(device));
+        CU(cudaGetDeviceProperties(&prop, device));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_raster, NT, 0));
+        f->raster_ctas = prop.multiProcessorCount * (per_sm > 0 ? per_sm : 1);
+    }
     *out = f;
     return CRB_OK;
 }
@@ -1227,7 +1296,7 @@ int crb_render_views(crb_filler *f, const float *v, const float *c, const float 
         Frame F;
         fill_frame(f, &F);
         F.T = T; F.nViews = (n_views - v0 < f->maxViews) ? n_views - v0 : f->maxViews;
-        F.flags = (flags & CRB_GURO) | CRB_CLEAR_FIRST;
+        F.flags = (flags & (CRB_GURO | 0xFFFF0000u)) | CRB_CLEAR_FIRST;   // high bits: undocumented experiment switches
         F.v = v; F.c = c; F.n = n;
         F.views = views + (size_t)v0 * 16;
         F.z = z_out ? z_out + (size_t)v0 * slab : nullptr;
