@@ -80,11 +80,12 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("CRB_LIB_OVERRIDE", LIB_PATH)   # experiments only: an alternative build of the same library
+    if not os.path.exists(path):
         raise ImportError(
-            f"{LIB_PATH} is missing: the CUDA library has not been built "
+            f"{path} is missing: the CUDA library has not been built "
             "(run `python -c 'import __graft_entry__ as g; g.build()'`). There is no CPU fallback.")
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = ctypes.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
         fn.restype = res

@@ -24,6 +24,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -68,7 +69,9 @@ struct Frame {
     // scratch
     float4 *rec0, *rec1, *rec2; // [nViews*T] screen-space triangle records (SoA of float4)
     float4 *nrec0, *nrec1;      // [nViews*T] view-space vertex normals n0 n1 n2.xy (n2.z rides in rec2.w); batched views only
-    unsigned *count;            // [nViews*nTiles] triangles per tile (zero between frames)
+    unsigned *count;            // [nViews*nTiles] triangles per tile, accumulated by k_setup, returned to zero by k_alloc
+    unsigned *tcount;           // [nViews*nTiles] the frame's final per-tile counts (read-only for k_fill / k_raster)
+    unsigned *busy, *empty;     // [nViews*nTiles] compacted (view,tile) indices with / without triangles; sizes in total[2], total[3]
     unsigned *offset;           // [nViews*nTiles] start of the tile's list
     unsigned *cursor;           // [nViews*nTiles] fill cursor
     float4 *ls0, *ls1, *ls2;    // [pairCap] staged triangle setups, tile by tile: (x0 y0 x1 y1) (x2 y2 z0 z1) (z2 d1 d2 d3)
@@ -258,7 +261,9 @@ __global__ void __launch_bounds__(NT) k_setup(const Frame F)
     const int view = blockIdx.y;
     const long long first = (long long)blockIdx.x * NT;
     const long long cnt = min((long long)NT, F.T - first);
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) F.total[0] = 0ull;  // k_alloc (next launch) accumulates
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {  // k_alloc (next launch) accumulates
+        F.total[0] = 0ull; F.total[2] = 0ull; F.total[3] = 0ull;
+    }
     stage_floats(F.v, first * 9, cnt * 9, sv);
     stage_floats(F.n, first * 9, cnt * 9, sn);
     if (F.views && threadIdx.x < 16) sM[threadIdx.x] = F.views[view * 16 + threadIdx.x];
@@ -352,21 +357,31 @@ __global__ void __launch_bounds__(NT) k_alloc(const Frame F)
 {
     __shared__ unsigned warp_sums[NT / 32];
     __shared__ unsigned long long block_base;
+    __shared__ unsigned busy_base, empty_base;
     const long long i = (long long)blockIdx.x * NT + threadIdx.x;
     const long long nAll = (long long)F.nViews * F.nTiles;
     const unsigned c = (i < nAll) ? F.count[i] : 0u;
-    unsigned tot;
+    unsigned tot, nbusy;
     const unsigned excl = block_exclusive_scan(c, warp_sums, tot);
-    if (threadIdx.x == 0) block_base = tot ? atomicAdd(F.total, (unsigned long long)tot) : 0ull;
+    const unsigned brank = block_exclusive_scan(c ? 1u : 0u, warp_sums, nbusy);
+    if (threadIdx.x == 0) {
+        const unsigned valid = (unsigned)min((long long)NT, nAll - (long long)blockIdx.x * NT);
+        block_base = tot ? atomicAdd(F.total, (unsigned long long)tot) : 0ull;
+        busy_base = (unsigned)atomicAdd(F.total + 2, (unsigned long long)nbusy);
+        empty_base = (unsigned)atomicAdd(F.total + 3, (unsigned long long)(valid - nbusy));
+    }
     __syncthreads();
     if (i < nAll) {
         const unsigned long long o = block_base + excl;
         F.offset[i] = (unsigned)(o > 0xFFFFFFFFull ? 0xFFFFFFFFull : o);
         F.cursor[i] = 0u;
+        F.tcount[i] = c;
+        F.count[i] = 0u;   // self-cleaning: the next frame's k_setup starts from zero
+        if (c) F.busy[busy_base + brank] = (unsigned)i;
+        else F.empty[empty_base + (threadIdx.x - brank)] = (unsigned)i;
     }
 }
 
-// K2c: scatter triangle indices into the tile lists.
 // flags of a staged triangle: bit k (k=0..2) -> barycentric k is evaluated with negated edge vector and denominator;
 // bit 4+k -> barycentric k may use the division-free rejection; bit 8 -> row spans may be bounded analytically.
 constexpr unsigned FL_SPAN = 256u;
@@ -449,7 +464,6 @@ struct __align__(16) TileSmem {
         } out;
     } u;
     unsigned warp_sums[NT / 32];
-    unsigned n[2], off[2];   // double-buffered bookkeeping of the current / prefetched tile
 };
 
 // Writes one tile of cleared pixels (fresh-filler values) -- the whole frame's "memset" is fused here.
@@ -514,42 +528,57 @@ __device__ __forceinline__ void span_bound(float A, float l2, float b, float wma
 // Persistent: gridDim.x CTAs walk the (view, tile) space with stride gridDim.x; the next tile's triangle count and list
 // offset are fetched while the current tile is processed, so neither CTA launch cost nor that dependent load sits on the
 // critical path of the 70 % of tiles that are empty and only need their fused clear.
-__global__ void __launch_bounds__(NT) k_raster(const Frame F)
+#ifndef CRB_RASTER_MIN_CTAS
+#define CRB_RASTER_MIN_CTAS 5
+#endif
+__global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame F)
 {
     __shared__ TileSmem S;
     const long long nAll = (long long)F.nViews * F.nTiles;
     const bool clear = (F.flags & CRB_CLEAR_FIRST) != 0;
     const bool overflow = *F.total > (unsigned long long)F.pairCap;
-    if (overflow) {   // frame skipped (host is told via crb_status); tile counts must still return to zero
-        for (long long t = (long long)blockIdx.x * NT + threadIdx.x; t < nAll; t += (long long)gridDim.x * NT) F.count[t] = 0u;
+    if (overflow) {   // frame skipped; the host is told via crb_status
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(F.total + 1, *F.total);
         return;
     }
-    if (threadIdx.x == 0) {
-        const long long t = blockIdx.x;
-        S.n[0] = (t < nAll) ? F.count[t] : 0u;
-        S.off[0] = (t < nAll) ? F.offset[t] : 0u;
+    // One CTA per busy tile.  The fused clear of the empty tiles (70 % of the T-Rex frame, pure stores) rides along:
+    // each busy CTA first issues the stores of up to ADOPT empty tiles, which then drain while it rasterizes -- memory-
+    // bound and issue-bound work overlap without competing for CTA slots.  Left-over empty tiles (scenes with few busy
+    // tiles) are cleared by the CTAs beyond the busy count, one tile each; the rest of the grid exits at once.
+    constexpr unsigned ADOPT = 4;
+    const unsigned nb = (unsigned)F.total[2], ne = (unsigned)F.total[3];
+    const unsigned cta = blockIdx.x;
+    if (cta >= nb) {
+        const unsigned long long e = (unsigned long long)ADOPT * nb + (cta - nb);
+        if (clear && e < ne) {
+            const unsigned t = F.empty[e];
+            const int view = (int)(t / (unsigned)F.nTiles), tile = (int)(t % (unsigned)F.nTiles);
+            const int ty = tile / F.tilesX, tx = tile - ty * F.tilesX;
+            write_clear_tile(F, view, tx * TW, ty * TH, min(TW, F.W - tx * TW), min(TH, F.row1 - F.row0 - ty * TH));
+        }
+        return;
     }
-    __syncthreads();
-
-    int cur = 0;
-    for (long long tIdx = blockIdx.x; tIdx < nAll; tIdx += gridDim.x, cur ^= 1) {
-    const unsigned n = S.n[cur], off = S.off[cur];
-    unsigned n_next = 0, off_next = 0;
-    if (threadIdx.x == 0) {   // prefetch the next tile's bookkeeping; consumed after this tile is done
-        const long long t = tIdx + gridDim.x;
-        if (t < nAll) { n_next = F.count[t]; off_next = F.offset[t]; }
-        if (n) F.count[tIdx] = 0u;  // self-cleaning: the next frame's k_setup starts from zero
+    const unsigned tIdx = F.busy[cta];                          // issued before the adopted clears so that their
+    const unsigned n = F.tcount[tIdx], off = F.offset[tIdx];    // latency hides behind the store traffic
+    if (clear) {
+        unsigned e = cta;
+        for (unsigned k = 0; k < ADOPT && e < ne; ++k, e += nb) {
+            const unsigned t = F.empty[e];
+            const int view = (int)(t / (unsigned)F.nTiles), tile = (int)(t % (unsigned)F.nTiles);
+            const int ty = tile / F.tilesX, tx = tile - ty * F.tilesX;
+            write_clear_tile(F, view, tx * TW, ty * TH, min(TW, F.W - tx * TW), min(TH, F.row1 - F.row0 - ty * TH));
+        }
     }
-    const int view = (int)(tIdx / F.nTiles), tile = (int)(tIdx % F.nTiles);
-    const int tx = tile % F.tilesX, ty = tile / F.tilesX;
+    const int view = (int)(tIdx / (unsigned)F.nTiles), tile = (int)(tIdx % (unsigned)F.nTiles);
+    const int ty = (int)((unsigned)tile / (unsigned)F.tilesX), tx = tile - ty * F.tilesX;
     const int x0 = tx * TW, yl0 = ty * TH;       // yl0: row inside the band's buffers
     const int y0 = F.row0 + yl0;                  // absolute image row
     const int tw = min(TW, F.W - x0), th = min(TH, F.row1 - y0);
-
-    if (n == 0 || (F.flags & 0x10000u)) {
+    if (F.flags & 0x10000u) {   // experiment switch: measure the store path alone
         if (clear) write_clear_tile(F, view, x0, yl0, tw, th);
-    } else {
+        return;
+    }
+    {
     for (int i = threadIdx.x; i < TH * KEY_STRIDE; i += NT) S.keys[i] = KEY_EMPTY;
 
     // ---- visibility: every (triangle,row) of the tile is one work item -------------------------------------
@@ -715,10 +744,7 @@ __global__ void __launch_bounds__(NT) k_raster(const Frame F)
             }
         }
     }
-    }  // busy tile
-    if (threadIdx.x == 0) { S.n[cur ^ 1] = n_next; S.off[cur ^ 1] = off_next; }
-    __syncthreads();  // publishes the prefetched bookkeeping; shared memory is free for the next tile
-    }  // tile loop
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -881,7 +907,7 @@ struct crb_filler {
     int maxViews;
     long long pairCap;
     float4 *rec0, *rec1, *rec2, *nrec0, *nrec1;
-    unsigned *count, *offset, *cursor;
+    unsigned *count, *tcount, *offset, *cursor, *busy, *empty;
     float4 *ls0, *ls1, *ls2;
     uint4 *ls3;
     unsigned long long *total;
@@ -900,7 +926,7 @@ struct crb_filler {
 namespace {
 
 struct WsLayout {
-    size_t rec0, rec1, rec2, nrec0, nrec1, count, offset, cursor, ls0, ls1, ls2, ls3, total, sv, sc, sn, bytes;
+    size_t rec0, rec1, rec2, nrec0, nrec1, count, tcount, offset, cursor, busy, empty, ls0, ls1, ls2, ls3, total, sv, sc, sn, bytes;
 };
 
 long long default_pair_cap(const crb_filler *f, long long T, int views)
@@ -923,8 +949,11 @@ WsLayout ws_layout(const crb_filler *f, long long T, int views, long long pairCa
     L.nrec0 = take(recs * sizeof(float4));
     L.nrec1 = take(recs * sizeof(float4));
     L.count = take((size_t)tiles * views * 4);
+    L.tcount = take((size_t)tiles * views * 4);
     L.offset = take((size_t)tiles * views * 4);
     L.cursor = take((size_t)tiles * views * 4);
+    L.busy = take((size_t)tiles * views * 4);
+    L.empty = take((size_t)tiles * views * 4);
     L.ls0 = take((size_t)pairCap * 16);
     L.ls1 = take((size_t)pairCap * 16);
     L.ls2 = take((size_t)pairCap * 16);
@@ -975,7 +1004,8 @@ void fill_frame(const crb_filler *f, Frame *F)
     F->tilesY = (f->row1 - f->row0 + TH - 1) / TH;
     F->nTiles = F->tilesX * F->tilesY;
     F->rec0 = f->rec0; F->rec1 = f->rec1; F->rec2 = f->rec2; F->nrec0 = f->nrec0; F->nrec1 = f->nrec1;
-    F->count = f->count; F->offset = f->offset; F->cursor = f->cursor;
+    F->count = f->count; F->tcount = f->tcount; F->offset = f->offset; F->cursor = f->cursor;
+    F->busy = f->busy; F->empty = f->empty;
     F->ls0 = f->ls0; F->ls1 = f->ls1; F->ls2 = f->ls2; F->ls3 = f->ls3;
     F->total = f->total;
     F->pairCap = f->pairCap;
@@ -1000,6 +1030,7 @@ int run_tiled(crb_filler *f, Frame &F, cudaStream_t st)
         if ((rc = launch_check(f, "k_setup"))) return rc;
     } else {
         CU(cudaMemsetAsync(f->total, 0, 8, st));
+        CU(cudaMemsetAsync(f->total + 2, 0, 16, st));
     }
     const long long nAll = (long long)F.nViews * F.nTiles;
     k_alloc<<<(unsigned)((nAll + NT - 1) / NT), NT, 0, st>>>(F);
@@ -1011,7 +1042,7 @@ int run_tiled(crb_filler *f, Frame &F, cudaStream_t st)
     const bool prof = f->prof_on && f->prof_n < PROF_MAX;
     if (prof) CU(cudaEventRecord(f->prof_ev[2 * f->prof_n], st));
     const long long nAllTiles = (long long)F.nTiles * F.nViews;
-    const unsigned gR = (unsigned)(nAllTiles < f->raster_ctas ? nAllTiles : f->raster_ctas);
+    const unsigned gR = (unsigned)((f->raster_ctas <= 0 || nAllTiles < f->raster_ctas) ? nAllTiles : f->raster_ctas);
     k_raster<<<gR, NT, 0, st>>>(F);
     if ((rc = launch_check(f, "k_raster"))) return rc;
     if (prof) {
@@ -1058,11 +1089,12 @@ int bind_ws_pointers(crb_filler *f, void *ws, size_t bytes, long long T, int vie
     f->maxT = T; f->maxViews = views; f->pairCap = pairCap;
     f->rec0 = (float4 *)(b + L.rec0); f->rec1 = (float4 *)(b + L.rec1); f->rec2 = (float4 *)(b + L.rec2);
     f->nrec0 = (float4 *)(b + L.nrec0); f->nrec1 = (float4 *)(b + L.nrec1);
-    f->count = (unsigned *)(b + L.count); f->offset = (unsigned *)(b + L.offset); f->cursor = (unsigned *)(b + L.cursor);
+    f->count = (unsigned *)(b + L.count); f->tcount = (unsigned *)(b + L.tcount); f->offset = (unsigned *)(b + L.offset); f->cursor = (unsigned *)(b + L.cursor);
+    f->busy = (unsigned *)(b + L.busy); f->empty = (unsigned *)(b + L.empty);
     f->ls0 = (float4 *)(b + L.ls0); f->ls1 = (float4 *)(b + L.ls1); f->ls2 = (float4 *)(b + L.ls2); f->ls3 = (uint4 *)(b + L.ls3);
     f->total = (unsigned long long *)(b + L.total);
     f->stage_v = (float *)(b + L.sv); f->stage_c = (float *)(b + L.sc); f->stage_n = (float *)(b + L.sn);
-    CU(cudaMemsetAsync(b + L.count, 0, L.offset - L.count, st));  // tile counts start at zero, k_raster keeps them so
+    CU(cudaMemsetAsync(b + L.count, 0, L.offset - L.count, st));  // tile counts start at zero, k_alloc keeps them so
     CU(cudaMemsetAsync(b + L.total, 0, 64, st));
     return CRB_OK;
 }
@@ -1118,7 +1150,9 @@ int crb_create(int h, int w, float fov, float z_near, float z_far, int device, c
         CU(cudaSetDevice(device));
         CU(cudaGetDeviceProperties(&prop, device));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_raster, NT, 0));
-        f->raster_ctas = prop.multiProcessorCount * (per_sm > 0 ? per_sm : 1);
+        f->raster_ctas = 0;   // 0 = one CTA per (view, tile): measured faster than a persistent walk (stores stream at 7 TB/s)
+        (void)prop; (void)per_sm;
+        if (const char *e = getenv("CRB_RASTER_CTAS")) f->raster_ctas = atoi(e);   // experiments: 0 = one CTA per tile
     }
     *out = f;
     return CRB_OK;

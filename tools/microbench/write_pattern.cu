@@ -25,6 +25,96 @@ __global__ void __launch_bounds__(NT) fill_tiles(float *z, float *c, float *n, i
     }
 }
 
+// the store mapping k_raster uses: thread -> (row = tid/8, 16-byte column tid%8 (+8,+16)); optional persistent walk,
+// optional static shared memory footprint (limits resident CTAs like the real kernel)
+template <int SMEM, bool PERSIST, int MINB>
+__global__ void __launch_bounds__(256, MINB) fill_like_raster(float *z, float *c, float *n, int W, int H, int V, const unsigned *cnt)
+{
+    __shared__ float pad[SMEM / 4 + 1];
+    if (SMEM && threadIdx.x == 9999) pad[0] = 1.f;
+    const int tilesX = W / 32, nTiles = tilesX * (H / 32);
+    const long long nAll = (long long)nTiles * V;
+    const long long step = PERSIST ? gridDim.x : nAll;
+    unsigned n_next = cnt ? cnt[blockIdx.x] : 0u;
+    for (long long t = blockIdx.x; t < nAll; t += step) {
+        const unsigned nn = n_next;
+        if (cnt && t + step < nAll) n_next = cnt[t + step];
+        if (nn) continue;
+        const int view = (int)(t / nTiles), tile = (int)(t % nTiles);
+        const int ty = tile / tilesX, tx = tile % tilesX;
+        const long long slab = (long long)view * W * H;
+        const int q = threadIdx.x & 7;
+        for (int r = threadIdx.x >> 3; r < 32; r += 32) {
+            const long long rowpix = slab + (long long)(ty * 32 + r) * W + tx * 32;
+            reinterpret_cast<float4 *>(z + rowpix)[q] = make_float4(1e6f, 1e6f, 1e6f, 1e6f);
+            float4 *o = reinterpret_cast<float4 *>(c + rowpix * 3);
+            o[q] = make_float4(0, 0, 0, 0); o[q + 8] = make_float4(0, 0, 0, 0); o[q + 16] = make_float4(0, 0, 0, 0);
+            o = reinterpret_cast<float4 *>(n + rowpix * 3);
+            o[q] = make_float4(0, 0, 0, 0); o[q + 8] = make_float4(0, 0, 0, 0); o[q + 16] = make_float4(0, 0, 0, 0);
+        }
+    }
+}
+
+// persistent walk in contiguous groups of G tiles per CTA visit: one coalesced load brings G counts, the group's
+// counts for the NEXT visit are prefetched a whole visit (G tiles of stores) ahead
+template <int SMEM, int MINB, int G>
+__global__ void __launch_bounds__(256, MINB) fill_grouped(float *z, float *c, float *n, int W, int H, int V, const unsigned *cnt)
+{
+    __shared__ float pad[SMEM / 4 + 1];
+    if (SMEM && threadIdx.x == 9999) pad[0] = 1.f;
+    const int tilesX = W / 32, nTiles = tilesX * (H / 32);
+    const long long nAll = (long long)nTiles * V;
+    const int lane = threadIdx.x & 31;
+    long long base = (long long)blockIdx.x * G;
+    unsigned mine_next = (lane < G && base + lane < nAll) ? cnt[base + lane] : 1u;
+    for (; base < nAll; base += (long long)gridDim.x * G) {
+        const unsigned mine = mine_next;
+        const long long nb = base + (long long)gridDim.x * G;
+        mine_next = (lane < G && nb + lane < nAll) ? cnt[nb + lane] : 1u;
+        for (int k = 0; k < G; ++k) {
+            const unsigned nn = __shfl_sync(0xffffffffu, mine, k);
+            if (nn) continue;
+            const long long t = base + k;
+            const int view = (int)(t / nTiles), tile = (int)(t % nTiles);
+            const int ty = tile / tilesX, tx = tile % tilesX;
+            const long long slab = (long long)view * W * H;
+            const int q = threadIdx.x & 7;
+            const int r = threadIdx.x >> 3;
+            const long long rowpix = slab + (long long)(ty * 32 + r) * W + tx * 32;
+            reinterpret_cast<float4 *>(z + rowpix)[q] = make_float4(1e6f, 1e6f, 1e6f, 1e6f);
+            float4 *o = reinterpret_cast<float4 *>(c + rowpix * 3);
+            o[q] = make_float4(0, 0, 0, 0); o[q + 8] = make_float4(0, 0, 0, 0); o[q + 16] = make_float4(0, 0, 0, 0);
+            o = reinterpret_cast<float4 *>(n + rowpix * 3);
+            o[q] = make_float4(0, 0, 0, 0); o[q + 8] = make_float4(0, 0, 0, 0); o[q + 16] = make_float4(0, 0, 0, 0);
+        }
+    }
+}
+template <int SMEM, int MINB, int G>
+void run_grouped(const char *name, float *z, float *c, float *n, int W, int H, int V, const unsigned *cnt)
+{
+    cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    const int grid = 148 * MINB;
+    for (int i = 0; i < 3; ++i) fill_grouped<SMEM, MINB, G><<<grid, 256>>>(z, c, n, W, H, V, cnt);
+    CK(cudaEventRecord(a));
+    for (int i = 0; i < 10; ++i) fill_grouped<SMEM, MINB, G><<<grid, 256>>>(z, c, n, W, H, V, cnt);
+    CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b));
+    float ms; CK(cudaEventElapsedTime(&ms, a, b));
+    printf("%-44s %7.2f us/view  %7.0f GB/s\n", name, ms / 10 / V * 1000, 28.0 * W * H * V / (ms / 10 / 1000) / 1e9);
+}
+
+template <int SMEM, bool PERSIST, int MINB>
+void run_like(const char *name, float *z, float *c, float *n, int W, int H, int V, const unsigned *cnt)
+{
+    cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    const int grid = PERSIST ? 148 * MINB : (W / 32) * (H / 32) * V;
+    for (int i = 0; i < 3; ++i) fill_like_raster<SMEM, PERSIST, MINB><<<grid, 256>>>(z, c, n, W, H, V, cnt);
+    CK(cudaEventRecord(a));
+    for (int i = 0; i < 10; ++i) fill_like_raster<SMEM, PERSIST, MINB><<<grid, 256>>>(z, c, n, W, H, V, cnt);
+    CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b));
+    float ms; CK(cudaEventElapsedTime(&ms, a, b));
+    printf("%-44s %7.2f us/view  %7.0f GB/s\n", name, ms / 10 / V * 1000, 28.0 * W * H * V / (ms / 10 / 1000) / 1e9);
+}
+
 __global__ void fill_linear(float4 *p, long long n4)
 {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
@@ -80,5 +170,19 @@ int main()
     run<1024, 1, 256>("tile 1024x1 nt256", z, c, n, W, H, V);
     run<1024, 4, 256>("tile 1024x4 nt256", z, c, n, W, H, V);
     run<64, 64, 256>("tile 64x64 nt256", z, c, n, W, H, V);
+    unsigned *cnt; CK(cudaMalloc(&cnt, 1024 * 32 * 4)); CK(cudaMemset(cnt, 0, 1024 * 32 * 4));
+    run_like<0, false, 8>("raster map, one CTA per tile", z, c, n, W, H, V, nullptr);
+    run_like<0, false, 8>("raster map, one CTA per tile, cnt load", z, c, n, W, H, V, cnt);
+    run_like<34000, false, 5>("raster map, CTA/tile, 34KB smem", z, c, n, W, H, V, cnt);
+    run_like<0, true, 8>("raster map, persistent 8/SM", z, c, n, W, H, V, cnt);
+    run_like<34000, true, 5>("raster map, persistent 5/SM 34KB", z, c, n, W, H, V, cnt);
+    run_like<34000, true, 4>("raster map, persistent 4/SM 34KB", z, c, n, W, H, V, cnt);
+    run_like<34000, true, 6>("raster map, persistent 6/SM 34KB", z, c, n, W, H, V, cnt);
+    run_like<0, true, 8>("persistent 8/SM, no cnt load", z, c, n, W, H, V, nullptr);
+    run_grouped<34000, 5, 2>("persistent 5/SM grouped x2", z, c, n, W, H, V, cnt);
+    run_grouped<34000, 5, 4>("persistent 5/SM grouped x4", z, c, n, W, H, V, cnt);
+    run_grouped<34000, 5, 8>("persistent 5/SM grouped x8", z, c, n, W, H, V, cnt);
+    run_grouped<34000, 5, 32>("persistent 5/SM grouped x32", z, c, n, W, H, V, cnt);
+    run_grouped<0, 8, 8>("persistent 8/SM grouped x8", z, c, n, W, H, V, cnt);
     return 0;
 }
