@@ -50,6 +50,13 @@ constexpr int PROF_MAX = 8192;  // k_raster launches that can be timed between t
 static_assert(CH == NT, "one staged triangle per thread");
 static_assert(TW == 32, "a tile row is one warp wide");
 
+// Per-(view,triangle) records written by k_setup.
+//   R_A (x0 y0 x1 y1)  R_B (x2 y2 z0 z1)  R_C (z2 l03 l13 l23)   screen-space vertices + the denominators of mu:14,17,20
+//   R_D (1/l03 1/l13 1/l23 flags)   correctly rounded reciprocals (rcp.rn) + FL_* bits
+//   R_E (bbox x, bbox y, n2.z, -)   packed half-open pixel rectangle (0,0 = not drawn)
+//   R_N0 (n0.xyz n1.x)  R_N1 (n1.yz n2.xy)   vertex normals in view space
+enum Rec { R_A = 0, R_B, R_C, R_D, R_E, R_N0, R_N1, NREC };
+
 struct ProjC {
     float p[16];   // row-major 4x4, proj_mat of pyx:85-90
     float xs, ys;  // (float)(w/2.0), (float)(h/2.0)  pyx:109
@@ -67,8 +74,10 @@ struct Frame {
     const float *v, *c, *n;     // [T,3,3]
     const float *views;         // [nViews,16] or nullptr
     // scratch
-    float4 *rec0, *rec1, *rec2; // [nViews*T] screen-space triangle records (SoA of float4)
-    float4 *nrec0, *nrec1;      // [nViews*T] view-space vertex normals n0 n1 n2.xy (n2.z rides in rec2.w); batched views only
+    // [nViews*T] per-(view,triangle) records, SoA of float4 (see enum Rec)
+    float4 *rec[NREC];
+    float4 *crec0, *crec1;      // [T] vertex colours packed: (c0.xyz c1.x) (c1.yz c2.xy); c2.z rides in crec2
+    float *crec2;               // [T]
     unsigned *count;            // [nViews*nTiles] triangles per tile, accumulated by k_setup, returned to zero by k_alloc
     unsigned *tcount;           // [nViews*nTiles] the frame's final per-tile counts (read-only for k_fill / k_raster)
     unsigned *busy, *empty;     // [nViews*nTiles] compacted (view,tile) indices with / without triangles; sizes in total[2], total[3]
@@ -76,6 +85,7 @@ struct Frame {
     unsigned *cursor;           // [nViews*nTiles] fill cursor
     float4 *ls0, *ls1, *ls2;    // [pairCap] staged triangle setups, tile by tile: (x0 y0 x1 y1) (x2 y2 z0 z1) (z2 d1 d2 d3)
     uint4 *ls3;                 // [pairCap] (bbox x, bbox y, triangle index, flags)
+    float4 *ls4;                // [pairCap] (1/d1 1/d2 1/d3 -) correctly rounded reciprocals of the denominators
     unsigned long long *total;  // [0] pairs of this frame, [1] sticky max of overflowing totals
     long long pairCap;
     // outputs (per view slab stride = rows*W (z) or rows*W*3)
@@ -165,7 +175,7 @@ __device__ __forceinline__ void barycentric(const Tri9 &t, float px, float py, f
 
 __device__ __forceinline__ Tri9 load_tri9(const Frame &F, long long ridx)
 {
-    const float4 a = F.rec0[ridx], b = F.rec1[ridx], c = F.rec2[ridx];
+    const float4 a = F.rec[R_A][ridx], b = F.rec[R_B][ridx], c = F.rec[R_C][ridx];
     Tri9 t;
     t.x0 = a.x; t.y0 = a.y; t.x1 = a.z; t.y1 = a.w;
     t.x2 = b.x; t.y2 = b.y; t.z0 = b.z; t.z1 = b.w;
@@ -173,32 +183,63 @@ __device__ __forceinline__ Tri9 load_tri9(const Frame &F, long long ridx)
     return t;
 }
 
-// pyx:219-242 for the pixel's winning triangle: depth, colour, normal (left-associated sums).  Returns false if the
-// fragment would not have been drawn (some barycentric < 0, NaN depth) -- cannot happen for a key that won, kept as a
-// guard.  `M` (may be nullptr) is the view matrix applied to the normals.
-__device__ __forceinline__ bool shade_fragment(const Frame &F, const Tri9 &t, long long tri, long long ridx, const float *M,
-                                               float px, float py, float &z, float c[3], float n[3])
+// flags of a triangle record / staged triangle
+constexpr unsigned FL_NEG = 1u;      // bits 0..2: barycentric k is evaluated with negated edge vector and denominator
+constexpr unsigned FL_REJ = 16u;     // bits 4..6: barycentric k may use the division-free rejection (denominator sane)
+constexpr unsigned FL_SPAN = 256u;   // row spans may be bounded analytically (all three sane, coordinates <= 2^18)
+constexpr unsigned FL_FDIV = 512u;   // all three denominators in [2^-40, 2^40]: div_rn_by() applies
+constexpr float SPAN_COORD_MAX = 262144.0f;  // 2^18: beyond this the float span bounds lose sub-pixel accuracy
+constexpr float FDIV_LO = 9.094947e-13f, FDIV_HI = 1.099511627776e12f;  // 2^-40, 2^40
+
+// Correctly rounded a/d from r = rcp.rn(d), without the division routine: q0 = RN(a*r) is within 2 ulp of a/d; one
+// residual step (e = a - d*q exactly via FMA, q += e*r) makes it faithful (<= 1 ulp), and Markstein's theorem then says
+// a second step from a faithful quotient with a correctly rounded reciprocal returns RN(a/d) itself.  Preconditions
+// (checked by the callers): |d| and |a| in [2^-40, 2^40], so no intermediate overflows, underflows or is subnormal.
+// tests/test_gpu_parity.py::test_fast_division_is_ieee checks it against div.rn on ~4e9 operand pairs.
+__device__ __forceinline__ float div_rn_by(float a, float d, float r)
 {
+    float q = a * r;
+    float e = __fmaf_rn(-d, q, a);
+    q = __fmaf_rn(e, r, q);
+    e = __fmaf_rn(-d, q, a);
+    return __fmaf_rn(e, r, q);
+}
+__device__ __forceinline__ bool fdiv_ok(float n1, float n2, float n3)
+{
+    const float a1 = fabsf(n1), a2 = fabsf(n2), a3 = fabsf(n3);
+    return fminf(fminf(a1, a2), a3) >= FDIV_LO && fmaxf(fmaxf(a1, a2), a3) <= FDIV_HI;   // NaN: false
+}
+
+// pyx:215-242 for the pixel's winning triangle: barycentrics (mu:5-34), depth, colour, normal (left-associated sums).
+// Returns false if the fragment would not have been drawn (some barycentric < 0, NaN depth) -- cannot happen for a key
+// that won, kept as a guard.
+__device__ __forceinline__ bool shade_fragment(const Frame &F, long long tri, long long ridx, float px, float py, float &z,
+                                               float c[3], float n[3])
+{
+    const float4 A = F.rec[R_A][ridx], B = F.rec[R_B][ridx], C = F.rec[R_C][ridx], D = F.rec[R_D][ridx];
+    // x0=A.x y0=A.y x1=A.z y1=A.w x2=B.x y2=B.y z0=B.z z1=B.w z2=C.x  l03=C.y l13=C.z l23=C.w
+    const float n1 = (A.z - B.x) * (py - B.y) - (A.w - B.y) * (px - B.x);
+    const float n2 = (B.x - A.x) * (py - A.y) - (B.y - A.y) * (px - A.x);
+    const float n3 = (A.x - A.z) * (py - A.w) - (A.y - A.w) * (px - A.z);
     float b1, b2, b3;
-    barycentric(t, px, py, b1, b2, b3);
-    if (b1 < 0.0f || b2 < 0.0f || b3 < 0.0f) return false;
-    z = (t.z0 * b1 + t.z1 * b2) + t.z2 * b3;
-    if (z != z) return false;
-    const float *cc = F.c + tri * 9, *nn = F.n + tri * 9;
-    float m[9];
-    if (M) {  // batched views: k_setup already rotated this triangle's normals into the view (nrec)
-        const float4 q0 = F.nrec0[ridx], q1 = F.nrec1[ridx];
-        m[0] = q0.x; m[1] = q0.y; m[2] = q0.z; m[3] = q0.w; m[4] = q1.x; m[5] = q1.y; m[6] = q1.z; m[7] = q1.w;
-        m[8] = F.rec2[ridx].w;
+    if ((__float_as_uint(D.w) & FL_FDIV) && fdiv_ok(n1, n2, n3)) {
+        b1 = div_rn_by(n1, C.y, D.x); b2 = div_rn_by(n2, C.z, D.y); b3 = div_rn_by(n3, C.w, D.z);
     } else {
-#pragma unroll
-        for (int k = 0; k < 9; ++k) m[k] = __ldg(nn + k);
+        b1 = n1 / C.y; b2 = n2 / C.z; b3 = n3 / C.w;
     }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        n[k] = (m[k] * b1 + m[3 + k] * b2) + m[6 + k] * b3;
-        c[k] = (__ldg(cc + k) * b1 + __ldg(cc + 3 + k) * b2) + __ldg(cc + 6 + k) * b3;
-    }
+    if (b1 < 0.0f || b2 < 0.0f || b3 < 0.0f) return false;
+    z = (B.z * b1 + B.w * b2) + C.x * b3;
+    if (z != z) return false;
+    const float4 N0 = F.rec[R_N0][ridx], N1 = F.rec[R_N1][ridx];
+    const float n2z = F.rec[R_E][ridx].z;
+    n[0] = (N0.x * b1 + N0.w * b2) + N1.z * b3;
+    n[1] = (N0.y * b1 + N1.x * b2) + N1.w * b3;
+    n[2] = (N0.z * b1 + N1.y * b2) + n2z * b3;
+    const float4 C0 = F.crec0[tri], C1 = F.crec1[tri];
+    const float c2z = F.crec2[tri];
+    c[0] = (C0.x * b1 + C0.w * b2) + C1.z * b3;
+    c[1] = (C0.y * b1 + C1.x * b2) + C1.w * b3;
+    c[2] = (C0.z * b1 + C1.y * b2) + c2z * b3;
     if (F.flags & CRB_GURO) {  // guro_illumination.py:23-27 (float32, left-to-right sums)
         const float dot = (n[0] * F.light[0] + n[1] * F.light[1]) + n[2] * F.light[2];
         const float nrm = sqrtf((n[0] * n[0] + n[1] * n[1]) + n[2] * n[2]);
@@ -257,6 +298,7 @@ __global__ void __launch_bounds__(NT) k_setup(const Frame F)
 {
     __shared__ __align__(16) float sv[NT * 9];
     __shared__ __align__(16) float sn[NT * 9];
+    __shared__ __align__(16) float sc[NT * 9];
     __shared__ float sM[16];
     const int view = blockIdx.y;
     const long long first = (long long)blockIdx.x * NT;
@@ -266,11 +308,18 @@ __global__ void __launch_bounds__(NT) k_setup(const Frame F)
     }
     stage_floats(F.v, first * 9, cnt * 9, sv);
     stage_floats(F.n, first * 9, cnt * 9, sn);
+    if (view == 0) stage_floats(F.c, first * 9, cnt * 9, sc);
     if (F.views && threadIdx.x < 16) sM[threadIdx.x] = F.views[view * 16 + threadIdx.x];
     __syncthreads();
     if (threadIdx.x >= cnt) return;
     const long long tri = first + threadIdx.x;
     const long long ridx = (long long)view * F.T + tri;
+    if (view == 0) {   // colours do not depend on the view: packed once per launch for the shading pass
+        const float *q = sc + threadIdx.x * 9;
+        F.crec0[tri] = make_float4(q[0], q[1], q[2], q[3]);
+        F.crec1[tri] = make_float4(q[4], q[5], q[6], q[7]);
+        F.crec2[tri] = q[8];
+    }
 
     float x[3], y[3], z[3], nx[3], ny[3], nz[3];
 #pragma unroll
@@ -309,14 +358,36 @@ __global__ void __launch_bounds__(NT) k_setup(const Frame F)
     const unsigned bx = drawn ? ((unsigned)xl | ((unsigned)xr << 16)) : 0u;
     const unsigned by = drawn ? ((unsigned)yt | ((unsigned)yb << 16)) : 0u;
 
-    F.rec2[ridx] = make_float4(z[2], __uint_as_float(bx), __uint_as_float(by), nz[2]);
+    F.rec[R_E][ridx] = make_float4(__uint_as_float(bx), __uint_as_float(by), nz[2], 0.0f);
     if (!drawn) return;
-    F.rec0[ridx] = make_float4(x[0], y[0], x[1], y[1]);
-    F.rec1[ridx] = make_float4(x[2], y[2], z[0], z[1]);
-    if (F.views) {
-        F.nrec0[ridx] = make_float4(nx[0], ny[0], nz[0], nx[1]);
-        F.nrec1[ridx] = make_float4(ny[1], nz[1], nx[2], ny[2]);
-    }
+    // denominators of mu:12-21 -- pure functions of the triangle, hoisted out of the per-pixel code (same bits)
+    const float l03 = (x[1] - x[2]) * (y[0] - y[2]) - (y[1] - y[2]) * (x[0] - x[2]);
+    const float l13 = (x[2] - x[0]) * (y[1] - y[0]) - (y[2] - y[0]) * (x[1] - x[0]);
+    const float l23 = (x[0] - x[1]) * (y[2] - y[1]) - (y[0] - y[1]) * (x[2] - x[1]);
+    // Division-free rejection (SURVEY 7, K3 obligation).  num/l3 is bit-identical to (-num)/(-l3), and negation commutes
+    // with every rounding that produced num, so the rasterizer evaluates each coordinate with l3' = |l3| (edge vector
+    // negated when l3 < 0, FL_NEG).  For L3_MIN <= l3' <= L3_MAX a numerator <= -REJ_EPS then gives a quotient that is a
+    // negative NON-ZERO float (|q| >= 1e-36), i.e. exactly the reference's `bar < 0` -- no division needed (FL_REJ).
+    // Everything else (denominator zero / tiny / huge / non-finite, numerator inside the guard band or NaN) takes the
+    // exact division path.
+    unsigned fl = 0;
+    const float a03 = fabsf(l03), a13 = fabsf(l13), a23 = fabsf(l23);
+    if (a03 >= L3_MIN && a03 <= L3_MAX) fl |= (FL_REJ << 0) | (l03 < 0.f ? (FL_NEG << 0) : 0u);
+    if (a13 >= L3_MIN && a13 <= L3_MAX) fl |= (FL_REJ << 1) | (l13 < 0.f ? (FL_NEG << 1) : 0u);
+    if (a23 >= L3_MIN && a23 <= L3_MAX) fl |= (FL_REJ << 2) | (l23 < 0.f ? (FL_NEG << 2) : 0u);
+    float cmax = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) cmax = fmaxf(cmax, fmaxf(fabsf(x[k]), fabsf(y[k])));
+    const bool finite_xy = (x[0] - x[0] == 0.f) && (x[1] - x[1] == 0.f) && (x[2] - x[2] == 0.f) && (y[0] - y[0] == 0.f) &&
+                           (y[1] - y[1] == 0.f) && (y[2] - y[2] == 0.f);
+    if ((fl & (7u * FL_REJ)) == 7u * FL_REJ && finite_xy && cmax <= SPAN_COORD_MAX) fl |= FL_SPAN;
+    if (fminf(fminf(a03, a13), a23) >= FDIV_LO && fmaxf(fmaxf(a03, a13), a23) <= FDIV_HI) fl |= FL_FDIV;
+    F.rec[R_A][ridx] = make_float4(x[0], y[0], x[1], y[1]);
+    F.rec[R_B][ridx] = make_float4(x[2], y[2], z[0], z[1]);
+    F.rec[R_C][ridx] = make_float4(z[2], l03, l13, l23);
+    F.rec[R_D][ridx] = make_float4(__frcp_rn(l03), __frcp_rn(l13), __frcp_rn(l23), __uint_as_float(fl));
+    F.rec[R_N0][ridx] = make_float4(nx[0], ny[0], nz[0], nx[1]);
+    F.rec[R_N1][ridx] = make_float4(ny[1], nz[1], nx[2], ny[2]);
     if (F.flags & CRB_PATH_ATOMIC) return;
 
     int tx0, tx1, ty0, ty1;
@@ -377,16 +448,14 @@ __global__ void __launch_bounds__(NT) k_alloc(const Frame F)
         F.cursor[i] = 0u;
         F.tcount[i] = c;
         F.count[i] = 0u;   // self-cleaning: the next frame's k_setup starts from zero
-        if (c) F.busy[busy_base + brank] = (unsigned)i;
-        else F.empty[empty_base + (threadIdx.x - brank)] = (unsigned)i;
+        const unsigned vw = (unsigned)(i / F.nTiles), tl = (unsigned)(i % F.nTiles);
+        const unsigned packed = (vw << 22) | ((tl / (unsigned)F.tilesX) << 11) | (tl % (unsigned)F.tilesX);   // view:10 ty:11 tx:11
+        if (c) F.busy[busy_base + brank] = packed;
+        else F.empty[empty_base + (threadIdx.x - brank)] = packed;
     }
 }
 
-// flags of a staged triangle: bit k (k=0..2) -> barycentric k is evaluated with negated edge vector and denominator;
-// bit 4+k -> barycentric k may use the division-free rejection; bit 8 -> row spans may be bounded analytically.
-constexpr unsigned FL_SPAN = 256u;
-constexpr float SPAN_COORD_MAX = 262144.0f;  // 2^18: beyond this the float span bounds lose sub-pixel accuracy
-
+// K2c: scatter the prepared setups into the tile lists (sign-normalised form the row loop wants).
 __global__ void __launch_bounds__(NT) k_fill(const Frame F)
 {
     if (*F.total > (unsigned long long)F.pairCap) return;  // overflow: frame is skipped, host is told via crb_status
@@ -394,30 +463,14 @@ __global__ void __launch_bounds__(NT) k_fill(const Frame F)
     const long long tri = (long long)blockIdx.x * NT + threadIdx.x;
     if (tri >= F.T) return;
     const long long ridx = (long long)view * F.T + tri;
-    const float4 c = F.rec2[ridx];
-    const unsigned bx = __float_as_uint(c.y), by = __float_as_uint(c.z);
+    const float4 E = F.rec[R_E][ridx];
+    const unsigned bx = __float_as_uint(E.x), by = __float_as_uint(E.y);
     if ((bx >> 16) == 0) return;  // not drawn (x_right >= 1 for every drawn triangle)
-    const float4 a = F.rec0[ridx], b = F.rec1[ridx];
-    // denominators of mu:12-21
-    const float l01 = a.z - b.x, l02 = a.w - b.y;
-    const float l03 = l01 * (a.y - b.y) - l02 * (a.x - b.x);
-    const float l11 = b.x - a.x, l12 = b.y - a.y;
-    const float l13 = l11 * (a.w - a.y) - l12 * (a.z - a.x);
-    const float l21 = a.x - a.z, l22 = a.y - a.w;
-    const float l23 = l21 * (b.y - a.w) - l22 * (b.x - a.z);
-    // Division-free rejection (SURVEY 7, K3 obligation).  num/l3 is bit-identical to (-num)/(-l3), and negation commutes
-    // with every rounding that produced num, so each coordinate is evaluated with l3' = |l3| (edge vector negated when
-    // l3 < 0).  For L3_MIN <= l3' <= L3_MAX a numerator <= -REJ_EPS then gives a quotient that is a negative NON-ZERO
-    // float (|q| >= 1e-36), i.e. exactly the reference's `bar < 0` -- no division needed.  Everything else (denominator
-    // zero / tiny / huge / non-finite, numerator inside the guard band or NaN) takes the exact division path.
-    unsigned fl = 0;
-    float d1 = l03, d2 = l13, d3 = l23;
-    if (fabsf(l03) >= L3_MIN && fabsf(l03) <= L3_MAX) { fl |= 16u; if (l03 < 0.f) { fl |= 1u; d1 = -l03; } }
-    if (fabsf(l13) >= L3_MIN && fabsf(l13) <= L3_MAX) { fl |= 32u; if (l13 < 0.f) { fl |= 2u; d2 = -l13; } }
-    if (fabsf(l23) >= L3_MIN && fabsf(l23) <= L3_MAX) { fl |= 64u; if (l23 < 0.f) { fl |= 4u; d3 = -l23; } }
-    const float cmax = fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))), fmaxf(fabsf(b.x), fabsf(b.y)));
-    if ((fl & 112u) == 112u && cmax <= SPAN_COORD_MAX) fl |= FL_SPAN;  // (NaN coordinates fail the comparison)
-    const float4 s2 = make_float4(c.x, d1, d2, d3);
+    const float4 a = F.rec[R_A][ridx], b = F.rec[R_B][ridx], c = F.rec[R_C][ridx], d = F.rec[R_D][ridx];
+    const unsigned fl = __float_as_uint(d.w);
+    // |l3| and |1/l3| where the coordinate is negated (RN(1/-x) = -RN(1/x): flipping the sign bit is exact)
+    const float4 s2 = make_float4(c.x, (fl & (FL_NEG << 0)) ? -c.y : c.y, (fl & (FL_NEG << 1)) ? -c.z : c.z, (fl & (FL_NEG << 2)) ? -c.w : c.w);
+    const float4 s4 = make_float4((fl & (FL_NEG << 0)) ? -d.x : d.x, (fl & (FL_NEG << 1)) ? -d.y : d.y, (fl & (FL_NEG << 2)) ? -d.z : d.z, 0.0f);
     const uint4 s3 = make_uint4(bx, by, (unsigned)tri, fl);
 
     int tx0, tx1, ty0, ty1;
@@ -427,7 +480,7 @@ __global__ void __launch_bounds__(NT) k_fill(const Frame F)
         for (int tx = tx0; tx <= tx1; ++tx) {
             const long long t = vb + ty * F.tilesX + tx;
             const unsigned at = F.offset[t] + atomicAdd(F.cursor + t, 1u);
-            F.ls0[at] = a; F.ls1[at] = b; F.ls2[at] = s2; F.ls3[at] = s3;
+            F.ls0[at] = a; F.ls1[at] = b; F.ls2[at] = s2; F.ls3[at] = s3; F.ls4[at] = s4;
         }
 }
 
@@ -455,6 +508,7 @@ struct __align__(16) TileSmem {
             float4 s1[CH];  // x2 y2 z0 z1
             float4 s2[CH];  // z2 d1 d2 d3   (d = sign-normalised denominators l03' l13' l23', see k_fill)
             uint4 s3[CH];   // bx by tri flags
+            float4 s4[CH];  // 1/d1 1/d2 1/d3 -
             unsigned rowStart[CH];
             unsigned char owner[CH * TH];  // row work item -> staged triangle
         } st;
@@ -552,25 +606,23 @@ __global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame 
         const unsigned long long e = (unsigned long long)ADOPT * nb + (cta - nb);
         if (clear && e < ne) {
             const unsigned t = F.empty[e];
-            const int view = (int)(t / (unsigned)F.nTiles), tile = (int)(t % (unsigned)F.nTiles);
-            const int ty = tile / F.tilesX, tx = tile - ty * F.tilesX;
+            const int view = (int)(t >> 22), ty = (int)((t >> 11) & 2047u), tx = (int)(t & 2047u);
             write_clear_tile(F, view, tx * TW, ty * TH, min(TW, F.W - tx * TW), min(TH, F.row1 - F.row0 - ty * TH));
         }
         return;
     }
-    const unsigned tIdx = F.busy[cta];                          // issued before the adopted clears so that their
+    const unsigned tpk = F.busy[cta];                           // issued before the adopted clears so that their
+    const int view = (int)(tpk >> 22), ty = (int)((tpk >> 11) & 2047u), tx = (int)(tpk & 2047u);
+    const unsigned tIdx = (unsigned)view * (unsigned)F.nTiles + (unsigned)(ty * F.tilesX + tx);
     const unsigned n = F.tcount[tIdx], off = F.offset[tIdx];    // latency hides behind the store traffic
     if (clear) {
         unsigned e = cta;
         for (unsigned k = 0; k < ADOPT && e < ne; ++k, e += nb) {
             const unsigned t = F.empty[e];
-            const int view = (int)(t / (unsigned)F.nTiles), tile = (int)(t % (unsigned)F.nTiles);
-            const int ty = tile / F.tilesX, tx = tile - ty * F.tilesX;
+            const int view = (int)(t >> 22), ty = (int)((t >> 11) & 2047u), tx = (int)(t & 2047u);
             write_clear_tile(F, view, tx * TW, ty * TH, min(TW, F.W - tx * TW), min(TH, F.row1 - F.row0 - ty * TH));
         }
     }
-    const int view = (int)(tIdx / (unsigned)F.nTiles), tile = (int)(tIdx % (unsigned)F.nTiles);
-    const int ty = (int)((unsigned)tile / (unsigned)F.tilesX), tx = tile - ty * F.tilesX;
     const int x0 = tx * TW, yl0 = ty * TH;       // yl0: row inside the band's buffers
     const int y0 = F.row0 + yl0;                  // absolute image row
     const int tw = min(TW, F.W - x0), th = min(TH, F.row1 - y0);
@@ -593,6 +645,7 @@ __global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame 
             S.u.st.s1[threadIdx.x] = F.ls1[at];
             S.u.st.s2[threadIdx.x] = F.ls2[at];
             S.u.st.s3[threadIdx.x] = d;
+            S.u.st.s4[threadIdx.x] = F.ls4[at];
             const int yt = max((int)(d.y & 0xFFFF), y0), yb = min((int)(d.y >> 16), y0 + th);
             rows = (unsigned)max(yb - yt, 0);
         }
@@ -612,16 +665,18 @@ __global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame 
         for (unsigned rb = threadIdx.x & ~31u; rb < totalRows; rb += NT) {
             const unsigned r = rb + lane;
             const bool active = r < totalRows;
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, c = a;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, c = a, rr = a;
+            bool fdiv = false;
             float l02 = 0.f, l12 = 0.f, l22 = 0.f, A1 = 0.f, A2 = 0.f, A3 = 0.f;
             float thr1 = 0.f, thr2 = 0.f, thr3 = 0.f;
             unsigned tri = 0;
             int xa = 0, xb = 0, y = y0;
             if (active) {
                 const unsigned o = S.u.st.owner[r];
-                a = S.u.st.s0[o]; b = S.u.st.s1[o]; c = S.u.st.s2[o];
+                a = S.u.st.s0[o]; b = S.u.st.s1[o]; c = S.u.st.s2[o]; rr = S.u.st.s4[o];
                 const uint4 d = S.u.st.s3[o];
                 tri = d.z;
+                fdiv = (d.w & FL_FDIV) != 0;
                 y = max((int)(d.y & 0xFFFF), y0) + (int)(r - S.u.st.rowStart[o]);
                 xa = max((int)(d.x & 0xFFFF), x0);
                 xb = min((int)(d.x >> 16), x0 + tw);
@@ -673,9 +728,15 @@ __global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame 
                     const int bit = __ffs(mask) - 1;
                     mask &= mask - 1;
                     const float px = (float)(x0 + bit);
-                    const float b1 = (A1 - l02 * (px - b.x)) / c.y;
-                    const float b2 = (A2 - l12 * (px - a.x)) / c.z;
-                    const float b3 = (A3 - l22 * (px - a.z)) / c.w;
+                    const float n1 = A1 - l02 * (px - b.x);
+                    const float n2 = A2 - l12 * (px - a.x);
+                    const float n3 = A3 - l22 * (px - a.z);
+                    float b1, b2, b3;
+                    if (fdiv && fdiv_ok(n1, n2, n3)) {
+                        b1 = div_rn_by(n1, c.y, rr.x); b2 = div_rn_by(n2, c.z, rr.y); b3 = div_rn_by(n3, c.w, rr.z);
+                    } else {
+                        b1 = n1 / c.y; b2 = n2 / c.z; b3 = n3 / c.w;
+                    }
                     if (!(b1 < 0.0f || b2 < 0.0f || b3 < 0.0f)) {              // pyx:216
                         const float z = (b.z * b1 + b.w * b2) + c.x * b3;          // pyx:219
                         if (z == z) smem_key_min(krow + bit, pack_key(z, tri));    // pyx:220 rejects NaN only
@@ -688,7 +749,6 @@ __global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame 
     __syncthreads();
 
     // ---- deferred shading of the winners, staged so that every global store is a full 16-byte vector -------
-    const float *M = F.views ? F.views + view * 16 : nullptr;
     const long long slab = (long long)view * F.slabPixels;
     const bool vec = clear && (tw == TW) && ((F.W & 3) == 0);
     const float bg = background_color(F);
@@ -702,9 +762,8 @@ __global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame 
         if (key != KEY_EMPTY && !(F.flags & 0x20000u)) {
             const unsigned tri = ~(unsigned)(key & 0xFFFFFFFFull);
             const long long ridx = (long long)view * F.T + tri;
-            const Tri9 t = load_tri9(F, ridx);
             float fz, fc[3], fn[3];
-            if (shade_fragment(F, t, tri, ridx, M, (float)(x0 + xx), (float)(y0 + yy), fz, fc, fn)) {
+            if (shade_fragment(F, tri, ridx, (float)(x0 + xx), (float)(y0 + yy), fz, fc, fn)) {
                 const float zold = clear ? Z_INIT : F.z[pix];
                 if (!(fz > zold)) {  // pyx:223: drawn unless new_z > z_buffer (equal depth overwrites)
                     z = fz; c[0] = fc[0]; c[1] = fc[1]; c[2] = fc[2]; nn[0] = fn[0]; nn[1] = fn[1]; nn[2] = fn[2];
@@ -756,8 +815,8 @@ __global__ void __launch_bounds__(NT) k_raster_atomic(const Frame F, unsigned lo
     const long long tri = ((long long)blockIdx.x * NT + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (tri >= F.T) return;
-    const float4 r2 = F.rec2[tri];
-    const unsigned bx = __float_as_uint(r2.y), by = __float_as_uint(r2.z);
+    const float4 r2 = F.rec[R_E][tri];
+    const unsigned bx = __float_as_uint(r2.x), by = __float_as_uint(r2.y);
     if ((bx >> 16) == 0) return;
     const Tri9 t = load_tri9(F, tri);
     const int xl = bx & 0xFFFF, xr = bx >> 16, yt = by & 0xFFFF, yb = by >> 16;
@@ -785,10 +844,9 @@ __global__ void __launch_bounds__(NT) k_shade_atomic(const Frame F, unsigned lon
     if (key != KEY_EMPTY) {
         keybuf[pix] = KEY_EMPTY;
         const unsigned tri = ~(unsigned)(key & 0xFFFFFFFFull);
-        const Tri9 t = load_tri9(F, tri);
         const int y = F.row0 + (int)(pix / F.W), x = (int)(pix % F.W);
         float fz, fc[3], fn[3];
-        if (shade_fragment(F, t, tri, tri, nullptr, (float)x, (float)y, fz, fc, fn)) {
+        if (shade_fragment(F, tri, tri, (float)x, (float)y, fz, fc, fn)) {
             const float zold = clear ? Z_INIT : F.z[pix];
             if (!(fz > zold)) {
                 z = fz; c[0] = fc[0]; c[1] = fc[1]; c[2] = fc[2]; nn[0] = fn[0]; nn[1] = fn[1]; nn[2] = fn[2];
@@ -867,6 +925,42 @@ __global__ void __launch_bounds__(NT) k_transform_view(const float *v, const flo
     no[i * 3] = x; no[i * 3 + 1] = y; no[i * 3 + 2] = z;
 }
 
+// Self-test of div_rn_by against the IEEE division instruction sequence: pseudo-random and adversarial operands
+// (all-ones / all-zeros significands, neighbours of powers of two) with exponents spanning the admitted range.
+__device__ __forceinline__ unsigned mix32(unsigned x)
+{
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ float selftest_operand(unsigned h, unsigned h2)
+{
+    unsigned mant = h & 0x7FFFFFu;
+    const unsigned kind = (h2 >> 8) & 15u;
+    if (kind == 0) mant = 0x7FFFFFu;              // 1.11...1
+    else if (kind == 1) mant = 0u;                // power of two
+    else if (kind == 2) mant = 1u;
+    else if (kind == 3) mant = 0x7FFFFEu;
+    else if (kind == 4) mant = 0x400000u;         // 1.5
+    else if (kind == 5) mant &= 0x7FF000u;        // short significands (screen coordinates are often like this)
+    const unsigned expo = 127u - 40u + (h2 % 81u);   // 2^-40 .. 2^40
+    return __uint_as_float(((h2 >> 31) << 31) | (expo << 23) | mant);
+}
+__global__ void __launch_bounds__(NT) k_selftest_fdiv(unsigned long long samples, unsigned seed, unsigned long long *out)
+{
+    unsigned long long bad = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * NT + threadIdx.x; i < samples; i += (unsigned long long)gridDim.x * NT) {
+        const unsigned h0 = mix32((unsigned)i ^ seed), h1 = mix32(h0 + (unsigned)(i >> 32) + 0x9e3779b9u);
+        const unsigned h2 = mix32(h1 ^ 0x85ebca6bu), h3 = mix32(h2 + 0xc2b2ae35u);
+        const float a = selftest_operand(h0, h1), d = selftest_operand(h2, h3);
+        const float fast = div_rn_by(a, d, __frcp_rn(d)), ref = __fdiv_rn(a, d);
+        if (__float_as_uint(fast) != __float_as_uint(ref)) {
+            if (!bad) { out[1] = __float_as_uint(a); out[2] = __float_as_uint(d); }
+            ++bad;
+        }
+    }
+    if (bad) atomicAdd(out, bad);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
@@ -906,10 +1000,12 @@ struct crb_filler {
     long long maxT;
     int maxViews;
     long long pairCap;
-    float4 *rec0, *rec1, *rec2, *nrec0, *nrec1;
+    float4 *rec[NREC], *crec0, *crec1;
+    float *crec2;
     unsigned *count, *tcount, *offset, *cursor, *busy, *empty;
     float4 *ls0, *ls1, *ls2;
     uint4 *ls3;
+    float4 *ls4;
     unsigned long long *total;
     float *stage_v, *stage_c, *stage_n;  // device staging for host-pointer calls
     // differential path scratch (library-owned, lazily allocated)
@@ -926,7 +1022,7 @@ struct crb_filler {
 namespace {
 
 struct WsLayout {
-    size_t rec0, rec1, rec2, nrec0, nrec1, count, tcount, offset, cursor, busy, empty, ls0, ls1, ls2, ls3, total, sv, sc, sn, bytes;
+    size_t rec[NREC], crec0, crec1, crec2, count, tcount, offset, cursor, busy, empty, ls0, ls1, ls2, ls3, ls4, total, sv, sc, sn, bytes;
 };
 
 long long default_pair_cap(const crb_filler *f, long long T, int views)
@@ -943,11 +1039,10 @@ WsLayout ws_layout(const crb_filler *f, long long T, int views, long long pairCa
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 256); return at; };
     const size_t recs = (size_t)(T > 0 ? T : 1) * views;
-    L.rec0 = take(recs * sizeof(float4));
-    L.rec1 = take(recs * sizeof(float4));
-    L.rec2 = take(recs * sizeof(float4));
-    L.nrec0 = take(recs * sizeof(float4));
-    L.nrec1 = take(recs * sizeof(float4));
+    for (int k = 0; k < NREC; ++k) L.rec[k] = take(recs * sizeof(float4));
+    L.crec0 = take((size_t)(T > 0 ? T : 1) * 16);
+    L.crec1 = take((size_t)(T > 0 ? T : 1) * 16);
+    L.crec2 = take((size_t)(T > 0 ? T : 1) * 4);
     L.count = take((size_t)tiles * views * 4);
     L.tcount = take((size_t)tiles * views * 4);
     L.offset = take((size_t)tiles * views * 4);
@@ -958,6 +1053,7 @@ WsLayout ws_layout(const crb_filler *f, long long T, int views, long long pairCa
     L.ls1 = take((size_t)pairCap * 16);
     L.ls2 = take((size_t)pairCap * 16);
     L.ls3 = take((size_t)pairCap * 16);
+    L.ls4 = take((size_t)pairCap * 16);
     L.total = take(64);
     L.sv = take((size_t)(T > 0 ? T : 1) * 36);
     L.sc = take((size_t)(T > 0 ? T : 1) * 36);
@@ -1003,10 +1099,11 @@ void fill_frame(const crb_filler *f, Frame *F)
     F->tilesX = (f->w + TW - 1) / TW;
     F->tilesY = (f->row1 - f->row0 + TH - 1) / TH;
     F->nTiles = F->tilesX * F->tilesY;
-    F->rec0 = f->rec0; F->rec1 = f->rec1; F->rec2 = f->rec2; F->nrec0 = f->nrec0; F->nrec1 = f->nrec1;
+    for (int k = 0; k < NREC; ++k) F->rec[k] = f->rec[k];
+    F->crec0 = f->crec0; F->crec1 = f->crec1; F->crec2 = f->crec2;
     F->count = f->count; F->tcount = f->tcount; F->offset = f->offset; F->cursor = f->cursor;
     F->busy = f->busy; F->empty = f->empty;
-    F->ls0 = f->ls0; F->ls1 = f->ls1; F->ls2 = f->ls2; F->ls3 = f->ls3;
+    F->ls0 = f->ls0; F->ls1 = f->ls1; F->ls2 = f->ls2; F->ls3 = f->ls3; F->ls4 = f->ls4;
     F->total = f->total;
     F->pairCap = f->pairCap;
     F->slabPixels = (long long)(f->row1 - f->row0) * f->w;
@@ -1078,6 +1175,7 @@ int run_atomic(crb_filler *f, Frame &F, cudaStream_t st)
 int bind_ws_pointers(crb_filler *f, void *ws, size_t bytes, long long T, int views, long long pairCap, cudaStream_t st)
 {
     if (views < 1) views = 1;
+    if (views > 1024) return fail(CRB_ERR_INVALID, "max_views > 1024 (views per launch; crb_render_views chunks longer batches itself)");
     if (T < 0) return fail(CRB_ERR_INVALID, "max_triangles < 0");
     if (pairCap <= 0) pairCap = default_pair_cap(f, T, views);
     if (pairCap > 0xFFFFFFF0ll) return fail(CRB_ERR_INVALID, "pair capacity exceeds 32-bit list offsets");
@@ -1087,11 +1185,11 @@ int bind_ws_pointers(crb_filler *f, void *ws, size_t bytes, long long T, int vie
     char *b = (char *)ws;
     f->ws = ws; f->ws_bytes = bytes;
     f->maxT = T; f->maxViews = views; f->pairCap = pairCap;
-    f->rec0 = (float4 *)(b + L.rec0); f->rec1 = (float4 *)(b + L.rec1); f->rec2 = (float4 *)(b + L.rec2);
-    f->nrec0 = (float4 *)(b + L.nrec0); f->nrec1 = (float4 *)(b + L.nrec1);
+    for (int k = 0; k < NREC; ++k) f->rec[k] = (float4 *)(b + L.rec[k]);
+    f->crec0 = (float4 *)(b + L.crec0); f->crec1 = (float4 *)(b + L.crec1); f->crec2 = (float *)(b + L.crec2);
     f->count = (unsigned *)(b + L.count); f->tcount = (unsigned *)(b + L.tcount); f->offset = (unsigned *)(b + L.offset); f->cursor = (unsigned *)(b + L.cursor);
     f->busy = (unsigned *)(b + L.busy); f->empty = (unsigned *)(b + L.empty);
-    f->ls0 = (float4 *)(b + L.ls0); f->ls1 = (float4 *)(b + L.ls1); f->ls2 = (float4 *)(b + L.ls2); f->ls3 = (uint4 *)(b + L.ls3);
+    f->ls0 = (float4 *)(b + L.ls0); f->ls1 = (float4 *)(b + L.ls1); f->ls2 = (float4 *)(b + L.ls2); f->ls3 = (uint4 *)(b + L.ls3); f->ls4 = (float4 *)(b + L.ls4);
     f->total = (unsigned long long *)(b + L.total);
     f->stage_v = (float *)(b + L.sv); f->stage_c = (float *)(b + L.sc); f->stage_n = (float *)(b + L.sn);
     CU(cudaMemsetAsync(b + L.count, 0, L.offset - L.count, st));  // tile counts start at zero, k_alloc keeps them so
@@ -1425,6 +1523,22 @@ int crb_status(crb_filler *f, int64_t *pairs_needed, int64_t *pair_capacity, voi
 }
 
 int64_t crb_launch_count(const crb_filler *f) { return f ? f->launches : 0; }
+
+int crb_selftest_fdiv(int device, uint64_t samples, unsigned seed, uint64_t *mismatches, uint32_t first_bad[2])
+{
+    if (!mismatches) return fail(CRB_ERR_INVALID, "mismatches is NULL");
+    CU(cudaSetDevice(device));
+    unsigned long long *d_out = nullptr, h_out[3] = {0, 0, 0};
+    CU(cudaMalloc(&d_out, sizeof(h_out)));
+    CU(cudaMemset(d_out, 0, sizeof(h_out)));
+    k_selftest_fdiv<<<148 * 8, NT>>>(samples, seed, d_out);
+    cudaError_t e = cudaMemcpy(h_out, d_out, sizeof(h_out), cudaMemcpyDeviceToHost);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(CRB_ERR_CUDA, "k_selftest_fdiv failed: %s", cudaGetErrorString(e));
+    *mismatches = h_out[0];
+    if (first_bad) { first_bad[0] = (uint32_t)h_out[1]; first_bad[1] = (uint32_t)h_out[2]; }
+    return CRB_OK;
+}
 
 int crb_profile(crb_filler *f, int enable)
 {

@@ -152,6 +152,12 @@ int crb_status(crb_filler *f, int64_t *pairs_needed, int64_t *pair_capacity, voi
 /* Number of kernel launches issued by this filler since creation (bench.py's gpu_launches). */
 int64_t crb_launch_count(const crb_filler *f);
 
+/* Self-test (GPU): the rasterizer replaces `x / d` for a per-triangle constant d by a correctly rounded quotient computed
+ * from rcp.rn(d) and two FMA residual steps.  This checks that sequence against the division instruction on `samples`
+ * pseudo-random + adversarial operand pairs; *mismatches must come back 0.  first_bad = bit patterns (a, d) of one
+ * failing pair, if any. */
+int crb_selftest_fdiv(int device, uint64_t samples, unsigned seed, uint64_t *mismatches, uint32_t first_bad[2]);
+
 /* Measurement aid: while enabled, every launch of the dominant kernel (the tile rasterizer + shader, k_raster) is
  * bracketed by CUDA events on the launching stream.  crb_profile_read waits for them and returns how many launches
  * were timed since the last read and their summed device time.  Not usable inside CUDA-graph capture. */

@@ -295,3 +295,17 @@ def test_batched_views_fused_guro_and_colour_only(Filler, O, trex):
         o.render_arrays(vk, trex._colors_by_triangles, nk)
         O.guro(o.get_color_buffer(), o.get_normals_buffer(), [0, 0, 1])
         assert bits_equal(out["color"][k].cpu().numpy(), o.get_color_buffer())
+
+
+def test_fast_division_is_ieee():
+    """div_rn_by (reciprocal + two FMA residual steps) must return exactly what the division instruction returns."""
+    import ctypes
+    from cython3dmodelrenderer_b200 import _lib
+    L = _lib.load_library()
+    bad, first = ctypes.c_uint64(), (ctypes.c_uint32 * 2)()
+    total = 0
+    for seed in range(4):
+        _lib.check(L.crb_selftest_fdiv(0, 1 << 30, seed * 7919 + 1, ctypes.byref(bad), first))
+        total += bad.value
+        assert bad.value == 0, f"{bad.value} mismatches, e.g. a={first[0]:#x} d={first[1]:#x}"
+    assert total == 0
