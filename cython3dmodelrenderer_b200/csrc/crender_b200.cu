@@ -38,7 +38,8 @@ namespace {
 constexpr int TW = 32;          // tile width in pixels  (one 128-byte line of z, three of colour / normals)
 constexpr int TH = 32;          // tile height in pixels
 constexpr int NT = 256;         // threads per CTA in every kernel
-constexpr int CH = 256;         // triangles staged in shared memory per pass of the tile rasterizer (== NT)
+constexpr int CH = 128;         // triangles staged in shared memory per pass of the tile rasterizer
+constexpr int FQ = 256;          // fragments a warp compacts per round (8 per row)
 constexpr int KEY_STRIDE = TW + 1;  // padded key row: rows of one column land in different banks
 constexpr unsigned long long KEY_EMPTY = 0xFFFFFFFFFFFFFFFFull;
 constexpr float Z_INIT = 1e6f;  // pyx:67
@@ -47,7 +48,7 @@ constexpr float L3_MIN = 1e-30f, L3_MAX = 1e30f;
 constexpr int MAX_DIM = 65535;  // bbox corners are packed in 16 bits
 constexpr int PROF_MAX = 8192;  // k_raster launches that can be timed between two crb_profile_read calls
 
-static_assert(CH == NT, "one staged triangle per thread");
+static_assert(CH <= NT && CH <= 256, "one staged triangle per thread, 8-bit owner index");
 static_assert(TW == 32, "a tile row is one warp wide");
 
 // Per-(view,triangle) records written by k_setup.
@@ -511,6 +512,8 @@ struct __align__(16) TileSmem {
             float4 s4[CH];  // 1/d1 1/d2 1/d3 -
             unsigned rowStart[CH];
             unsigned char owner[CH * TH];  // row work item -> staged triangle
+            float4 slot[NT / 32][32][2];   // per warp: the 32 rows of the current trip (A1 A2 A3 l02 | l12 l22 tri info)
+            unsigned short fq[NT / 32][FQ];  // per warp: compacted fragments of the trip (lane | x << 5)
         } st;
         struct {
             float col[TH * TW * 3];
@@ -665,15 +668,15 @@ __global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame 
         for (unsigned rb = threadIdx.x & ~31u; rb < totalRows; rb += NT) {
             const unsigned r = rb + lane;
             const bool active = r < totalRows;
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, c = a, rr = a;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, c = a;
             bool fdiv = false;
             float l02 = 0.f, l12 = 0.f, l22 = 0.f, A1 = 0.f, A2 = 0.f, A3 = 0.f;
             float thr1 = 0.f, thr2 = 0.f, thr3 = 0.f;
-            unsigned tri = 0;
+            unsigned tri = 0, o = 0;
             int xa = 0, xb = 0, y = y0;
             if (active) {
-                const unsigned o = S.u.st.owner[r];
-                a = S.u.st.s0[o]; b = S.u.st.s1[o]; c = S.u.st.s2[o]; rr = S.u.st.s4[o];
+                o = S.u.st.owner[r];
+                a = S.u.st.s0[o]; b = S.u.st.s1[o]; c = S.u.st.s2[o];
                 const uint4 d = S.u.st.s3[o];
                 tri = d.z;
                 fdiv = (d.w & FL_FDIV) != 0;
@@ -720,28 +723,58 @@ __global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame 
                 const bool keep = (i < len) && !(n1 < thr1 || n2 < thr2 || n3 < thr3);   // else: certainly bar < 0
                 mask |= (keep ? 1u : 0u) << ((xa + i - x0) & 31);
             }
-            // pass 2 (exact): divisions, depth, key -- one surviving pixel per lane per trip
-            const int maxcnt = __reduce_max_sync(0xFFFFFFFFu, __popc(mask));
-            unsigned long long *krow = S.keys + (y - y0) * KEY_STRIDE;
-            for (int j = 0; j < maxcnt; ++j) {
-                if (mask) {
-                    const int bit = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    const float px = (float)(x0 + bit);
-                    const float n1 = A1 - l02 * (px - b.x);
-                    const float n2 = A2 - l12 * (px - a.x);
-                    const float n3 = A3 - l22 * (px - a.z);
-                    float b1, b2, b3;
-                    if (fdiv && fdiv_ok(n1, n2, n3)) {
-                        b1 = div_rn_by(n1, c.y, rr.x); b2 = div_rn_by(n2, c.z, rr.y); b3 = div_rn_by(n3, c.w, rr.z);
-                    } else {
-                        b1 = n1 / c.y; b2 = n2 / c.z; b3 = n3 / c.w;
-                    }
-                    if (!(b1 < 0.0f || b2 < 0.0f || b3 < 0.0f)) {              // pyx:216
-                        const float z = (b.z * b1 + b.w * b2) + c.x * b3;          // pyx:219
-                        if (z == z) smem_key_min(krow + bit, pack_key(z, tri));    // pyx:220 rejects NaN only
+            // pass 2 (exact): the surviving pixels of the warp's 32 rows are compacted into a per-warp queue, so that
+            // every lane then evaluates one fragment per step whatever the spread of span lengths (the per-row loop this
+            // replaces ran at 13 of 32 lanes).  A fragment finds its row through the slot its owner lane published.
+            const unsigned wid = threadIdx.x >> 5;
+            S.u.st.slot[wid][lane][0] = make_float4(A1, A2, A3, l02);
+            S.u.st.slot[wid][lane][1] = make_float4(l12, l22, __uint_as_float(tri),
+                                                    __uint_as_float(o | ((unsigned)(y - y0) << 8) | (fdiv ? 65536u : 0u)));
+            unsigned short *fq = S.u.st.fq[wid];
+            while (__any_sync(0xFFFFFFFFu, mask != 0u)) {   // one round unless some row has more than 8 survivors
+                const int cnt = min(__popc(mask), FQ / 32);
+                int inc = cnt;
+#pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) {
+                    const int t = __shfl_up_sync(0xFFFFFFFFu, inc, dd);
+                    if ((int)lane >= dd) inc += t;
+                }
+                const int total = __shfl_sync(0xFFFFFFFFu, inc, 31), pre = inc - cnt;
+                const int maxc = __reduce_max_sync(0xFFFFFFFFu, cnt);
+                for (int j = 0; j < maxc; ++j) {
+                    if (j < cnt) {
+                        const int bit = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        fq[pre + j] = (unsigned short)(lane | ((unsigned)bit << 5));
                     }
                 }
+                __syncwarp();
+                for (int base2 = 0; base2 < total; base2 += 32) {
+                    const int idx = base2 + (int)lane;
+                    if (idx < total) {
+                        const unsigned e = fq[idx];
+                        const unsigned src = e & 31u, bit = e >> 5;
+                        const float4 q0 = S.u.st.slot[wid][src][0], q1 = S.u.st.slot[wid][src][1];
+                        const unsigned info = __float_as_uint(q1.w), o2 = info & 255u;
+                        const float4 pa = S.u.st.s0[o2], pb = S.u.st.s1[o2], pc = S.u.st.s2[o2], pr = S.u.st.s4[o2];
+                        const float px = (float)(x0 + (int)bit);
+                        const float n1 = q0.x - q0.w * (px - pb.x);
+                        const float n2 = q0.y - q1.x * (px - pa.x);
+                        const float n3 = q0.z - q1.y * (px - pa.z);
+                        float b1, b2, b3;
+                        if ((info & 65536u) && fdiv_ok(n1, n2, n3)) {
+                            b1 = div_rn_by(n1, pc.y, pr.x); b2 = div_rn_by(n2, pc.z, pr.y); b3 = div_rn_by(n3, pc.w, pr.z);
+                        } else {
+                            b1 = n1 / pc.y; b2 = n2 / pc.z; b3 = n3 / pc.w;
+                        }
+                        if (!(b1 < 0.0f || b2 < 0.0f || b3 < 0.0f)) {                 // pyx:216
+                            const float z = (pb.z * b1 + pb.w * b2) + pc.x * b3;          // pyx:219
+                            if (z == z)                                                   // pyx:220 rejects NaN only
+                                smem_key_min(S.keys + ((info >> 8) & 31u) * KEY_STRIDE + bit, pack_key(z, __float_as_uint(q1.z)));
+                        }
+                    }
+                }
+                __syncwarp();
             }
             __syncwarp();
         }
