@@ -383,6 +383,117 @@ def run_gpu_arm(args):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------------------------------------------------
+# secondary workloads (not the headline line): BASELINE.json configs C2 and C4
+# --------------------------------------------------------------------------------------------------------------------
+def run_extra_workload(args):
+    """bunny_4096_guro (C2: bunny + igor texture, 4096^2, fused clear + render + Guro pass, one GPU) and
+    sphere_8192_bands (C4: 10 M-triangle UV sphere at 8192^2, screen-row bands over N GPUs, optional NCCL all-gather).
+    Same JSON shape as the headline line; `scaling` is "strong" for the band-sharded frame (total work is fixed)."""
+    import torch
+    import torch.distributed as dist
+    from conftest import load_indexed
+    from cython3dmodelrenderer_b200 import AdvancedPixelBufferFiller, sharding, synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if args.workload == "bunny_4096_guro":
+        res, model, band = 4096, load_indexed("bunny"), None
+    else:
+        res = args.res or 8192
+        scale = res / 8192.0
+        model = synthetic.uv_sphere(max(8, int(3200 * scale)), max(3, int(1564 * scale)))
+        band = sharding.band_shard(res, rank, world)
+    T = int(model._vertices_by_triangles.shape[0])
+    f = AdvancedPixelBufferFiller(res, res, fov=FOV, device=local, band=band)
+    dv, dc, dn = (torch.from_numpy(a).to(dev) for a in
+                  (model._vertices_by_triangles, model._colors_by_triangles, model._normals_by_triangles))
+    light = -np.asarray([0, 0, 1], dtype="float32")
+    light = light / np.linalg.norm(light)
+
+    def step():
+        f.clear()
+        f.render_arrays(dv, dc, dn, check_status=False)
+        if args.workload == "bunny_4096_guro":
+            f.illuminate_guro(light)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    f.clear(); f.render_arrays(dv, dc, dn)        # sizes the workspace, checks the pair list
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    launches0 = f.launch_count
+    f.profile(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    k_launches, k_ms = f.profile_read()
+    f.profile(False)
+    gather = None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        if args.gather != "none":     # final NCCL all-gather of the row bands (north_star: "a final NCCL gather over NVLink")
+            z, c, n = f.device_buffers()
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            full = [sharding.gather_bands(b, res) for b in (z, c, n)]
+            g1.record()
+            barrier()
+            gms = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+            dist.all_reduce(gms, op=dist.ReduceOp.MAX)
+            gather = {"ms": float(gms.item()), "bytes": 28 * res * res, "what": "all_gather of z+colour+normal row bands",
+                      "covered_pixels": int((full[0] < 1e5).sum().item())}
+    z = f.device_buffers()[0]
+    cov = torch.tensor([int((z < 1e5).sum().item())], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(cov)
+    fps = args.steps / (ms / 1000.0)
+    peak, peak_src = peaks()
+    rows = res if band is None else band[1] - band[0]
+    alg = 108 * T + 28 * rows * res       # per GPU: every rank reads all triangles, writes its own rows
+    k_avg = k_ms / max(k_launches, 1)
+    if rank == 0:
+        line = {
+            "metric": f"{args.workload} frames/s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if band is not None else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic UV sphere (SURVEY 8d C4)" if band is not None else "bunny fixture + igor texture (tests/golden/bunny_fit.npz)",
+            "config": {"workload": args.workload, "res": res, "fov": FOV, "triangles": T,
+                       "sharding": "screen-row bands, tile aligned" if band is not None else "none",
+                       "l2": "frame buffers %.2f GB per GPU vs 126 MB L2" % (28 * rows * res / 1e9)},
+            "gtri_per_s": fps * T / 1e9, "clocks": clocks.summary(), "gpu_launches": f.launch_count - launches0,
+            "roofline": {"bound": "hbm", "kernel": "k_raster", "achieved": alg / (k_avg / 1000.0) / 1e9 if k_avg else None,
+                         "peak": peak, "unit": "GB/s", "frac": (alg / (k_avg / 1000.0) / 1e9 / peak) if k_avg else None,
+                         "traffic": None, "peak_source": peak_src, "avg_launch_ms": k_avg,
+                         "algorithmic_bytes_per_launch": alg, "share_of_step": k_ms / e0.elapsed_time(e1)},
+            "gather": gather, "checks": {"covered_pixels": int(cov.item())},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -394,9 +505,16 @@ def main():
     ap.add_argument("--e2e-frames", type=int, default=200)
     ap.add_argument("--cpu-frames", type=int, default=60)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="trex_1024_orbit",
+                    choices=["trex_1024_orbit", "bunny_4096_guro", "sphere_8192_bands"])
+    ap.add_argument("--res", type=int, default=0, help="sphere_8192_bands only: override the resolution (scaled sphere)")
+    ap.add_argument("--gather", default="none", choices=["none", "bands", "u8"],
+                    help="also time the final NCCL gather (reported beside, never inside, the headline value)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload != "trex_1024_orbit":
+        run_extra_workload(args)
     else:
         run_gpu_arm(args)
 

@@ -1,0 +1,102 @@
+"""Multi-GPU host logic on CPU: world_size-2 (and 3) gloo process groups.  The shards are rendered with the oracle (the
+CUDA path needs a GPU); what is under test is the partitioning (view blocks, tile-aligned row bands) and the gathers of
+cython3dmodelrenderer_b200.sharding -- the results must equal the unsharded frame bit for bit."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import bits_equal, load_indexed
+from cython3dmodelrenderer_b200 import sharding
+from cython3dmodelrenderer_b200 import views as VW
+
+
+def test_view_shard_partitions_exactly():
+    for n in (0, 1, 7, 128, 1024, 1025):
+        for world in (1, 2, 3, 8):
+            blocks = [sharding.view_shard(n, r, world) for r in range(world)]
+            assert sum(c for _, c in blocks) == n
+            pos = 0
+            for first, count in blocks:
+                assert first == pos
+                pos += count
+    assert sharding.view_shard(1024, 3, 8) == (384, 128)
+
+
+def test_band_shard_partitions_exactly_and_tile_aligned():
+    for h in (1, 31, 32, 33, 300, 1024, 8192):
+        for world in (1, 2, 3, 4, 8):
+            bands = [sharding.band_shard(h, r, world) for r in range(world)]
+            assert bands[0][0] == 0 and bands[-1][1] == h
+            for (a0, a1), (b0, b1) in zip(bands, bands[1:]):
+                assert a1 == b0 and a0 <= a1
+            assert all(a % 32 == 0 or a == h for a, _ in bands)
+    assert sharding.band_shard(8192, 1, 8) == (1024, 2048)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import oracle as O
+        m = load_indexed("trex")
+        # ---- view sharding: 5 views over `world` ranks (ragged), all_gather and gather-to-0 -----------------------
+        h, w, V = 48, 64, 5
+        views = VW.orbit_views(V)
+        first, count = sharding.view_shard(V, rank, world)
+        z = np.zeros((count, h, w), np.float32)
+        col = np.zeros((count, h, w, 3), np.float32)
+        for i in range(count):
+            vk, nk = VW.transform_arrays_host(views[first + i], m._vertices_by_triangles, m._normals_by_triangles)
+            f = O.OracleFiller(h, w, fov=45.0)
+            f.render_arrays(vk, m._colors_by_triangles, nk)
+            z[i], col[i] = f.get_z_buffer(), f.get_color_buffer()
+        z_all = sharding.gather_views(torch.from_numpy(z), V)
+        col_0 = sharding.gather_views(torch.from_numpy(col), V, dst=0)
+        assert z_all.shape == (V, h, w)
+        assert (col_0 is None) == (rank != 0)
+        # ---- band sharding: 100-row frame, tile-aligned bands -------------------------------------------------------
+        H, W = 100, 72
+        r0, r1 = sharding.band_shard(H, rank, world)
+        full = O.OracleFiller(H, W, fov=45.0)
+        full.render_model(m)
+        zb = torch.from_numpy(full.get_z_buffer()[r0:r1].copy())     # what a band filler produces (tests/test_gpu_parity)
+        nb = torch.from_numpy(full.get_normals_buffer()[r0:r1].copy())
+        z_band = sharding.gather_bands(zb, H)
+        n_band = sharding.gather_bands(nb, H, dst=0)
+        if rank == 0:
+            np.savez(os.path.join(out_dir, "r0.npz"), z_all=z_all.numpy(), col_0=col_0.numpy(), z_band=z_band.numpy(),
+                     n_band=n_band.numpy(), z_full=full.get_z_buffer(), n_full=full.get_normals_buffer())
+        else:
+            np.savez(os.path.join(out_dir, f"r{rank}.npz"), z_all=z_all.numpy(), z_band=z_band.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_results_equal_unsharded(world, tmp_path):
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    from oracle import oracle as O
+    m = load_indexed("trex")
+    r0 = np.load(tmp_path / "r0.npz")
+    views = VW.orbit_views(5)
+    for k in range(5):
+        vk, nk = VW.transform_arrays_host(views[k], m._vertices_by_triangles, m._normals_by_triangles)
+        f = O.OracleFiller(48, 64, fov=45.0)
+        f.render_arrays(vk, m._colors_by_triangles, nk)
+        assert bits_equal(r0["z_all"][k], f.get_z_buffer())
+        assert bits_equal(r0["col_0"][k], f.get_color_buffer())
+    assert bits_equal(r0["z_band"], r0["z_full"]) and bits_equal(r0["n_band"], r0["n_full"])
+    for r in range(1, world):
+        rr = np.load(tmp_path / f"r{r}.npz")
+        assert bits_equal(rr["z_all"], r0["z_all"]) and bits_equal(rr["z_band"], r0["z_full"])
