@@ -7,5 +7,6 @@ Everything else of the reference (Model, Renderer, illumination, run.py) is used
 """
 from ._lib import CrenderError, build, load_library, projection_matrix  # noqa: F401
 from .pixel_buffer_filler import AdvancedPixelBufferFiller  # noqa: F401
+from .pipeline import HostFramePipeline  # noqa: F401
 
-__all__ = ["AdvancedPixelBufferFiller", "CrenderError", "build", "load_library", "projection_matrix"]
+__all__ = ["AdvancedPixelBufferFiller", "HostFramePipeline", "CrenderError", "build", "load_library", "projection_matrix"]

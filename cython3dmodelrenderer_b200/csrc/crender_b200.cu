@@ -17,6 +17,7 @@
 //
 // Not a port: nothing here mirrors the reference's loop structure, locking or memory layout.
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <climits>
@@ -46,6 +47,7 @@ constexpr float Z_INIT = 1e6f;  // pyx:67
 constexpr float REJ_EPS = 1e-6f;      // fast-reject guard band on barycentric numerators (see tri_fast_setup)
 constexpr float L3_MIN = 1e-30f, L3_MAX = 1e30f;
 constexpr int MAX_DIM = 65535;  // bbox corners are packed in 16 bits
+constexpr int BOX_ROWS = 8;       // rows per TMA box (clear pattern and shaded rows go out 8 tile rows at a time)
 constexpr int PROF_MAX = 8192;  // k_raster launches that can be timed between two crb_profile_read calls
 
 static_assert(CH <= NT && CH <= 256, "one staged triangle per thread, 8-bit owner index");
@@ -87,7 +89,8 @@ struct Frame {
     float4 *ls0, *ls1, *ls2;    // [pairCap] staged triangle setups, tile by tile: (x0 y0 x1 y1) (x2 y2 z0 z1) (z2 d1 d2 d3)
     uint4 *ls3;                 // [pairCap] (bbox x, bbox y, triangle index, flags)
     float4 *ls4;                // [pairCap] (1/d1 1/d2 1/d3 -) correctly rounded reciprocals of the denominators
-    unsigned long long *total;  // [0] pairs of this frame, [1] sticky max of overflowing totals
+    unsigned long long *total;  // [0] pairs of this frame, [1] sticky max of overflowing totals, [2] busy tiles, [3] empty tiles
+    unsigned long long *hstats; // mapped host word: (tiles of the launch << 32 | busy tiles), posted by k_raster for the next launch's grid size
     long long pairCap;
     // outputs (per view slab stride = rows*W (z) or rows*W*3)
     float *z, *color, *normals;
@@ -501,8 +504,27 @@ __device__ __forceinline__ void smem_key_min(unsigned long long *p, unsigned lon
     }
 }
 
-struct __align__(16) TileSmem {
-    unsigned long long keys[TH * KEY_STRIDE];
+// Tensor maps (TMA) of the three output arrays of one launch, as 3-D tensors [view][row][x] (x in floats: W for z,
+// 3W for colour / normals) with boxes of BOX_ROWS rows x one tile width.  Built on the host per launch (the output
+// pointers are per call).  `use` bit k = map k is valid (CRB_BUF_* order); 0 = the launch uses plain stores only.
+struct __align__(64) TMaps {
+    CUtensorMap z, c, n;
+    unsigned use;
+};
+
+__device__ __forceinline__ void tma_store_box(const CUtensorMap *m, const void *smem, int cx, int cy, int cv)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                 :: "l"((unsigned long long)m), "r"(cx), "r"(cy), "r"(cv), "r"((unsigned)__cvta_generic_to_shared(smem))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// generic-proxy shared-memory writes -> visible to the async proxy (TMA) once a barrier has ordered them
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+struct __align__(128) TileSmem {
+    // TMA sources first (128-byte aligned): shaded colour / normal rows of the tile, then the clear pattern
     union {
         struct {
             float4 s0[CH];  // x0 y0 x1 y1
@@ -520,26 +542,32 @@ struct __align__(16) TileSmem {
             float nrm[TH * TW * 3];
         } out;
     } u;
+    float zpat[BOX_ROWS * TW];        // Z_INIT
+    float cpat[BOX_ROWS * TW * 3];    // background colour
+    float npat[BOX_ROWS * TW * 3];    // 0
+    unsigned long long keys[TH * KEY_STRIDE];
     unsigned warp_sums[NT / 32];
 };
 
-// Writes one tile of cleared pixels (fresh-filler values) -- the whole frame's "memset" is fused here.
-__device__ __forceinline__ void write_clear_tile(const Frame &F, int view, int x0, int yl0, int tw, int th)
+// Writes one tile of cleared pixels (fresh-filler values) with plain stores -- the path for images whose rows are not
+// 16-byte multiples, launches without tensor maps, and buffers the maps do not cover.
+__device__ __forceinline__ void write_clear_tile(const Frame &F, unsigned skip, int view, int x0, int yl0, int tw, int th)
 {
     const long long slab = (long long)view * F.slabPixels;
     const bool vec = (tw == TW) && ((F.W & 3) == 0);
     const float bg = background_color(F);
+    const bool wz = F.z && !(skip & CRB_BUF_Z), wc = F.color && !(skip & CRB_BUF_COLOR), wn = F.normals && !(skip & CRB_BUF_NORMALS);
     if (vec) {
         // thread -> (row = tid/8 (+32 per pass), 16-byte column q = tid%8 (+8, +16)): shifts only, 128-byte runs
         const int q = threadIdx.x & 7;
         for (int r = threadIdx.x >> 3; r < th; r += NT / 8) {
             const long long rowpix = slab + (long long)(yl0 + r) * F.W + x0;
-            if (F.z) reinterpret_cast<float4 *>(F.z + rowpix)[q] = make_float4(Z_INIT, Z_INIT, Z_INIT, Z_INIT);
-            if (F.color) {
+            if (wz) reinterpret_cast<float4 *>(F.z + rowpix)[q] = make_float4(Z_INIT, Z_INIT, Z_INIT, Z_INIT);
+            if (wc) {
                 float4 *o = reinterpret_cast<float4 *>(F.color + rowpix * 3);
                 o[q] = make_float4(bg, bg, bg, bg); o[q + 8] = make_float4(bg, bg, bg, bg); o[q + 16] = make_float4(bg, bg, bg, bg);
             }
-            if (F.normals) {
+            if (wn) {
                 float4 *o = reinterpret_cast<float4 *>(F.normals + rowpix * 3);
                 o[q] = make_float4(0.f, 0.f, 0.f, 0.f); o[q + 8] = make_float4(0.f, 0.f, 0.f, 0.f); o[q + 16] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
@@ -548,9 +576,9 @@ __device__ __forceinline__ void write_clear_tile(const Frame &F, int view, int x
         for (int i = threadIdx.x; i < th * tw; i += NT) {
             const int r = i / tw, xx = i % tw;
             const long long p = slab + (long long)(yl0 + r) * F.W + x0 + xx;
-            if (F.z) F.z[p] = Z_INIT;
-            if (F.color) { F.color[p * 3] = bg; F.color[p * 3 + 1] = bg; F.color[p * 3 + 2] = bg; }
-            if (F.normals) { F.normals[p * 3] = 0.f; F.normals[p * 3 + 1] = 0.f; F.normals[p * 3 + 2] = 0.f; }
+            if (wz) F.z[p] = Z_INIT;
+            if (wc) { F.color[p * 3] = bg; F.color[p * 3 + 1] = bg; F.color[p * 3 + 2] = bg; }
+            if (wn) { F.normals[p * 3] = 0.f; F.normals[p * 3 + 1] = 0.f; F.normals[p * 3 + 2] = 0.f; }
         }
     }
     if (F.color_u8) {
@@ -559,6 +587,22 @@ __device__ __forceinline__ void write_clear_tile(const Frame &F, int view, int x
         for (int i = threadIdx.x; i < th * tw * 3; i += NT) {
             const int r = i / (tw * 3), xx = i % (tw * 3);
             F.color_u8[((long long)view * F.slabPixels + (long long)(rows - 1 - (yl0 + r)) * F.W + x0) * 3 + xx] = b8;
+        }
+    }
+}
+
+// The same clear through TMA: lane 0 of warp w issues the boxes j = w, w+8 of the tile's 12 (3 arrays x 4 row blocks),
+// each a BOX_ROWS x 32-pixel store from the constant pattern in shared memory.  Boxes are clipped by the hardware at the
+// right / bottom edge of the image.  Whatever the maps do not cover goes through write_clear_tile.
+__device__ __forceinline__ void tma_clear_tile(const Frame &F, const TMaps &M, TileSmem &S, int view, int x0, int yl0, int th)
+{
+    if ((threadIdx.x & 31) == 0) {
+        for (int j = threadIdx.x >> 5; j < 12; j += NT / 32) {
+            const int which = j >> 2, r = (j & 3) * BOX_ROWS;
+            if (r >= th) continue;
+            if (which == 0) { if (M.use & CRB_BUF_Z) tma_store_box(&M.z, S.zpat, x0, yl0 + r, view); }
+            else if (which == 1) { if (M.use & CRB_BUF_COLOR) tma_store_box(&M.c, S.cpat, x0 * 3, yl0 + r, view); }
+            else { if (M.use & CRB_BUF_NORMALS) tma_store_box(&M.n, S.npat, x0 * 3, yl0 + r, view); }
         }
     }
 }
@@ -582,58 +626,14 @@ __device__ __forceinline__ void span_bound(float A, float l2, float b, float wma
     else lo = fmaxf(lo, e - 1.0f);                 // x >= e
 }
 
-// Persistent: gridDim.x CTAs walk the (view, tile) space with stride gridDim.x; the next tile's triangle count and list
-// offset are fetched while the current tile is processed, so neither CTA launch cost nor that dependent load sits on the
-// critical path of the 70 % of tiles that are empty and only need their fused clear.
-#ifndef CRB_RASTER_MIN_CTAS
-#define CRB_RASTER_MIN_CTAS 5
-#endif
-__global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame F)
+// Visibility + deferred shading of one busy tile (n triangles staged at list offset off).
+__device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, TileSmem &S, const bool clear, const int view,
+                                            const int tx, const int ty, const unsigned n, const unsigned off)
 {
-    __shared__ TileSmem S;
-    const long long nAll = (long long)F.nViews * F.nTiles;
-    const bool clear = (F.flags & CRB_CLEAR_FIRST) != 0;
-    const bool overflow = *F.total > (unsigned long long)F.pairCap;
-    if (overflow) {   // frame skipped; the host is told via crb_status
-        if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(F.total + 1, *F.total);
-        return;
-    }
-    // One CTA per busy tile.  The fused clear of the empty tiles (70 % of the T-Rex frame, pure stores) rides along:
-    // each busy CTA first issues the stores of up to ADOPT empty tiles, which then drain while it rasterizes -- memory-
-    // bound and issue-bound work overlap without competing for CTA slots.  Left-over empty tiles (scenes with few busy
-    // tiles) are cleared by the CTAs beyond the busy count, one tile each; the rest of the grid exits at once.
-    constexpr unsigned ADOPT = 4;
-    const unsigned nb = (unsigned)F.total[2], ne = (unsigned)F.total[3];
-    const unsigned cta = blockIdx.x;
-    if (cta >= nb) {
-        const unsigned long long e = (unsigned long long)ADOPT * nb + (cta - nb);
-        if (clear && e < ne) {
-            const unsigned t = F.empty[e];
-            const int view = (int)(t >> 22), ty = (int)((t >> 11) & 2047u), tx = (int)(t & 2047u);
-            write_clear_tile(F, view, tx * TW, ty * TH, min(TW, F.W - tx * TW), min(TH, F.row1 - F.row0 - ty * TH));
-        }
-        return;
-    }
-    const unsigned tpk = F.busy[cta];                           // issued before the adopted clears so that their
-    const int view = (int)(tpk >> 22), ty = (int)((tpk >> 11) & 2047u), tx = (int)(tpk & 2047u);
-    const unsigned tIdx = (unsigned)view * (unsigned)F.nTiles + (unsigned)(ty * F.tilesX + tx);
-    const unsigned n = F.tcount[tIdx], off = F.offset[tIdx];    // latency hides behind the store traffic
-    if (clear) {
-        unsigned e = cta;
-        for (unsigned k = 0; k < ADOPT && e < ne; ++k, e += nb) {
-            const unsigned t = F.empty[e];
-            const int view = (int)(t >> 22), ty = (int)((t >> 11) & 2047u), tx = (int)(t & 2047u);
-            write_clear_tile(F, view, tx * TW, ty * TH, min(TW, F.W - tx * TW), min(TH, F.row1 - F.row0 - ty * TH));
-        }
-    }
     const int x0 = tx * TW, yl0 = ty * TH;       // yl0: row inside the band's buffers
     const int y0 = F.row0 + yl0;                  // absolute image row
     const int tw = min(TW, F.W - x0), th = min(TH, F.row1 - y0);
-    if (F.flags & 0x10000u) {   // experiment switch: measure the store path alone
-        if (clear) write_clear_tile(F, view, x0, yl0, tw, th);
-        return;
-    }
-    {
+    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < TH * KEY_STRIDE; i += NT) S.keys[i] = KEY_EMPTY;
 
     // ---- visibility: every (triangle,row) of the tile is one work item -------------------------------------
@@ -654,7 +654,6 @@ __global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame 
         }
         unsigned totalRows;
         const unsigned start = block_exclusive_scan(rows, S.warp_sums, totalRows);
-        if (F.flags & 0x40000u) totalRows = 0;
         if (threadIdx.x < m) {
             S.u.st.rowStart[threadIdx.x] = start;
             for (unsigned j = 0; j < rows; ++j) S.u.st.owner[start + j] = (unsigned char)threadIdx.x;
@@ -664,22 +663,22 @@ __global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame 
         // Row work items, 32 per warp per trip.  Trip counts are warp-uniform and the body is predicated, so the warp
         // stays converged (a per-thread `for (r = tid; ...)` with early `continue`s lets lanes drift apart under
         // independent thread scheduling: measured 7.5 active lanes per instruction).
-        const unsigned lane = threadIdx.x & 31u;
         for (unsigned rb = threadIdx.x & ~31u; rb < totalRows; rb += NT) {
             const unsigned r = rb + lane;
             const bool active = r < totalRows;
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, c = a;
-            bool fdiv = false;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+            bool fdiv = false, span = false;
             float l02 = 0.f, l12 = 0.f, l22 = 0.f, A1 = 0.f, A2 = 0.f, A3 = 0.f;
             float thr1 = 0.f, thr2 = 0.f, thr3 = 0.f;
             unsigned tri = 0, o = 0;
             int xa = 0, xb = 0, y = y0;
             if (active) {
                 o = S.u.st.owner[r];
-                a = S.u.st.s0[o]; b = S.u.st.s1[o]; c = S.u.st.s2[o];
+                a = S.u.st.s0[o]; b = S.u.st.s1[o];
                 const uint4 d = S.u.st.s3[o];
                 tri = d.z;
                 fdiv = (d.w & FL_FDIV) != 0;
+                span = (d.w & FL_SPAN) != 0;
                 y = max((int)(d.y & 0xFFFF), y0) + (int)(r - S.u.st.rowStart[o]);
                 xa = max((int)(d.x & 0xFFFF), x0);
                 xb = min((int)(d.x >> 16), x0 + tw);
@@ -696,37 +695,54 @@ __global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame 
                 thr3 = (d.w & 64u) ? -REJ_EPS : -INFINITY;
                 const float py = (float)y;
                 A1 = l01 * (py - b.y); A2 = l11 * (py - a.y); A3 = l21 * (py - a.w);
-                if (d.w & FL_SPAN) {
-                    // analytic, conservative span of this row: replaces a per-pixel rejection loop over the bbox row
-                    float lo = (float)xa, hi = (float)(xb - 1);
-                    const float fa = lo, fb = hi;
-                    span_bound(A1, l02, b.x, fmaxf(fabsf(fa - b.x), fabsf(fb - b.x)), lo, hi);
-                    span_bound(A2, l12, a.x, fmaxf(fabsf(fa - a.x), fabsf(fb - a.x)), lo, hi);
-                    span_bound(A3, l22, a.z, fmaxf(fabsf(fa - a.z), fabsf(fb - a.z)), lo, hi);
-                    if (lo <= hi) {
-                        xa = max(xa, (int)ceilf(lo));      // lo, hi lie within [xa-2, xb+1]: the conversions are exact
-                        xb = min(xb, (int)floorf(hi) + 1);
-                    } else {
-                        xb = xa;
-                    }
-                }
             }
-            // pass 1 (cheap, predicated): numerators over the span -> mask of pixels that need the exact path
-            const int len = max(xb - xa, 0);
-            const int maxlen = __reduce_max_sync(0xFFFFFFFFu, len);
+            // pass 1: which pixels of the row need the exact path.  A pixel is certainly outside (bar_k < 0) when a
+            // numerator is below its threshold; each numerator is a monotone function of x (every rounding in
+            // A - l2*(px - b) is monotone), so the pixels that survive all three tests form ONE interval.
             unsigned mask = 0;
-            for (int i = 0; i < maxlen; ++i) {
-                const float px = (float)(xa + i);
-                const float n1 = A1 - l02 * (px - b.x);
-                const float n2 = A2 - l12 * (px - a.x);
-                const float n3 = A3 - l22 * (px - a.z);
-                const bool keep = (i < len) && !(n1 < thr1 || n2 < thr2 || n3 < thr3);   // else: certainly bar < 0
-                mask |= (keep ? 1u : 0u) << ((xa + i - x0) & 31);
+            if (span) {
+                // analytic, conservative interval first, then its two ends are walked inwards with the very test the
+                // per-pixel loop applies until they rest on surviving pixels: same mask as testing every pixel
+                float lo = (float)xa, hi = (float)(xb - 1);
+                const float fa = lo, fb = hi;
+                span_bound(A1, l02, b.x, fmaxf(fabsf(fa - b.x), fabsf(fb - b.x)), lo, hi);
+                span_bound(A2, l12, a.x, fmaxf(fabsf(fa - a.x), fabsf(fb - a.x)), lo, hi);
+                span_bound(A3, l22, a.z, fmaxf(fabsf(fa - a.z), fabsf(fb - a.z)), lo, hi);
+                if (lo <= hi) {
+                    xa = max(xa, (int)ceilf(lo));      // lo, hi lie within [xa-2, xb+1]: the conversions are exact
+                    xb = min(xb, (int)floorf(hi) + 1);
+                } else {
+                    xb = xa;
+                }
+                while (xa < xb) {
+                    const float px = (float)xa;
+                    if (!(A1 - l02 * (px - b.x) < thr1 || A2 - l12 * (px - a.x) < thr2 || A3 - l22 * (px - a.z) < thr3)) break;
+                    ++xa;
+                }
+                while (xa < xb) {
+                    const float px = (float)(xb - 1);
+                    if (!(A1 - l02 * (px - b.x) < thr1 || A2 - l12 * (px - a.x) < thr2 || A3 - l22 * (px - a.z) < thr3)) break;
+                    --xb;
+                }
+                if (xa < xb) mask = (0xFFFFFFFFu >> (32 - (xb - xa))) << (xa - x0);
+            }
+            if (__any_sync(0xFFFFFFFFu, active && !span)) {
+                // rows of triangles without the analytic bound (huge / non-finite coordinates or denominators): every
+                // pixel of the rectangle row is tested
+                const int len = (active && !span) ? max(xb - xa, 0) : 0;
+                const int maxlen = __reduce_max_sync(0xFFFFFFFFu, len);
+                for (int i = 0; i < maxlen; ++i) {
+                    const float px = (float)(xa + i);
+                    const float n1 = A1 - l02 * (px - b.x);
+                    const float n2 = A2 - l12 * (px - a.x);
+                    const float n3 = A3 - l22 * (px - a.z);
+                    const bool keep = (i < len) && !(n1 < thr1 || n2 < thr2 || n3 < thr3);   // else: certainly bar < 0
+                    mask |= (keep ? 1u : 0u) << ((xa + i - x0) & 31);
+                }
             }
             // pass 2 (exact): the surviving pixels of the warp's 32 rows are compacted into a per-warp queue, so that
             // every lane then evaluates one fragment per step whatever the spread of span lengths (the per-row loop this
             // replaces ran at 13 of 32 lanes).  A fragment finds its row through the slot its owner lane published.
-            const unsigned wid = threadIdx.x >> 5;
             S.u.st.slot[wid][lane][0] = make_float4(A1, A2, A3, l02);
             S.u.st.slot[wid][lane][1] = make_float4(l12, l22, __uint_as_float(tri),
                                                     __uint_as_float(o | ((unsigned)(y - y0) << 8) | (fdiv ? 65536u : 0u)));
@@ -781,9 +797,11 @@ __global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame 
     }
     __syncthreads();
 
-    // ---- deferred shading of the winners, staged so that every global store is a full 16-byte vector -------
+    // ---- deferred shading of the winners, staged so that colour / normals leave as whole rows ---------------
     const long long slab = (long long)view * F.slabPixels;
-    const bool vec = clear && (tw == TW) && ((F.W & 3) == 0);
+    const bool tma = clear && M.use != 0u;                                  // colour / normal rows leave through TMA boxes
+    const bool vec = clear && !tma && (tw == TW) && ((F.W & 3) == 0);       // ... or as 16-byte vector stores
+    const bool stage = tma || vec;
     const float bg = background_color(F);
     for (int p = threadIdx.x; p < TH * TW; p += NT) {
         const int yy = p / TW, xx = p % TW;
@@ -792,7 +810,7 @@ __global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame 
         float z = Z_INIT, c[3] = {bg, bg, bg}, nn[3] = {0.f, 0.f, 0.f};
         bool write = clear;
         const long long pix = slab + (long long)(yl0 + yy) * F.W + x0 + xx;
-        if (key != KEY_EMPTY && !(F.flags & 0x20000u)) {
+        if (key != KEY_EMPTY) {
             const unsigned tri = ~(unsigned)(key & 0xFFFFFFFFull);
             const long long ridx = (long long)view * F.T + tri;
             float fz, fc[3], fn[3];
@@ -804,7 +822,7 @@ __global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame 
                 }
             }
         }
-        if (vec) {
+        if (stage) {
             S.u.out.col[p * 3] = c[0]; S.u.out.col[p * 3 + 1] = c[1]; S.u.out.col[p * 3 + 2] = c[2];
             S.u.out.nrm[p * 3] = nn[0]; S.u.out.nrm[p * 3 + 1] = nn[1]; S.u.out.nrm[p * 3 + 2] = nn[2];
             if (F.z) F.z[pix] = z;
@@ -819,7 +837,18 @@ __global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame 
             o[0] = to_u8(c[0]); o[1] = to_u8(c[1]); o[2] = to_u8(c[2]);
         }
     }
-    if (vec) {
+    if (tma) {
+        fence_async_smem();
+        __syncthreads();
+        if (lane == 0) {   // warp w: array w/4 (colour, normals), row block w%4
+            const int r = (int)(wid & 3u) * BOX_ROWS;
+            if (r < th) {
+                if (wid < 4) { if (M.use & CRB_BUF_COLOR) tma_store_box(&M.c, S.u.out.col + r * TW * 3, x0 * 3, yl0 + r, view); }
+                else if (M.use & CRB_BUF_NORMALS) tma_store_box(&M.n, S.u.out.nrm + r * TW * 3, x0 * 3, yl0 + r, view);
+            }
+            tma_commit();
+        }
+    } else if (vec) {
         __syncthreads();
         const int q = threadIdx.x & 7;
         for (int r = threadIdx.x >> 3; r < th; r += NT / 8) {
@@ -836,7 +865,71 @@ __global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame 
             }
         }
     }
+}
+
+// One CTA per busy tile when the grid is large enough (it is sized from the busy-tile count the host last saw, see
+// run_tiled), a strided walk otherwise.  The fused clear of the empty tiles (70 % of a T-Rex frame, pure stores) is
+// spread over the whole grid and issued FIRST: with TMA it costs a dozen instructions per tile and drains while the CTA
+// rasterizes its busy tile -- memory-bound and issue-bound work overlap.
+#ifndef CRB_RASTER_MIN_CTAS
+#define CRB_RASTER_MIN_CTAS 5
+#endif
+__global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame F, const __grid_constant__ TMaps M)
+{
+    __shared__ TileSmem S;
+    const unsigned long long pairs = F.total[0];
+    const unsigned nb = (unsigned)F.total[2], ne = (unsigned)F.total[3];
+    if (pairs > (unsigned long long)F.pairCap) {   // frame skipped; the host is told via crb_status
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(F.total + 1, pairs);
+        return;
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && F.hstats)
+        *reinterpret_cast<volatile unsigned long long *>(F.hstats) = ((unsigned long long)(nb + ne) << 32) | nb;
+    const bool clear = (F.flags & CRB_CLEAR_FIRST) != 0;
+    const unsigned G = gridDim.x;
+    unsigned cta = blockIdx.x;
+    unsigned tpk = 0, n = 0, off = 0;
+    if (cta < nb) {                                   // first busy tile: its bookkeeping loads fly during the clears
+        tpk = F.busy[cta];
+        const unsigned tIdx = (tpk >> 22) * (unsigned)F.nTiles + ((tpk >> 11) & 2047u) * (unsigned)F.tilesX + (tpk & 2047u);
+        n = F.tcount[tIdx]; off = F.offset[tIdx];
+    }
+    if (clear && blockIdx.x < ne) {
+        const bool tma = M.use != 0u;
+        const unsigned rest = ((F.z ? CRB_BUF_Z : 0u) | (F.color ? CRB_BUF_COLOR : 0u) | (F.normals ? CRB_BUF_NORMALS : 0u)) & ~M.use;   // arrays the maps do not cover
+        if (tma) {
+            const float bg = background_color(F);
+            for (int i = threadIdx.x; i < BOX_ROWS * TW * 3; i += NT) {
+                S.cpat[i] = bg; S.npat[i] = 0.0f;
+                if (i < BOX_ROWS * TW) S.zpat[i] = Z_INIT;
+            }
+            fence_async_smem();
+            __syncthreads();
+        }
+        for (unsigned e = blockIdx.x; e < ne; e += G) {
+            const unsigned t = F.empty[e];
+            const int view = (int)(t >> 22), ty = (int)((t >> 11) & 2047u), tx = (int)(t & 2047u);
+            const int th = min(TH, F.row1 - F.row0 - ty * TH);
+            if (tma) {
+                tma_clear_tile(F, M, S, view, tx * TW, ty * TH, th);
+                if (rest || F.color_u8) write_clear_tile(F, M.use, view, tx * TW, ty * TH, min(TW, F.W - tx * TW), th);
+            } else {
+                write_clear_tile(F, 0u, view, tx * TW, ty * TH, min(TW, F.W - tx * TW), th);
+            }
+        }
+        if (tma && (threadIdx.x & 31) == 0) tma_commit();
+    }
+    for (; cta < nb; cta += G) {
+        if (cta != blockIdx.x) {
+            if ((threadIdx.x & 31) == 0) tma_wait_read();   // the previous tile's rows have left shared memory
+            __syncthreads();
+            tpk = F.busy[cta];
+            const unsigned tIdx = (tpk >> 22) * (unsigned)F.nTiles + ((tpk >> 11) & 2047u) * (unsigned)F.tilesX + (tpk & 2047u);
+            n = F.tcount[tIdx]; off = F.offset[tIdx];
+        }
+        raster_tile(F, M, S, clear, (int)(tpk >> 22), (int)(tpk & 2047u), (int)((tpk >> 11) & 2047u), n, off);
+    }
+    if ((threadIdx.x & 31) == 0) tma_wait_read();           // shared memory must outlive the bulk reads
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1046,7 +1139,11 @@ struct crb_filler {
     long long keybuf_pixels;
     long long launches;
     // optional timing of the dominant kernel (k_raster) with CUDA events on the launching stream
-    int raster_ctas;       // persistent grid of k_raster: SM count x resident CTAs per SM
+    int raster_ctas;       // experiments: fixed k_raster grid (0 = automatic)
+    int sm_count;
+    int use_tma;           // output rows leave through TMA boxes where the layout allows (CRB_NO_TMA=1 disables)
+    unsigned long long *hstats;      // pinned + mapped: busy-tile statistics of the most recent k_raster launch
+    unsigned long long *hstats_dev;
     bool prof_on;
     int prof_n;
     cudaEvent_t *prof_ev;  // 2 * PROF_MAX events, created on first use
@@ -1138,6 +1235,7 @@ void fill_frame(const crb_filler *f, Frame *F)
     F->busy = f->busy; F->empty = f->empty;
     F->ls0 = f->ls0; F->ls1 = f->ls1; F->ls2 = f->ls2; F->ls3 = f->ls3; F->ls4 = f->ls4;
     F->total = f->total;
+    F->hstats = f->hstats_dev;
     F->pairCap = f->pairCap;
     F->slabPixels = (long long)(f->row1 - f->row0) * f->w;
 }
@@ -1148,6 +1246,50 @@ int launch_check(crb_filler *f, const char *name)
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(CRB_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e));
     return CRB_OK;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// [views][rows][W*comps] float32, boxes of BOX_ROWS x (TW*comps).  Returns false if the layout cannot be described.
+bool encode_map(CUtensorMap *m, float *base, int comps, const Frame &F)
+{
+    EncodeTiledFn fn = encode_tiled_fn();
+    const long long rows = F.row1 - F.row0;
+    if (!fn || !base || rows <= 0 || (reinterpret_cast<uintptr_t>(base) & 15u)) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)F.W * comps, (cuuint64_t)rows, (cuuint64_t)F.nViews};
+    const cuuint64_t strides[2] = {(cuuint64_t)F.W * comps * 4, (cuuint64_t)rows * F.W * comps * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)(TW * comps), (cuuint32_t)BOX_ROWS, 1u};
+    const cuuint32_t es[3] = {1u, 1u, 1u};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// All or nothing: every non-NULL output array gets a map, or the launch uses plain stores.
+unsigned encode_maps(TMaps *M, const Frame &F)
+{
+    unsigned use = 0;
+    if (F.z) { if (!encode_map(&M->z, F.z, 1, F)) return 0u; use |= CRB_BUF_Z; }
+    if (F.color) { if (!encode_map(&M->c, F.color, 3, F)) return 0u; use |= CRB_BUF_COLOR; }
+    if (F.normals) { if (!encode_map(&M->n, F.normals, 3, F)) return 0u; use |= CRB_BUF_NORMALS; }
+    return use;
 }
 
 // project/setup/count -> alloc -> fill -> raster+shade for up to maxViews views
@@ -1172,8 +1314,26 @@ int run_tiled(crb_filler *f, Frame &F, cudaStream_t st)
     const bool prof = f->prof_on && f->prof_n < PROF_MAX;
     if (prof) CU(cudaEventRecord(f->prof_ev[2 * f->prof_n], st));
     const long long nAllTiles = (long long)F.nTiles * F.nViews;
-    const unsigned gR = (unsigned)((f->raster_ctas <= 0 || nAllTiles < f->raster_ctas) ? nAllTiles : f->raster_ctas);
-    k_raster<<<gR, NT, 0, st>>>(F);
+    // Grid: one CTA per busy tile.  The busy count is only known on the device, so the grid is sized from the busy
+    // FRACTION the previous launch posted (+12 % and a floor of one wave); k_raster walks with stride gridDim when the
+    // estimate was low, and an all-tiles grid is used until a first launch has reported.
+    long long gR = nAllTiles;
+    if (f->raster_ctas > 0) gR = f->raster_ctas;
+    else if (f->hstats && f->raster_ctas == 0) {
+        const unsigned long long hs = *reinterpret_cast<volatile unsigned long long *>(f->hstats);
+        const double tiles = (double)(hs >> 32), busy = (double)(hs & 0xFFFFFFFFull);
+        if (tiles > 0) {
+            gR = (long long)(busy / tiles * 1.125 * (double)nAllTiles) + 64;
+            const long long wave = (long long)f->sm_count * CRB_RASTER_MIN_CTAS;
+            if (gR < wave) gR = wave;
+        }
+    }
+    if (gR > nAllTiles) gR = nAllTiles;
+    if (gR < 1) gR = 1;
+    TMaps M;
+    memset(&M, 0, sizeof(M));
+    if (f->use_tma && (F.flags & CRB_CLEAR_FIRST) && !(F.W & 3)) M.use = encode_maps(&M, F);
+    k_raster<<<(unsigned)gR, NT, 0, st>>>(F, M);
     if ((rc = launch_check(f, "k_raster"))) return rc;
     if (prof) {
         CU(cudaEventRecord(f->prof_ev[2 * f->prof_n + 1], st));
@@ -1276,14 +1436,23 @@ int crb_create(int h, int w, float fov, float z_near, float z_far, int device, c
     f->fov = fov; f->z_near = z_near; f->z_far = z_far;
     f->proj = P;
     {
-        cudaDeviceProp prop;
-        int per_sm = 0;
+        int sms = 0;
         CU(cudaSetDevice(device));
-        CU(cudaGetDeviceProperties(&prop, device));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_raster, NT, 0));
-        f->raster_ctas = 0;   // 0 = one CTA per (view, tile): measured faster than a persistent walk (stores stream at 7 TB/s)
-        (void)prop; (void)per_sm;
-        if (const char *e = getenv("CRB_RASTER_CTAS")) f->raster_ctas = atoi(e);   // experiments: 0 = one CTA per tile
+        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        f->sm_count = sms > 0 ? sms : 148;
+        f->raster_ctas = 0;
+        if (const char *e = getenv("CRB_RASTER_CTAS")) f->raster_ctas = atoi(e);   // experiments: >0 fixed grid, <0 one CTA per tile
+        f->use_tma = 1;
+        if (const char *e = getenv("CRB_NO_TMA")) f->use_tma = atoi(e) ? 0 : 1;
+        void *hp = nullptr, *dp = nullptr;
+        if (cudaHostAlloc(&hp, 64, cudaHostAllocMapped) == cudaSuccess && cudaHostGetDevicePointer(&dp, hp, 0) == cudaSuccess) {
+            memset(hp, 0, 64);
+            f->hstats = (unsigned long long *)hp;
+            f->hstats_dev = (unsigned long long *)dp;
+        } else {
+            if (hp) cudaFreeHost(hp);
+            cudaGetLastError();
+        }
     }
     *out = f;
     return CRB_OK;
@@ -1296,6 +1465,7 @@ void crb_destroy(crb_filler *f)
     if (f->own_buffers) { cudaFree(f->z); cudaFree(f->color); cudaFree(f->normals); }
     if (f->own_ws) cudaFree(f->ws);
     if (f->keybuf) cudaFree(f->keybuf);
+    if (f->hstats) cudaFreeHost(f->hstats);
     if (f->prof_ev) {
         for (int i = 0; i < 2 * PROF_MAX; ++i) cudaEventDestroy(f->prof_ev[i]);
         delete[] f->prof_ev;
@@ -1436,7 +1606,7 @@ int crb_render_host(crb_filler *f, const float *v, const float *c, const float *
     if (rc) return rc;
     rc = crb_download(f, download_mask, z_out, color_out, normals_out, stream);
     if (rc) return rc;
-    CU(cudaStreamSynchronize(st));
+    if (!(flags & CRB_NO_SYNC)) CU(cudaStreamSynchronize(st));
     return CRB_OK;
 }
 
@@ -1461,7 +1631,7 @@ int crb_render_views(crb_filler *f, const float *v, const float *c, const float 
         Frame F;
         fill_frame(f, &F);
         F.T = T; F.nViews = (n_views - v0 < f->maxViews) ? n_views - v0 : f->maxViews;
-        F.flags = (flags & (CRB_GURO | 0xFFFF0000u)) | CRB_CLEAR_FIRST;   // high bits: undocumented experiment switches
+        F.flags = (flags & CRB_GURO) | CRB_CLEAR_FIRST;
         F.v = v; F.c = c; F.n = n;
         F.views = views + (size_t)v0 * 16;
         F.z = z_out ? z_out + (size_t)v0 * slab : nullptr;
@@ -1552,6 +1722,14 @@ int crb_status(crb_filler *f, int64_t *pairs_needed, int64_t *pair_capacity, voi
                     f->pairCap);
     }
     if (pairs_needed) *pairs_needed = (int64_t)t[0];
+    return CRB_OK;
+}
+
+int crb_sync(crb_filler *f, void *stream)
+{
+    if (check_filler(f)) return CRB_ERR_INVALID;
+    CU(cudaSetDevice(f->device));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
     return CRB_OK;
 }
 

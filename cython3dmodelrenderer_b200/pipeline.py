@@ -1,0 +1,113 @@
+"""Frame pipelining for host-resident callers.
+
+One `render_model` through the host-buffer C-ABI call (crb_render_host) is H2D of the three [T,3,3] arrays, the
+render, and D2H of the requested buffers -- at 1024^2 the D2H of z + colour + normals (29.4 MB) is ~90 % of the wall
+time and the GPU idles meanwhile.  `HostFramePipeline` keeps `depth` fillers (each with its own CUDA stream, device
+buffers, workspace and pinned host outputs) and submits frames round-robin with CRB_NO_SYNC, so frame k+1's upload
+and render overlap frame k's download; every frame still gets fresh-filler semantics (pyx:65-67) and the same bits.
+
+The reference has no equivalent (a new filler per frame, synchronous, run.py:21-25); this is the throughput-oriented
+way to drive the same path from host memory.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+from .pixel_buffer_filler import AdvancedPixelBufferFiller, _check_tri_array
+
+_BITS = {"z": _lib.CRB_BUF_Z, "color": _lib.CRB_BUF_COLOR, "normals": _lib.CRB_BUF_NORMALS}
+
+
+class _Slot:
+    pass
+
+
+class HostFramePipeline:
+    def __init__(self, h, w, fov=90.0, z_near=0.1, z_far=1000.0, depth=2, device=None, want=("z", "color", "normals")):
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        self.want = tuple(want)
+        self.mask = 0
+        for name in self.want:
+            self.mask |= _BITS[name]
+        self.slots = []
+        for _ in range(depth):
+            s = _Slot()
+            s.filler = AdvancedPixelBufferFiller(h, w, fov=fov, z_near=z_near, z_far=z_far, device=device)
+            torch = s.filler._torch
+            s.stream = torch.cuda.Stream(device=s.filler._dev)
+            s.out = {name: s.filler._mirror(name) for name in self.want}      # pinned host tensors
+            s.out_np = {name: s.filler._host_np[name] for name in self.want}
+            s.stage = None
+            s.busy = False
+            self.slots.append(s)
+        self._torch = torch
+        self._next = 0
+        self._L = self.slots[0].filler._L
+
+    def _ptr(self, s, name):
+        return s.out[name].data_ptr() if name in s.out else None
+
+    def submit(self, v, c, n):
+        """Queues one fresh-filler frame; returns the slot index to pass to `result`.  v, c, n: [T,3,3] float32, either
+        pinned torch CPU tensors (used in place -- do not modify them before `result`) or NumPy arrays (copied into
+        the slot's pinned staging first)."""
+        torch = self._torch
+        i = self._next
+        self._next = (i + 1) % len(self.slots)
+        s = self.slots[i]
+        if s.busy:       # its host buffers are about to be reused
+            self.result(i)
+        if all(isinstance(a, torch.Tensor) for a in (v, c, n)):
+            for a in (v, c, n):
+                if a.is_cuda or a.dtype != torch.float32 or a.dim() != 3 or tuple(a.shape[1:]) != (3, 3) or not a.is_contiguous():
+                    raise ValueError("tensor inputs must be contiguous CPU float32 [T,3,3]")
+            T = int(v.shape[0])
+            pv, pc, pn = v.data_ptr(), c.data_ptr(), n.data_ptr()
+        else:
+            v = _check_tri_array(v, "vertices"); c = _check_tri_array(c, "colors"); n = _check_tri_array(n, "normals")
+            T = int(v.shape[0])
+            if s.stage is None or s.stage.shape[1] < T:
+                s.stage = torch.empty((3, max(T, 1), 3, 3), dtype=torch.float32, pin_memory=True)
+                s.stage_np = s.stage.numpy()
+            s.stage_np[0, :T] = v; s.stage_np[1, :T] = c; s.stage_np[2, :T] = n
+            pv, pc, pn = s.stage[0].data_ptr(), s.stage[1].data_ptr(), s.stage[2].data_ptr()
+        s.filler._ensure_workspace(T)
+        s.args = (pv, pc, pn, T)
+        s.keep = (v, c, n)
+        self._launch(s)
+        s.busy = True
+        return i
+
+    def _launch(self, s):
+        pv, pc, pn, T = s.args
+        check(self._L.crb_render_host(s.filler._handle, pv, pc, pn, T, _lib.CRB_CLEAR_FIRST | _lib.CRB_NO_SYNC, self.mask,
+                                      self._ptr(s, "z"), self._ptr(s, "color"), self._ptr(s, "normals"),
+                                      ctypes.c_void_p(s.stream.cuda_stream)))
+
+    def result(self, i):
+        """Waits for slot i's frame; returns {name: numpy array} (pinned memory, valid until the slot is resubmitted)."""
+        s = self.slots[i]
+        while s.busy:
+            need, cap = ctypes.c_int64(), ctypes.c_int64()
+            st = ctypes.c_void_p(s.stream.cuda_stream)
+            rc = self._L.crb_status(s.filler._handle, ctypes.byref(need), ctypes.byref(cap), st)   # synchronises the stream
+            if rc == _lib.CRB_ERR_OVERFLOW:     # the frame was skipped: enlarge the pair list and queue it again
+                f = s.filler
+                f._ensure_workspace(s.args[3], f._ws_views, int(need.value * 1.25) + 1024)
+                self._launch(s)
+                continue
+            check(rc)
+            s.busy = False
+            s.keep = None
+        return s.out_np
+
+    def drain(self):
+        for i in range(len(self.slots)):
+            self.result(i)
+
+    @property
+    def launch_count(self):
+        return sum(s.filler.launch_count for s in self.slots)

@@ -47,6 +47,8 @@ extern "C" {
 #define CRB_PATH_ATOMIC 2u     /* differential path: per-triangle raster with global 64-bit atomicMin + deferred
                                   shading (no binning).  Same results; kept for cross-checking the tiled path. */
 #define CRB_GURO 4u            /* N1: fuse GuroIllumination (guro_illumination.py:20-27) into the shading pass   */
+#define CRB_NO_SYNC 8u         /* crb_render_host only: return once the work is queued; crb_sync() before reading
+                                  the host outputs or reusing the host inputs (frame pipelining over several fillers) */
 
 /* which-buffer masks for crb_download / crb_render_host */
 #define CRB_BUF_Z 1u
@@ -109,10 +111,13 @@ int crb_render(crb_filler *f, const float *v, const float *c, const float *n, in
                void *stream);
 
 /* Same, all pointers HOST memory (pinned recommended): H2D of the three arrays, render, D2H of the buffers named in
- * `download_mask` (CRB_BUF_*; NULL pointers allowed for buffers not requested), then a stream synchronize.  This is
- * the call that replaces the body of render_model for a host-resident caller. */
+ * `download_mask` (CRB_BUF_*; NULL pointers allowed for buffers not requested), then a stream synchronize (unless
+ * CRB_NO_SYNC).  This is the call that replaces the body of render_model for a host-resident caller. */
 int crb_render_host(crb_filler *f, const float *v, const float *c, const float *n, int64_t T, unsigned flags,
                     unsigned download_mask, float *z_out, float *color_out, float *normals_out, void *stream);
+
+/* Waits for everything queued on `stream` (pairs with CRB_NO_SYNC). */
+int crb_sync(crb_filler *f, void *stream);
 
 /* Batched views (config C5; the reference has no camera stage -- views are made by mutating the model on the host,
  * crender/cy/data_structures/model.py:238-256).  views: DEVICE [n_views,16] f32 = {R (9, row-major), p (3), q (3), pad}:

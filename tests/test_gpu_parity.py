@@ -358,3 +358,79 @@ def test_full_size_sphere_properties(Filler):
         assert torch.equal(cb.view(torch.int32), c[r0:r1].view(torch.int32))
         assert torch.equal(nb.view(torch.int32), n[r0:r1].view(torch.int32))
         del b
+
+
+@pytest.mark.parametrize("mode", ["tma", "plain", "tiny_grid", "tma_tiny_grid"])
+@pytest.mark.parametrize("size", [(96, 128), (100, 76), (50, 36), (257, 388), (64, 30)])
+def test_fused_clear_store_paths(mode, size, Filler, O, monkeypatch):
+    """clear()+render takes the store path the layout allows: TMA boxes (rows that are 16-byte multiples), clipped by
+    the hardware on partial tiles, or plain stores (W % 4 != 0, CRB_NO_TMA=1); a grid smaller than the number of busy
+    tiles makes k_raster walk several tiles per CTA (CRB_RASTER_CTAS).  All of them must give the oracle's bits."""
+    monkeypatch.setenv("CRB_NO_TMA", "1" if mode in ("plain", "tiny_grid") else "0")
+    if "tiny_grid" in mode:
+        monkeypatch.setenv("CRB_RASTER_CTAS", "3")
+    h, w = size
+    for seed in (3, 5, 8):
+        m = random_scene(seed, T=300)
+        g, o = Filler(h, w, fov=60.0), O.OracleFiller(h, w, fov=60.0)
+        g.render_model(random_scene(seed + 50, T=40))      # stale contents the fused clear must wipe
+        g.clear()
+        for _ in range(2):                                 # second frame: grid sized from the first frame's statistics
+            g.clear()
+            g.render_model(m)
+        o.render_model(m)
+        assert_same(buffers(g), buffers(o), f"{mode} {h}x{w} seed {seed}")
+
+
+def test_batched_views_partial_outputs_tma(Filler, O, trex):
+    """render_views with only some of the three arrays requested (maps exist only for those)."""
+    import torch
+    from cython3dmodelrenderer_b200 import views as VW
+    h, w = 96, 160
+    dv, dc, dn = (torch.from_numpy(a).cuda() for a in
+                  (trex._vertices_by_triangles, trex._colors_by_triangles, trex._normals_by_triangles))
+    views = VW.orbit_views(8, first=1, count=3)
+    f = Filler(h, w, fov=45.0)
+    full = f.render_views(dv, dc, dn, views)
+    for want in (("z",), ("color",), ("normals", "z")):
+        part = f.render_views(dv, dc, dn, views, want=want)
+        assert set(part) == set(want)
+        for name in want:
+            assert torch.equal(part[name].view(torch.int32), full[name].view(torch.int32)), (want, name)
+    vk, nk = VW.transform_arrays_host(views[2], trex._vertices_by_triangles, trex._normals_by_triangles)
+    o = O.OracleFiller(h, w, fov=45.0)
+    o.render_arrays(vk, trex._colors_by_triangles, nk)
+    assert_same(tuple(full[k][2].cpu().numpy() for k in ("z", "color", "normals")), buffers(o), "view 2")
+
+
+def test_host_frame_pipeline_matches_oracle(O, trex):
+    """Pipelined host-buffer frames (crb_render_host + CRB_NO_SYNC over several fillers) give per frame the oracle's
+    fresh-filler result, in submission order, for NumPy and pinned-tensor inputs alike."""
+    import torch
+    from cython3dmodelrenderer_b200 import HostFramePipeline, views as VW
+    h, w = 192, 256
+    pipe = HostFramePipeline(h, w, fov=45.0, depth=3)
+    views = VW.orbit_views(7)
+    frames = [VW.transform_arrays_host(views[k], trex._vertices_by_triangles, trex._normals_by_triangles) for k in range(7)]
+    want = []
+    for vk, nk in frames:
+        o = O.OracleFiller(h, w, fov=45.0)
+        o.render_arrays(vk, trex._colors_by_triangles, nk)
+        want.append(buffers(o))
+    pending = []
+    got = [None] * 7
+    for k, (vk, nk) in enumerate(frames):
+        if k % 2:
+            args = [torch.from_numpy(a).pin_memory() for a in (vk, trex._colors_by_triangles, nk)]
+        else:
+            args = [vk, trex._colors_by_triangles, nk]
+        pending.append((k, pipe.submit(*args), args))
+        if len(pending) == 3:
+            kk, slot, _ = pending.pop(0)
+            r = pipe.result(slot)
+            got[kk] = (r["z"].copy(), r["color"].copy(), r["normals"].copy())
+    for kk, slot, _ in pending:
+        r = pipe.result(slot)
+        got[kk] = (r["z"].copy(), r["color"].copy(), r["normals"].copy())
+    for k in range(7):
+        assert_same(got[k], want[k], f"pipelined frame {k}")
