@@ -39,6 +39,8 @@ namespace {
 constexpr int TW = 32;          // tile width in pixels  (one 128-byte line of z, three of colour / normals)
 constexpr int TH = 32;          // tile height in pixels
 constexpr int NT = 256;         // threads per CTA in every kernel
+constexpr unsigned FLAG_DBG_NOCLEAR = 0x10000u, FLAG_DBG_NOSHADE = 0x20000u, FLAG_DBG_NOROWS = 0x40000u, FLAG_DBG_NOOUT = 0x80000u;  // ablation switches (CRB_DEBUG_SKIP)
+constexpr unsigned FLAG_OUT_TMA = 0x100u;   // internal Frame.flags bit: shaded colour / normal rows leave through TMA boxes
 constexpr int CH = 128;         // triangles staged in shared memory per pass of the tile rasterizer
 constexpr int FQ = 256;          // fragments a warp compacts per round (8 per row)
 constexpr int KEY_STRIDE = TW + 1;  // padded key row: rows of one column land in different banks
@@ -54,11 +56,13 @@ static_assert(CH <= NT && CH <= 256, "one staged triangle per thread, 8-bit owne
 static_assert(TW == 32, "a tile row is one warp wide");
 
 // Per-(view,triangle) records written by k_setup.
-//   R_A (x0 y0 x1 y1)  R_B (x2 y2 z0 z1)  R_C (z2 l03 l13 l23)   screen-space vertices + the denominators of mu:14,17,20
-//   R_D (1/l03 1/l13 1/l23 flags)   correctly rounded reciprocals (rcp.rn) + FL_* bits
-//   R_E (bbox x, bbox y, n2.z, -)   packed half-open pixel rectangle (0,0 = not drawn)
-//   R_N0 (n0.xyz n1.x)  R_N1 (n1.yz n2.xy)   vertex normals in view space
-enum Rec { R_A = 0, R_B, R_C, R_D, R_E, R_N0, R_N1, NREC };
+//   shade record: ONE 128-byte line = 8 float4, everything the shading pass needs for a pixel (a single L2 round trip,
+//   prefetched into L1 when a tile stages the triangle):
+//     S_A (x0 y0 x1 y1)  S_B (x2 y2 z0 z1)  S_C (z2 l03 l13 l23)      screen-space vertices + denominators of mu:14,17,20
+//     S_N0 (n0.xyz n1.x)  S_N1 (n1.yz n2.xy)  S_X (n2.z c0.xyz)  S_C1 (c1.xyz c2.x)  S_C2 (c2.yz flags -)
+//   recD (1/l03 1/l13 1/l23 flags)   correctly rounded reciprocals (rcp.rn) + FL_* bits, for k_fill
+//   recE (bbox x, bbox y, -, -)      packed half-open pixel rectangle (0,0 = not drawn)
+enum ShadeRec { S_A = 0, S_B, S_C, S_N0, S_N1, S_X, S_C1, S_C2, SREC };
 
 struct ProjC {
     float p[16];   // row-major 4x4, proj_mat of pyx:85-90
@@ -77,13 +81,12 @@ struct Frame {
     const float *v, *c, *n;     // [T,3,3]
     const float *views;         // [nViews,16] or nullptr
     // scratch
-    // [nViews*T] per-(view,triangle) records, SoA of float4 (see enum Rec)
-    float4 *rec[NREC];
-    float4 *crec0, *crec1;      // [T] vertex colours packed: (c0.xyz c1.x) (c1.yz c2.xy); c2.z rides in crec2
-    float *crec2;               // [T]
+    // per-(view,triangle) records (see enum ShadeRec)
+    float4 *shrec;              // [nViews*T*8] shade records
+    float4 *recD, *recE;        // [nViews*T]
     unsigned *count;            // [nViews*nTiles] triangles per tile, accumulated by k_setup, returned to zero by k_alloc
-    unsigned *tcount;           // [nViews*nTiles] the frame's final per-tile counts (read-only for k_fill / k_raster)
-    unsigned *busy, *empty;     // [nViews*nTiles] compacted (view,tile) indices with / without triangles; sizes in total[2], total[3]
+    uint4 *busy;                // [nViews*nTiles] compacted busy tiles: (view:10 ty:11 tx:11, triangles, list offset, -); count in total[2]
+    unsigned *empty;            // [nViews*nTiles] compacted tiles without triangles (same packing); count in total[3]
     unsigned *offset;           // [nViews*nTiles] start of the tile's list
     unsigned *cursor;           // [nViews*nTiles] fill cursor
     float4 *ls0, *ls1, *ls2;    // [pairCap] staged triangle setups, tile by tile: (x0 y0 x1 y1) (x2 y2 z0 z1) (z2 d1 d2 d3)
@@ -179,7 +182,8 @@ __device__ __forceinline__ void barycentric(const Tri9 &t, float px, float py, f
 
 __device__ __forceinline__ Tri9 load_tri9(const Frame &F, long long ridx)
 {
-    const float4 a = F.rec[R_A][ridx], b = F.rec[R_B][ridx], c = F.rec[R_C][ridx];
+    const float4 *R = F.shrec + ridx * SREC;
+    const float4 a = R[S_A], b = R[S_B], c = R[S_C];
     Tri9 t;
     t.x0 = a.x; t.y0 = a.y; t.x1 = a.z; t.y1 = a.w;
     t.x2 = b.x; t.y2 = b.y; t.z0 = b.z; t.z1 = b.w;
@@ -216,34 +220,26 @@ __device__ __forceinline__ bool fdiv_ok(float n1, float n2, float n3)
 
 // pyx:215-242 for the pixel's winning triangle: barycentrics (mu:5-34), depth, colour, normal (left-associated sums).
 // Returns false if the fragment would not have been drawn (some barycentric < 0, NaN depth) -- cannot happen for a key
-// that won, kept as a guard.
-__device__ __forceinline__ bool shade_fragment(const Frame &F, long long tri, long long ridx, float px, float py, float &z,
-                                               float c[3], float n[3])
+// that won, kept as a guard.  All operands come from the triangle's 128-byte shade record.
+__device__ __forceinline__ bool shade_fragment(const Frame &F, long long ridx, float px, float py, float &z, float c[3], float n[3])
 {
-    const float4 A = F.rec[R_A][ridx], B = F.rec[R_B][ridx], C = F.rec[R_C][ridx], D = F.rec[R_D][ridx];
+    const float4 *R = F.shrec + ridx * SREC;
+    const float4 A = R[S_A], B = R[S_B], C = R[S_C];
     // x0=A.x y0=A.y x1=A.z y1=A.w x2=B.x y2=B.y z0=B.z z1=B.w z2=C.x  l03=C.y l13=C.z l23=C.w
     const float n1 = (A.z - B.x) * (py - B.y) - (A.w - B.y) * (px - B.x);
     const float n2 = (B.x - A.x) * (py - A.y) - (B.y - A.y) * (px - A.x);
     const float n3 = (A.x - A.z) * (py - A.w) - (A.y - A.w) * (px - A.z);
-    float b1, b2, b3;
-    if ((__float_as_uint(D.w) & FL_FDIV) && fdiv_ok(n1, n2, n3)) {
-        b1 = div_rn_by(n1, C.y, D.x); b2 = div_rn_by(n2, C.z, D.y); b3 = div_rn_by(n3, C.w, D.z);
-    } else {
-        b1 = n1 / C.y; b2 = n2 / C.z; b3 = n3 / C.w;
-    }
+    const float b1 = n1 / C.y, b2 = n2 / C.z, b3 = n3 / C.w;
     if (b1 < 0.0f || b2 < 0.0f || b3 < 0.0f) return false;
     z = (B.z * b1 + B.w * b2) + C.x * b3;
     if (z != z) return false;
-    const float4 N0 = F.rec[R_N0][ridx], N1 = F.rec[R_N1][ridx];
-    const float n2z = F.rec[R_E][ridx].z;
+    const float4 N0 = R[S_N0], N1 = R[S_N1], X = R[S_X], C1 = R[S_C1], C2 = R[S_C2];
     n[0] = (N0.x * b1 + N0.w * b2) + N1.z * b3;
     n[1] = (N0.y * b1 + N1.x * b2) + N1.w * b3;
-    n[2] = (N0.z * b1 + N1.y * b2) + n2z * b3;
-    const float4 C0 = F.crec0[tri], C1 = F.crec1[tri];
-    const float c2z = F.crec2[tri];
-    c[0] = (C0.x * b1 + C0.w * b2) + C1.z * b3;
-    c[1] = (C0.y * b1 + C1.x * b2) + C1.w * b3;
-    c[2] = (C0.z * b1 + C1.y * b2) + c2z * b3;
+    n[2] = (N0.z * b1 + N1.y * b2) + X.x * b3;
+    c[0] = (X.y * b1 + C1.x * b2) + C1.w * b3;
+    c[1] = (X.z * b1 + C1.y * b2) + C2.x * b3;
+    c[2] = (X.w * b1 + C1.z * b2) + C2.y * b3;
     if (F.flags & CRB_GURO) {  // guro_illumination.py:23-27 (float32, left-to-right sums)
         const float dot = (n[0] * F.light[0] + n[1] * F.light[1]) + n[2] * F.light[2];
         const float nrm = sqrtf((n[0] * n[0] + n[1] * n[1]) + n[2] * n[2]);
@@ -312,19 +308,12 @@ __global__ void __launch_bounds__(NT) k_setup(const Frame F)
     }
     stage_floats(F.v, first * 9, cnt * 9, sv);
     stage_floats(F.n, first * 9, cnt * 9, sn);
-    if (view == 0) stage_floats(F.c, first * 9, cnt * 9, sc);
+    stage_floats(F.c, first * 9, cnt * 9, sc);
     if (F.views && threadIdx.x < 16) sM[threadIdx.x] = F.views[view * 16 + threadIdx.x];
     __syncthreads();
     if (threadIdx.x >= cnt) return;
     const long long tri = first + threadIdx.x;
     const long long ridx = (long long)view * F.T + tri;
-    if (view == 0) {   // colours do not depend on the view: packed once per launch for the shading pass
-        const float *q = sc + threadIdx.x * 9;
-        F.crec0[tri] = make_float4(q[0], q[1], q[2], q[3]);
-        F.crec1[tri] = make_float4(q[4], q[5], q[6], q[7]);
-        F.crec2[tri] = q[8];
-    }
-
     float x[3], y[3], z[3], nx[3], ny[3], nz[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -362,7 +351,7 @@ __global__ void __launch_bounds__(NT) k_setup(const Frame F)
     const unsigned bx = drawn ? ((unsigned)xl | ((unsigned)xr << 16)) : 0u;
     const unsigned by = drawn ? ((unsigned)yt | ((unsigned)yb << 16)) : 0u;
 
-    F.rec[R_E][ridx] = make_float4(__uint_as_float(bx), __uint_as_float(by), nz[2], 0.0f);
+    F.recE[ridx] = make_float4(__uint_as_float(bx), __uint_as_float(by), 0.0f, 0.0f);
     if (!drawn) return;
     // denominators of mu:12-21 -- pure functions of the triangle, hoisted out of the per-pixel code (same bits)
     const float l03 = (x[1] - x[2]) * (y[0] - y[2]) - (y[1] - y[2]) * (x[0] - x[2]);
@@ -386,12 +375,17 @@ __global__ void __launch_bounds__(NT) k_setup(const Frame F)
                            (y[1] - y[1] == 0.f) && (y[2] - y[2] == 0.f);
     if ((fl & (7u * FL_REJ)) == 7u * FL_REJ && finite_xy && cmax <= SPAN_COORD_MAX) fl |= FL_SPAN;
     if (fminf(fminf(a03, a13), a23) >= FDIV_LO && fmaxf(fmaxf(a03, a13), a23) <= FDIV_HI) fl |= FL_FDIV;
-    F.rec[R_A][ridx] = make_float4(x[0], y[0], x[1], y[1]);
-    F.rec[R_B][ridx] = make_float4(x[2], y[2], z[0], z[1]);
-    F.rec[R_C][ridx] = make_float4(z[2], l03, l13, l23);
-    F.rec[R_D][ridx] = make_float4(__frcp_rn(l03), __frcp_rn(l13), __frcp_rn(l23), __uint_as_float(fl));
-    F.rec[R_N0][ridx] = make_float4(nx[0], ny[0], nz[0], nx[1]);
-    F.rec[R_N1][ridx] = make_float4(ny[1], nz[1], nx[2], ny[2]);
+    float4 *R = F.shrec + ridx * SREC;
+    const float *q = sc + threadIdx.x * 9;
+    R[S_A] = make_float4(x[0], y[0], x[1], y[1]);
+    R[S_B] = make_float4(x[2], y[2], z[0], z[1]);
+    R[S_C] = make_float4(z[2], l03, l13, l23);
+    R[S_N0] = make_float4(nx[0], ny[0], nz[0], nx[1]);
+    R[S_N1] = make_float4(ny[1], nz[1], nx[2], ny[2]);
+    R[S_X] = make_float4(nz[2], q[0], q[1], q[2]);
+    R[S_C1] = make_float4(q[3], q[4], q[5], q[6]);
+    R[S_C2] = make_float4(q[7], q[8], __uint_as_float(fl), 0.0f);
+    F.recD[ridx] = make_float4(__frcp_rn(l03), __frcp_rn(l13), __frcp_rn(l23), __uint_as_float(fl));
     if (F.flags & CRB_PATH_ATOMIC) return;
 
     int tx0, tx1, ty0, ty1;
@@ -448,13 +442,13 @@ __global__ void __launch_bounds__(NT) k_alloc(const Frame F)
     __syncthreads();
     if (i < nAll) {
         const unsigned long long o = block_base + excl;
-        F.offset[i] = (unsigned)(o > 0xFFFFFFFFull ? 0xFFFFFFFFull : o);
+        const unsigned o32 = (unsigned)(o > 0xFFFFFFFFull ? 0xFFFFFFFFull : o);
+        F.offset[i] = o32;
         F.cursor[i] = 0u;
-        F.tcount[i] = c;
         F.count[i] = 0u;   // self-cleaning: the next frame's k_setup starts from zero
         const unsigned vw = (unsigned)(i / F.nTiles), tl = (unsigned)(i % F.nTiles);
         const unsigned packed = (vw << 22) | ((tl / (unsigned)F.tilesX) << 11) | (tl % (unsigned)F.tilesX);   // view:10 ty:11 tx:11
-        if (c) F.busy[busy_base + brank] = packed;
+        if (c) F.busy[busy_base + brank] = make_uint4(packed, c, o32, 0u);
         else F.empty[empty_base + (threadIdx.x - brank)] = packed;
     }
 }
@@ -467,10 +461,11 @@ __global__ void __launch_bounds__(NT) k_fill(const Frame F)
     const long long tri = (long long)blockIdx.x * NT + threadIdx.x;
     if (tri >= F.T) return;
     const long long ridx = (long long)view * F.T + tri;
-    const float4 E = F.rec[R_E][ridx];
+    const float4 E = F.recE[ridx];
     const unsigned bx = __float_as_uint(E.x), by = __float_as_uint(E.y);
     if ((bx >> 16) == 0) return;  // not drawn (x_right >= 1 for every drawn triangle)
-    const float4 a = F.rec[R_A][ridx], b = F.rec[R_B][ridx], c = F.rec[R_C][ridx], d = F.rec[R_D][ridx];
+    const float4 *R = F.shrec + ridx * SREC;
+    const float4 a = R[S_A], b = R[S_B], c = R[S_C], d = F.recD[ridx];
     const unsigned fl = __float_as_uint(d.w);
     // |l3| and |1/l3| where the coordinate is negated (RN(1/-x) = -RN(1/x): flipping the sign bit is exact)
     const float4 s2 = make_float4(c.x, (fl & (FL_NEG << 0)) ? -c.y : c.y, (fl & (FL_NEG << 1)) ? -c.z : c.z, (fl & (FL_NEG << 2)) ? -c.w : c.w);
@@ -523,8 +518,26 @@ __device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wa
 // generic-proxy shared-memory writes -> visible to the async proxy (TMA) once a barrier has ordered them
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// Optional phase timing (build with -DCRB_PHASE_TIMING): lane 0 of every warp accumulates the cycles it spends in each
+// phase of k_raster into g_phase[]; read with crb_phase_cycles().  Compiled out of the product build.
+__device__ unsigned long long g_phase[16];
+#ifdef CRB_PHASE_TIMING
+#define PH_DECL long long ph_t = clock64();
+#define PH(k)                                                                      \
+    do {                                                                           \
+        if ((threadIdx.x & 31) == 0) {                                             \
+            const long long now_ = clock64();                                      \
+            atomicAdd(&g_phase[k], (unsigned long long)(now_ - ph_t));             \
+            ph_t = now_;                                                           \
+        }                                                                          \
+    } while (0)
+#else
+#define PH_DECL
+#define PH(k) do { } while (0)
+#endif
+
 struct __align__(128) TileSmem {
-    // TMA sources first (128-byte aligned): shaded colour / normal rows of the tile, then the clear pattern
+    // TMA source first (128-byte aligned): shaded colour / normal rows of the tile
     union {
         struct {
             float4 s0[CH];  // x0 y0 x1 y1
@@ -541,16 +554,19 @@ struct __align__(128) TileSmem {
             float col[TH * TW * 3];
             float nrm[TH * TW * 3];
         } out;
+        struct {                              // clear CTAs only: the constant pattern their TMA boxes are stored from
+            float z[BOX_ROWS * TW];           //   Z_INIT
+            float c[BOX_ROWS * TW * 3];       //   background colour
+            float n[BOX_ROWS * TW * 3];       //   0
+        } pat;
     } u;
-    float zpat[BOX_ROWS * TW];        // Z_INIT
-    float cpat[BOX_ROWS * TW * 3];    // background colour
-    float npat[BOX_ROWS * TW * 3];    // 0
     unsigned long long keys[TH * KEY_STRIDE];
     unsigned warp_sums[NT / 32];
 };
 
 // Writes one tile of cleared pixels (fresh-filler values) with plain stores -- the path for images whose rows are not
-// 16-byte multiples, launches without tensor maps, and buffers the maps do not cover.
+// 16-byte multiples, launches without tensor maps, and the uint8 image.
+template <int NTH>
 __device__ __forceinline__ void write_clear_tile(const Frame &F, unsigned skip, int view, int x0, int yl0, int tw, int th)
 {
     const long long slab = (long long)view * F.slabPixels;
@@ -560,7 +576,7 @@ __device__ __forceinline__ void write_clear_tile(const Frame &F, unsigned skip, 
     if (vec) {
         // thread -> (row = tid/8 (+32 per pass), 16-byte column q = tid%8 (+8, +16)): shifts only, 128-byte runs
         const int q = threadIdx.x & 7;
-        for (int r = threadIdx.x >> 3; r < th; r += NT / 8) {
+        for (int r = threadIdx.x >> 3; r < th; r += NTH / 8) {
             const long long rowpix = slab + (long long)(yl0 + r) * F.W + x0;
             if (wz) reinterpret_cast<float4 *>(F.z + rowpix)[q] = make_float4(Z_INIT, Z_INIT, Z_INIT, Z_INIT);
             if (wc) {
@@ -573,7 +589,7 @@ __device__ __forceinline__ void write_clear_tile(const Frame &F, unsigned skip, 
             }
         }
     } else {
-        for (int i = threadIdx.x; i < th * tw; i += NT) {
+        for (int i = threadIdx.x; i < th * tw; i += NTH) {
             const int r = i / tw, xx = i % tw;
             const long long p = slab + (long long)(yl0 + r) * F.W + x0 + xx;
             if (wz) F.z[p] = Z_INIT;
@@ -584,25 +600,9 @@ __device__ __forceinline__ void write_clear_tile(const Frame &F, unsigned skip, 
     if (F.color_u8) {
         const int rows = F.row1 - F.row0;
         const unsigned char b8 = to_u8(bg);
-        for (int i = threadIdx.x; i < th * tw * 3; i += NT) {
+        for (int i = threadIdx.x; i < th * tw * 3; i += NTH) {
             const int r = i / (tw * 3), xx = i % (tw * 3);
             F.color_u8[((long long)view * F.slabPixels + (long long)(rows - 1 - (yl0 + r)) * F.W + x0) * 3 + xx] = b8;
-        }
-    }
-}
-
-// The same clear through TMA: lane 0 of warp w issues the boxes j = w, w+8 of the tile's 12 (3 arrays x 4 row blocks),
-// each a BOX_ROWS x 32-pixel store from the constant pattern in shared memory.  Boxes are clipped by the hardware at the
-// right / bottom edge of the image.  Whatever the maps do not cover goes through write_clear_tile.
-__device__ __forceinline__ void tma_clear_tile(const Frame &F, const TMaps &M, TileSmem &S, int view, int x0, int yl0, int th)
-{
-    if ((threadIdx.x & 31) == 0) {
-        for (int j = threadIdx.x >> 5; j < 12; j += NT / 32) {
-            const int which = j >> 2, r = (j & 3) * BOX_ROWS;
-            if (r >= th) continue;
-            if (which == 0) { if (M.use & CRB_BUF_Z) tma_store_box(&M.z, S.zpat, x0, yl0 + r, view); }
-            else if (which == 1) { if (M.use & CRB_BUF_COLOR) tma_store_box(&M.c, S.cpat, x0 * 3, yl0 + r, view); }
-            else { if (M.use & CRB_BUF_NORMALS) tma_store_box(&M.n, S.npat, x0 * 3, yl0 + r, view); }
         }
     }
 }
@@ -634,12 +634,14 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
     const int y0 = F.row0 + yl0;                  // absolute image row
     const int tw = min(TW, F.W - x0), th = min(TH, F.row1 - y0);
     const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    PH_DECL
     for (int i = threadIdx.x; i < TH * KEY_STRIDE; i += NT) S.keys[i] = KEY_EMPTY;
 
     // ---- visibility: every (triangle,row) of the tile is one work item -------------------------------------
     for (unsigned base = 0; base < n; base += CH) {
         const unsigned m = min((unsigned)CH, n - base);
         __syncthreads();  // keys initialised / previous pass finished with the staging area
+        PH(2);
         unsigned rows = 0;
         if (threadIdx.x < m) {   // coalesced copy of the setups k_fill prepared for this tile
             const unsigned at = off + base + threadIdx.x;
@@ -649,6 +651,13 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
             S.u.st.s2[threadIdx.x] = F.ls2[at];
             S.u.st.s3[threadIdx.x] = d;
             S.u.st.s4[threadIdx.x] = F.ls4[at];
+            {   // the shading pass will want this triangle's 128-byte record: start pulling it into L1 now
+                const char *sr = reinterpret_cast<const char *>(F.shrec + ((long long)view * F.T + d.z) * SREC);
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(sr));
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(sr + 32));
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(sr + 64));
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(sr + 96));
+            }
             const int yt = max((int)(d.y & 0xFFFF), y0), yb = min((int)(d.y >> 16), y0 + th);
             rows = (unsigned)max(yb - yt, 0);
         }
@@ -658,14 +667,20 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
             S.u.st.rowStart[threadIdx.x] = start;
             for (unsigned j = 0; j < rows; ++j) S.u.st.owner[start + j] = (unsigned char)threadIdx.x;
         }
+        PH(3);
         __syncthreads();
+        PH(4);
 
         // Row work items, 32 per warp per trip.  Trip counts are warp-uniform and the body is predicated, so the warp
         // stays converged (a per-thread `for (r = tid; ...)` with early `continue`s lets lanes drift apart under
         // independent thread scheduling: measured 7.5 active lanes per instruction).
-        for (unsigned rb = threadIdx.x & ~31u; rb < totalRows; rb += NT) {
+        if (F.flags & FLAG_DBG_NOROWS) totalRows = 0;
+        // every warp takes an equal, contiguous share of the rows (the tile waits for its slowest warp)
+        const unsigned share = (totalRows + NT / 32 - 1) / (NT / 32);
+        const unsigned rEnd = min(totalRows, (wid + 1u) * share);
+        for (unsigned rb = wid * share; rb < rEnd; rb += 32) {
             const unsigned r = rb + lane;
-            const bool active = r < totalRows;
+            const bool active = r < rEnd;
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
             bool fdiv = false, span = false;
             float l02 = 0.f, l12 = 0.f, l22 = 0.f, A1 = 0.f, A2 = 0.f, A3 = 0.f;
@@ -794,12 +809,14 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
             }
             __syncwarp();
         }
+        PH(5);
     }
     __syncthreads();
+    PH(6);
 
     // ---- deferred shading of the winners, staged so that colour / normals leave as whole rows ---------------
     const long long slab = (long long)view * F.slabPixels;
-    const bool tma = clear && M.use != 0u;                                  // colour / normal rows leave through TMA boxes
+    const bool tma = clear && M.use != 0u && (F.flags & FLAG_OUT_TMA);     // colour / normal rows leave through TMA boxes
     const bool vec = clear && !tma && (tw == TW) && ((F.W & 3) == 0);       // ... or as 16-byte vector stores
     const bool stage = tma || vec;
     const float bg = background_color(F);
@@ -810,11 +827,11 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
         float z = Z_INIT, c[3] = {bg, bg, bg}, nn[3] = {0.f, 0.f, 0.f};
         bool write = clear;
         const long long pix = slab + (long long)(yl0 + yy) * F.W + x0 + xx;
-        if (key != KEY_EMPTY) {
+        if (key != KEY_EMPTY && !(F.flags & FLAG_DBG_NOSHADE)) {
             const unsigned tri = ~(unsigned)(key & 0xFFFFFFFFull);
             const long long ridx = (long long)view * F.T + tri;
             float fz, fc[3], fn[3];
-            if (shade_fragment(F, tri, ridx, (float)(x0 + xx), (float)(y0 + yy), fz, fc, fn)) {
+            if (shade_fragment(F, ridx, (float)(x0 + xx), (float)(y0 + yy), fz, fc, fn)) {
                 const float zold = clear ? Z_INIT : F.z[pix];
                 if (!(fz > zold)) {  // pyx:223: drawn unless new_z > z_buffer (equal depth overwrites)
                     z = fz; c[0] = fc[0]; c[1] = fc[1]; c[2] = fc[2]; nn[0] = fn[0]; nn[1] = fn[1]; nn[2] = fn[2];
@@ -825,7 +842,7 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
         if (stage) {
             S.u.out.col[p * 3] = c[0]; S.u.out.col[p * 3 + 1] = c[1]; S.u.out.col[p * 3 + 2] = c[2];
             S.u.out.nrm[p * 3] = nn[0]; S.u.out.nrm[p * 3 + 1] = nn[1]; S.u.out.nrm[p * 3 + 2] = nn[2];
-            if (F.z) F.z[pix] = z;
+            if (F.z && !(F.flags & FLAG_DBG_NOOUT)) F.z[pix] = z;
         } else if (write) {
             if (F.z) F.z[pix] = z;
             if (F.color) { F.color[pix * 3] = c[0]; F.color[pix * 3 + 1] = c[1]; F.color[pix * 3 + 2] = c[2]; }
@@ -837,9 +854,12 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
             o[0] = to_u8(c[0]); o[1] = to_u8(c[1]); o[2] = to_u8(c[2]);
         }
     }
+    PH(7);
+    if (F.flags & FLAG_DBG_NOOUT) return;
     if (tma) {
         fence_async_smem();
         __syncthreads();
+        PH(8);
         if (lane == 0) {   // warp w: array w/4 (colour, normals), row block w%4
             const int r = (int)(wid & 3u) * BOX_ROWS;
             if (r < th) {
@@ -865,71 +885,105 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
             }
         }
     }
+    PH(9);
 }
 
-// One CTA per busy tile when the grid is large enough (it is sized from the busy-tile count the host last saw, see
-// run_tiled), a strided walk otherwise.  The fused clear of the empty tiles (70 % of a T-Rex frame, pure stores) is
-// spread over the whole grid and issued FIRST: with TMA it costs a dozen instructions per tile and drains while the CTA
-// rasterizes its busy tile -- memory-bound and issue-bound work overlap.
+// The fused clear through TMA: one tile = up to 12 boxes (3 arrays x 4 row blocks of BOX_ROWS rows) stored from the
+// constant pattern in shared memory; the hardware clips boxes at the image edge.  Called by one lane.
+__device__ __forceinline__ void tma_clear_tile(const Frame &F, const TMaps &M, const TileSmem &S, unsigned t)
+{
+    const int rows = F.row1 - F.row0;
+    const int view = (int)(t >> 22), yl0 = (int)((t >> 11) & 2047u) * TH, x0 = (int)(t & 2047u) * TW;
+#pragma unroll
+    for (int r = 0; r < TH; r += BOX_ROWS) {
+        if (yl0 + r < rows) {
+            if (M.use & CRB_BUF_Z) tma_store_box(&M.z, S.u.pat.z, x0, yl0 + r, view);
+            if (M.use & CRB_BUF_COLOR) tma_store_box(&M.c, S.u.pat.c, x0 * 3, yl0 + r, view);
+            if (M.use & CRB_BUF_NORMALS) tma_store_box(&M.n, S.u.pat.n, x0 * 3, yl0 + r, view);
+        }
+    }
+}
+
+// Grid roles.  Busy tiles: one CTA each when the grid is large enough (it is sized from the busy-tile count the host
+// last saw, see run_tiled), a strided walk otherwise.  The frame's clear is fused: with tensor maps every fourth CTA
+// (blockIdx % 4 == 3) is a "clear CTA" that only issues the TMA boxes of the tiles without triangles (70 % of a T-Rex
+// frame) -- a few thousand cycles of queueing, no arithmetic -- so those stores drain beside the rasterizing CTAs that
+// share its SM for the whole length of the kernel.  Launches without tensor maps clear with plain stores up front,
+// every CTA adopting its share of the empty tiles.
 #ifndef CRB_RASTER_MIN_CTAS
 #define CRB_RASTER_MIN_CTAS 5
 #endif
 __global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame F, const __grid_constant__ TMaps M)
 {
     __shared__ TileSmem S;
-    const unsigned long long pairs = F.total[0];
-    const unsigned nb = (unsigned)F.total[2], ne = (unsigned)F.total[3];
-    if (pairs > (unsigned long long)F.pairCap) {   // frame skipped; the host is told via crb_status
-        if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(F.total + 1, pairs);
-        return;
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0 && F.hstats)
-        *reinterpret_cast<volatile unsigned long long *>(F.hstats) = ((unsigned long long)(nb + ne) << 32) | nb;
+    PH_DECL
     const bool clear = (F.flags & CRB_CLEAR_FIRST) != 0;
-    const unsigned G = gridDim.x;
-    unsigned cta = blockIdx.x;
-    unsigned tpk = 0, n = 0, off = 0;
-    if (cta < nb) {                                   // first busy tile: its bookkeeping loads fly during the clears
-        tpk = F.busy[cta];
-        const unsigned tIdx = (tpk >> 22) * (unsigned)F.nTiles + ((tpk >> 11) & 2047u) * (unsigned)F.tilesX + (tpk & 2047u);
-        n = F.tcount[tIdx]; off = F.offset[tIdx];
-    }
-    if (clear && blockIdx.x < ne) {
-        const bool tma = M.use != 0u;
-        const unsigned rest = ((F.z ? CRB_BUF_Z : 0u) | (F.color ? CRB_BUF_COLOR : 0u) | (F.normals ? CRB_BUF_NORMALS : 0u)) & ~M.use;   // arrays the maps do not cover
-        if (tma) {
+    const bool split = clear && M.use != 0u;
+    const unsigned nAll = (unsigned)F.nTiles * (unsigned)F.nViews;
+    unsigned bidx = blockIdx.x, Gb = gridDim.x;
+    if (split) {
+        const unsigned Gc = gridDim.x >> 2, ci = blockIdx.x >> 2;
+        Gb = gridDim.x - Gc;
+        if ((blockIdx.x & 3u) == 3u) {
+            // ---- clear CTA: warp w issues the tiles e = ci + (w + 8k) * Gc
+            const unsigned stride = Gc * (NT / 32);
+            unsigned e = ci + (threadIdx.x >> 5) * Gc;
+            unsigned t = e < nAll ? F.empty[e] : 0u;              // speculative: flies with the totals
+            const unsigned long long pairs = F.total[0];
+            const unsigned ne = (unsigned)F.total[3];
+            if (pairs > (unsigned long long)F.pairCap || (F.flags & FLAG_DBG_NOCLEAR)) return;     // frame skipped: buffers stay untouched
             const float bg = background_color(F);
             for (int i = threadIdx.x; i < BOX_ROWS * TW * 3; i += NT) {
-                S.cpat[i] = bg; S.npat[i] = 0.0f;
-                if (i < BOX_ROWS * TW) S.zpat[i] = Z_INIT;
+                S.u.pat.c[i] = bg; S.u.pat.n[i] = 0.0f;
+                if (i < BOX_ROWS * TW) S.u.pat.z[i] = Z_INIT;
             }
             fence_async_smem();
             __syncthreads();
+            if ((threadIdx.x & 31) == 0) {
+                while (e < ne) {
+                    const unsigned en = e + stride;
+                    const unsigned tn = en < ne ? F.empty[en] : 0u;
+                    tma_clear_tile(F, M, S, t);
+                    e = en; t = tn;
+                }
+                tma_commit();
+                tma_wait_read();
+            }
+            return;
         }
-        for (unsigned e = blockIdx.x; e < ne; e += G) {
+        bidx = ci * 3u + (blockIdx.x & 3u);
+    }
+    uint4 rec = bidx < nAll ? F.busy[bidx] : make_uint4(0u, 0u, 0u, 0u);   // speculative: flies with the totals
+    const unsigned long long pairs = F.total[0];
+    const unsigned nb = (unsigned)F.total[2];
+    if (pairs > (unsigned long long)F.pairCap) {   // frame skipped; the host is told via crb_status
+        if (bidx == 0 && threadIdx.x == 0) atomicMax(F.total + 1, pairs);
+        return;
+    }
+    if (bidx == 0 && threadIdx.x == 0 && F.hstats)
+        *reinterpret_cast<volatile unsigned long long *>(F.hstats) = ((unsigned long long)nAll << 32) | nb;
+    if (clear && !split && !(F.flags & FLAG_DBG_NOCLEAR)) {
+        const unsigned ne = (unsigned)F.total[3];
+        for (unsigned e = bidx; e < ne; e += Gb) {
             const unsigned t = F.empty[e];
             const int view = (int)(t >> 22), ty = (int)((t >> 11) & 2047u), tx = (int)(t & 2047u);
-            const int th = min(TH, F.row1 - F.row0 - ty * TH);
-            if (tma) {
-                tma_clear_tile(F, M, S, view, tx * TW, ty * TH, th);
-                if (rest || F.color_u8) write_clear_tile(F, M.use, view, tx * TW, ty * TH, min(TW, F.W - tx * TW), th);
-            } else {
-                write_clear_tile(F, 0u, view, tx * TW, ty * TH, min(TW, F.W - tx * TW), th);
-            }
+            write_clear_tile<NT>(F, 0u, view, tx * TW, ty * TH, min(TW, F.W - tx * TW), min(TH, F.row1 - F.row0 - ty * TH));
         }
-        if (tma && (threadIdx.x & 31) == 0) tma_commit();
     }
-    for (; cta < nb; cta += G) {
-        if (cta != blockIdx.x) {
+    PH(0);
+    for (unsigned cta = bidx; cta < nb; cta += Gb) {
+        if (cta != bidx) {
             if ((threadIdx.x & 31) == 0) tma_wait_read();   // the previous tile's rows have left shared memory
             __syncthreads();
-            tpk = F.busy[cta];
-            const unsigned tIdx = (tpk >> 22) * (unsigned)F.nTiles + ((tpk >> 11) & 2047u) * (unsigned)F.tilesX + (tpk & 2047u);
-            n = F.tcount[tIdx]; off = F.offset[tIdx];
+            rec = F.busy[cta];
         }
-        raster_tile(F, M, S, clear, (int)(tpk >> 22), (int)(tpk & 2047u), (int)((tpk >> 11) & 2047u), n, off);
+        raster_tile(F, M, S, clear, (int)(rec.x >> 22), (int)(rec.x & 2047u), (int)((rec.x >> 11) & 2047u), rec.y, rec.z);
     }
+#ifdef CRB_PHASE_TIMING
+    ph_t = clock64();
+#endif
     if ((threadIdx.x & 31) == 0) tma_wait_read();           // shared memory must outlive the bulk reads
+    PH(10);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -941,7 +995,7 @@ __global__ void __launch_bounds__(NT) k_raster_atomic(const Frame F, unsigned lo
     const long long tri = ((long long)blockIdx.x * NT + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (tri >= F.T) return;
-    const float4 r2 = F.rec[R_E][tri];
+    const float4 r2 = F.recE[tri];
     const unsigned bx = __float_as_uint(r2.x), by = __float_as_uint(r2.y);
     if ((bx >> 16) == 0) return;
     const Tri9 t = load_tri9(F, tri);
@@ -972,7 +1026,7 @@ __global__ void __launch_bounds__(NT) k_shade_atomic(const Frame F, unsigned lon
         const unsigned tri = ~(unsigned)(key & 0xFFFFFFFFull);
         const int y = F.row0 + (int)(pix / F.W), x = (int)(pix % F.W);
         float fz, fc[3], fn[3];
-        if (shade_fragment(F, tri, tri, (float)x, (float)y, fz, fc, fn)) {
+        if (shade_fragment(F, tri, (float)x, (float)y, fz, fc, fn)) {
             const float zold = clear ? Z_INIT : F.z[pix];
             if (!(fz > zold)) {
                 z = fz; c[0] = fc[0]; c[1] = fc[1]; c[2] = fc[2]; nn[0] = fn[0]; nn[1] = fn[1]; nn[2] = fn[2];
@@ -990,10 +1044,6 @@ __global__ void __launch_bounds__(NT) k_shade_atomic(const Frame F, unsigned lon
 // small kernels: fills, post-passes, view export
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT) k_fill_u64(unsigned long long *p, long long n, unsigned long long v)
-{
-    for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) p[i] = v;
-}
-__global__ void __launch_bounds__(NT) k_fill_u32(unsigned *p, long long n, unsigned v)
 {
     for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) p[i] = v;
 }
@@ -1126,9 +1176,9 @@ struct crb_filler {
     long long maxT;
     int maxViews;
     long long pairCap;
-    float4 *rec[NREC], *crec0, *crec1;
-    float *crec2;
-    unsigned *count, *tcount, *offset, *cursor, *busy, *empty;
+    float4 *shrec, *recD, *recE;
+    unsigned *count, *offset, *cursor, *empty;
+    uint4 *busy;
     float4 *ls0, *ls1, *ls2;
     uint4 *ls3;
     float4 *ls4;
@@ -1141,7 +1191,9 @@ struct crb_filler {
     // optional timing of the dominant kernel (k_raster) with CUDA events on the launching stream
     int raster_ctas;       // experiments: fixed k_raster grid (0 = automatic)
     int sm_count;
-    int use_tma;           // output rows leave through TMA boxes where the layout allows (CRB_NO_TMA=1 disables)
+    int use_tma;           // tensor maps are built where the layout allows (CRB_NO_TMA=1 disables): k_clear stores TMA boxes
+    unsigned dbg_flags;    // ablation switches (CRB_DEBUG_SKIP), never set in production
+    int out_tma;           // ... and so does k_raster for the shaded colour / normal rows (CRB_OUT_TMA=0 disables)
     unsigned long long *hstats;      // pinned + mapped: busy-tile statistics of the most recent k_raster launch
     unsigned long long *hstats_dev;
     bool prof_on;
@@ -1152,7 +1204,7 @@ struct crb_filler {
 namespace {
 
 struct WsLayout {
-    size_t rec[NREC], crec0, crec1, crec2, count, tcount, offset, cursor, busy, empty, ls0, ls1, ls2, ls3, ls4, total, sv, sc, sn, bytes;
+    size_t shrec, recD, recE, count, offset, cursor, busy, empty, ls0, ls1, ls2, ls3, ls4, total, sv, sc, sn, bytes;
 };
 
 long long default_pair_cap(const crb_filler *f, long long T, int views)
@@ -1169,15 +1221,13 @@ WsLayout ws_layout(const crb_filler *f, long long T, int views, long long pairCa
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 256); return at; };
     const size_t recs = (size_t)(T > 0 ? T : 1) * views;
-    for (int k = 0; k < NREC; ++k) L.rec[k] = take(recs * sizeof(float4));
-    L.crec0 = take((size_t)(T > 0 ? T : 1) * 16);
-    L.crec1 = take((size_t)(T > 0 ? T : 1) * 16);
-    L.crec2 = take((size_t)(T > 0 ? T : 1) * 4);
+    L.shrec = take(recs * SREC * sizeof(float4));
+    L.recD = take(recs * sizeof(float4));
+    L.recE = take(recs * sizeof(float4));
     L.count = take((size_t)tiles * views * 4);
-    L.tcount = take((size_t)tiles * views * 4);
     L.offset = take((size_t)tiles * views * 4);
     L.cursor = take((size_t)tiles * views * 4);
-    L.busy = take((size_t)tiles * views * 4);
+    L.busy = take((size_t)tiles * views * 16);
     L.empty = take((size_t)tiles * views * 4);
     L.ls0 = take((size_t)pairCap * 16);
     L.ls1 = take((size_t)pairCap * 16);
@@ -1229,9 +1279,8 @@ void fill_frame(const crb_filler *f, Frame *F)
     F->tilesX = (f->w + TW - 1) / TW;
     F->tilesY = (f->row1 - f->row0 + TH - 1) / TH;
     F->nTiles = F->tilesX * F->tilesY;
-    for (int k = 0; k < NREC; ++k) F->rec[k] = f->rec[k];
-    F->crec0 = f->crec0; F->crec1 = f->crec1; F->crec2 = f->crec2;
-    F->count = f->count; F->tcount = f->tcount; F->offset = f->offset; F->cursor = f->cursor;
+    F->shrec = f->shrec; F->recD = f->recD; F->recE = f->recE;
+    F->count = f->count; F->offset = f->offset; F->cursor = f->cursor;
     F->busy = f->busy; F->empty = f->empty;
     F->ls0 = f->ls0; F->ls1 = f->ls1; F->ls2 = f->ls2; F->ls3 = f->ls3; F->ls4 = f->ls4;
     F->total = f->total;
@@ -1304,16 +1353,23 @@ int run_tiled(crb_filler *f, Frame &F, cudaStream_t st)
         CU(cudaMemsetAsync(f->total, 0, 8, st));
         CU(cudaMemsetAsync(f->total + 2, 0, 16, st));
     }
-    const long long nAll = (long long)F.nViews * F.nTiles;
-    k_alloc<<<(unsigned)((nAll + NT - 1) / NT), NT, 0, st>>>(F);
+    const long long nAllTiles = (long long)F.nViews * F.nTiles;
+    k_alloc<<<(unsigned)((nAllTiles + NT - 1) / NT), NT, 0, st>>>(F);
     if ((rc = launch_check(f, "k_alloc"))) return rc;
+
+    // From here on the frame is written: the raster stage = k_fill -> k_raster.
+    const bool prof = f->prof_on && f->prof_n < PROF_MAX;
+    if (prof) CU(cudaEventRecord(f->prof_ev[2 * f->prof_n], st));
+    TMaps M;
+    memset(&M, 0, sizeof(M));
+    const bool clear = (F.flags & CRB_CLEAR_FIRST) != 0;
+    if (f->use_tma && clear && !(F.W & 3) && !F.color_u8) M.use = encode_maps(&M, F);
+    if (M.use && f->out_tma) F.flags |= FLAG_OUT_TMA;
+    F.flags |= f->dbg_flags;
     if (F.T > 0) {
         k_fill<<<dim3(gT, F.nViews), NT, 0, st>>>(F);
         if ((rc = launch_check(f, "k_fill"))) return rc;
     }
-    const bool prof = f->prof_on && f->prof_n < PROF_MAX;
-    if (prof) CU(cudaEventRecord(f->prof_ev[2 * f->prof_n], st));
-    const long long nAllTiles = (long long)F.nTiles * F.nViews;
     // Grid: one CTA per busy tile.  The busy count is only known on the device, so the grid is sized from the busy
     // FRACTION the previous launch posted (+12 % and a floor of one wave); k_raster walks with stride gridDim when the
     // estimate was low, and an all-tiles grid is used until a first launch has reported.
@@ -1330,9 +1386,7 @@ int run_tiled(crb_filler *f, Frame &F, cudaStream_t st)
     }
     if (gR > nAllTiles) gR = nAllTiles;
     if (gR < 1) gR = 1;
-    TMaps M;
-    memset(&M, 0, sizeof(M));
-    if (f->use_tma && (F.flags & CRB_CLEAR_FIRST) && !(F.W & 3)) M.use = encode_maps(&M, F);
+    if (M.use) gR = 4 * ((gR + 2) / 3);     // three rasterizing CTAs + one clear CTA per group of four (see k_raster)
     k_raster<<<(unsigned)gR, NT, 0, st>>>(F, M);
     if ((rc = launch_check(f, "k_raster"))) return rc;
     if (prof) {
@@ -1378,10 +1432,9 @@ int bind_ws_pointers(crb_filler *f, void *ws, size_t bytes, long long T, int vie
     char *b = (char *)ws;
     f->ws = ws; f->ws_bytes = bytes;
     f->maxT = T; f->maxViews = views; f->pairCap = pairCap;
-    for (int k = 0; k < NREC; ++k) f->rec[k] = (float4 *)(b + L.rec[k]);
-    f->crec0 = (float4 *)(b + L.crec0); f->crec1 = (float4 *)(b + L.crec1); f->crec2 = (float *)(b + L.crec2);
-    f->count = (unsigned *)(b + L.count); f->tcount = (unsigned *)(b + L.tcount); f->offset = (unsigned *)(b + L.offset); f->cursor = (unsigned *)(b + L.cursor);
-    f->busy = (unsigned *)(b + L.busy); f->empty = (unsigned *)(b + L.empty);
+    f->shrec = (float4 *)(b + L.shrec); f->recD = (float4 *)(b + L.recD); f->recE = (float4 *)(b + L.recE);
+    f->count = (unsigned *)(b + L.count); f->offset = (unsigned *)(b + L.offset); f->cursor = (unsigned *)(b + L.cursor);
+    f->busy = (uint4 *)(b + L.busy); f->empty = (unsigned *)(b + L.empty);
     f->ls0 = (float4 *)(b + L.ls0); f->ls1 = (float4 *)(b + L.ls1); f->ls2 = (float4 *)(b + L.ls2); f->ls3 = (uint4 *)(b + L.ls3); f->ls4 = (float4 *)(b + L.ls4);
     f->total = (unsigned long long *)(b + L.total);
     f->stage_v = (float *)(b + L.sv); f->stage_c = (float *)(b + L.sc); f->stage_n = (float *)(b + L.sn);
@@ -1444,6 +1497,8 @@ int crb_create(int h, int w, float fov, float z_near, float z_far, int device, c
         if (const char *e = getenv("CRB_RASTER_CTAS")) f->raster_ctas = atoi(e);   // experiments: >0 fixed grid, <0 one CTA per tile
         f->use_tma = 1;
         if (const char *e = getenv("CRB_NO_TMA")) f->use_tma = atoi(e) ? 0 : 1;
+        f->out_tma = 1;
+        if (const char *e = getenv("CRB_DEBUG_SKIP")) f->dbg_flags = ((unsigned)atoi(e) & 15u) << 16;
         void *hp = nullptr, *dp = nullptr;
         if (cudaHostAlloc(&hp, 64, cudaHostAllocMapped) == cudaSuccess && cudaHostGetDevicePointer(&dp, hp, 0) == cudaSuccess) {
             memset(hp, 0, 64);
@@ -1734,6 +1789,19 @@ int crb_sync(crb_filler *f, void *stream)
 }
 
 int64_t crb_launch_count(const crb_filler *f) { return f ? f->launches : 0; }
+
+int crb_phase_cycles(uint64_t out[16], int reset)
+{
+    if (!out) return fail(CRB_ERR_INVALID, "out is NULL");
+    unsigned long long h[16];
+    CU(cudaMemcpyFromSymbol(h, g_phase, sizeof(h)));
+    for (int i = 0; i < 16; ++i) out[i] = h[i];
+    if (reset) {
+        memset(h, 0, sizeof(h));
+        CU(cudaMemcpyToSymbol(g_phase, h, sizeof(h)));
+    }
+    return CRB_OK;
+}
 
 int crb_selftest_fdiv(int device, uint64_t samples, unsigned seed, uint64_t *mismatches, uint32_t first_bad[2])
 {

@@ -169,6 +169,10 @@ int crb_selftest_fdiv(int device, uint64_t samples, unsigned seed, uint64_t *mis
 int crb_profile(crb_filler *f, int enable);
 int crb_profile_read(crb_filler *f, int *launches, double *total_ms);
 
+/* Development aid: warp-cycles spent per phase of k_raster, accumulated on the current device since the last reset.
+ * All zeros unless the library was built with -DCRB_PHASE_TIMING (the product build is not). */
+int crb_phase_cycles(uint64_t out[16], int reset);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

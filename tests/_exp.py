@@ -11,7 +11,7 @@ z = torch.empty((V, res, res), device='cuda'); c = torch.empty((V, res, res, 3),
 
 
 def run(label, env, zz=z, cc=c, nn=n):
-    for k in ("CRB_NO_TMA", "CRB_RASTER_CTAS"):
+    for k in ("CRB_NO_TMA", "CRB_RASTER_CTAS", "CRB_OUT_TMA", "CRB_DEBUG_SKIP"):
         os.environ.pop(k, None)
     os.environ.update(env)
     f = AdvancedPixelBufferFiller(res, res, fov=45.0)
@@ -34,10 +34,10 @@ def run(label, env, zz=z, cc=c, nn=n):
     print(f"{label:34s} total {e0.elapsed_time(e1)/10/V*1000:6.2f} us/view   k_raster {ms/k/32*1000:6.2f} us/view", flush=True)
 
 
-run("default (tma, grid from stats)", {})
-run("plain stores, grid from stats", {"CRB_NO_TMA": "1"})
-run("tma, one CTA per tile", {"CRB_RASTER_CTAS": "-1"})
-run("plain stores, one CTA per tile", {"CRB_NO_TMA": "1", "CRB_RASTER_CTAS": "-1"})
-run("tma, persistent 740", {"CRB_RASTER_CTAS": "740"})
-run("default, colour only", {}, None, c, None)
-run("default, z only", {}, z, None, None)
+run("default", {})
+run("no clear", {"CRB_DEBUG_SKIP": "1"})
+run("no shading", {"CRB_DEBUG_SKIP": "2"})
+run("no rows", {"CRB_DEBUG_SKIP": "4"})
+run("no busy-tile output", {"CRB_DEBUG_SKIP": "8"})
+run("only staging (15)", {"CRB_DEBUG_SKIP": "15"})
+run("vector rows", {"CRB_OUT_TMA": "0"})
