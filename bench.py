@@ -324,31 +324,45 @@ def run_gpu_arm(args):
     # overlap frame k's download.  Same call (crb_render_host, CRB_NO_SYNC), same bytes per frame, every frame's three
     # buffers land in host memory before its slot is reused.
     from cython3dmodelrenderer_b200.pipeline import HostFramePipeline
-    pipe = HostFramePipeline(RES, RES, fov=FOV, depth=args.e2e_depth, device=local)
-    for i in range(2 * args.e2e_depth):
-        pipe.submit(*host_in[i % 4])
-    pipe.drain()
-    launches_e2e0 = pipe.launch_count
-    barrier()
-    t0 = time.perf_counter()
-    last = 0
-    for i in range(e2e_frames):
-        last = pipe.submit(*host_in[i % 4])
-    pipe.drain()
-    e2e_s = time.perf_counter() - t0
+
+    def run_pipeline(sparse):
+        pipe = HostFramePipeline(RES, RES, fov=FOV, depth=args.e2e_depth, device=local, sparse=sparse)
+        for i in range(2 * args.e2e_depth):
+            pipe.submit(*host_in[i % 4])
+        pipe.drain()
+        if sparse:
+            pipe.readback_tiles()
+        l0 = pipe.launch_count
+        barrier()
+        t0 = time.perf_counter()
+        last = 0
+        for i in range(e2e_frames):
+            last = pipe.submit(*host_in[i % 4])
+        pipe.drain()
+        dt = time.perf_counter() - t0
+        cov = int((pipe.result(last)["z"] < 1e5).sum())
+        tiles = pipe.readback_tiles() if sparse else None
+        return dt, cov, pipe.launch_count - l0, tiles
+
+    dense_s, dense_cov, dense_launches, _ = run_pipeline(False)
+    e2e_s, e2e_cov, e2e_launches, tiles_copied = run_pipeline(True)
     if world > 1:
-        t = torch.tensor([e2e_s, sync_s], dtype=torch.float64, device=dev)
+        t = torch.tensor([e2e_s, sync_s, dense_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s, sync_s = float(t[0].item()), float(t[1].item())
-    e2e_cov = int((pipe.result(last)["z"] < 1e5).sum())
+        e2e_s, sync_s, dense_s = (float(x) for x in t.tolist())
+    d2h_sparse = tiles_copied * 32 * 32 * 28 / e2e_frames
     e2e = {"value": world * e2e_frames / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": 108 * T,
-           "d2h_bytes_per_step": 28 * RES * RES, "frames_timed": e2e_frames, "pipeline_depth": args.e2e_depth,
-           "gpu_launches": pipe.launch_count - launches_e2e0,
-           "api": "HostFramePipeline.submit -> crb_render_host(CRB_NO_SYNC): pinned host [T,3,3] arrays in, z+colour+normals "
-                  "(f32, 28 B/pixel) out to pinned host memory, every frame; wall clock over all frames incl. the final drain",
+           "d2h_bytes_per_step": d2h_sparse, "frames_timed": e2e_frames, "pipeline_depth": args.e2e_depth,
+           "gpu_launches": e2e_launches,
+           "api": "HostFramePipeline.submit -> crb_render_host(CRB_NO_SYNC | CRB_DL_SPARSE): pinned host [T,3,3] arrays in; z+colour+"
+                  "normals (f32, 28 B/pixel) complete in pinned host memory after every frame; only tiles that are busy in the frame "
+                  "or were busy in the frame the host arrays showed before cross PCIe (bit-identical to a full download); wall "
+                  "clock over all frames incl. the final drain",
+           "dense_value": world * e2e_frames / dense_s, "dense_d2h_bytes_per_step": 28 * RES * RES,
+           "dense_api": "same pipeline with sparse=False: cudaMemcpy of all three buffers (29.4 MB) every frame",
            "synchronous_value": world * e2e_frames / sync_s,
-           "synchronous_api": "crb_render_host, one frame per call, stream-synchronised before returning",
-           "pcie_floor_note": "29.4 MB D2H per frame: the copy engine alone bounds this at ~1.9 k frames/s on a 55 GB/s link"}
+           "synchronous_api": "crb_render_host, one frame per call, full download, stream-synchronised before returning",
+           "pcie_floor_note": "a full 29.4 MB download per frame bounds the dense variants at ~1.9 k frames/s on a 55 GB/s link"}
 
     # ---- single frame through a CUDA graph (config C1: one render_model per frame, fresh buffers) -----------------
     single = None
@@ -397,7 +411,7 @@ def run_gpu_arm(args):
                        "the 1.5 MB mesh is re-read per view by design" % (V * 28 * RES * RES / 1e9)},
             "gtri_per_s": fps * T / 1e9, "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cpu, "single_frame": single,
-            "checks": {"covered_pixels_view0": covered0, "e2e_covered_pixels": e2e_cov, "e2e_sync_covered_pixels": sync_cov, "pairs_last_launch": int(need.value),
+            "checks": {"covered_pixels_view0": covered0, "e2e_covered_pixels": e2e_cov, "e2e_dense_covered_pixels": dense_cov, "e2e_sync_covered_pixels": sync_cov, "pairs_last_launch": int(need.value),
                        "pair_capacity": int(cap.value)},
         }
         print(json.dumps(line), flush=True)
@@ -476,6 +490,8 @@ def run_extra_workload(args):
         ms = float(t.item())
         if args.gather != "none":     # final NCCL all-gather of the row bands (north_star: "a final NCCL gather over NVLink")
             z, c, n = f.device_buffers()
+            for b in (z, c, n):                     # first use of the communicator / buffers is not what is being timed
+                sharding.gather_bands(b, res)
             barrier()
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             g0.record()

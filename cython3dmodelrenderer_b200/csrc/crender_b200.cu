@@ -1059,6 +1059,48 @@ __global__ void __launch_bounds__(NT) k_init_buffers(float *z, float *color, flo
     }
 }
 
+// Sparse read-back (crb_render_host + CRB_DL_SPARSE).  The host copy of the three buffers persists between calls, every
+// call renders a FRESH frame, and a tile no triangle touches holds fresh-filler values both before and after -- so only
+// tiles that are busy now, or were busy in the frame the host copy currently shows, need to cross PCIe.  One CTA per
+// tile copies the tile's rows from the device buffers straight into the mapped pinned host arrays (16-byte stores,
+// 128 / 384-byte runs) and records the tile's state for the next call; everything else exits at once.  The host arrays
+// end up bit-identical to a full download (tests/test_gpu_parity.py::test_sparse_readback_*).
+__global__ void __launch_bounds__(NT) k_readback(const Frame F, unsigned char *shown_busy, float *hz, float *hc, float *hn,
+                                                  unsigned long long *tiles_copied)
+{
+    if (F.total[0] > (unsigned long long)F.pairCap) return;      // frame skipped: the host copy stays as it is
+    const unsigned t = blockIdx.x;
+    const bool busy = F.cursor[t] != 0u;                          // k_fill left the tile's pair count here
+    const bool dirty = busy || shown_busy[t] != 0;
+    __syncthreads();
+    if (!dirty) return;
+    if (threadIdx.x == 0) {
+        shown_busy[t] = busy ? 1 : 0;
+        atomicAdd(tiles_copied, 1ull);
+    }
+    const int tx = (int)(t % (unsigned)F.tilesX), ty = (int)(t / (unsigned)F.tilesX);
+    const int x0 = tx * TW, yl0 = ty * TH;
+    const int tw = min(TW, F.W - x0), th = min(TH, F.row1 - F.row0 - yl0);
+    if (tw == TW && !(F.W & 3)) {
+        // 56 float4 per tile row: 8 of z, 24 of colour, 24 of normals
+        for (int i = threadIdx.x; i < th * 56; i += NT) {
+            const int r = i / 56, q = i % 56;
+            const long long rowpix = (long long)(yl0 + r) * F.W + x0;
+            if (q < 8) { if (hz) reinterpret_cast<float4 *>(hz + rowpix)[q] = reinterpret_cast<const float4 *>(F.z + rowpix)[q]; }
+            else if (q < 32) { if (hc) reinterpret_cast<float4 *>(hc + rowpix * 3)[q - 8] = reinterpret_cast<const float4 *>(F.color + rowpix * 3)[q - 8]; }
+            else if (hn) reinterpret_cast<float4 *>(hn + rowpix * 3)[q - 32] = reinterpret_cast<const float4 *>(F.normals + rowpix * 3)[q - 32];
+        }
+    } else {
+        for (int i = threadIdx.x; i < th * tw; i += NT) {
+            const int r = i / tw, xx = i % tw;
+            const long long p = (long long)(yl0 + r) * F.W + x0 + xx;
+            if (hz) hz[p] = F.z[p];
+            if (hc) { hc[p * 3] = F.color[p * 3]; hc[p * 3 + 1] = F.color[p * 3 + 1]; hc[p * 3 + 2] = F.color[p * 3 + 2]; }
+            if (hn) { hn[p * 3] = F.normals[p * 3]; hn[p * 3 + 1] = F.normals[p * 3 + 1]; hn[p * 3 + 2] = F.normals[p * 3 + 2]; }
+        }
+    }
+}
+
 // guro_illumination.py:20-27 over the whole buffer, in place
 __global__ void __launch_bounds__(NT) k_guro(float *color, const float *normals, long long pixels, float l0, float l1, float l2)
 {
@@ -1192,6 +1234,11 @@ struct crb_filler {
     int raster_ctas;       // experiments: fixed k_raster grid (0 = automatic)
     int sm_count;
     int use_tma;           // tensor maps are built where the layout allows (CRB_NO_TMA=1 disables): k_clear stores TMA boxes
+    unsigned char *shown_busy;   // sparse read-back: per tile, was it busy in the frame the caller's host arrays show
+    long long shown_tiles;
+    unsigned long long *tiles_copied;   // device counter behind crb_readback_stats
+    const void *map_host[3];     // host pointers already resolved to device-visible addresses
+    void *map_dev[3];
     unsigned dbg_flags;    // ablation switches (CRB_DEBUG_SKIP), never set in production
     int out_tma;           // ... and so does k_raster for the shaded colour / normal rows (CRB_OUT_TMA=0 disables)
     unsigned long long *hstats;      // pinned + mapped: busy-tile statistics of the most recent k_raster launch
@@ -1521,6 +1568,8 @@ void crb_destroy(crb_filler *f)
     if (f->own_ws) cudaFree(f->ws);
     if (f->keybuf) cudaFree(f->keybuf);
     if (f->hstats) cudaFreeHost(f->hstats);
+    if (f->shown_busy) cudaFree(f->shown_busy);
+    if (f->tiles_copied) cudaFree(f->tiles_copied);
     if (f->prof_ev) {
         for (int i = 0; i < 2 * PROF_MAX; ++i) cudaEventDestroy(f->prof_ev[i]);
         delete[] f->prof_ev;
@@ -1659,8 +1708,48 @@ int crb_render_host(crb_filler *f, const float *v, const float *c, const float *
     }
     int rc = crb_render(f, f->stage_v, f->stage_c, f->stage_n, T, flags, stream);
     if (rc) return rc;
-    rc = crb_download(f, download_mask, z_out, color_out, normals_out, stream);
-    if (rc) return rc;
+    const bool sparse = (flags & CRB_DL_SPARSE) && (flags & CRB_CLEAR_FIRST) && !(flags & CRB_PATH_ATOMIC);
+    float *hp[3] = {(download_mask & CRB_BUF_Z) ? z_out : nullptr, (download_mask & CRB_BUF_COLOR) ? color_out : nullptr,
+                    (download_mask & CRB_BUF_NORMALS) ? normals_out : nullptr};
+    bool mapped = sparse;
+    for (int k = 0; k < 3 && mapped; ++k) {     // the host arrays must be pinned + device-visible for the tile copies
+        if (!hp[k]) continue;
+        if (f->map_host[k] != hp[k]) {
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, hp[k]) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
+                cudaGetLastError();
+                mapped = false;
+                break;
+            }
+            f->map_host[k] = hp[k];
+            f->map_dev[k] = at.devicePointer;
+        }
+        hp[k] = (float *)f->map_dev[k];
+    }
+    if (sparse && !mapped) return fail(CRB_ERR_INVALID, "CRB_DL_SPARSE needs pinned (cudaHostAlloc / cudaHostRegister'ed, mapped) output arrays");
+    if (sparse) {
+        Frame F;
+        fill_frame(f, &F);
+        F.z = f->z; F.color = f->color; F.normals = f->normals;
+        if (f->shown_tiles != F.nTiles) {
+            if (f->shown_busy) cudaFree(f->shown_busy);
+            f->shown_busy = nullptr;
+            CU(cudaMalloc(&f->shown_busy, (size_t)(F.nTiles > 0 ? F.nTiles : 1)));
+            CU(cudaMemsetAsync(f->shown_busy, 0, (size_t)(F.nTiles > 0 ? F.nTiles : 1), st));
+            f->shown_tiles = F.nTiles;
+        }
+        if (!f->tiles_copied) {
+            CU(cudaMalloc(&f->tiles_copied, 8));
+            CU(cudaMemsetAsync(f->tiles_copied, 0, 8, st));
+        }
+        if (F.nTiles > 0) {
+            k_readback<<<(unsigned)F.nTiles, NT, 0, st>>>(F, f->shown_busy, hp[0], hp[1], hp[2], f->tiles_copied);
+            if ((rc = launch_check(f, "k_readback"))) return rc;
+        }
+    } else {
+        rc = crb_download(f, download_mask, z_out, color_out, normals_out, stream);
+        if (rc) return rc;
+    }
     if (!(flags & CRB_NO_SYNC)) CU(cudaStreamSynchronize(st));
     return CRB_OK;
 }
@@ -1785,6 +1874,28 @@ int crb_sync(crb_filler *f, void *stream)
     if (check_filler(f)) return CRB_ERR_INVALID;
     CU(cudaSetDevice(f->device));
     CU(cudaStreamSynchronize((cudaStream_t)stream));
+    return CRB_OK;
+}
+
+int crb_readback_stats(crb_filler *f, int64_t *tiles_copied, int reset, void *stream)
+{
+    if (check_filler(f) || !tiles_copied) return fail(CRB_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(f->device));
+    unsigned long long n = 0;
+    if (f->tiles_copied) {
+        CU(cudaMemcpyAsync(&n, f->tiles_copied, 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        CU(cudaStreamSynchronize((cudaStream_t)stream));
+        if (reset) CU(cudaMemsetAsync(f->tiles_copied, 0, 8, (cudaStream_t)stream));
+    }
+    *tiles_copied = (int64_t)n;
+    return CRB_OK;
+}
+
+int crb_readback_reset(crb_filler *f, void *stream)
+{
+    if (check_filler(f)) return CRB_ERR_INVALID;
+    CU(cudaSetDevice(f->device));
+    if (f->shown_busy) CU(cudaMemsetAsync(f->shown_busy, 0, (size_t)(f->shown_tiles > 0 ? f->shown_tiles : 1), (cudaStream_t)stream));
     return CRB_OK;
 }
 

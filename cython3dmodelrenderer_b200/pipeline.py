@@ -25,9 +25,15 @@ class _Slot:
 
 
 class HostFramePipeline:
-    def __init__(self, h, w, fov=90.0, z_near=0.1, z_far=1000.0, depth=2, device=None, want=("z", "color", "normals")):
+    def __init__(self, h, w, fov=90.0, z_near=0.1, z_far=1000.0, depth=2, device=None, want=("z", "color", "normals"),
+                 sparse=True):
+        """sparse=True: CRB_DL_SPARSE read-back -- each slot's pinned host arrays persist between its frames, so only the
+        tiles that are busy in the new frame or were busy in the frame the arrays still show are copied (by a kernel that
+        writes into the mapped host memory); the arrays are bit-identical to a full download but READ-ONLY for the caller.
+        sparse=False: plain cudaMemcpy of the whole buffers every frame."""
         if depth < 1:
             raise ValueError("depth must be >= 1")
+        self.sparse = bool(sparse)
         self.want = tuple(want)
         self.mask = 0
         for name in self.want:
@@ -40,6 +46,12 @@ class HostFramePipeline:
             s.stream = torch.cuda.Stream(device=s.filler._dev)
             s.out = {name: s.filler._mirror(name) for name in self.want}      # pinned host tensors
             s.out_np = {name: s.filler._host_np[name] for name in self.want}
+            if self.sparse:          # the state CRB_DL_SPARSE assumes before the first frame: fresh-filler values (pyx:65-67)
+                for name, arr in s.out_np.items():
+                    arr[...] = 1e6 if name == "z" else 0.0
+                s.out_np = {name: arr.view() for name, arr in s.out_np.items()}
+                for arr in s.out_np.values():
+                    arr.flags.writeable = False
             s.stage = None
             s.busy = False
             self.slots.append(s)
@@ -83,7 +95,7 @@ class HostFramePipeline:
 
     def _launch(self, s):
         pv, pc, pn, T = s.args
-        check(self._L.crb_render_host(s.filler._handle, pv, pc, pn, T, _lib.CRB_CLEAR_FIRST | _lib.CRB_NO_SYNC, self.mask,
+        check(self._L.crb_render_host(s.filler._handle, pv, pc, pn, T, _lib.CRB_CLEAR_FIRST | _lib.CRB_NO_SYNC | (_lib.CRB_DL_SPARSE if self.sparse else 0), self.mask,
                                       self._ptr(s, "z"), self._ptr(s, "color"), self._ptr(s, "normals"),
                                       ctypes.c_void_p(s.stream.cuda_stream)))
 
@@ -107,6 +119,15 @@ class HostFramePipeline:
     def drain(self):
         for i in range(len(self.slots)):
             self.result(i)
+
+    def readback_tiles(self, reset=True):
+        """Tiles (32x32 pixels) copied to the host by the sparse read-back since the last reset, over all slots."""
+        total = 0
+        for s in self.slots:
+            n = ctypes.c_int64()
+            check(self._L.crb_readback_stats(s.filler._handle, ctypes.byref(n), int(reset), ctypes.c_void_p(s.stream.cuda_stream)))
+            total += n.value
+        return total
 
     @property
     def launch_count(self):

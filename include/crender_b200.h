@@ -50,6 +50,14 @@ extern "C" {
 #define CRB_NO_SYNC 8u         /* crb_render_host only: return once the work is queued; crb_sync() before reading
                                   the host outputs or reusing the host inputs (frame pipelining over several fillers) */
 
+#define CRB_DL_SPARSE 16u      /* crb_render_host + CRB_CLEAR_FIRST only: sparse read-back.  The caller promises that the host
+                                  output arrays still hold what the previous CRB_DL_SPARSE call of this filler left in them
+                                  (fresh-filler values -- z 1e6, colour 0, normals 0 -- before the first call, or after
+                                  crb_readback_reset).  Only tiles that are busy now or were busy in that previous frame are
+                                  then copied, by a kernel writing into the pinned + mapped host arrays; the arrays end up
+                                  bit-identical to a full download.  The arrays must come from cudaHostAlloc /
+                                  cudaHostRegister (e.g. torch pin_memory). */
+
 /* which-buffer masks for crb_download / crb_render_host */
 #define CRB_BUF_Z 1u
 #define CRB_BUF_COLOR 2u
@@ -153,6 +161,11 @@ int crb_upload(crb_filler *f, unsigned mask, const float *z_host, const float *c
  * produced; if it exceeded the workspace's pair capacity the frame was NOT drawn (buffers untouched) and the return
  * value is CRB_ERR_OVERFLOW -- re-bind a workspace with pair_capacity >= pairs_needed and render again. */
 int crb_status(crb_filler *f, int64_t *pairs_needed, int64_t *pair_capacity, void *stream);
+
+/* Sparse read-back bookkeeping: tiles (32x32 pixels, 28 KB for all three buffers) copied since the last reset of the
+ * counter; crb_readback_reset declares that the caller's host arrays hold fresh-filler values again. */
+int crb_readback_stats(crb_filler *f, int64_t *tiles_copied, int reset, void *stream);
+int crb_readback_reset(crb_filler *f, void *stream);
 
 /* Number of kernel launches issued by this filler since creation (bench.py's gpu_launches). */
 int64_t crb_launch_count(const crb_filler *f);

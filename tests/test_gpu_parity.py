@@ -404,13 +404,14 @@ def test_batched_views_partial_outputs_tma(Filler, O, trex):
     assert_same(tuple(full[k][2].cpu().numpy() for k in ("z", "color", "normals")), buffers(o), "view 2")
 
 
-def test_host_frame_pipeline_matches_oracle(O, trex):
+@pytest.mark.parametrize("sparse", [True, False])
+def test_host_frame_pipeline_matches_oracle(sparse, O, trex):
     """Pipelined host-buffer frames (crb_render_host + CRB_NO_SYNC over several fillers) give per frame the oracle's
     fresh-filler result, in submission order, for NumPy and pinned-tensor inputs alike."""
     import torch
     from cython3dmodelrenderer_b200 import HostFramePipeline, views as VW
     h, w = 192, 256
-    pipe = HostFramePipeline(h, w, fov=45.0, depth=3)
+    pipe = HostFramePipeline(h, w, fov=45.0, depth=3, sparse=sparse)
     views = VW.orbit_views(7)
     frames = [VW.transform_arrays_host(views[k], trex._vertices_by_triangles, trex._normals_by_triangles) for k in range(7)]
     want = []
@@ -435,3 +436,28 @@ def test_host_frame_pipeline_matches_oracle(O, trex):
         got[kk] = (r["z"].copy(), r["color"].copy(), r["normals"].copy())
     for k in range(7):
         assert_same(got[k], want[k], f"pipelined frame {k}")
+
+
+@pytest.mark.parametrize("size", [(96, 128), (100, 76), (50, 37), (257, 388)])
+def test_sparse_readback_equals_full_download(size, O):
+    """CRB_DL_SPARSE: a sequence of unrelated fresh frames through ONE slot (so every frame's host arrays start from the
+    previous frame's content) -- small scenes that leave most tiles empty, an empty scene, a dense one -- must leave the
+    host arrays bit-identical to the oracle's fresh-filler result each time, while copying fewer tiles than a dense
+    download would."""
+    from cython3dmodelrenderer_b200 import HostFramePipeline
+    h, w = size
+    pipe = HostFramePipeline(h, w, fov=60.0, depth=1, sparse=True)
+    tiles = ((h + 31) // 32) * ((w + 31) // 32)
+    scenes = [random_scene(11, T=6, span=0.3), random_scene(12, T=300), random_scene(13, T=0), random_scene(14, T=3, span=0.2),
+              random_scene(15, T=2000, span=0.8), random_scene(16, T=5, span=0.5)]
+    copied = []
+    for k, m in enumerate(scenes):
+        slot = pipe.submit(m._vertices_by_triangles, m._colors_by_triangles, m._normals_by_triangles)
+        r = pipe.result(slot)
+        o = O.OracleFiller(h, w, fov=60.0)
+        o.render_model(m)
+        assert_same((r["z"], r["color"], r["normals"]), buffers(o), f"sparse frame {k} {h}x{w}")
+        assert not r["z"].flags.writeable
+        copied.append(pipe.readback_tiles())
+    assert all(c <= tiles for c in copied)
+    assert copied[2] <= tiles and copied[3] < tiles or tiles <= 4      # tiny scenes after an empty one copy few tiles
