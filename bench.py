@@ -280,12 +280,13 @@ def run_gpu_arm(args):
     views_per_launch = V * args.steps / max(k_launches, 1)
     k_avg_ms = k_ms / max(k_launches, 1)
     achieved = alg_bytes_frame * views_per_launch / (k_avg_ms / 1000.0) / 1e9 if k_avg_ms > 0 else None
-    roofline = {"bound": "hbm", "kernel": "k_raster (tile rasterizer + deferred shading + fused clear)",
+    roofline = {"bound": "hbm", "kernel": "k_raster (tile rasterizer + deferred shading; every fourth CTA issues the fused clear as TMA boxes)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                 "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_frame * views_per_launch,
                 "avg_launch_ms": k_avg_ms, "launches_timed": k_launches, "share_of_step": k_ms / ms if ms else None,
-                "whole_step_achieved_gbs": alg_bytes_frame * V * args.steps / (e0.elapsed_time(e1) / 1000.0) / 1e9}
-    prof = os.path.join(ROOT, "profiles", "r01_k_raster_traffic.json")
+                "whole_step_achieved_gbs": alg_bytes_frame * V * args.steps / (e0.elapsed_time(e1) / 1000.0) / 1e9,
+                "whole_step_frac": alg_bytes_frame * V * args.steps / (e0.elapsed_time(e1) / 1000.0) / 1e9 / peak}
+    prof = os.path.join(ROOT, "profiles", "r01_k_raster_traffic.json")   # from the ncu --set full capture of the same launch
     if os.path.exists(prof):
         try:
             roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
