@@ -455,11 +455,19 @@ def run_extra_workload(args):
     light = -np.asarray([0, 0, 1], dtype="float32")
     light = light / np.linalg.norm(light)
 
+    from cython3dmodelrenderer_b200 import views as VW
+    ident = torch.from_numpy(VW.view_matrix()[None, :]).to(dev)     # identity rotation, zero pivot / translation
+    zb, cb, nb_ = f.device_buffers()
+
     def step():
-        f.clear()
-        f.render_arrays(dv, dc, dn, check_status=False)
         if args.workload == "bunny_4096_guro":
-            f.illuminate_guro(light)
+            # one frame = fused clear + raster + shading with the Guro light applied in the shading pass (CRB_GURO),
+            # written straight into the filler's own buffers (identity view: x*1 + 0 terms are exact)
+            f.render_views(dv, dc, dn, ident, z_out=zb[None], color_out=cb[None], normals_out=nb_[None], guro_light=[0, 0, 1],
+                           chunk=1, check_status=False)
+        else:
+            f.clear()
+            f.render_arrays(dv, dc, dn, check_status=False)
 
     def barrier():
         torch.cuda.synchronize()

@@ -39,6 +39,11 @@ namespace {
 constexpr int TW = 32;          // tile width in pixels  (one 128-byte line of z, three of colour / normals)
 constexpr int TH = 32;          // tile height in pixels
 constexpr int NT = 256;         // threads per CTA in every kernel
+#ifdef CRB_ABLATION
+#define DBG(F, bit) (((F).flags & (bit)) != 0u)
+#else
+#define DBG(F, bit) ((void)(bit), false)
+#endif
 constexpr unsigned FLAG_DBG_NOCLEAR = 0x10000u, FLAG_DBG_NOSHADE = 0x20000u, FLAG_DBG_NOROWS = 0x40000u, FLAG_DBG_NOOUT = 0x80000u;  // ablation switches (CRB_DEBUG_SKIP)
 constexpr unsigned FLAG_OUT_TMA = 0x100u;   // internal Frame.flags bit: shaded colour / normal rows leave through TMA boxes
 constexpr int CH = 128;         // triangles staged in shared memory per pass of the tile rasterizer
@@ -211,6 +216,10 @@ __device__ __forceinline__ float div_rn_by(float a, float d, float r)
     q = __fmaf_rn(e, r, q);
     e = __fmaf_rn(-d, q, a);
     return __fmaf_rn(e, r, q);
+}
+__device__ __forceinline__ bool fdiv_ok_lo(float n1, float n2, float n3)
+{
+    return fminf(fminf(fabsf(n1), fabsf(n2)), fabsf(n3)) >= FDIV_LO;   // NaN: false
 }
 __device__ __forceinline__ bool fdiv_ok(float n1, float n2, float n3)
 {
@@ -674,7 +683,7 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
         // Row work items, 32 per warp per trip.  Trip counts are warp-uniform and the body is predicated, so the warp
         // stays converged (a per-thread `for (r = tid; ...)` with early `continue`s lets lanes drift apart under
         // independent thread scheduling: measured 7.5 active lanes per instruction).
-        if (F.flags & FLAG_DBG_NOROWS) totalRows = 0;
+        if (DBG(F, FLAG_DBG_NOROWS)) totalRows = 0;
         for (unsigned rb = threadIdx.x & ~31u; rb < totalRows; rb += NT) {
             const unsigned r = rb + lane;
             const bool active = r < totalRows;
@@ -757,7 +766,7 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
             // replaces ran at 13 of 32 lanes).  A fragment finds its row through the slot its owner lane published.
             S.u.st.slot[wid][lane][0] = make_float4(A1, A2, A3, l02);
             S.u.st.slot[wid][lane][1] = make_float4(l12, l22, __uint_as_float(tri),
-                                                    __uint_as_float(o | ((unsigned)(y - y0) << 8) | (fdiv ? 65536u : 0u)));
+                                                    __uint_as_float(o | ((unsigned)(y - y0) << 8) | (fdiv ? 65536u : 0u) | (span ? 131072u : 0u)));
             unsigned short *fq = S.u.st.fq[wid];
             while (__any_sync(0xFFFFFFFFu, mask != 0u)) {   // one round unless some row has more than 8 survivors
                 const int cnt = min(__popc(mask), FQ / 32);
@@ -790,7 +799,8 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
                         const float n2 = q0.y - q1.x * (px - pa.x);
                         const float n3 = q0.z - q1.y * (px - pa.z);
                         float b1, b2, b3;
-                        if ((info & 65536u) && fdiv_ok(n1, n2, n3)) {
+                        // FL_SPAN rows have |numerator| < 2^40 by construction (coordinates <= 2^18): only the lower bound is tested
+                        if ((info & 65536u) && ((info & 131072u) ? fdiv_ok_lo(n1, n2, n3) : fdiv_ok(n1, n2, n3))) {
                             b1 = div_rn_by(n1, pc.y, pr.x); b2 = div_rn_by(n2, pc.z, pr.y); b3 = div_rn_by(n3, pc.w, pr.z);
                         } else {
                             b1 = n1 / pc.y; b2 = n2 / pc.z; b3 = n3 / pc.w;
@@ -824,7 +834,7 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
         float z = Z_INIT, c[3] = {bg, bg, bg}, nn[3] = {0.f, 0.f, 0.f};
         bool write = clear;
         const long long pix = slab + (long long)(yl0 + yy) * F.W + x0 + xx;
-        if (key != KEY_EMPTY && !(F.flags & FLAG_DBG_NOSHADE)) {
+        if (key != KEY_EMPTY && !DBG(F, FLAG_DBG_NOSHADE)) {
             const unsigned tri = ~(unsigned)(key & 0xFFFFFFFFull);
             const long long ridx = (long long)view * F.T + tri;
             float fz, fc[3], fn[3];
@@ -839,7 +849,7 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
         if (stage) {
             S.u.out.col[p * 3] = c[0]; S.u.out.col[p * 3 + 1] = c[1]; S.u.out.col[p * 3 + 2] = c[2];
             S.u.out.nrm[p * 3] = nn[0]; S.u.out.nrm[p * 3 + 1] = nn[1]; S.u.out.nrm[p * 3 + 2] = nn[2];
-            if (F.z && !(F.flags & FLAG_DBG_NOOUT)) F.z[pix] = z;
+            if (F.z && !DBG(F, FLAG_DBG_NOOUT)) F.z[pix] = z;
         } else if (write) {
             if (F.z) F.z[pix] = z;
             if (F.color) { F.color[pix * 3] = c[0]; F.color[pix * 3 + 1] = c[1]; F.color[pix * 3 + 2] = c[2]; }
@@ -852,7 +862,7 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
         }
     }
     PH(7);
-    if (F.flags & FLAG_DBG_NOOUT) return;
+    if (DBG(F, FLAG_DBG_NOOUT)) return;
     if (tma) {
         fence_async_smem();
         __syncthreads();
@@ -929,7 +939,7 @@ __global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame 
             unsigned t = e < nAll ? F.empty[e] : 0u;              // speculative: flies with the totals
             const unsigned long long pairs = F.total[0];
             const unsigned ne = (unsigned)F.total[3];
-            if (pairs > (unsigned long long)F.pairCap || (F.flags & FLAG_DBG_NOCLEAR)) return;     // frame skipped: buffers stay untouched
+            if (pairs > (unsigned long long)F.pairCap || DBG(F, FLAG_DBG_NOCLEAR)) return;     // frame skipped: buffers stay untouched
             const float bg = background_color(F);
             for (int i = threadIdx.x; i < BOX_ROWS * TW * 3; i += NT) {
                 S.u.pat.c[i] = bg; S.u.pat.n[i] = 0.0f;
@@ -960,7 +970,7 @@ __global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame 
     }
     if (bidx == 0 && threadIdx.x == 0 && F.hstats)
         *reinterpret_cast<volatile unsigned long long *>(F.hstats) = ((unsigned long long)nAll << 32) | nb;
-    if (clear && !split && !(F.flags & FLAG_DBG_NOCLEAR)) {
+    if (clear && !split && !DBG(F, FLAG_DBG_NOCLEAR)) {
         const unsigned ne = (unsigned)F.total[3];
         for (unsigned e = bidx; e < ne; e += Gb) {
             const unsigned t = F.empty[e];
