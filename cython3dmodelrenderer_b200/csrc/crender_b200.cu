@@ -980,12 +980,13 @@ __global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame 
     }
     PH(0);
     for (unsigned cta = bidx; cta < nb; cta += Gb) {
+        const uint4 cur = rec;
         if (cta != bidx) {
             if ((threadIdx.x & 31) == 0) tma_wait_read();   // the previous tile's rows have left shared memory
             __syncthreads();
-            rec = F.busy[cta];
         }
-        raster_tile(F, M, S, clear, (int)(rec.x >> 22), (int)(rec.x & 2047u), (int)((rec.x >> 11) & 2047u), rec.y, rec.z);
+        if (cta + Gb < nb) rec = F.busy[cta + Gb];          // the next tile's record arrives while this one is rasterized
+        raster_tile(F, M, S, clear, (int)(cur.x >> 22), (int)(cur.x & 2047u), (int)((cur.x >> 11) & 2047u), cur.y, cur.z);
     }
 #ifdef CRB_PHASE_TIMING
     ph_t = clock64();
@@ -1247,6 +1248,11 @@ struct crb_filler {
     unsigned long long *tiles_copied;   // device counter behind crb_readback_stats
     const void *map_host[3];     // host pointers already resolved to device-visible addresses
     void *map_dev[3];
+    size_t set_bytes;      // size of one workspace set
+    cudaStream_t s_prep, s_raster;      // batched views: setup/binning of launch i+1 runs beside the rasterizer of launch i
+    cudaEvent_t ev_start, ev_fill[2], ev_raster[2];
+    int chunk_pipeline;    // CRB_CHUNK_PIPELINE=0 disables
+    int tiles_per_cta;     // k_raster grid = estimated busy tiles / this (CRB_TILES_PER_CTA)
     unsigned dbg_flags;    // ablation switches (CRB_DEBUG_SKIP), never set in production
     int out_tma;           // ... and so does k_raster for the shaded colour / normal rows (CRB_OUT_TMA=0 disables)
     unsigned long long *hstats;      // pinned + mapped: busy-tile statistics of the most recent k_raster launch
@@ -1259,7 +1265,7 @@ struct crb_filler {
 namespace {
 
 struct WsLayout {
-    size_t shrec, recD, recE, count, offset, cursor, busy, empty, ls0, ls1, ls2, ls3, ls4, total, sv, sc, sn, bytes;
+    size_t shrec, recD, recE, count, offset, cursor, busy, empty, ls0, ls1, ls2, ls3, ls4, total, set_bytes, sv, sc, sn, bytes;
 };
 
 long long default_pair_cap(const crb_filler *f, long long T, int views)
@@ -1290,6 +1296,8 @@ WsLayout ws_layout(const crb_filler *f, long long T, int views, long long pairCa
     L.ls3 = take((size_t)pairCap * 16);
     L.ls4 = take((size_t)pairCap * 16);
     L.total = take(64);
+    L.set_bytes = o;            // everything above exists twice (two launches of a batch in flight, see crb_render_views)
+    o = 2 * L.set_bytes;
     L.sv = take((size_t)(T > 0 ? T : 1) * 36);
     L.sc = take((size_t)(T > 0 ? T : 1) * 36);
     L.sn = take((size_t)(T > 0 ? T : 1) * 36);
@@ -1323,7 +1331,7 @@ int host_projection(int h, int w, float fov, float z_near, float z_far, ProjC *P
     return CRB_OK;
 }
 
-void fill_frame(const crb_filler *f, Frame *F)
+void fill_frame(const crb_filler *f, Frame *F, int set = 0)
 {
     memset(F, 0, sizeof(*F));
     F->proj = f->proj;
@@ -1334,11 +1342,13 @@ void fill_frame(const crb_filler *f, Frame *F)
     F->tilesX = (f->w + TW - 1) / TW;
     F->tilesY = (f->row1 - f->row0 + TH - 1) / TH;
     F->nTiles = F->tilesX * F->tilesY;
-    F->shrec = f->shrec; F->recD = f->recD; F->recE = f->recE;
-    F->count = f->count; F->offset = f->offset; F->cursor = f->cursor;
-    F->busy = f->busy; F->empty = f->empty;
-    F->ls0 = f->ls0; F->ls1 = f->ls1; F->ls2 = f->ls2; F->ls3 = f->ls3; F->ls4 = f->ls4;
-    F->total = f->total;
+    const size_t so = set ? f->set_bytes : 0;     // the second workspace set lies set_bytes behind the first
+    auto at = [so](auto *p) { return reinterpret_cast<decltype(p)>(reinterpret_cast<char *>(p) + so); };
+    F->shrec = at(f->shrec); F->recD = at(f->recD); F->recE = at(f->recE);
+    F->count = at(f->count); F->offset = at(f->offset); F->cursor = at(f->cursor);
+    F->busy = at(f->busy); F->empty = at(f->empty);
+    F->ls0 = at(f->ls0); F->ls1 = at(f->ls1); F->ls2 = at(f->ls2); F->ls3 = at(f->ls3); F->ls4 = at(f->ls4);
+    F->total = at(f->total);
     F->hstats = f->hstats_dev;
     F->pairCap = f->pairCap;
     F->slabPixels = (long long)(f->row1 - f->row0) * f->w;
@@ -1397,23 +1407,35 @@ unsigned encode_maps(TMaps *M, const Frame &F)
 }
 
 // project/setup/count -> alloc -> fill -> raster+shade for up to maxViews views
-int run_tiled(crb_filler *f, Frame &F, cudaStream_t st, int slot = 0)
+// project/setup/count -> alloc -> fill for up to maxViews views
+int run_prep(crb_filler *f, Frame &F, cudaStream_t st)
 {
-    slot &= 7;                                   // busy-tile statistics are kept per position in a batch of launches
-    if (F.hstats) F.hstats += slot;
     int rc;
     const unsigned gT = (unsigned)((F.T + NT - 1) / NT);
     if (F.T > 0) {
         k_setup<<<dim3(gT, F.nViews), NT, 0, st>>>(F);
         if ((rc = launch_check(f, "k_setup"))) return rc;
     } else {
-        CU(cudaMemsetAsync(f->total, 0, 8, st));
-        CU(cudaMemsetAsync(f->total + 2, 0, 16, st));
+        CU(cudaMemsetAsync(F.total, 0, 8, st));
+        CU(cudaMemsetAsync(F.total + 2, 0, 16, st));
     }
     const long long nAllTiles = (long long)F.nViews * F.nTiles;
     k_alloc<<<(unsigned)((nAllTiles + NT - 1) / NT), NT, 0, st>>>(F);
     if ((rc = launch_check(f, "k_alloc"))) return rc;
+    if (F.T > 0) {
+        k_fill<<<dim3(gT, F.nViews), NT, 0, st>>>(F);
+        if ((rc = launch_check(f, "k_fill"))) return rc;
+    }
+    return CRB_OK;
+}
 
+// raster + shade (+ fused clear) of the frame run_prep binned
+int run_raster(crb_filler *f, Frame &F, cudaStream_t st, int slot)
+{
+    int rc;
+    slot &= 7;                                   // busy-tile statistics are kept per position in a batch of launches
+    if (F.hstats) F.hstats += slot;
+    const long long nAllTiles = (long long)F.nViews * F.nTiles;
     const bool prof = f->prof_on && f->prof_n < PROF_MAX;
     TMaps M;
     memset(&M, 0, sizeof(M));
@@ -1421,10 +1443,6 @@ int run_tiled(crb_filler *f, Frame &F, cudaStream_t st, int slot = 0)
     if (f->use_tma && clear && !(F.W & 3) && !F.color_u8) M.use = encode_maps(&M, F);
     if (M.use && f->out_tma) F.flags |= FLAG_OUT_TMA;
     F.flags |= f->dbg_flags;
-    if (F.T > 0) {
-        k_fill<<<dim3(gT, F.nViews), NT, 0, st>>>(F);
-        if ((rc = launch_check(f, "k_fill"))) return rc;
-    }
     // Grid: one CTA per busy tile.  The busy count is only known on the device, so the grid is sized from the busy
     // FRACTION the previous launch posted (+12 % and a floor of one wave); k_raster walks with stride gridDim when the
     // estimate was low, and an all-tiles grid is used until a first launch has reported.
@@ -1434,7 +1452,7 @@ int run_tiled(crb_filler *f, Frame &F, cudaStream_t st, int slot = 0)
         const unsigned long long hs = *reinterpret_cast<volatile unsigned long long *>(f->hstats + slot);
         const double tiles = (double)(hs >> 32), busy = (double)(hs & 0xFFFFFFFFull);
         if (tiles > 0) {
-            gR = (long long)(busy / tiles * 1.125 * (double)nAllTiles) + 64;
+            gR = (long long)(busy / tiles * 1.125 * (double)nAllTiles / (double)f->tiles_per_cta) + 64;
             const long long wave = (long long)f->sm_count * CRB_RASTER_MIN_CTAS;
             if (gR < wave) gR = wave;
         }
@@ -1450,6 +1468,12 @@ int run_tiled(crb_filler *f, Frame &F, cudaStream_t st, int slot = 0)
         f->prof_n++;
     }
     return CRB_OK;
+}
+
+int run_tiled(crb_filler *f, Frame &F, cudaStream_t st, int slot = 0)
+{
+    int rc = run_prep(f, F, st);
+    return rc ? rc : run_raster(f, F, st, slot);
 }
 
 int run_atomic(crb_filler *f, Frame &F, cudaStream_t st)
@@ -1494,8 +1518,11 @@ int bind_ws_pointers(crb_filler *f, void *ws, size_t bytes, long long T, int vie
     f->ls0 = (float4 *)(b + L.ls0); f->ls1 = (float4 *)(b + L.ls1); f->ls2 = (float4 *)(b + L.ls2); f->ls3 = (uint4 *)(b + L.ls3); f->ls4 = (float4 *)(b + L.ls4);
     f->total = (unsigned long long *)(b + L.total);
     f->stage_v = (float *)(b + L.sv); f->stage_c = (float *)(b + L.sc); f->stage_n = (float *)(b + L.sn);
-    CU(cudaMemsetAsync(b + L.count, 0, L.offset - L.count, st));  // tile counts start at zero, k_alloc keeps them so
-    CU(cudaMemsetAsync(b + L.total, 0, 64, st));
+    f->set_bytes = L.set_bytes;
+    for (int k = 0; k < 2; ++k) {
+        CU(cudaMemsetAsync(b + k * L.set_bytes + L.count, 0, L.offset - L.count, st));  // tile counts start at zero, k_alloc keeps them so
+        CU(cudaMemsetAsync(b + k * L.set_bytes + L.total, 0, 64, st));
+    }
     return CRB_OK;
 }
 
@@ -1552,6 +1579,23 @@ int crb_create(int h, int w, float fov, float z_near, float z_far, int device, c
         f->raster_ctas = 0;
         if (const char *e = getenv("CRB_RASTER_CTAS")) f->raster_ctas = atoi(e);   // experiments: >0 fixed grid, <0 one CTA per tile
         f->use_tma = 1;
+        f->chunk_pipeline = 1;
+        if (const char *e = getenv("CRB_CHUNK_PIPELINE")) f->chunk_pipeline = atoi(e) ? 1 : 0;
+        {
+            int lo = 0, hi = 0;
+            CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            int pp = lo;           // equal priorities measured best (a high-priority front end costs the rasterizer more than it gains)
+            if (const char *e = getenv("CRB_PREP_PRIORITY")) pp = atoi(e) ? hi : lo;
+            CU(cudaStreamCreateWithPriority(&f->s_prep, cudaStreamNonBlocking, pp));
+            CU(cudaStreamCreateWithPriority(&f->s_raster, cudaStreamNonBlocking, lo));
+        }
+        CU(cudaEventCreateWithFlags(&f->ev_start, cudaEventDisableTiming));
+        for (int k = 0; k < 2; ++k) {
+            CU(cudaEventCreateWithFlags(&f->ev_fill[k], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&f->ev_raster[k], cudaEventDisableTiming));
+        }
+        f->tiles_per_cta = 1;
+        if (const char *e = getenv("CRB_TILES_PER_CTA")) { int k = atoi(e); if (k >= 1 && k <= 64) f->tiles_per_cta = k; }
         if (const char *e = getenv("CRB_NO_TMA")) f->use_tma = atoi(e) ? 0 : 1;
         f->out_tma = 1;
         if (const char *e = getenv("CRB_DEBUG_SKIP")) f->dbg_flags = ((unsigned)atoi(e) & 15u) << 16;
@@ -1577,6 +1621,13 @@ void crb_destroy(crb_filler *f)
     if (f->own_ws) cudaFree(f->ws);
     if (f->keybuf) cudaFree(f->keybuf);
     if (f->hstats) cudaFreeHost(f->hstats);
+    if (f->s_prep) cudaStreamDestroy(f->s_prep);
+    if (f->s_raster) cudaStreamDestroy(f->s_raster);
+    if (f->ev_start) cudaEventDestroy(f->ev_start);
+    for (int k = 0; k < 2; ++k) {
+        if (f->ev_fill[k]) cudaEventDestroy(f->ev_fill[k]);
+        if (f->ev_raster[k]) cudaEventDestroy(f->ev_raster[k]);
+    }
     if (f->shown_busy) cudaFree(f->shown_busy);
     if (f->tiles_copied) cudaFree(f->tiles_copied);
     if (f->prof_ev) {
@@ -1780,9 +1831,22 @@ int crb_render_views(crb_filler *f, const float *v, const float *c, const float 
     CU(cudaSetDevice(f->device));
     const long long slab = (long long)(f->row1 - f->row0) * f->w;
     if (slab == 0) return CRB_OK;
-    for (int v0 = 0; v0 < n_views; v0 += f->maxViews) {
+    // Launches of maxViews views each.  With more than one launch, launch i+1's setup / binning kernels run on a second
+    // stream beside launch i's rasterizer (two workspace sets): the memory-bound front end hides behind the issue-bound
+    // rasterizer.  Rasterizer launches themselves stay serialised (they would only share the SMs).
+    cudaStream_t user = (cudaStream_t)stream;
+    const int launches = (n_views + f->maxViews - 1) / f->maxViews;
+    const bool pipe = f->chunk_pipeline && launches > 1;
+    if (pipe) {
+        CU(cudaEventRecord(f->ev_start, user));
+        CU(cudaStreamWaitEvent(f->s_prep, f->ev_start, 0));
+        CU(cudaStreamWaitEvent(f->s_raster, f->ev_start, 0));
+    }
+    int i = 0;
+    for (int v0 = 0; v0 < n_views; v0 += f->maxViews, ++i) {
+        const int set = pipe ? (i & 1) : 0;
         Frame F;
-        fill_frame(f, &F);
+        fill_frame(f, &F, set);
         F.T = T; F.nViews = (n_views - v0 < f->maxViews) ? n_views - v0 : f->maxViews;
         F.flags = (flags & CRB_GURO) | CRB_CLEAR_FIRST;
         F.v = v; F.c = c; F.n = n;
@@ -1792,9 +1856,20 @@ int crb_render_views(crb_filler *f, const float *v, const float *c, const float 
         F.normals = normals_out ? normals_out + (size_t)v0 * slab * 3 : nullptr;
         F.color_u8 = color_u8_out ? color_u8_out + (size_t)v0 * slab * 3 : nullptr;
         if (light) { F.light[0] = light[0]; F.light[1] = light[1]; F.light[2] = light[2]; }
-        int rc = run_tiled(f, F, (cudaStream_t)stream, v0 / f->maxViews);
-        if (rc) return rc;
+        int rc;
+        if (!pipe) {
+            rc = run_tiled(f, F, user, i);
+            if (rc) return rc;
+            continue;
+        }
+        if (i >= 2) CU(cudaStreamWaitEvent(f->s_prep, f->ev_raster[set], 0));    // the set's previous frame has been rasterized
+        if ((rc = run_prep(f, F, f->s_prep))) return rc;
+        CU(cudaEventRecord(f->ev_fill[set], f->s_prep));
+        CU(cudaStreamWaitEvent(f->s_raster, f->ev_fill[set], 0));
+        if ((rc = run_raster(f, F, f->s_raster, i))) return rc;
+        CU(cudaEventRecord(f->ev_raster[set], f->s_raster));
     }
+    if (pipe) CU(cudaStreamWaitEvent(user, f->ev_raster[(launches - 1) & 1], 0));
     return CRB_OK;
 }
 
@@ -1864,18 +1939,33 @@ int crb_status(crb_filler *f, int64_t *pairs_needed, int64_t *pair_capacity, voi
     if (check_filler(f)) return CRB_ERR_INVALID;
     if (!f->ws) return fail(CRB_ERR_STATE, "workspace not bound");
     CU(cudaSetDevice(f->device));
-    unsigned long long t[2] = {0, 0};
+    unsigned long long t[2] = {0, 0}, u[2] = {0, 0};
+    unsigned long long *total1 = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(f->total) + f->set_bytes);
     CU(cudaMemcpyAsync(t, f->total, 16, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU(cudaMemcpyAsync(u, total1, 16, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CU(cudaStreamSynchronize((cudaStream_t)stream));
+    if (u[0] > t[0]) t[0] = u[0];
+    if (u[1] > t[1]) t[1] = u[1];
     if (pair_capacity) *pair_capacity = f->pairCap;
     if (t[1] > (unsigned long long)f->pairCap) {
         if (pairs_needed) *pairs_needed = (int64_t)t[1];
         CU(cudaMemsetAsync(f->total + 1, 0, 8, (cudaStream_t)stream));
+        CU(cudaMemsetAsync(total1 + 1, 0, 8, (cudaStream_t)stream));
         return fail(CRB_ERR_OVERFLOW, "frame needs %llu (triangle,tile) pairs, workspace holds %lld; frame not drawn", t[1],
                     f->pairCap);
     }
     if (pairs_needed) *pairs_needed = (int64_t)t[0];
     return CRB_OK;
+}
+
+int crb_set_option(crb_filler *f, int option, int value)
+{
+    if (check_filler(f)) return CRB_ERR_INVALID;
+    switch (option) {
+    case CRB_OPT_CHUNK_PIPELINE: f->chunk_pipeline = value ? 1 : 0; return CRB_OK;
+    case CRB_OPT_TMA: f->use_tma = value ? 1 : 0; return CRB_OK;
+    default: return fail(CRB_ERR_INVALID, "unknown option %d", option);
+    }
 }
 
 int crb_sync(crb_filler *f, void *stream)

@@ -124,6 +124,13 @@ int crb_render(crb_filler *f, const float *v, const float *c, const float *n, in
 int crb_render_host(crb_filler *f, const float *v, const float *c, const float *n, int64_t T, unsigned flags,
                     unsigned download_mask, float *z_out, float *color_out, float *normals_out, void *stream);
 
+/* Tuning switches (defaults: all on).  CRB_OPT_CHUNK_PIPELINE: crb_render_views runs the setup / binning kernels of launch
+ * i+1 on an internal stream beside the rasterizer of launch i (two workspace sets).  CRB_OPT_TMA: tensor-map (TMA box) stores
+ * for the fused clear and the shaded rows where the layout allows.  Results do not depend on either. */
+#define CRB_OPT_CHUNK_PIPELINE 1
+#define CRB_OPT_TMA 2
+int crb_set_option(crb_filler *f, int option, int value);
+
 /* Waits for everything queued on `stream` (pairs with CRB_NO_SYNC). */
 int crb_sync(crb_filler *f, void *stream);
 

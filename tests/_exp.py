@@ -15,7 +15,7 @@ z = torch.empty((V, res, res), device='cuda'); c = torch.empty((V, res, res, 3),
 
 
 def run(label, env, zz=z, cc=c, nn=n):
-    for k in ("CRB_NO_TMA", "CRB_RASTER_CTAS", "CRB_OUT_TMA", "CRB_DEBUG_SKIP"):
+    for k in ("CRB_NO_TMA", "CRB_RASTER_CTAS", "CRB_OUT_TMA", "CRB_DEBUG_SKIP", "CRB_TILES_PER_CTA"):
         os.environ.pop(k, None)
     os.environ.update(env)
     f = AdvancedPixelBufferFiller(res, res, fov=45.0)
@@ -39,9 +39,8 @@ def run(label, env, zz=z, cc=c, nn=n):
 
 
 run("default", {})
-run("no clear", {"CRB_DEBUG_SKIP": "1"})
-run("no shading", {"CRB_DEBUG_SKIP": "2"})
-run("no rows", {"CRB_DEBUG_SKIP": "4"})
-run("no busy-tile output", {"CRB_DEBUG_SKIP": "8"})
+for k in (2, 3, 4, 8):
+    run(f"{k} tiles per CTA", {"CRB_TILES_PER_CTA": str(k)})
 run("only staging (15)", {"CRB_DEBUG_SKIP": "15"})
-run("vector rows", {"CRB_OUT_TMA": "0"})
+run("only staging, 2 tiles per CTA", {"CRB_DEBUG_SKIP": "15", "CRB_TILES_PER_CTA": "2"})
+run("only staging, 4 tiles per CTA", {"CRB_DEBUG_SKIP": "15", "CRB_TILES_PER_CTA": "4"})

@@ -461,3 +461,26 @@ def test_sparse_readback_equals_full_download(size, O):
         copied.append(pipe.readback_tiles())
     assert all(c <= tiles for c in copied)
     assert copied[2] <= tiles and copied[3] < tiles or tiles <= 4      # tiny scenes after an empty one copy few tiles
+
+
+def test_chunk_pipeline_and_tma_switches_do_not_change_results(Filler, trex):
+    """crb_set_option: the two-stream launch pipeline (two workspace sets) and the TMA stores are tuning switches."""
+    import torch
+    from cython3dmodelrenderer_b200 import _lib, views as VW
+    h, w = 128, 160
+    dv, dc, dn = (torch.from_numpy(a).cuda() for a in
+                  (trex._vertices_by_triangles, trex._colors_by_triangles, trex._normals_by_triangles))
+    views = VW.orbit_views(9)
+    ref = None
+    for pipe, tma in ((1, 1), (0, 1), (1, 0), (0, 0)):
+        f = Filler(h, w, fov=45.0)
+        _lib.check(f._L.crb_set_option(f._handle, _lib.CRB_OPT_CHUNK_PIPELINE, pipe))
+        _lib.check(f._L.crb_set_option(f._handle, _lib.CRB_OPT_TMA, tma))
+        for _ in range(2):      # twice: the second batch reuses both workspace sets
+            out = f.render_views(dv, dc, dn, views, chunk=2)
+        got = {k: out[k].cpu().numpy().view(np.uint32) for k in ("z", "color", "normals")}
+        if ref is None:
+            ref = got
+        else:
+            for k in ref:
+                assert np.array_equal(ref[k], got[k]), (pipe, tma, k)
