@@ -67,7 +67,7 @@ def test_dense_scenes_bit_exact(seed, Filler, O):
 
 @pytest.mark.parametrize("case", ["trex_1024x1024_fov45", "trex_512x512_fov90", "trex_333x777_fov60",
                                   "trex_2048x2048_fov45", "bunny_1024x1024_fov45", "bunny_500x300_fov30",
-                                  "bunny_4096x4096_fov45"])
+                                  "bunny_2048x2048_fov45", "bunny_4096x4096_fov45"])
 def test_reference_golden_checksums(case, Filler, trex, bunny):
     info = CHECKS["cases"][case]
     m = {"trex": trex, "bunny": bunny}[info["model"]]
@@ -484,3 +484,30 @@ def test_chunk_pipeline_and_tma_switches_do_not_change_results(Filler, trex):
         else:
             for k in ref:
                 assert np.array_equal(ref[k], got[k]), (pipe, tma, k)
+
+
+def test_integration_stub_flow_without_torch(O, trex):
+    """a maintainer's ctypes binding -- crb_create, crb_alloc_owned (library-owned device
+    memory), crb_render_host with plain (pageable) NumPy arrays in and out, compositing two calls -- no torch anywhere."""
+    import ctypes
+    from cython3dmodelrenderer_b200 import _lib
+    L = _lib.load_library()
+    h, w = 200, 240
+    f = ctypes.c_void_p()
+    _lib.check(L.crb_create(h, w, 45.0, 0.1, 1000.0, 0, ctypes.byref(f)))
+    try:
+        v, c, n = (np.ascontiguousarray(a) for a in (trex._vertices_by_triangles, trex._colors_by_triangles, trex._normals_by_triangles))
+        _lib.check(L.crb_alloc_owned(f, v.shape[0], 1, 0))
+        z = np.empty((h, w), np.float32); col = np.empty((h, w, 3), np.float32); nrm = np.empty((h, w, 3), np.float32)
+        o = O.OracleFiller(h, w, fov=45.0)
+        for rep in range(2):                     # the second call composites into the first (equal depths overwrite)
+            half = slice(0, v.shape[0] // 2) if rep == 0 else slice(None)
+            _lib.check(L.crb_render_host(f, v[half].ctypes.data, c[half].ctypes.data, n[half].ctypes.data, v[half].shape[0], 0,
+                                         _lib.CRB_BUF_ALL, z.ctypes.data, col.ctypes.data, nrm.ctypes.data, None))
+            o.render_arrays(v[half], c[half], n[half])
+            assert_same((z, col, nrm), buffers(o), f"stub call {rep}")
+        need, cap = ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(L.crb_status(f, ctypes.byref(need), ctypes.byref(cap), None))
+        assert 0 < need.value <= cap.value
+    finally:
+        L.crb_destroy(f)
