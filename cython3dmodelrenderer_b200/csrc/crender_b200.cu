@@ -47,6 +47,7 @@ constexpr int NT = 256;         // threads per CTA in every kernel
 constexpr unsigned FLAG_DBG_NOCLEAR = 0x10000u, FLAG_DBG_NOSHADE = 0x20000u, FLAG_DBG_NOROWS = 0x40000u, FLAG_DBG_NOOUT = 0x80000u;  // ablation switches (CRB_DEBUG_SKIP)
 constexpr unsigned FLAG_OUT_TMA = 0x100u;   // internal Frame.flags bit: shaded colour / normal rows leave through TMA boxes
 constexpr int CH = 128;         // triangles staged in shared memory per pass of the tile rasterizer
+constexpr unsigned HEAVY_N = 64;  // tiles with more triangles than this are rasterized first (longest first: shorter kernel tail)
 constexpr int FQ = 256;          // fragments a warp compacts per round (8 per row)
 constexpr int KEY_STRIDE = TW + 1;  // padded key row: rows of one column land in different banks
 constexpr unsigned long long KEY_EMPTY = 0xFFFFFFFFFFFFFFFFull;
@@ -91,6 +92,8 @@ struct Frame {
     float4 *recD, *recE;        // [nViews*T]
     unsigned *count;            // [nViews*nTiles] triangles per tile, accumulated by k_setup, returned to zero by k_alloc
     uint4 *busy;                // [nViews*nTiles] compacted busy tiles: (view:10 ty:11 tx:11, triangles, list offset, -); count in total[2]
+    uint4 *busyH;               // [nViews*nTiles] the same for tiles with more than HEAVY_N triangles; count in total[4]
+    unsigned gridHeavy;         // rasterizing CTA roles [0, gridHeavy) walk busyH, the others walk busy
     unsigned *empty;            // [nViews*nTiles] compacted tiles without triangles (same packing); count in total[3]
     unsigned *offset;           // [nViews*nTiles] start of the tile's list
     unsigned *cursor;           // [nViews*nTiles] fill cursor
@@ -313,7 +316,7 @@ __global__ void __launch_bounds__(NT) k_setup(const Frame F)
     const long long first = (long long)blockIdx.x * NT;
     const long long cnt = min((long long)NT, F.T - first);
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {  // k_alloc (next launch) accumulates
-        F.total[0] = 0ull; F.total[2] = 0ull; F.total[3] = 0ull;
+        F.total[0] = 0ull; F.total[2] = 0ull; F.total[3] = 0ull; F.total[4] = 0ull;
     }
     stage_floats(F.v, first * 9, cnt * 9, sv);
     stage_floats(F.n, first * 9, cnt * 9, sn);
@@ -439,13 +442,16 @@ __global__ void __launch_bounds__(NT) k_alloc(const Frame F)
     const long long i = (long long)blockIdx.x * NT + threadIdx.x;
     const long long nAll = (long long)F.nViews * F.nTiles;
     const unsigned c = (i < nAll) ? F.count[i] : 0u;
-    unsigned tot, nbusy;
+    unsigned tot, nbusy, nheavy;
     const unsigned excl = block_exclusive_scan(c, warp_sums, tot);
     const unsigned brank = block_exclusive_scan(c ? 1u : 0u, warp_sums, nbusy);
+    const unsigned hrank = block_exclusive_scan(c > HEAVY_N ? 1u : 0u, warp_sums, nheavy);
+    __shared__ unsigned heavy_base;
     if (threadIdx.x == 0) {
         const unsigned valid = (unsigned)min((long long)NT, nAll - (long long)blockIdx.x * NT);
         block_base = tot ? atomicAdd(F.total, (unsigned long long)tot) : 0ull;
-        busy_base = (unsigned)atomicAdd(F.total + 2, (unsigned long long)nbusy);
+        busy_base = (unsigned)atomicAdd(F.total + 2, (unsigned long long)(nbusy - nheavy));
+        heavy_base = (unsigned)atomicAdd(F.total + 4, (unsigned long long)nheavy);
         empty_base = (unsigned)atomicAdd(F.total + 3, (unsigned long long)(valid - nbusy));
     }
     __syncthreads();
@@ -457,7 +463,8 @@ __global__ void __launch_bounds__(NT) k_alloc(const Frame F)
         F.count[i] = 0u;   // self-cleaning: the next frame's k_setup starts from zero
         const unsigned vw = (unsigned)(i / F.nTiles), tl = (unsigned)(i % F.nTiles);
         const unsigned packed = (vw << 22) | ((tl / (unsigned)F.tilesX) << 11) | (tl % (unsigned)F.tilesX);   // view:10 ty:11 tx:11
-        if (c) F.busy[busy_base + brank] = make_uint4(packed, c, o32, 0u);
+        if (c > HEAVY_N) F.busyH[heavy_base + hrank] = make_uint4(packed, c, o32, 0u);
+        else if (c) F.busy[busy_base + (brank - hrank)] = make_uint4(packed, c, o32, 0u);
         else F.empty[empty_base + (threadIdx.x - brank)] = packed;
     }
 }
@@ -961,15 +968,24 @@ __global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame 
         }
         bidx = ci * 3u + (blockIdx.x & 3u);
     }
-    uint4 rec = bidx < nAll ? F.busy[bidx] : make_uint4(0u, 0u, 0u, 0u);   // speculative: flies with the totals
+    // the first gridHeavy roles take the tiles with many triangles, in blockIdx (= dispatch) order before everything else
+    const unsigned GH = F.gridHeavy;
+    const bool heavyRole = bidx < GH;
+    const uint4 *lst = heavyRole ? F.busyH : F.busy;
+    const unsigned first = heavyRole ? bidx : bidx - GH, stride = heavyRole ? GH : Gb - GH;
+    uint4 rec = first < nAll ? lst[first] : make_uint4(0u, 0u, 0u, 0u);   // speculative: flies with the totals
     const unsigned long long pairs = F.total[0];
-    const unsigned nb = (unsigned)F.total[2];
+    const unsigned nLight = (unsigned)F.total[2], nHeavy = (unsigned)F.total[4];
+    const unsigned nb = heavyRole ? nHeavy : nLight;
     if (pairs > (unsigned long long)F.pairCap) {   // frame skipped; the host is told via crb_status
         if (bidx == 0 && threadIdx.x == 0) atomicMax(F.total + 1, pairs);
         return;
     }
-    if (bidx == 0 && threadIdx.x == 0 && F.hstats)
-        *reinterpret_cast<volatile unsigned long long *>(F.hstats) = ((unsigned long long)nAll << 32) | nb;
+    if (bidx == 0 && threadIdx.x == 0 && F.hstats) {
+        volatile unsigned long long *hs = reinterpret_cast<volatile unsigned long long *>(F.hstats);
+        hs[0] = ((unsigned long long)nAll << 32) | nLight;
+        hs[1] = nHeavy;
+    }
     if (clear && !split && !DBG(F, FLAG_DBG_NOCLEAR)) {
         const unsigned ne = (unsigned)F.total[3];
         for (unsigned e = bidx; e < ne; e += Gb) {
@@ -979,13 +995,13 @@ __global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame 
         }
     }
     PH(0);
-    for (unsigned cta = bidx; cta < nb; cta += Gb) {
+    for (unsigned cta = first; cta < nb; cta += stride) {
         const uint4 cur = rec;
-        if (cta != bidx) {
+        if (cta != first) {
             if ((threadIdx.x & 31) == 0) tma_wait_read();   // the previous tile's rows have left shared memory
             __syncthreads();
         }
-        if (cta + Gb < nb) rec = F.busy[cta + Gb];          // the next tile's record arrives while this one is rasterized
+        if (cta + stride < nb) rec = lst[cta + stride];     // the next tile's record arrives while this one is rasterized
         raster_tile(F, M, S, clear, (int)(cur.x >> 22), (int)(cur.x & 2047u), (int)((cur.x >> 11) & 2047u), cur.y, cur.z);
     }
 #ifdef CRB_PHASE_TIMING
@@ -1229,7 +1245,7 @@ struct crb_filler {
     long long pairCap;
     float4 *shrec, *recD, *recE;
     unsigned *count, *offset, *cursor, *empty;
-    uint4 *busy;
+    uint4 *busy, *busyH;
     float4 *ls0, *ls1, *ls2;
     uint4 *ls3;
     float4 *ls4;
@@ -1265,7 +1281,7 @@ struct crb_filler {
 namespace {
 
 struct WsLayout {
-    size_t shrec, recD, recE, count, offset, cursor, busy, empty, ls0, ls1, ls2, ls3, ls4, total, set_bytes, sv, sc, sn, bytes;
+    size_t shrec, recD, recE, count, offset, cursor, busy, busyH, empty, ls0, ls1, ls2, ls3, ls4, total, set_bytes, sv, sc, sn, bytes;
 };
 
 long long default_pair_cap(const crb_filler *f, long long T, int views)
@@ -1289,6 +1305,7 @@ WsLayout ws_layout(const crb_filler *f, long long T, int views, long long pairCa
     L.offset = take((size_t)tiles * views * 4);
     L.cursor = take((size_t)tiles * views * 4);
     L.busy = take((size_t)tiles * views * 16);
+    L.busyH = take((size_t)tiles * views * 16);
     L.empty = take((size_t)tiles * views * 4);
     L.ls0 = take((size_t)pairCap * 16);
     L.ls1 = take((size_t)pairCap * 16);
@@ -1346,7 +1363,7 @@ void fill_frame(const crb_filler *f, Frame *F, int set = 0)
     auto at = [so](auto *p) { return reinterpret_cast<decltype(p)>(reinterpret_cast<char *>(p) + so); };
     F->shrec = at(f->shrec); F->recD = at(f->recD); F->recE = at(f->recE);
     F->count = at(f->count); F->offset = at(f->offset); F->cursor = at(f->cursor);
-    F->busy = at(f->busy); F->empty = at(f->empty);
+    F->busy = at(f->busy); F->busyH = at(f->busyH); F->empty = at(f->empty);
     F->ls0 = at(f->ls0); F->ls1 = at(f->ls1); F->ls2 = at(f->ls2); F->ls3 = at(f->ls3); F->ls4 = at(f->ls4);
     F->total = at(f->total);
     F->hstats = f->hstats_dev;
@@ -1434,7 +1451,7 @@ int run_raster(crb_filler *f, Frame &F, cudaStream_t st, int slot)
 {
     int rc;
     slot &= 7;                                   // busy-tile statistics are kept per position in a batch of launches
-    if (F.hstats) F.hstats += slot;
+    if (F.hstats) F.hstats += 2 * slot;
     const long long nAllTiles = (long long)F.nViews * F.nTiles;
     const bool prof = f->prof_on && f->prof_n < PROF_MAX;
     TMaps M;
@@ -1446,19 +1463,25 @@ int run_raster(crb_filler *f, Frame &F, cudaStream_t st, int slot)
     // Grid: one CTA per busy tile.  The busy count is only known on the device, so the grid is sized from the busy
     // FRACTION the previous launch posted (+12 % and a floor of one wave); k_raster walks with stride gridDim when the
     // estimate was low, and an all-tiles grid is used until a first launch has reported.
-    long long gR = nAllTiles;
-    if (f->raster_ctas > 0) gR = f->raster_ctas;
+    long long gL = nAllTiles, gH = nAllTiles / 16 + 1;     // light / heavy rasterizing roles
+    if (f->raster_ctas > 0) { gL = f->raster_ctas; gH = f->raster_ctas / 8 + 1; }
     else if (f->hstats && f->raster_ctas == 0) {
-        const unsigned long long hs = *reinterpret_cast<volatile unsigned long long *>(f->hstats + slot);
-        const double tiles = (double)(hs >> 32), busy = (double)(hs & 0xFFFFFFFFull);
+        const unsigned long long hs = *reinterpret_cast<volatile unsigned long long *>(f->hstats + 2 * slot);
+        const unsigned long long hh = *reinterpret_cast<volatile unsigned long long *>(f->hstats + 2 * slot + 1);
+        const double tiles = (double)(hs >> 32), light = (double)(hs & 0xFFFFFFFFull), heavy = (double)hh;
         if (tiles > 0) {
-            gR = (long long)(busy / tiles * 1.125 * (double)nAllTiles / (double)f->tiles_per_cta) + 64;
+            gL = (long long)(light / tiles * 1.125 * (double)nAllTiles / (double)f->tiles_per_cta) + 56;
+            gH = (long long)(heavy / tiles * 1.125 * (double)nAllTiles) + 8;
             const long long wave = (long long)f->sm_count * CRB_RASTER_MIN_CTAS;
-            if (gR < wave) gR = wave;
+            if (gL + gH < wave) gL = wave - gH;
         }
     }
-    if (gR > nAllTiles) gR = nAllTiles;
-    if (gR < 1) gR = 1;
+    if (gH > nAllTiles) gH = nAllTiles;
+    if (gL > nAllTiles) gL = nAllTiles;
+    if (gH < 1) gH = 1;
+    if (gL < 1) gL = 1;
+    F.gridHeavy = (unsigned)gH;
+    long long gR = gL + gH;
     if (M.use) gR = 4 * ((gR + 2) / 3);     // three rasterizing CTAs + one clear CTA per group of four (see k_raster)
     if (prof) CU(cudaEventRecord(f->prof_ev[2 * f->prof_n], st));
     k_raster<<<(unsigned)gR, NT, 0, st>>>(F, M);
@@ -1514,7 +1537,7 @@ int bind_ws_pointers(crb_filler *f, void *ws, size_t bytes, long long T, int vie
     f->maxT = T; f->maxViews = views; f->pairCap = pairCap;
     f->shrec = (float4 *)(b + L.shrec); f->recD = (float4 *)(b + L.recD); f->recE = (float4 *)(b + L.recE);
     f->count = (unsigned *)(b + L.count); f->offset = (unsigned *)(b + L.offset); f->cursor = (unsigned *)(b + L.cursor);
-    f->busy = (uint4 *)(b + L.busy); f->empty = (unsigned *)(b + L.empty);
+    f->busy = (uint4 *)(b + L.busy); f->busyH = (uint4 *)(b + L.busyH); f->empty = (unsigned *)(b + L.empty);
     f->ls0 = (float4 *)(b + L.ls0); f->ls1 = (float4 *)(b + L.ls1); f->ls2 = (float4 *)(b + L.ls2); f->ls3 = (uint4 *)(b + L.ls3); f->ls4 = (float4 *)(b + L.ls4);
     f->total = (unsigned long long *)(b + L.total);
     f->stage_v = (float *)(b + L.sv); f->stage_c = (float *)(b + L.sc); f->stage_n = (float *)(b + L.sn);
@@ -1600,8 +1623,8 @@ int crb_create(int h, int w, float fov, float z_near, float z_far, int device, c
         f->out_tma = 1;
         if (const char *e = getenv("CRB_DEBUG_SKIP")) f->dbg_flags = ((unsigned)atoi(e) & 15u) << 16;
         void *hp = nullptr, *dp = nullptr;
-        if (cudaHostAlloc(&hp, 64, cudaHostAllocMapped) == cudaSuccess && cudaHostGetDevicePointer(&dp, hp, 0) == cudaSuccess) {
-            memset(hp, 0, 64);
+        if (cudaHostAlloc(&hp, 128, cudaHostAllocMapped) == cudaSuccess && cudaHostGetDevicePointer(&dp, hp, 0) == cudaSuccess) {
+            memset(hp, 0, 128);
             f->hstats = (unsigned long long *)hp;
             f->hstats_dev = (unsigned long long *)dp;
         } else {
