@@ -201,7 +201,7 @@ def run_reference_arm(args):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------------------------
@@ -226,7 +226,7 @@ def run_gpu_arm(args):
     T = int(model._vertices_by_triangles.shape[0])
     V = args.views
     n_total = world * V
-    views_np = VW.orbit_views(n_total, first=rank * V, count=V)
+    views_np = VW.orbit_views(n_total, first=rank, count=V, stride=world)      # view k -> rank k mod N: equal work per rank
     f = AdvancedPixelBufferFiller(RES, RES, fov=FOV, device=local)
     dv, dc, dn = (torch.from_numpy(a).to(dev) for a in
                   (model._vertices_by_triangles, model._colors_by_triangles, model._normals_by_triangles))
@@ -430,7 +430,7 @@ def run_gpu_arm(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic orbit of the T-Rex fixture (tests/golden/trex_fit.npz = README fit_model flow)",
             "config": {"workload": "trex_1024_orbit", "res": RES, "fov": FOV, "triangles": T, "views_per_gpu_per_step": V,
-                       "orbit_views_total": n_total, "views_per_launch": args.chunk, "illumination": False,
+                       "orbit_views_total": n_total, "view_to_rank": "k mod N", "views_per_launch": args.chunk, "illumination": False,
                        "buffers": "z+color+normals f32, fresh per view", "l2": "outputs %.2f GB/step per GPU >> 126 MB L2; "
                        "the 1.5 MB mesh is re-read per view by design" % (V * 28 * RES * RES / 1e9)},
             "gtri_per_s": fps * T / 1e9, "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches,
@@ -438,7 +438,7 @@ def run_gpu_arm(args):
             "checks": {"covered_pixels_view0": covered0, "e2e_covered_pixels": e2e_cov, "e2e_dense_covered_pixels": dense_cov, "e2e_sync_covered_pixels": sync_cov, "pairs_last_launch": int(need.value),
                        "pair_capacity": int(cap.value)},
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -559,13 +559,30 @@ def run_extra_workload(args):
                          "algorithmic_bytes_per_launch": alg, "share_of_step": k_ms / e0.elapsed_time(e1)},
             "gather": gather, "checks": {"covered_pixels": int(cov.item())},
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The JSON line goes to the process's original stdout; everything else (NCCL banners, library chatter) was sent to
+    stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)          # anything a library prints on fd 1 (e.g. "NCCL version ...") must not precede the JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -23,6 +23,12 @@ def view_shard(n_views, rank, world):
     return first, count
 
 
+def view_shard_strided(n_views, rank, world):
+    """Round-robin alternative: the views k with k % world == rank (what bench.py uses -- frames of neighbouring view
+    angles cost alike, so striding balances the ranks where contiguous arcs do not).  Returns the list of view indices."""
+    return list(range(int(rank), int(n_views), int(world)))
+
+
 def band_shard(h, rank, world, align=TILE_ROWS):
     """Row band [row0,row1) of an h-row image for `rank`, aligned to `align` rows (last band takes the ragged end).
     Bands partition [0,h) exactly; ranks beyond the number of tile rows get an empty band."""

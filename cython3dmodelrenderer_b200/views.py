@@ -26,12 +26,14 @@ def rot_y(theta):
     return np.array([[c, 0.0, s], [0.0, 1.0, 0.0], [-s, 0.0, c]])
 
 
-def orbit_views(n_total, first=0, count=None, center=(0.0, 0.0, 1.0)):
-    """Views first..first+count-1 of an n_total-view orbit about the y axis through `center` (theta = 2*pi*k/n_total)."""
-    count = n_total - first if count is None else count
+def orbit_views(n_total, first=0, count=None, center=(0.0, 0.0, 1.0), stride=1):
+    """Views first, first+stride, ... (count of them) of an n_total-view orbit about the y axis through `center`
+    (theta = 2*pi*k/n_total).  stride = world size, first = rank gives every rank an evenly spread sample of the orbit
+    (view k -> GPU k mod N): frames of different view angles cost differently, contiguous arcs would not balance."""
+    count = (n_total - first + stride - 1) // stride if count is None else count
     out = np.zeros((count, 16), dtype=np.float32)
     for i in range(count):
-        out[i] = view_matrix(rot_y(2.0 * np.pi * (first + i) / n_total), p=center)
+        out[i] = view_matrix(rot_y(2.0 * np.pi * (first + i * stride) / n_total), p=center)
     return out
 
 

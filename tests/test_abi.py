@@ -3,6 +3,7 @@ declares, and its host-only entry points behave like the reference constructor."
 import ctypes
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -84,3 +85,18 @@ def test_input_validation_matches_reference_messages():
     with pytest.raises(ValueError, match="wrong number of dimensions"):
         _check_tri_array(np.zeros((2, 9), np.float32), "v")
     assert _check_tri_array(np.zeros((2, 3, 3), np.float32), "v").shape == (2, 3, 3)
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py's stdout contract (one JSON line, nothing else on fd 1), exercised with the CPU reference arm."""
+    import json
+    import subprocess
+    bench = os.path.join(ROOT, "bench.py")
+    r = subprocess.run([sys.executable, bench, "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout[:500]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["cpu_baseline"]["kind"] in ("reference", "port")
