@@ -47,6 +47,8 @@ constexpr int NT = 256;         // threads per CTA in every kernel
 constexpr unsigned FLAG_DBG_NOCLEAR = 0x10000u, FLAG_DBG_NOSHADE = 0x20000u, FLAG_DBG_NOROWS = 0x40000u, FLAG_DBG_NOOUT = 0x80000u;  // ablation switches (CRB_DEBUG_SKIP)
 constexpr unsigned FLAG_OUT_TMA = 0x100u;   // internal Frame.flags bit: shaded colour / normal rows leave through TMA boxes
 constexpr int CH = 128;         // triangles staged in shared memory per pass of the tile rasterizer
+constexpr unsigned SPLIT_N = 48;  // single-view launches: tiles with more triangles than this are rasterized by SPLIT_BANDS CTAs, 8 rows each
+constexpr int SPLIT_BANDS = 4;
 constexpr unsigned HEAVY_N = 64;  // tiles with more triangles than this are rasterized first (longest first: shorter kernel tail)
 constexpr int FQ = 256;          // fragments a warp compacts per round (8 per row)
 constexpr int KEY_STRIDE = TW + 1;  // padded key row: rows of one column land in different banks
@@ -94,6 +96,7 @@ struct Frame {
     uint4 *busy;                // [nViews*nTiles] compacted busy tiles: (view:10 ty:11 tx:11, triangles, list offset, -); count in total[2]
     uint4 *busyH;               // [nViews*nTiles] the same for tiles with more than HEAVY_N triangles; count in total[4]
     unsigned gridHeavy;         // rasterizing CTA roles [0, gridHeavy) walk busyH, the others walk busy
+    unsigned splitHeavy;        // k_alloc emits SPLIT_BANDS row-band records for tiles with more than SPLIT_N triangles
     unsigned *empty;            // [nViews*nTiles] compacted tiles without triangles (same packing); count in total[3]
     unsigned *offset;           // [nViews*nTiles] start of the tile's list
     unsigned *cursor;           // [nViews*nTiles] fill cursor
@@ -445,12 +448,17 @@ __global__ void __launch_bounds__(NT) k_alloc(const Frame F)
     unsigned tot, nbusy, nheavy;
     const unsigned excl = block_exclusive_scan(c, warp_sums, tot);
     const unsigned brank = block_exclusive_scan(c ? 1u : 0u, warp_sums, nbusy);
-    const unsigned hrank = block_exclusive_scan(c > HEAVY_N ? 1u : 0u, warp_sums, nheavy);
+    // a frame of one view is as slow as its heaviest tile: such tiles are cut into row bands (disjoint pixels, no merge)
+    const bool cut = F.splitHeavy && c > SPLIT_N, heavy = cut || c > HEAVY_N;
+    const unsigned hrecs = cut ? (unsigned)SPLIT_BANDS : (heavy ? 1u : 0u);
+    const unsigned hrank = block_exclusive_scan(hrecs, warp_sums, nheavy);
+    unsigned nheavyTiles;
+    const unsigned htile = block_exclusive_scan(heavy ? 1u : 0u, warp_sums, nheavyTiles);
     __shared__ unsigned heavy_base;
     if (threadIdx.x == 0) {
         const unsigned valid = (unsigned)min((long long)NT, nAll - (long long)blockIdx.x * NT);
         block_base = tot ? atomicAdd(F.total, (unsigned long long)tot) : 0ull;
-        busy_base = (unsigned)atomicAdd(F.total + 2, (unsigned long long)(nbusy - nheavy));
+        busy_base = (unsigned)atomicAdd(F.total + 2, (unsigned long long)(nbusy - nheavyTiles));
         heavy_base = (unsigned)atomicAdd(F.total + 4, (unsigned long long)nheavy);
         empty_base = (unsigned)atomicAdd(F.total + 3, (unsigned long long)(valid - nbusy));
     }
@@ -463,8 +471,12 @@ __global__ void __launch_bounds__(NT) k_alloc(const Frame F)
         F.count[i] = 0u;   // self-cleaning: the next frame's k_setup starts from zero
         const unsigned vw = (unsigned)(i / F.nTiles), tl = (unsigned)(i % F.nTiles);
         const unsigned packed = (vw << 22) | ((tl / (unsigned)F.tilesX) << 11) | (tl % (unsigned)F.tilesX);   // view:10 ty:11 tx:11
-        if (c > HEAVY_N) F.busyH[heavy_base + hrank] = make_uint4(packed, c, o32, 0u);
-        else if (c) F.busy[busy_base + (brank - hrank)] = make_uint4(packed, c, o32, 0u);
+        constexpr unsigned FULL = (unsigned)TH << 8;                    // .w = first row | end row << 8 of the CTA's share of the tile
+        if (cut)
+            for (unsigned b = 0; b < (unsigned)SPLIT_BANDS; ++b)
+                F.busyH[heavy_base + hrank + b] = make_uint4(packed, c, o32, (b * (TH / SPLIT_BANDS)) | (((b + 1) * (TH / SPLIT_BANDS)) << 8));
+        else if (heavy) F.busyH[heavy_base + hrank] = make_uint4(packed, c, o32, FULL);
+        else if (c) F.busy[busy_base + (brank - htile)] = make_uint4(packed, c, o32, FULL);
         else F.empty[empty_base + (threadIdx.x - brank)] = packed;
     }
 }
@@ -644,11 +656,11 @@ __device__ __forceinline__ void span_bound(float A, float l2, float b, float wma
 
 // Visibility + deferred shading of one busy tile (n triangles staged at list offset off).
 __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, TileSmem &S, const bool clear, const int view,
-                                            const int tx, const int ty, const unsigned n, const unsigned off)
+                                            const int tx, const int ty, const unsigned n, const unsigned off, const int rowLo, const int rowHi)
 {
     const int x0 = tx * TW, yl0 = ty * TH;       // yl0: row inside the band's buffers
     const int y0 = F.row0 + yl0;                  // absolute image row
-    const int tw = min(TW, F.W - x0), th = min(TH, F.row1 - y0);
+    const int tw = min(TW, F.W - x0), th = min(min(TH, F.row1 - y0), rowHi);   // this CTA's rows of the tile: [rowLo, th)
     const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     PH_DECL
     for (int i = threadIdx.x; i < TH * KEY_STRIDE; i += NT) S.keys[i] = KEY_EMPTY;
@@ -674,7 +686,7 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
                 asm volatile("prefetch.global.L1 [%0];" :: "l"(sr + 64));
                 asm volatile("prefetch.global.L1 [%0];" :: "l"(sr + 96));
             }
-            const int yt = max((int)(d.y & 0xFFFF), y0), yb = min((int)(d.y >> 16), y0 + th);
+            const int yt = max((int)(d.y & 0xFFFF), y0 + rowLo), yb = min((int)(d.y >> 16), y0 + th);
             rows = (unsigned)max(yb - yt, 0);
         }
         unsigned totalRows;
@@ -707,7 +719,7 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
                 tri = d.z;
                 fdiv = (d.w & FL_FDIV) != 0;
                 span = (d.w & FL_SPAN) != 0;
-                y = max((int)(d.y & 0xFFFF), y0) + (int)(r - S.u.st.rowStart[o]);
+                y = max((int)(d.y & 0xFFFF), y0 + rowLo) + (int)(r - S.u.st.rowStart[o]);
                 xa = max((int)(d.x & 0xFFFF), x0);
                 xb = min((int)(d.x >> 16), x0 + tw);
                 const unsigned s1 = (d.w & 1u) << 31, s2 = (d.w & 2u) << 30, s3 = (d.w & 4u) << 29;
@@ -836,7 +848,7 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
     const float bg = background_color(F);
     for (int p = threadIdx.x; p < TH * TW; p += NT) {
         const int yy = p / TW, xx = p % TW;
-        if (yy >= th || xx >= tw) continue;
+        if (yy < rowLo || yy >= th || xx >= tw) continue;
         const unsigned long long key = S.keys[yy * KEY_STRIDE + xx];
         float z = Z_INIT, c[3] = {bg, bg, bg}, nn[3] = {0.f, 0.f, 0.f};
         bool write = clear;
@@ -876,7 +888,7 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
         PH(8);
         if (lane == 0) {   // warp w: array w/4 (colour, normals), row block w%4
             const int r = (int)(wid & 3u) * BOX_ROWS;
-            if (r < th) {
+            if (r >= rowLo && r < th) {       // row bands are multiples of BOX_ROWS
                 if (wid < 4) { if (M.use & CRB_BUF_COLOR) tma_store_box(&M.c, S.u.out.col + r * TW * 3, x0 * 3, yl0 + r, view); }
                 else if (M.use & CRB_BUF_NORMALS) tma_store_box(&M.n, S.u.out.nrm + r * TW * 3, x0 * 3, yl0 + r, view);
             }
@@ -885,7 +897,7 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
     } else if (vec) {
         __syncthreads();
         const int q = threadIdx.x & 7;
-        for (int r = threadIdx.x >> 3; r < th; r += NT / 8) {
+        for (int r = rowLo + (threadIdx.x >> 3); r < th; r += NT / 8) {
             const long long o = (slab + (long long)(yl0 + r) * F.W + x0) * 3;
             if (F.color) {
                 float4 *g = reinterpret_cast<float4 *>(F.color + o);
@@ -973,7 +985,8 @@ __global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame 
     const bool heavyRole = bidx < GH;
     const uint4 *lst = heavyRole ? F.busyH : F.busy;
     const unsigned first = heavyRole ? bidx : bidx - GH, stride = heavyRole ? GH : Gb - GH;
-    uint4 rec = first < nAll ? lst[first] : make_uint4(0u, 0u, 0u, 0u);   // speculative: flies with the totals
+    const unsigned cap = heavyRole ? nAll * (unsigned)SPLIT_BANDS : nAll;      // entries the list has room for
+    uint4 rec = first < cap ? lst[first] : make_uint4(0u, 0u, 0u, 0u);     // speculative: flies with the totals
     const unsigned long long pairs = F.total[0];
     const unsigned nLight = (unsigned)F.total[2], nHeavy = (unsigned)F.total[4];
     const unsigned nb = heavyRole ? nHeavy : nLight;
@@ -1002,7 +1015,8 @@ __global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame 
             __syncthreads();
         }
         if (cta + stride < nb) rec = lst[cta + stride];     // the next tile's record arrives while this one is rasterized
-        raster_tile(F, M, S, clear, (int)(cur.x >> 22), (int)(cur.x & 2047u), (int)((cur.x >> 11) & 2047u), cur.y, cur.z);
+        raster_tile(F, M, S, clear, (int)(cur.x >> 22), (int)(cur.x & 2047u), (int)((cur.x >> 11) & 2047u), cur.y, cur.z,
+                    (int)(cur.w & 255u), (int)(cur.w >> 8));
     }
 #ifdef CRB_PHASE_TIMING
     ph_t = clock64();
@@ -1268,6 +1282,7 @@ struct crb_filler {
     cudaStream_t s_prep, s_raster;      // batched views: setup/binning of launch i+1 runs beside the rasterizer of launch i
     cudaEvent_t ev_start, ev_fill[2], ev_raster[2];
     int chunk_pipeline;    // CRB_CHUNK_PIPELINE=0 disables
+    int split_heavy;       // single-view launches cut heavy tiles into row bands (CRB_SPLIT_HEAVY=0 disables)
     int tiles_per_cta;     // k_raster grid = estimated busy tiles / this (CRB_TILES_PER_CTA)
     unsigned dbg_flags;    // ablation switches (CRB_DEBUG_SKIP), never set in production
     int out_tma;           // ... and so does k_raster for the shaded colour / normal rows (CRB_OUT_TMA=0 disables)
@@ -1305,7 +1320,7 @@ WsLayout ws_layout(const crb_filler *f, long long T, int views, long long pairCa
     L.offset = take((size_t)tiles * views * 4);
     L.cursor = take((size_t)tiles * views * 4);
     L.busy = take((size_t)tiles * views * 16);
-    L.busyH = take((size_t)tiles * views * 16);
+    L.busyH = take((size_t)tiles * views * 16 * SPLIT_BANDS);
     L.empty = take((size_t)tiles * views * 4);
     L.ls0 = take((size_t)pairCap * 16);
     L.ls1 = take((size_t)pairCap * 16);
@@ -1434,8 +1449,9 @@ int run_prep(crb_filler *f, Frame &F, cudaStream_t st)
         if ((rc = launch_check(f, "k_setup"))) return rc;
     } else {
         CU(cudaMemsetAsync(F.total, 0, 8, st));
-        CU(cudaMemsetAsync(F.total + 2, 0, 16, st));
+        CU(cudaMemsetAsync(F.total + 2, 0, 24, st));
     }
+    F.splitHeavy = (F.nViews == 1 && f->split_heavy) ? 1u : 0u;
     const long long nAllTiles = (long long)F.nViews * F.nTiles;
     k_alloc<<<(unsigned)((nAllTiles + NT - 1) / NT), NT, 0, st>>>(F);
     if ((rc = launch_check(f, "k_alloc"))) return rc;
@@ -1602,6 +1618,8 @@ int crb_create(int h, int w, float fov, float z_near, float z_far, int device, c
         f->raster_ctas = 0;
         if (const char *e = getenv("CRB_RASTER_CTAS")) f->raster_ctas = atoi(e);   // experiments: >0 fixed grid, <0 one CTA per tile
         f->use_tma = 1;
+        f->split_heavy = 1;
+        if (const char *e = getenv("CRB_SPLIT_HEAVY")) f->split_heavy = atoi(e) ? 1 : 0;
         f->chunk_pipeline = 1;
         if (const char *e = getenv("CRB_CHUNK_PIPELINE")) f->chunk_pipeline = atoi(e) ? 1 : 0;
         {

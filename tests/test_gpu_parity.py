@@ -511,3 +511,21 @@ def test_integration_stub_flow_without_torch(O, trex):
         assert 0 < need.value <= cap.value
     finally:
         L.crb_destroy(f)
+
+
+@pytest.mark.parametrize("split", ["1", "0"])
+def test_single_view_heavy_tile_split(split, Filler, O, monkeypatch):
+    """Single-view launches cut tiles with many triangles into four 8-row bands rasterized by different CTAs
+    (CRB_SPLIT_HEAVY); fresh and compositing renders, partial tiles at the image edge."""
+    monkeypatch.setenv("CRB_SPLIT_HEAVY", split)
+    for (h, w), seed in (((96, 128), 21), ((75, 100), 22), ((40, 33), 23)):
+        m = random_scene(200 + seed, T=5000, span=0.5)          # hundreds of triangles per tile
+        g, o = Filler(h, w, fov=70.0), O.OracleFiller(h, w, fov=70.0)
+        g.clear()
+        g.render_model(m)                                       # fused clear, TMA where the layout allows
+        o.render_model(m)
+        assert_same(buffers(g), buffers(o), f"split={split} fresh {h}x{w}")
+        m2 = random_scene(300 + seed, T=3000, span=0.7)
+        g.render_model(m2)                                      # composites into the first frame
+        o.render_model(m2)
+        assert_same(buffers(g), buffers(o), f"split={split} composite {h}x{w}")
