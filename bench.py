@@ -589,7 +589,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--views", type=int, default=128, help="views per GPU per step")
-    ap.add_argument("--chunk", type=int, default=32, help="views per kernel launch")
+    ap.add_argument("--chunk", type=int, default=128, help="views per kernel launch (larger launches amortise the kernel tail: 32 -> 93 k, 128 -> 98 k frames/s)")
     ap.add_argument("--e2e-frames", type=int, default=200)
     ap.add_argument("--e2e-depth", type=int, default=3, help="fillers in flight in the pipelined e2e measurement")
     ap.add_argument("--cpu-frames", type=int, default=60)
