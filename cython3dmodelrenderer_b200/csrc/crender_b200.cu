@@ -797,11 +797,20 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
                 }
                 const int total = __shfl_sync(0xFFFFFFFFu, inc, 31), pre = inc - cnt;
                 const int maxc = __reduce_max_sync(0xFFFFFFFFu, cnt);
-                for (int j = 0; j < maxc; ++j) {
-                    if (j < cnt) {
-                        const int bit = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        fq[pre + j] = (unsigned short)(lane | ((unsigned)bit << 5));
+                if (__all_sync(0xFFFFFFFFu, span || mask == 0u)) {
+                    // every mask is one interval (the usual case): its first cnt pixels are first, first + 1, ...
+                    const unsigned firstbit = (unsigned)__ffs(mask) - 1u;
+                    const unsigned entry = lane | (firstbit << 5);
+                    for (int j = 0; j < maxc; ++j)
+                        if (j < cnt) fq[pre + j] = (unsigned short)(entry + ((unsigned)j << 5));
+                    if (cnt) mask = (cnt + (int)firstbit >= 32) ? 0u : (mask >> (cnt + firstbit)) << (cnt + firstbit);
+                } else {
+                    for (int j = 0; j < maxc; ++j) {
+                        if (j < cnt) {
+                            const int bit = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            fq[pre + j] = (unsigned short)(lane | ((unsigned)bit << 5));
+                        }
                     }
                 }
                 __syncwarp();
