@@ -531,7 +531,8 @@ __device__ __forceinline__ void smem_key_min(unsigned long long *p, unsigned lon
 // 3W for colour / normals) with boxes of BOX_ROWS rows x one tile width.  Built on the host per launch (the output
 // pointers are per call).  `use` bit k = map k is valid (CRB_BUF_* order); 0 = the launch uses plain stores only.
 struct __align__(64) TMaps {
-    CUtensorMap z, c, n;
+    CUtensorMap z, c, n;        // boxes of BOX_ROWS rows: the shaded rows of a busy tile
+    CUtensorMap zt, ct, nt;     // boxes of a whole tile (TH rows): the fused clear
     unsigned use;
 };
 
@@ -583,9 +584,9 @@ struct __align__(128) TileSmem {
             float nrm[TH * TW * 3];
         } out;
         struct {                              // clear CTAs only: the constant pattern their TMA boxes are stored from
-            float z[BOX_ROWS * TW];           //   Z_INIT
-            float c[BOX_ROWS * TW * 3];       //   background colour
-            float n[BOX_ROWS * TW * 3];       //   0
+            float z[TH * TW];                 //   Z_INIT
+            float c[TH * TW * 3];             //   background colour
+            float n[TH * TW * 3];             //   0
         } pat;
     } u;
     unsigned long long keys[TH * KEY_STRIDE];
@@ -923,20 +924,14 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
     PH(9);
 }
 
-// The fused clear through TMA: one tile = up to 12 boxes (3 arrays x 4 row blocks of BOX_ROWS rows) stored from the
-// constant pattern in shared memory; the hardware clips boxes at the image edge.  Called by one lane.
-__device__ __forceinline__ void tma_clear_tile(const Frame &F, const TMaps &M, const TileSmem &S, unsigned t)
+// The fused clear through TMA: one tile = three whole-tile boxes (z, colour, normals) stored from the constant pattern in
+// shared memory; the hardware clips boxes at the image edge.  Called by one lane.
+__device__ __forceinline__ void tma_clear_tile(const TMaps &M, const TileSmem &S, unsigned t)
 {
-    const int rows = F.row1 - F.row0;
     const int view = (int)(t >> 22), yl0 = (int)((t >> 11) & 2047u) * TH, x0 = (int)(t & 2047u) * TW;
-#pragma unroll
-    for (int r = 0; r < TH; r += BOX_ROWS) {
-        if (yl0 + r < rows) {
-            if (M.use & CRB_BUF_Z) tma_store_box(&M.z, S.u.pat.z, x0, yl0 + r, view);
-            if (M.use & CRB_BUF_COLOR) tma_store_box(&M.c, S.u.pat.c, x0 * 3, yl0 + r, view);
-            if (M.use & CRB_BUF_NORMALS) tma_store_box(&M.n, S.u.pat.n, x0 * 3, yl0 + r, view);
-        }
-    }
+    if (M.use & CRB_BUF_Z) tma_store_box(&M.zt, S.u.pat.z, x0, yl0, view);
+    if (M.use & CRB_BUF_COLOR) tma_store_box(&M.ct, S.u.pat.c, x0 * 3, yl0, view);
+    if (M.use & CRB_BUF_NORMALS) tma_store_box(&M.nt, S.u.pat.n, x0 * 3, yl0, view);
 }
 
 // Grid roles.  Busy tiles: one CTA each when the grid is large enough (it is sized from the busy-tile count the host
@@ -969,9 +964,10 @@ __global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame 
             const unsigned ne = (unsigned)F.total[3];
             if (pairs > (unsigned long long)F.pairCap || DBG(F, FLAG_DBG_NOCLEAR)) return;     // frame skipped: buffers stay untouched
             const float bg = background_color(F);
-            for (int i = threadIdx.x; i < BOX_ROWS * TW * 3; i += NT) {
-                S.u.pat.c[i] = bg; S.u.pat.n[i] = 0.0f;
-                if (i < BOX_ROWS * TW) S.u.pat.z[i] = Z_INIT;
+            for (int i = threadIdx.x; i < TH * TW * 3 / 4; i += NT) {
+                reinterpret_cast<float4 *>(S.u.pat.c)[i] = make_float4(bg, bg, bg, bg);
+                reinterpret_cast<float4 *>(S.u.pat.n)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < TH * TW / 4) reinterpret_cast<float4 *>(S.u.pat.z)[i] = make_float4(Z_INIT, Z_INIT, Z_INIT, Z_INIT);
             }
             fence_async_smem();
             __syncthreads();
@@ -979,7 +975,7 @@ __global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame 
                 while (e < ne) {
                     const unsigned en = e + stride;
                     const unsigned tn = en < ne ? F.empty[en] : 0u;
-                    tma_clear_tile(F, M, S, t);
+                    tma_clear_tile(M, S, t);
                     e = en; t = tn;
                 }
                 tma_commit();
@@ -1424,14 +1420,14 @@ EncodeTiledFn encode_tiled_fn()
 }
 
 // [views][rows][W*comps] float32, boxes of BOX_ROWS x (TW*comps).  Returns false if the layout cannot be described.
-bool encode_map(CUtensorMap *m, float *base, int comps, const Frame &F)
+bool encode_map(CUtensorMap *m, float *base, int comps, const Frame &F, int box_rows)
 {
     EncodeTiledFn fn = encode_tiled_fn();
     const long long rows = F.row1 - F.row0;
     if (!fn || !base || rows <= 0 || (reinterpret_cast<uintptr_t>(base) & 15u)) return false;
     const cuuint64_t dims[3] = {(cuuint64_t)F.W * comps, (cuuint64_t)rows, (cuuint64_t)F.nViews};
     const cuuint64_t strides[2] = {(cuuint64_t)F.W * comps * 4, (cuuint64_t)rows * F.W * comps * 4};
-    const cuuint32_t box[3] = {(cuuint32_t)(TW * comps), (cuuint32_t)BOX_ROWS, 1u};
+    const cuuint32_t box[3] = {(cuuint32_t)(TW * comps), (cuuint32_t)box_rows, 1u};
     const cuuint32_t es[3] = {1u, 1u, 1u};
     return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -1441,9 +1437,9 @@ bool encode_map(CUtensorMap *m, float *base, int comps, const Frame &F)
 unsigned encode_maps(TMaps *M, const Frame &F)
 {
     unsigned use = 0;
-    if (F.z) { if (!encode_map(&M->z, F.z, 1, F)) return 0u; use |= CRB_BUF_Z; }
-    if (F.color) { if (!encode_map(&M->c, F.color, 3, F)) return 0u; use |= CRB_BUF_COLOR; }
-    if (F.normals) { if (!encode_map(&M->n, F.normals, 3, F)) return 0u; use |= CRB_BUF_NORMALS; }
+    if (F.z) { if (!encode_map(&M->z, F.z, 1, F, BOX_ROWS) || !encode_map(&M->zt, F.z, 1, F, TH)) return 0u; use |= CRB_BUF_Z; }
+    if (F.color) { if (!encode_map(&M->c, F.color, 3, F, BOX_ROWS) || !encode_map(&M->ct, F.color, 3, F, TH)) return 0u; use |= CRB_BUF_COLOR; }
+    if (F.normals) { if (!encode_map(&M->n, F.normals, 3, F, BOX_ROWS) || !encode_map(&M->nt, F.normals, 3, F, TH)) return 0u; use |= CRB_BUF_NORMALS; }
     return use;
 }
 
