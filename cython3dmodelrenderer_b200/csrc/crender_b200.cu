@@ -49,6 +49,10 @@ constexpr unsigned FLAG_OUT_TMA = 0x100u;   // internal Frame.flags bit: shaded 
 constexpr int CH = 128;         // triangles staged in shared memory per pass of the tile rasterizer
 constexpr unsigned SPLIT_N = 48;  // single-view launches: tiles with more triangles than this are rasterized by SPLIT_BANDS CTAs, 8 rows each
 constexpr int SPLIT_BANDS = 4;
+#ifndef CRB_CLEAR_EVERY
+#define CRB_CLEAR_EVERY 4
+#endif
+constexpr unsigned CE = CRB_CLEAR_EVERY;  // every CE-th CTA of k_raster is a clear CTA (power of two)
 constexpr unsigned HEAVY_N = 64;  // tiles with more triangles than this are rasterized first (longest first: shorter kernel tail)
 constexpr int FQ = 256;          // fragments a warp compacts per round (8 per row)
 constexpr int KEY_STRIDE = TW + 1;  // padded key row: rows of one column land in different banks
@@ -953,9 +957,9 @@ __global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame 
     const unsigned nAll = (unsigned)F.nTiles * (unsigned)F.nViews;
     unsigned bidx = blockIdx.x, Gb = gridDim.x;
     if (split) {
-        const unsigned Gc = gridDim.x >> 2, ci = blockIdx.x >> 2;
+        const unsigned Gc = gridDim.x / CE, ci = blockIdx.x / CE;
         Gb = gridDim.x - Gc;
-        if ((blockIdx.x & 3u) == 3u) {
+        if ((blockIdx.x & (CE - 1u)) == CE - 1u) {
             // ---- clear CTA: warp w issues the tiles e = ci + (w + 8k) * Gc
             const unsigned stride = Gc * (NT / 32);
             unsigned e = ci + (threadIdx.x >> 5) * Gc;
@@ -983,7 +987,7 @@ __global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame 
             }
             return;
         }
-        bidx = ci * 3u + (blockIdx.x & 3u);
+        bidx = ci * (CE - 1u) + (blockIdx.x & (CE - 1u));
     }
     // the first gridHeavy roles take the tiles with many triangles, in blockIdx (= dispatch) order before everything else
     const unsigned GH = F.gridHeavy;
@@ -1503,7 +1507,7 @@ int run_raster(crb_filler *f, Frame &F, cudaStream_t st, int slot)
     if (gL < 1) gL = 1;
     F.gridHeavy = (unsigned)gH;
     long long gR = gL + gH;
-    if (M.use) gR = 4 * ((gR + 2) / 3);     // three rasterizing CTAs + one clear CTA per group of four (see k_raster)
+    if (M.use) gR = (long long)CE * ((gR + CE - 2) / (CE - 1));     // CE - 1 rasterizing CTAs + one clear CTA per group of CE (see k_raster)
     if (prof) CU(cudaEventRecord(f->prof_ev[2 * f->prof_n], st));
     k_raster<<<(unsigned)gR, NT, 0, st>>>(F, M);
     if ((rc = launch_check(f, "k_raster"))) return rc;
