@@ -288,6 +288,29 @@ def run_gpu_arm(args):
     f.profile(False)
     _lib.check(f._L.crb_set_option(f._handle, _lib.CRB_OPT_CHUNK_PIPELINE, 1))
 
+    # optional: the final NCCL gather of the view-sharded result to rank 0 (reported beside, never inside, `value`)
+    gather = None
+    if world > 1 and args.gather != "none":
+        from cython3dmodelrenderer_b200 import sharding
+        parts = {"z": z} if args.gather == "z" else {"z": z, "color": col, "normals": nrm}
+        for t_ in parts.values():
+            sharding.gather_views(t_[:8].contiguous(), 8 * world, dst=0)      # communicator / buffer warm-up
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        got = {k: sharding.gather_views(t_, n_total, dst=0) for k, t_ in parts.items()}
+        g1.record()
+        barrier()
+        gms = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(gms, op=dist.ReduceOp.MAX)
+        nbytes = sum(t_.numel() * t_.element_size() for t_ in parts.values()) * world
+        gather = {"what": "gather of the per-rank view slabs to rank 0 (NCCL over NVLink): " + "+".join(parts), "ms": float(gms.item()),
+                  "bytes": nbytes, "gb_per_s": nbytes / float(gms.item()) / 1e6,
+                  "frames_per_s_including_gather": n_total / ((ms / args.steps + float(gms.item())) / 1000.0)}
+        if rank == 0:
+            gather["covered_pixels_view0_of_rank1"] = int((got["z"][V] < 1e5).sum().item())
+        del got
+
     # sanity: the timed output is a real frame (covered pixel count of view 0 of rank 0 is the reference's 252 539)
     covered0 = int((z[0] < 1e5).sum().item())
 
@@ -434,7 +457,7 @@ def run_gpu_arm(args):
                        "buffers": "z+color+normals f32, fresh per view", "l2": "outputs %.2f GB/step per GPU >> 126 MB L2; "
                        "the 1.5 MB mesh is re-read per view by design" % (V * 28 * RES * RES / 1e9)},
             "gtri_per_s": fps * T / 1e9, "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches,
-            "roofline": roofline, "cpu_baseline": cpu, "single_frame": single,
+            "roofline": roofline, "cpu_baseline": cpu, "single_frame": single, "gather": gather,
             "checks": {"covered_pixels_view0": covered0, "e2e_covered_pixels": e2e_cov, "e2e_dense_covered_pixels": dense_cov, "e2e_sync_covered_pixels": sync_cov, "pairs_last_launch": int(need.value),
                        "pair_capacity": int(cap.value)},
         }
@@ -597,7 +620,7 @@ def main():
     ap.add_argument("--workload", default="trex_1024_orbit",
                     choices=["trex_1024_orbit", "bunny_4096_guro", "sphere_8192_bands"])
     ap.add_argument("--res", type=int, default=0, help="sphere_8192_bands only: override the resolution (scaled sphere)")
-    ap.add_argument("--gather", default="none", choices=["none", "bands", "u8"],
+    ap.add_argument("--gather", default="none", choices=["none", "bands", "u8", "z", "all"],
                     help="also time the final NCCL gather (reported beside, never inside, the headline value)")
     args = ap.parse_args()
     if args.impl == "reference":
