@@ -45,6 +45,7 @@ constexpr int NT = 256;         // threads per CTA in every kernel
 #define DBG(F, bit) ((void)(bit), false)
 #endif
 constexpr unsigned FLAG_DBG_NOCLEAR = 0x10000u, FLAG_DBG_NOSHADE = 0x20000u, FLAG_DBG_NOROWS = 0x40000u, FLAG_DBG_NOOUT = 0x80000u;  // ablation switches (CRB_DEBUG_SKIP)
+constexpr unsigned FLAG_OUT_DIRECT = 0x200u;   // experiment: shaded pixels stored straight from registers (12-byte strided stores)
 constexpr unsigned FLAG_OUT_TMA = 0x100u;   // internal Frame.flags bit: shaded colour / normal rows leave through TMA boxes
 constexpr int CH = 128;         // triangles staged in shared memory per pass of the tile rasterizer
 constexpr unsigned SPLIT_N = 48;  // single-view launches: tiles with more triangles than this are rasterized by SPLIT_BANDS CTAs, 8 rows each
@@ -857,7 +858,7 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
     // ---- deferred shading of the winners, staged so that colour / normals leave as whole rows ---------------
     const long long slab = (long long)view * F.slabPixels;
     const bool tma = clear && M.use != 0u && (F.flags & FLAG_OUT_TMA);     // colour / normal rows leave through TMA boxes
-    const bool vec = clear && !tma && (tw == TW) && ((F.W & 3) == 0);       // ... or as 16-byte vector stores
+    const bool vec = clear && !tma && (tw == TW) && ((F.W & 3) == 0) && !(F.flags & FLAG_OUT_DIRECT);   // ... or as 16-byte vector stores
     const bool stage = tma || vec;
     const float bg = background_color(F);
     for (int p = threadIdx.x; p < TH * TW; p += NT) {
@@ -1483,7 +1484,8 @@ int run_raster(crb_filler *f, Frame &F, cudaStream_t st, int slot)
     memset(&M, 0, sizeof(M));
     const bool clear = (F.flags & CRB_CLEAR_FIRST) != 0;
     if (f->use_tma && clear && !(F.W & 3) && !F.color_u8) M.use = encode_maps(&M, F);
-    if (M.use && f->out_tma) F.flags |= FLAG_OUT_TMA;
+    if (M.use && f->out_tma == 1) F.flags |= FLAG_OUT_TMA;
+    if (f->out_tma == 2) F.flags |= FLAG_OUT_DIRECT;
     F.flags |= f->dbg_flags;
     // Grid: one CTA per busy tile.  The busy count is only known on the device, so the grid is sized from the busy
     // FRACTION the previous launch posted (+12 % and a floor of one wave); k_raster walks with stride gridDim when the
@@ -1648,6 +1650,7 @@ int crb_create(int h, int w, float fov, float z_near, float z_far, int device, c
         if (const char *e = getenv("CRB_TILES_PER_CTA")) { int k = atoi(e); if (k >= 1 && k <= 64) f->tiles_per_cta = k; }
         if (const char *e = getenv("CRB_NO_TMA")) f->use_tma = atoi(e) ? 0 : 1;
         f->out_tma = 1;
+        if (const char *e = getenv("CRB_OUT_TMA")) f->out_tma = atoi(e);   // 1 TMA boxes, 0 vector stores, 2 direct stores (experiment)
         if (const char *e = getenv("CRB_DEBUG_SKIP")) f->dbg_flags = ((unsigned)atoi(e) & 15u) << 16;
         void *hp = nullptr, *dp = nullptr;
         if (cudaHostAlloc(&hp, 128, cudaHostAllocMapped) == cudaSuccess && cudaHostGetDevicePointer(&dp, hp, 0) == cudaSuccess) {
@@ -2014,6 +2017,7 @@ int crb_set_option(crb_filler *f, int option, int value)
     switch (option) {
     case CRB_OPT_CHUNK_PIPELINE: f->chunk_pipeline = value ? 1 : 0; return CRB_OK;
     case CRB_OPT_TMA: f->use_tma = value ? 1 : 0; return CRB_OK;
+    case CRB_OPT_TMA_ROWS: f->out_tma = value ? 1 : 0; return CRB_OK;
     default: return fail(CRB_ERR_INVALID, "unknown option %d", option);
     }
 }

@@ -129,6 +129,7 @@ int crb_render_host(crb_filler *f, const float *v, const float *c, const float *
  * for the fused clear and the shaded rows where the layout allows.  Results do not depend on either. */
 #define CRB_OPT_CHUNK_PIPELINE 1
 #define CRB_OPT_TMA 2
+#define CRB_OPT_TMA_ROWS 3   /* shaded colour / normal rows of busy tiles as TMA boxes (1) or 16-byte vector stores (0) */
 int crb_set_option(crb_filler *f, int option, int value);
 
 /* Waits for everything queued on `stream` (pairs with CRB_NO_SYNC). */

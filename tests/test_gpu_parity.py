@@ -360,14 +360,14 @@ def test_full_size_sphere_properties(Filler):
         del b
 
 
-@pytest.mark.parametrize("mode", ["tma", "tma_vec_rows", "plain", "tiny_grid", "tma_tiny_grid"])
+@pytest.mark.parametrize("mode", ["tma", "tma_vec_rows", "tma_direct_rows", "plain", "tiny_grid", "tma_tiny_grid"])
 @pytest.mark.parametrize("size", [(96, 128), (100, 76), (50, 36), (257, 388), (64, 30)])
 def test_fused_clear_store_paths(mode, size, Filler, O, monkeypatch):
     """clear()+render takes the store path the layout allows: TMA boxes (rows that are 16-byte multiples), clipped by
     the hardware on partial tiles, or plain stores (W % 4 != 0, CRB_NO_TMA=1); a grid smaller than the number of busy
     tiles makes k_raster walk several tiles per CTA (CRB_RASTER_CTAS).  All of them must give the oracle's bits."""
     monkeypatch.setenv("CRB_NO_TMA", "1" if mode in ("plain", "tiny_grid") else "0")
-    monkeypatch.setenv("CRB_OUT_TMA", "0" if mode == "tma_vec_rows" else "1")
+    monkeypatch.setenv("CRB_OUT_TMA", {"tma_vec_rows": "0", "tma_direct_rows": "2"}.get(mode, "1"))
     if "tiny_grid" in mode:
         monkeypatch.setenv("CRB_RASTER_CTAS", "3")
     h, w = size
