@@ -56,7 +56,13 @@ constexpr int SPLIT_BANDS = 4;
 constexpr unsigned CE = CRB_CLEAR_EVERY;  // every CE-th CTA of k_raster is a clear CTA (power of two)
 constexpr unsigned HEAVY_N = 64;  // tiles with more triangles than this are rasterized first (longest first: shorter kernel tail)
 constexpr int FQ = 256;          // fragments a warp compacts per round (8 per row)
-constexpr int KEY_STRIDE = TW + 1;  // padded key row: rows of one column land in different banks
+#ifndef CRB_KEY_STRIDE
+#define CRB_KEY_STRIDE 35
+#endif
+// 64-bit keys, row stride 35 = 3 (mod 16 bank pairs): the fragments a warp evaluates together are a few consecutive pixels of
+// consecutive rows (a small triangle), and with a shift of three bank pairs per row they spread over all the banks
+// (stride 33 shifted one pair per row: 60 % of the key accesses were bank-conflict replays)
+constexpr int KEY_STRIDE = CRB_KEY_STRIDE;
 constexpr unsigned long long KEY_EMPTY = 0xFFFFFFFFFFFFFFFFull;
 constexpr float Z_INIT = 1e6f;  // pyx:67
 constexpr float REJ_EPS = 1e-6f;      // fast-reject guard band on barycentric numerators (see tri_fast_setup)
@@ -581,7 +587,7 @@ struct __align__(128) TileSmem {
             float4 s4[CH];  // 1/d1 1/d2 1/d3 -
             unsigned rowStart[CH];
             unsigned char owner[CH * TH];  // row work item -> staged triangle
-            float4 slot[NT / 32][32][2];   // per warp: the 32 rows of the current trip (A1 A2 A3 l02 | l12 l22 tri info)
+            float4 slot[NT / 32][2][32];   // per warp: the 32 rows of the current trip, [0] A1 A2 A3 l02, [1] l12 l22 tri info
             unsigned short fq[NT / 32][FQ];  // per warp: compacted fragments of the trip (lane | x << 5)
         } st;
         struct {
@@ -789,8 +795,8 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
             // pass 2 (exact): the surviving pixels of the warp's 32 rows are compacted into a per-warp queue, so that
             // every lane then evaluates one fragment per step whatever the spread of span lengths (the per-row loop this
             // replaces ran at 13 of 32 lanes).  A fragment finds its row through the slot its owner lane published.
-            S.u.st.slot[wid][lane][0] = make_float4(A1, A2, A3, l02);
-            S.u.st.slot[wid][lane][1] = make_float4(l12, l22, __uint_as_float(tri),
+            S.u.st.slot[wid][0][lane] = make_float4(A1, A2, A3, l02);
+            S.u.st.slot[wid][1][lane] = make_float4(l12, l22, __uint_as_float(tri),
                                                     __uint_as_float(o | ((unsigned)(y - y0) << 8) | (fdiv ? 65536u : 0u) | (span ? 131072u : 0u)));
             unsigned short *fq = S.u.st.fq[wid];
             while (__any_sync(0xFFFFFFFFu, mask != 0u)) {   // one round unless some row has more than 8 survivors
@@ -825,7 +831,7 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
                     if (idx < total) {
                         const unsigned e = fq[idx];
                         const unsigned src = e & 31u, bit = e >> 5;
-                        const float4 q0 = S.u.st.slot[wid][src][0], q1 = S.u.st.slot[wid][src][1];
+                        const float4 q0 = S.u.st.slot[wid][0][src], q1 = S.u.st.slot[wid][1][src];
                         const unsigned info = __float_as_uint(q1.w), o2 = info & 255u;
                         const float4 pa = S.u.st.s0[o2], pb = S.u.st.s1[o2], pc = S.u.st.s2[o2], pr = S.u.st.s4[o2];
                         const float px = (float)(x0 + (int)bit);
