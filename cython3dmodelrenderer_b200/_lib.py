@@ -15,7 +15,7 @@ HEADER = os.path.join(os.path.dirname(_HERE), "include", "crender_b200.h")
 
 CRB_OK = 0
 CRB_ERR_INVALID, CRB_ERR_CUDA, CRB_ERR_ZERODIV, CRB_ERR_STATE, CRB_ERR_OVERFLOW = -1, -2, -3, -4, -5
-CRB_CLEAR_FIRST, CRB_PATH_ATOMIC, CRB_GURO, CRB_NO_SYNC, CRB_DL_SPARSE = 1, 2, 4, 8, 16
+CRB_CLEAR_FIRST, CRB_PATH_ATOMIC, CRB_GURO, CRB_NO_SYNC, CRB_DL_SPARSE, CRB_DEFER_JOIN = 1, 2, 4, 8, 16, 32
 CRB_OPT_CHUNK_PIPELINE, CRB_OPT_TMA, CRB_OPT_TMA_ROWS = 1, 2, 3
 CRB_BUF_Z, CRB_BUF_COLOR, CRB_BUF_NORMALS, CRB_BUF_ALL = 1, 2, 4, 7
 
@@ -46,6 +46,7 @@ SIGNATURES = {
     "crb_render_host": (_i, [_vp, _vp, _vp, _vp, _i64, _u, _u, _vp, _vp, _vp, _vp]),
     "crb_render_views": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _i, _vp, _vp, _vp, _vp, _u, _fp, _vp]),
     "crb_set_option": (_i, [_vp, _i, _i]),
+    "crb_join": (_i, [_vp, _vp]),
     "crb_sync": (_i, [_vp, _vp]),
     "crb_readback_stats": (_i, [_vp, _i64p, _i, _vp]),
     "crb_readback_reset": (_i, [_vp, _vp]),

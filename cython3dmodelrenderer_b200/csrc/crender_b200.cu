@@ -1298,6 +1298,9 @@ struct crb_filler {
     cudaStream_t s_prep, s_raster;      // batched views: setup/binning of launch i+1 runs beside the rasterizer of launch i
     cudaEvent_t ev_start, ev_fill[2], ev_raster[2];
     int chunk_pipeline;    // CRB_CHUNK_PIPELINE=0 disables
+    unsigned launch_seq;   // launches issued through the two-stream pipeline (parity = workspace set)
+    int set_used[2];       // the set has a rasterizer launch whose completion is recorded in ev_raster[set]
+    int pending_join;      // 1 + set of the last pipelined launch the caller's stream has not been made to wait for (CRB_DEFER_JOIN)
     int split_heavy;       // single-view launches cut heavy tiles into row bands (CRB_SPLIT_HEAVY=0 disables)
     int tiles_per_cta;     // k_raster grid = estimated busy tiles / this (CRB_TILES_PER_CTA)
     unsigned dbg_flags;    // ablation switches (CRB_DEBUG_SKIP), never set in production
@@ -1555,6 +1558,16 @@ int run_atomic(crb_filler *f, Frame &F, cudaStream_t st)
     return launch_check(f, "k_shade_atomic");
 }
 
+// CRB_DEFER_JOIN left rasterizer work in flight that the caller's stream does not know about: order `st` behind it.
+int join_pending(crb_filler *f, cudaStream_t st)
+{
+    if (f->pending_join) {
+        CU(cudaStreamWaitEvent(st, f->ev_raster[f->pending_join - 1], 0));
+        f->pending_join = 0;
+    }
+    return CRB_OK;
+}
+
 int bind_ws_pointers(crb_filler *f, void *ws, size_t bytes, long long T, int views, long long pairCap, cudaStream_t st)
 {
     if (views < 1) views = 1;
@@ -1679,6 +1692,8 @@ void crb_destroy(crb_filler *f)
     if (f->own_buffers) { cudaFree(f->z); cudaFree(f->color); cudaFree(f->normals); }
     if (f->own_ws) cudaFree(f->ws);
     if (f->keybuf) cudaFree(f->keybuf);
+    if (f->s_prep) cudaStreamSynchronize(f->s_prep);        // nothing of ours may still be running when the caller frees memory
+    if (f->s_raster) cudaStreamSynchronize(f->s_raster);
     if (f->hstats) cudaFreeHost(f->hstats);
     if (f->s_prep) cudaStreamDestroy(f->s_prep);
     if (f->s_raster) cudaStreamDestroy(f->s_raster);
@@ -1744,6 +1759,7 @@ int crb_bind_workspace(crb_filler *f, void *workspace, size_t bytes, int64_t max
     if (check_filler(f)) return CRB_ERR_INVALID;
     if (f->own_ws) return fail(CRB_ERR_STATE, "workspace is library-owned");
     CU(cudaSetDevice(f->device));
+    { int jrc = join_pending(f, (cudaStream_t)stream); if (jrc) return jrc; }
     return bind_ws_pointers(f, workspace, bytes, max_triangles, max_views, pair_capacity, (cudaStream_t)stream);
 }
 
@@ -1786,6 +1802,7 @@ int crb_init_buffers(crb_filler *f, void *stream)
     if (check_filler(f)) return CRB_ERR_INVALID;
     if (!f->z || !f->color || !f->normals) return fail(CRB_ERR_STATE, "buffers not bound");
     CU(cudaSetDevice(f->device));
+    { int jrc = join_pending(f, (cudaStream_t)stream); if (jrc) return jrc; }
     const long long px = (long long)(f->row1 - f->row0) * f->w;
     if (px == 0) return CRB_OK;
     k_init_buffers<<<1184, NT, 0, (cudaStream_t)stream>>>(f->z, f->color, f->normals, px);
@@ -1802,6 +1819,7 @@ int crb_render(crb_filler *f, const float *v, const float *c, const float *n, in
     if (T > f->maxT) return fail(CRB_ERR_STATE, "T=%lld exceeds the workspace's max_triangles=%lld", (long long)T, f->maxT);
     if (T > 0xFFFFFFF0ll) return fail(CRB_ERR_INVALID, "T exceeds 32-bit triangle indices");
     CU(cudaSetDevice(f->device));
+    { int jrc = join_pending(f, (cudaStream_t)stream); if (jrc) return jrc; }
     if ((long long)(f->row1 - f->row0) * f->w == 0) return CRB_OK;
     Frame F;
     fill_frame(f, &F);
@@ -1819,6 +1837,7 @@ int crb_render_host(crb_filler *f, const float *v, const float *c, const float *
     if (T < 0 || T > f->maxT) return fail(CRB_ERR_STATE, "T=%lld outside the workspace's [0,%lld]", (long long)T, f->maxT);
     if (T > 0 && (!v || !c || !n)) return fail(CRB_ERR_INVALID, "NULL triangle array");
     CU(cudaSetDevice(f->device));
+    { int jrc = join_pending(f, (cudaStream_t)stream); if (jrc) return jrc; }
     cudaStream_t st = (cudaStream_t)stream;
     if (T > 0) {
         CU(cudaMemcpyAsync(f->stage_v, v, (size_t)T * 36, cudaMemcpyHostToDevice, st));
@@ -1895,15 +1914,20 @@ int crb_render_views(crb_filler *f, const float *v, const float *c, const float 
     // rasterizer.  Rasterizer launches themselves stay serialised (they would only share the SMs).
     cudaStream_t user = (cudaStream_t)stream;
     const int launches = (n_views + f->maxViews - 1) / f->maxViews;
-    const bool pipe = f->chunk_pipeline && launches > 1;
-    if (pipe) {
+    const bool defer = (flags & CRB_DEFER_JOIN) != 0;
+    const bool pipe = f->chunk_pipeline && (launches > 1 || defer) && launches > 0;
+    if (!pipe) {
+        int rc = join_pending(f, user);
+        if (rc) return rc;
+    } else {
+        // everything the caller queued so far (inputs produced, earlier results consumed) comes first
         CU(cudaEventRecord(f->ev_start, user));
         CU(cudaStreamWaitEvent(f->s_prep, f->ev_start, 0));
         CU(cudaStreamWaitEvent(f->s_raster, f->ev_start, 0));
     }
-    int i = 0;
+    int i = 0, last_set = 0;
     for (int v0 = 0; v0 < n_views; v0 += f->maxViews, ++i) {
-        const int set = pipe ? (i & 1) : 0;
+        const int set = pipe ? (int)(f->launch_seq++ & 1u) : 0;
         Frame F;
         fill_frame(f, &F, set);
         F.T = T; F.nViews = (n_views - v0 < f->maxViews) ? n_views - v0 : f->maxViews;
@@ -1921,15 +1945,27 @@ int crb_render_views(crb_filler *f, const float *v, const float *c, const float 
             if (rc) return rc;
             continue;
         }
-        if (i >= 2) CU(cudaStreamWaitEvent(f->s_prep, f->ev_raster[set], 0));    // the set's previous frame has been rasterized
+        if (f->set_used[set]) CU(cudaStreamWaitEvent(f->s_prep, f->ev_raster[set], 0));   // the set's previous frame has been rasterized
         if ((rc = run_prep(f, F, f->s_prep))) return rc;
         CU(cudaEventRecord(f->ev_fill[set], f->s_prep));
         CU(cudaStreamWaitEvent(f->s_raster, f->ev_fill[set], 0));
         if ((rc = run_raster(f, F, f->s_raster, i))) return rc;
         CU(cudaEventRecord(f->ev_raster[set], f->s_raster));
+        f->set_used[set] = 1;
+        last_set = set;
     }
-    if (pipe) CU(cudaStreamWaitEvent(user, f->ev_raster[(launches - 1) & 1], 0));
+    if (pipe) {
+        f->pending_join = 1 + last_set;
+        if (!defer) return join_pending(f, user);
+    }
     return CRB_OK;
+}
+
+int crb_join(crb_filler *f, void *stream)
+{
+    if (check_filler(f)) return CRB_ERR_INVALID;
+    CU(cudaSetDevice(f->device));
+    return join_pending(f, (cudaStream_t)stream);
 }
 
 int crb_transform_view(crb_filler *f, const float *v, const float *n, int64_t T, const float *view, float *v_out,
@@ -1948,6 +1984,7 @@ int crb_guro(crb_filler *f, const float light[3], void *stream)
     if (check_filler(f) || !light) return fail(CRB_ERR_INVALID, "NULL argument");
     if (!f->color || !f->normals) return fail(CRB_ERR_STATE, "buffers not bound");
     CU(cudaSetDevice(f->device));
+    { int jrc = join_pending(f, (cudaStream_t)stream); if (jrc) return jrc; }
     const long long px = (long long)(f->row1 - f->row0) * f->w;
     if (px == 0) return CRB_OK;
     k_guro<<<1184, NT, 0, (cudaStream_t)stream>>>(f->color, f->normals, px, light[0], light[1], light[2]);
@@ -1959,6 +1996,7 @@ int crb_color_u8_flipped(crb_filler *f, uint8_t *out_u8, void *stream)
     if (check_filler(f) || !out_u8) return fail(CRB_ERR_INVALID, "NULL argument");
     if (!f->color) return fail(CRB_ERR_STATE, "buffers not bound");
     CU(cudaSetDevice(f->device));
+    { int jrc = join_pending(f, (cudaStream_t)stream); if (jrc) return jrc; }
     if ((long long)(f->row1 - f->row0) * f->w == 0) return CRB_OK;
     k_color_u8_flipped<<<1184, NT, 0, (cudaStream_t)stream>>>(f->color, out_u8, f->row1 - f->row0, f->w);
     return launch_check(f, "k_color_u8_flipped");
@@ -1969,6 +2007,7 @@ int crb_download(crb_filler *f, unsigned mask, float *z_host, float *color_host,
     if (check_filler(f)) return CRB_ERR_INVALID;
     if (!f->z || !f->color || !f->normals) return fail(CRB_ERR_STATE, "buffers not bound");
     CU(cudaSetDevice(f->device));
+    { int jrc = join_pending(f, (cudaStream_t)stream); if (jrc) return jrc; }
     const size_t px = (size_t)(f->row1 - f->row0) * f->w;
     cudaStream_t st = (cudaStream_t)stream;
     if (px == 0) return CRB_OK;
@@ -1984,6 +2023,7 @@ int crb_upload(crb_filler *f, unsigned mask, const float *z_host, const float *c
     if (check_filler(f)) return CRB_ERR_INVALID;
     if (!f->z || !f->color || !f->normals) return fail(CRB_ERR_STATE, "buffers not bound");
     CU(cudaSetDevice(f->device));
+    { int jrc = join_pending(f, (cudaStream_t)stream); if (jrc) return jrc; }
     const size_t px = (size_t)(f->row1 - f->row0) * f->w;
     cudaStream_t st = (cudaStream_t)stream;
     if (px == 0) return CRB_OK;
@@ -1998,6 +2038,7 @@ int crb_status(crb_filler *f, int64_t *pairs_needed, int64_t *pair_capacity, voi
     if (check_filler(f)) return CRB_ERR_INVALID;
     if (!f->ws) return fail(CRB_ERR_STATE, "workspace not bound");
     CU(cudaSetDevice(f->device));
+    { int jrc = join_pending(f, (cudaStream_t)stream); if (jrc) return jrc; }
     unsigned long long t[2] = {0, 0}, u[2] = {0, 0};
     unsigned long long *total1 = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(f->total) + f->set_bytes);
     CU(cudaMemcpyAsync(t, f->total, 16, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
@@ -2032,6 +2073,7 @@ int crb_sync(crb_filler *f, void *stream)
 {
     if (check_filler(f)) return CRB_ERR_INVALID;
     CU(cudaSetDevice(f->device));
+    { int jrc = join_pending(f, (cudaStream_t)stream); if (jrc) return jrc; }
     CU(cudaStreamSynchronize((cudaStream_t)stream));
     return CRB_OK;
 }

@@ -100,6 +100,8 @@ class AdvancedPixelBufferFiller:
         T = max(int(T), self._ws_T, 1)
         views = max(int(views), self._ws_views)
         pair_cap = max(int(pair_cap), self._pair_cap if pair_cap else 0)
+        if self._ws is not None:
+            check(self._L.crb_join(self._handle, self._stream()))     # deferred rasterizer work still uses the old workspace
         torch.cuda.current_stream(self._dev).synchronize()
         nbytes = self._L.crb_workspace_bytes(self._handle, T, views, pair_cap)
         with torch.cuda.device(self._dev):
@@ -265,13 +267,15 @@ class AdvancedPixelBufferFiller:
         return out
 
     def render_views(self, v, c, n, views, z_out=None, color_out=None, normals_out=None, color_u8_out=None,
-                     want=("z", "color", "normals"), guro_light=None, chunk=32, check_status=True):
+                     want=("z", "color", "normals"), guro_light=None, chunk=32, check_status=True, defer_join=False):
         """Batched multi-view render (config C5): every view gets fresh-filler buffers in its own slab.
 
         v, c, n: torch CUDA float32 [T,3,3] (device-resident base mesh);  views: [V,16] float32 (numpy or CUDA tensor,
         see views.py).  Outputs are torch CUDA tensors [V,rows,w(,3)], allocated here unless passed in; `want` selects
         which float32 buffers are produced, `color_u8_out=True` (or a tensor) adds run.py:26's flipped uint8 image.
         `guro_light` = raw light direction (as given to GuroIllumination) fuses the illumination into the shading pass.
+        `defer_join=True` (with check_status=False): the call returns without ordering the current stream behind the
+        rasterizer, so the next batch's front end overlaps it; call `join()` before using the outputs.
         Returns a dict of the produced tensors."""
         torch = self._torch
         for a in (v, c, n):
@@ -308,6 +312,8 @@ class AdvancedPixelBufferFiller:
             l = l / np.linalg.norm(l)
             light = (ctypes.c_float * 3)(*[float(x) for x in l])
             flags |= _lib.CRB_GURO
+        if defer_join and not check_status:
+            flags |= _lib.CRB_DEFER_JOIN
         self._ensure_workspace(T, views=min(int(chunk), max(V, 1)))
         ptr = lambda t: None if t is None else t.data_ptr()
         while True:
@@ -324,6 +330,10 @@ class AdvancedPixelBufferFiller:
             check(rc)
             break
         return out
+
+    def join(self):
+        """Orders the current stream behind batches issued with defer_join=True."""
+        check(self._L.crb_join(self._handle, self._stream()))
 
     def transform_view(self, v, n, view):
         """The camera-space [T,3,3] arrays one view produces (what the reference would be handed for that view)."""

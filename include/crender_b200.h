@@ -50,6 +50,10 @@ extern "C" {
 #define CRB_NO_SYNC 8u         /* crb_render_host only: return once the work is queued; crb_sync() before reading
                                   the host outputs or reusing the host inputs (frame pipelining over several fillers) */
 
+#define CRB_DEFER_JOIN 32u     /* crb_render_views only: return without ordering `stream` behind the rasterizer (which runs on an
+                                  internal stream), so that the NEXT batch's setup / binning kernels overlap this batch's
+                                  rasterization.  The outputs may only be used on `stream` after crb_join(); every other
+                                  entry point that touches the filler joins by itself. */
 #define CRB_DL_SPARSE 16u      /* crb_render_host + CRB_CLEAR_FIRST only: sparse read-back.  The caller promises that the host
                                   output arrays still hold what the previous CRB_DL_SPARSE call of this filler left in them
                                   (fresh-filler values -- z 1e6, colour 0, normals 0 -- before the first call, or after
@@ -131,6 +135,9 @@ int crb_render_host(crb_filler *f, const float *v, const float *c, const float *
 #define CRB_OPT_TMA 2
 #define CRB_OPT_TMA_ROWS 3   /* shaded colour / normal rows of busy tiles as TMA boxes (1) or 16-byte vector stores (0) */
 int crb_set_option(crb_filler *f, int option, int value);
+
+/* Orders `stream` behind rasterizer work left in flight by CRB_DEFER_JOIN (no host synchronisation). */
+int crb_join(crb_filler *f, void *stream);
 
 /* Waits for everything queued on `stream` (pairs with CRB_NO_SYNC). */
 int crb_sync(crb_filler *f, void *stream);

@@ -529,3 +529,29 @@ def test_single_view_heavy_tile_split(split, Filler, O, monkeypatch):
         g.render_model(m2)                                      # composites into the first frame
         o.render_model(m2)
         assert_same(buffers(g), buffers(o), f"split={split} composite {h}x{w}")
+
+
+def test_deferred_join_batches_match_joined_batches(Filler, trex):
+    """CRB_DEFER_JOIN: back-to-back batches whose front end overlaps the previous batch's rasterizer (alternating
+    workspace sets across calls) give the same slabs as joined calls; other entry points join by themselves."""
+    import torch
+    from cython3dmodelrenderer_b200 import views as VW
+    h, w = 128, 160
+    dv, dc, dn = (torch.from_numpy(a).cuda() for a in
+                  (trex._vertices_by_triangles, trex._colors_by_triangles, trex._normals_by_triangles))
+    batches = [VW.orbit_views(12, first=3 * k, count=3) for k in range(4)]
+    f = Filler(h, w, fov=45.0)
+    want = [{k: t.clone() for k, t in f.render_views(dv, dc, dn, b, chunk=3).items()} for b in batches]
+    g = Filler(h, w, fov=45.0)
+    outs = []
+    for b in batches:
+        outs.append(g.render_views(dv, dc, dn, b, chunk=3, check_status=False, defer_join=True))
+    g.join()
+    for k, (o, wnt) in enumerate(zip(outs, want)):
+        for name in ("z", "color", "normals"):
+            assert torch.equal(o[name].view(torch.int32), wnt[name].view(torch.int32)), (k, name)
+    # an entry point that is not render_views joins on its own: the composited frame sees the finished batch state
+    o2 = g.render_views(dv, dc, dn, batches[0], chunk=3, check_status=False, defer_join=True)
+    g.clear(); g.render_arrays(dv, dc, dn)        # crb_render + crb_status join first
+    z, c, n = g.device_buffers()
+    assert int((z < 1e5).sum()) > 100 and torch.equal(o2["z"].view(torch.int32), want[0]["z"].view(torch.int32))
