@@ -555,3 +555,35 @@ def test_deferred_join_batches_match_joined_batches(Filler, trex):
     g.clear(); g.render_arrays(dv, dc, dn)        # crb_render + crb_status join first
     z, c, n = g.device_buffers()
     assert int((z < 1e5).sum()) > 100 and torch.equal(o2["z"].view(torch.int32), want[0]["z"].view(torch.int32))
+
+
+def test_reference_renderer_flow_with_the_drop_in_filler(Filler, trex, capfd):
+    """The run.py flow (run.py:20-26) with the reference's OWN Renderer and GuroIllumination classes driving this filler
+    (crender/cy/renderer.py:42-49: render_model, in-place illumination on the live views, get_color_buffer), next to
+    the same flow on the reference's own Cython filler: the images written by cv2.imwrite would be byte-identical."""
+    from oracle import build_ref
+    if not build_ref.built():
+        pytest.skip("oracle/_ref (reference Cython build) not present")
+    import sys
+    from conftest import ROOT
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    from crender.cy import Renderer
+    from crender.cy.illumination import GuroIllumination
+    from crender.cy.pixel_buffer_filler import AdvancedPixelBufferFiller as RefFiller
+    from crender.cy.triangle_iterator import SimpleIterator
+    h = w = 256
+    images = []
+    for cls in (RefFiller, Filler):
+        filler = cls(h, w, fov=45, n_threads=1)
+        renderer = Renderer(filler, GuroIllumination(np.array([0, 0, 1], dtype="float32")), SimpleIterator, h, w)
+        image = renderer.render(trex)
+        images.append((np.array(image, copy=True), image[::-1].astype("uint8"),
+                       filler.get_normals_buffer().copy(), filler.get_z_buffer().copy()))
+    capfd.readouterr()
+    (ri, ru8, rn, rz), (gi, gu8, gn, gz) = images
+    assert int((rz < 1e5).sum()) > 5000
+    assert bits_equal(gz, rz) and bits_equal(gn, rn)
+    assert bits_equal(gi, ri), "lit colour buffer differs from the reference flow"
+    assert np.array_equal(gu8, ru8)
