@@ -46,46 +46,99 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled every 100 ms while the timed region runs."""
+    """SM clock + throttle reasons sampled every few ms while the timed region runs: NVML in a thread (no process to
+    spawn, so even a 20 ms region gets several samples); `nvidia-smi -lms` as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, period_s=0.004):
+        self.index, self.rows, self.proc, self.period = index, [], None, period_s
+        self.nvml, self.stop_flag, self.how, self.err = None, False, None, None
+
+    def _nvml_setup(self):
+        """Everything that can be done before the load starts: handle, constants, the one-sample closure."""
+        n, hnd = self.nvml
+        R = {"hw_slowdown": getattr(n, "nvmlClocksEventReasonHwSlowdown", getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
+             "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+             "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+             "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap", getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4))}
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        mx = n.nvmlDeviceGetMaxClockInfo(hnd, n.NVML_CLOCK_SM)
+
+        def one():
+            try:
+                sm = n.nvmlDeviceGetClockInfo(hnd, n.NVML_CLOCK_SM)
+                bits = get_reasons(hnd)
+                self.rows.append((float(sm), float(mx), [k for k, b in R.items() if bits & b]))
+            except Exception as ex:
+                self.err = repr(ex)[:120]
+        self.one = one
+
+    def _nvml_loop(self):
+        while not self.stop_flag:
+            self.one()
+            time.sleep(self.period)
 
     def __enter__(self):
         try:
+            import pynvml as n
+            n.nvmlInit()
+            idx = self.index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                idx = int(vis.split(",")[self.index])
+            self.nvml = (n, n.nvmlDeviceGetHandleByIndex(idx))
+            self.how = "nvml"
+            self._nvml_setup()
+            self.t = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.t.start()
+            return self
+        except Exception as ex:
+            self.err = repr(ex)[:120]
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.how = "nvidia-smi -lms 20"
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
         return self
 
+    def sample_now(self, n=3):
+        """Synchronous samples from the calling thread -- called right after the timed steps have been queued, while the
+        GPU is still working through them (a short region may end before the sampling thread is scheduled once)."""
+        one = getattr(self, "one", None)
+        for _ in range(n):
+            if one:
+                one()
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            r = [x.strip() for x in line.split(",")]
+            try:
+                self.rows.append((float(r[0]), float(r[1]),
+                                  [name for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7])
+                                   if v.lower().startswith("active")]))
+            except Exception:
+                pass
 
     def __exit__(self, *a):
-        if self.proc:
-            time.sleep(0.15)
+        if self.nvml:
+            self.stop_flag = True
+            self.t.join(timeout=1)
+        elif self.proc:
+            time.sleep(0.05)
             self.proc.terminate()
             self.t.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                pass
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"], "how": self.how, "error": self.err}
+        reasons = sorted({r for row in self.rows for r in row[2]})
+        return {"sm_mhz": statistics.median(r[0] for r in self.rows), "sm_max_mhz": max(r[1] for r in self.rows),
+                "reasons": reasons, "samples": len(self.rows), "how": self.how}
 
 
 # --------------------------------------------------------------------------------------------------------------------
@@ -261,6 +314,7 @@ def run_gpu_arm(args):
             step()
         f.join()
         e1.record()
+        clocks.sample_now()      # the GPU is still inside the timed steps here (launches are asynchronous)
         barrier()
     ms = e0.elapsed_time(e1)
     k_launches, k_ms = f.profile_read()
@@ -538,6 +592,7 @@ def run_extra_workload(args):
         for _ in range(args.steps):
             step()
         e1.record()
+        clocks.sample_now()
         barrier()
     ms = e0.elapsed_time(e1)
     k_launches, k_ms = f.profile_read()
