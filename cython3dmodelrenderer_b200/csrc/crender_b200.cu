@@ -267,7 +267,8 @@ __device__ __forceinline__ bool shade_fragment(const Frame &F, long long ridx, f
     c[1] = (X.z * b1 + C1.y * b2) + C2.x * b3;
     c[2] = (X.w * b1 + C1.z * b2) + C2.y * b3;
     if (F.flags & CRB_GURO) {  // guro_illumination.py:23-27 (float32, left-to-right sums)
-        const float dot = (n[0] * F.light[0] + n[1] * F.light[1]) + n[2] * F.light[2];
+        // np.sum accumulates from the identity +0.0 (all -0.0 products sum to +0.0, not -0.0)
+        const float dot = (__fadd_rn(0.0f, n[0] * F.light[0]) + n[1] * F.light[1]) + n[2] * F.light[2];
         const float nrm = sqrtf((n[0] * n[0] + n[1] * n[1]) + n[2] * n[2]);
         float s = dot / (nrm + 1e-6f);
         if (s < 0.0f) s = 0.0f;
@@ -278,16 +279,11 @@ __device__ __forceinline__ bool shade_fragment(const Frame &F, long long ridx, f
 }
 
 // Colour of a pixel no triangle covers.  Plain renders: 0 (pyx:66).  With the fused Guro pass the reference still runs
-// draw_illumination over the whole buffer: normal (0,0,0) gives shadow = clip(0*l/(0+1e-6)) whose SIGN follows the light
-// (e.g. -0.0 for the default light), and 0 * -0.0 = -0.0 is what lands in the buffer -- reproduced for bit parity.
-__device__ __forceinline__ float background_color(const Frame &F)
+// draw_illumination over the whole buffer: normal (0,0,0) gives np.sum(...) = +0.0 whatever the signs of the light
+// (the sum starts from the identity +0.0), shadow = clip(+0 / (0 + 1e-6)) = +0 and 0 * +0 = +0.
+__device__ __forceinline__ float background_color(const Frame &)
 {
-    if (!(F.flags & CRB_GURO)) return 0.0f;
-    const float dot = (0.0f * F.light[0] + 0.0f * F.light[1]) + 0.0f * F.light[2];
-    float s = dot / (sqrtf(0.0f) + 1e-6f);
-    if (s < 0.0f) s = 0.0f;
-    if (s > 1.0f) s = 1.0f;
-    return 0.0f * s;
+    return 0.0f;
 }
 
 // run.py:26 .astype('uint8'): C truncation toward zero, then the low 8 bits.
@@ -1162,7 +1158,7 @@ __global__ void __launch_bounds__(NT) k_guro(float *color, const float *normals,
     const long long stride = (long long)gridDim.x * NT;
     for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < pixels; i += stride) {
         const float n0 = normals[i * 3], n1 = normals[i * 3 + 1], n2 = normals[i * 3 + 2];
-        const float dot = (n0 * l0 + n1 * l1) + n2 * l2;
+        const float dot = (__fadd_rn(0.0f, n0 * l0) + n1 * l1) + n2 * l2;   // np.sum accumulates from +0.0
         const float nrm = sqrtf((n0 * n0 + n1 * n1) + n2 * n2);
         float s = dot / (nrm + 1e-6f);
         if (s < 0.0f) s = 0.0f;

@@ -222,7 +222,13 @@ void oracle_guro(int h, int w, const float light[3], float *cbuf, const float *n
     size_t px = (size_t)h * (size_t)w;
     for (size_t i = 0; i < px; ++i) {
         const float *nn = nbuf + i * 3;
-        float dot = nn[0] * light[0] + nn[1] * light[1] + nn[2] * light[2];
+        /* np.sum(n_buffer * light, axis=-1) (guro_illumination.py:23) accumulates from the identity +0.0, so products
+         * that are all -0.0 (zero normal components times a light of (-0,-0,-1), the default) sum to +0.0, not -0.0:
+         * checked against NumPy 2.3 through the golden lit-colour checksums */
+        float dot = 0.0f;
+        dot += nn[0] * light[0];
+        dot += nn[1] * light[1];
+        dot += nn[2] * light[2];
         float nrm = sqrtf(nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]);
         float s = dot / (nrm + 1e-6f);
         if (s < 0.0f) s = 0.0f;

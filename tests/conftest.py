@@ -63,3 +63,8 @@ def trex():
 @pytest.fixture(scope="session")
 def bunny():
     return load_indexed("bunny")
+
+
+@pytest.fixture(scope="session")
+def basketball():
+    return load_indexed("basketball")

@@ -7,6 +7,7 @@ Outputs (tests/golden/):
   trex_fit.npz    -- T-Rex after the README flow (run.py:29-39): indexed arrays from which the three
                      [T,3,3] float32 inputs of render_model are rebuilt bit-exactly (v = vertices[tri_v], ...)
   bunny_fit.npz   -- bunny.obj + igor_texture.png after fit_model (SURVEY.md section 8d, config C2/C3 substitute)
+  basketball_fit.npz -- basketball.obj (quads, fan-triangulated by the reference) + igor_texture.png after fit_model
   checksums.json  -- sha256 of the reference's z / colour / normal buffers (n_threads=1) for a list of
                      (model, h, w, fov) cases, plus the projection-matrix known answers
   trex_128.npz    -- full reference output buffers for T-Rex at 128x128 (small enough to commit)
@@ -68,13 +69,17 @@ def main():
     fit_model(bunny)
     np.savez_compressed(os.path.join(HERE, "trex_fit.npz"), **indexed(trex))
     np.savez_compressed(os.path.join(HERE, "bunny_fit.npz"), **indexed(bunny))
+    # config C3 substitute (igor.obj is absent from the reference tree): the quad-faced basketball with igor's texture
+    ball = Model.read_model("objects/basketball.obj", external_texture_filename="objects/igor_texture.png")
+    fit_model(ball)
+    np.savez_compressed(os.path.join(HERE, "basketball_fit.npz"), **indexed(ball))
 
     cases = {}
-    models = {"trex": trex, "bunny": bunny}
+    models = {"trex": trex, "bunny": bunny, "basketball": ball}
     for name, h, w, fov in [("trex", 1024, 1024, 45.0), ("trex", 512, 512, 90.0), ("trex", 333, 777, 60.0),
                             ("trex", 128, 128, 45.0), ("trex", 2048, 2048, 45.0),
                             ("bunny", 1024, 1024, 45.0), ("bunny", 2048, 2048, 45.0), ("bunny", 4096, 4096, 45.0),
-                            ("bunny", 500, 300, 30.0)]:
+                            ("bunny", 500, 300, 30.0), ("basketball", 2048, 2048, 45.0), ("basketball", 1000, 1500, 70.0)]:
         m = models[name]
         z, c, n = render(m, h, w, fov)
         cases[f"{name}_{h}x{w}_fov{fov:g}"] = dict(
@@ -89,6 +94,15 @@ def main():
     cases["trex_then_bunny_640x480_fov50"] = dict(
         model="trex+bunny", h=640, w=480, fov=50.0, z=sha(f.get_z_buffer()), color=sha(f.get_color_buffer()),
         normals=sha(f.get_normals_buffer()), covered=int((f.get_z_buffer() < 1e5).sum()))
+    # Renderer.render with GuroIllumination (crender/cy/renderer.py:47-49, guro_illumination.py:20-27): the lit colour buffer
+    from crender.cy.illumination import GuroIllumination
+    for name, h, w, fov, light in [("trex", 1024, 1024, 45.0, [0, 0, 1]), ("bunny", 2048, 2048, 45.0, [0, 0, 1]),
+                                   ("basketball", 777, 555, 60.0, [0.3, -0.5, 1.0])]:
+        z, c, n = render(models[name], h, w, fov)
+        c = c.copy()
+        GuroIllumination(light).draw_illumination(c, n)
+        cases[f"{name}_{h}x{w}_fov{fov:g}_guro"] = dict(model=name, h=h, w=w, fov=fov, light=light, color_lit=sha(c),
+                                                        covered=int((z < 1e5).sum()))
     inputs = {k: dict(v=sha(m._vertices_by_triangles), c=sha(m._colors_by_triangles), n=sha(m._normals_by_triangles))
               for k, m in models.items()}
     with open(os.path.join(HERE, "checksums.json"), "w") as fo:

@@ -67,10 +67,11 @@ def test_dense_scenes_bit_exact(seed, Filler, O):
 
 @pytest.mark.parametrize("case", ["trex_1024x1024_fov45", "trex_512x512_fov90", "trex_333x777_fov60",
                                   "trex_2048x2048_fov45", "bunny_1024x1024_fov45", "bunny_500x300_fov30",
-                                  "bunny_2048x2048_fov45", "bunny_4096x4096_fov45"])
-def test_reference_golden_checksums(case, Filler, trex, bunny):
+                                  "bunny_2048x2048_fov45", "bunny_4096x4096_fov45", "basketball_2048x2048_fov45",
+                                  "basketball_1000x1500_fov70"])
+def test_reference_golden_checksums(case, Filler, trex, bunny, basketball):
     info = CHECKS["cases"][case]
-    m = {"trex": trex, "bunny": bunny}[info["model"]]
+    m = {"trex": trex, "bunny": bunny, "basketball": basketball}[info["model"]]
     f = Filler(info["h"], info["w"], fov=info["fov"], n_threads=8)
     f.render_model(m)
     z, c, n = f.get_z_buffer(), f.get_color_buffer(), f.get_normals_buffer()
@@ -587,3 +588,23 @@ def test_reference_renderer_flow_with_the_drop_in_filler(Filler, trex, capfd):
     assert bits_equal(gz, rz) and bits_equal(gn, rn)
     assert bits_equal(gi, ri), "lit colour buffer differs from the reference flow"
     assert np.array_equal(gu8, ru8)
+
+
+@pytest.mark.parametrize("case", sorted(k for k in CHECKS["cases"] if k.endswith("_guro")))
+def test_reference_golden_lit_colour(case, Filler, trex, bunny, basketball):
+    """The reference's Renderer.render + GuroIllumination result (golden checksum of the lit colour buffer), three ways:
+    NumPy illumination on the live host views, crb_guro on the device buffers, and CRB_GURO fused into shading."""
+    import torch
+    from cython3dmodelrenderer_b200 import views as VW
+    info = CHECKS["cases"][case]
+    m = {"trex": trex, "bunny": bunny, "basketball": basketball}[info["model"]]
+    light = -np.asarray(info["light"], dtype="float32")
+    light = light / np.linalg.norm(light)
+    f = Filler(info["h"], info["w"], fov=info["fov"])
+    f.render_model(m)
+    assert int((f.get_z_buffer() < 1e5).sum()) == info["covered"]
+    f.illuminate_guro(light)
+    assert sha(f.get_color_buffer()) == info["color_lit"]
+    dv, dc, dn = (torch.from_numpy(a).cuda() for a in (m._vertices_by_triangles, m._colors_by_triangles, m._normals_by_triangles))
+    out = f.render_views(dv, dc, dn, VW.view_matrix()[None, :], want=("color",), guro_light=info["light"])
+    assert sha(out["color"][0].cpu().numpy()) == info["color_lit"]

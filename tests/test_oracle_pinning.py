@@ -20,8 +20,8 @@ def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
-def test_fixture_inputs_match_reference_checksums(trex, bunny):
-    for name, m in (("trex", trex), ("bunny", bunny)):
+def test_fixture_inputs_match_reference_checksums(trex, bunny, basketball):
+    for name, m in (("trex", trex), ("bunny", bunny), ("basketball", basketball)):
         want = CHECKS["inputs"][name]
         assert sha(m._vertices_by_triangles) == want["v"]
         assert sha(m._colors_by_triangles) == want["c"]
@@ -69,18 +69,30 @@ def test_barycentric_known_answers():
     assert not np.isfinite(O.barycentric(deg, 5, 1)).any()
 
 
-@pytest.mark.parametrize("case", sorted(k for k in CHECKS["cases"] if not k.startswith("trex_then")))
-def test_oracle_reproduces_reference_checksums(case, trex, bunny):
+@pytest.mark.parametrize("case", sorted(k for k in CHECKS["cases"] if not k.startswith("trex_then") and not k.endswith("_guro")))
+def test_oracle_reproduces_reference_checksums(case, trex, bunny, basketball):
     info = CHECKS["cases"][case]
     if info["h"] * info["w"] > 2048 * 2048 and os.environ.get("CRB_FULL_GOLDEN", "1") != "1":
         pytest.skip("large case")
-    m = {"trex": trex, "bunny": bunny}[info["model"]]
+    m = {"trex": trex, "bunny": bunny, "basketball": basketball}[info["model"]]
     f = O.OracleFiller(info["h"], info["w"], fov=info["fov"])
     f.render_model(m)
     assert int((f.get_z_buffer() < 1e5).sum()) == info["covered"]
     assert sha(f.get_z_buffer()) == info["z"]
     assert sha(f.get_color_buffer()) == info["color"]
     assert sha(f.get_normals_buffer()) == info["normals"]
+
+
+@pytest.mark.parametrize("case", sorted(k for k in CHECKS["cases"] if k.endswith("_guro")))
+def test_oracle_reproduces_reference_lit_colour(case, trex, bunny, basketball):
+    """Renderer.render with the reference's GuroIllumination (renderer.py:47-49): checksum of the lit colour buffer."""
+    info = CHECKS["cases"][case]
+    m = {"trex": trex, "bunny": bunny, "basketball": basketball}[info["model"]]
+    f = O.OracleFiller(info["h"], info["w"], fov=info["fov"])
+    f.render_model(m)
+    assert int((f.get_z_buffer() < 1e5).sum()) == info["covered"]
+    c = O.guro(f.get_color_buffer().copy(), f.get_normals_buffer(), info["light"])
+    assert sha(c) == info["color_lit"]
 
 
 def test_oracle_compositing_checksum(trex, bunny):
