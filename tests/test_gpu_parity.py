@@ -608,3 +608,33 @@ def test_reference_golden_lit_colour(case, Filler, trex, bunny, basketball):
     dv, dc, dn = (torch.from_numpy(a).cuda() for a in (m._vertices_by_triangles, m._colors_by_triangles, m._normals_by_triangles))
     out = f.render_views(dv, dc, dn, VW.view_matrix()[None, :], want=("color",), guro_light=info["light"])
     assert sha(out["color"][0].cpu().numpy()) == info["color_lit"]
+
+
+def test_repeated_renders_are_bit_identical(Filler, trex):
+    """Determinism under load (a stand-in for racecheck): the same dense frame and the same batch of views rendered many
+    times, with the fused clear, must give the same bits every time."""
+    import torch
+    from cython3dmodelrenderer_b200 import views as VW
+    m = random_scene(77, T=20000, span=0.6)
+    dv, dc, dn = (torch.from_numpy(a).cuda() for a in (m._vertices_by_triangles, m._colors_by_triangles, m._normals_by_triangles))
+    f = Filler(512, 512, fov=70.0)
+    ref = None
+    for it in range(25):
+        f.clear()
+        f.render_arrays(dv, dc, dn, check_status=(it == 0))
+        z, c, n = f.device_buffers()
+        cur = (z.clone(), c.clone(), n.clone())
+        if ref is None:
+            ref = cur
+        else:
+            for a, b in zip(ref, cur):
+                assert torch.equal(a.view(torch.int32), b.view(torch.int32)), f"iteration {it}"
+    tv, tc, tn = (torch.from_numpy(a).cuda() for a in (trex._vertices_by_triangles, trex._colors_by_triangles, trex._normals_by_triangles))
+    g = Filler(256, 256, fov=45.0)
+    views = VW.orbit_views(24)
+    first = {k: t.clone() for k, t in g.render_views(tv, tc, tn, views, chunk=8).items()}
+    for it in range(10):
+        out = g.render_views(tv, tc, tn, views, chunk=8, check_status=False, defer_join=(it % 2 == 0))
+        g.join()
+        for k in first:
+            assert torch.equal(first[k].view(torch.int32), out[k].view(torch.int32)), (it, k)
