@@ -498,6 +498,38 @@ def run_gpu_arm(args):
     except Exception as ex:  # graph capture is an extra, never fatal
         single = {"error": str(ex)[:200]}
 
+    # ---- the literal reference usage (run.py:20-26 idiom): host model in, host NumPy buffers out, synchronous ------------
+    drop_in = None
+    if rank == 0:
+        from conftest import TriModel
+        vk, nk = VW.transform_arrays_host(views_np[0], model._vertices_by_triangles, model._normals_by_triangles)
+        mk = TriModel(vk, model._colors_by_triangles, nk)
+
+        def per_frame(fn, nrep=20):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            t0_ = time.perf_counter()
+            for _ in range(nrep):
+                fn()
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0_) / nrep * 1e3
+
+        def new_filler():
+            ff = AdvancedPixelBufferFiller(RES, RES, fov=FOV, n_threads=8, device=local)
+            ff.render_model(mk)
+            return ff.get_color_buffer(), ff.get_normals_buffer(), ff.get_z_buffer()
+        fr = AdvancedPixelBufferFiller(RES, RES, fov=FOV, device=local)
+
+        def reused():
+            fr.clear()
+            fr.render_model(mk)
+            return fr.get_color_buffer(), fr.get_normals_buffer(), fr.get_z_buffer()
+        drop_in = {"new_filler_per_frame_ms": per_frame(new_filler), "one_filler_clear_render_get3_ms": per_frame(reused),
+                   "what": "AdvancedPixelBufferFiller(...).render_model(model) + the three get_*_buffer() calls on host NumPy data, "
+                           "synchronous, full 29.4 MB download (the unmodified run.py flow with the import swapped)"}
+        del fr
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         kind, cores, times = cpu_frames(model, views_np, frames=args.cpu_frames)
@@ -515,7 +547,7 @@ def run_gpu_arm(args):
                        "buffers": "z+color+normals f32, fresh per view", "l2": "outputs %.2f GB/step per GPU >> 126 MB L2; "
                        "the 1.5 MB mesh is re-read per view by design" % (V * 28 * RES * RES / 1e9)},
             "gtri_per_s": fps * T / 1e9, "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches,
-            "roofline": roofline, "cpu_baseline": cpu, "single_frame": single, "gather": gather,
+            "roofline": roofline, "cpu_baseline": cpu, "single_frame": single, "drop_in": drop_in, "gather": gather,
             "checks": {"covered_pixels_view0": covered0, "e2e_covered_pixels": e2e_cov, "e2e_dense_covered_pixels": dense_cov, "e2e_sync_covered_pixels": sync_cov, "pairs_last_launch": int(need.value),
                        "pair_capacity": int(cap.value)},
         }
