@@ -638,3 +638,39 @@ def test_repeated_renders_are_bit_identical(Filler, trex):
         g.join()
         for k in first:
             assert torch.equal(first[k].view(torch.int32), out[k].view(torch.int32)), (it, k)
+
+
+@pytest.mark.parametrize("size", [(1, 1), (1, 37), (33, 1), (2, 3), (31, 32), (32, 33)])
+def test_degenerate_image_sizes(size, Filler, O):
+    h, w = size
+    for seed in (1, 2):
+        m = random_scene(400 + seed, T=50)
+        g, o = Filler(h, w, fov=60.0), O.OracleFiller(h, w, fov=60.0)
+        g.clear()
+        g.render_model(m)
+        o.render_model(m)
+        assert_same(buffers(g), buffers(o), f"{h}x{w} seed {seed}")
+
+
+def test_screen_filling_triangles_and_one_crowded_tile(Filler, O):
+    """Two extremes of the binning: triangles that cover every tile of a 1536x1024 frame (thousands of tiles per triangle),
+    and 30 000 small triangles inside a single tile (one list far longer than a staging batch, heavy-tile bands)."""
+    rng = np.random.default_rng(5)
+    big = np.array([[[-30, -30, 2.0], [30, -30, 2.0], [0, 40, 2.0]],
+                    [[-25, 25, 1.5], [0, -35, 1.5], [25, 25, 1.5]],
+                    [[-1.0, -1.0, 1.0], [1.0, -1.0, 3.0], [0.0, 1.2, 0.5]]], dtype=np.float32)
+    nb = -np.abs(rng.standard_normal((3, 3, 3))).astype(np.float32)
+    cb = (rng.random((3, 3, 3)) * 255).astype(np.float32)
+    T = 30000
+    ctr = np.array([0.2, -0.1, 1.0], dtype=np.float32) + rng.uniform(-0.008, 0.008, (T, 1, 3)).astype(np.float32) * np.float32([1, 1, 20])
+    small = (ctr + rng.uniform(-0.004, 0.004, (T, 3, 3)).astype(np.float32) * np.float32([1, 1, 0])).astype(np.float32)
+    ns = -np.abs(rng.standard_normal((T, 3, 3))).astype(np.float32)
+    cs = (rng.random((T, 3, 3)) * 255).astype(np.float32)
+    m = TriModel(np.concatenate([big, small]), np.concatenate([cb, cs]), np.concatenate([nb, ns]))
+    h, w = 1024, 1536
+    g, o = Filler(h, w, fov=45.0), O.OracleFiller(h, w, fov=45.0)
+    g.clear()
+    g.render_model(m)
+    o.render_model(m)
+    assert int((o.get_z_buffer() < 1e5).sum()) > h * w // 2
+    assert_same(buffers(g), buffers(o), "big + crowded")
