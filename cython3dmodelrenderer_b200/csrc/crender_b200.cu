@@ -47,7 +47,10 @@ constexpr int NT = 256;         // threads per CTA in every kernel
 constexpr unsigned FLAG_DBG_NOCLEAR = 0x10000u, FLAG_DBG_NOSHADE = 0x20000u, FLAG_DBG_NOROWS = 0x40000u, FLAG_DBG_NOOUT = 0x80000u;  // ablation switches (CRB_DEBUG_SKIP)
 constexpr unsigned FLAG_OUT_DIRECT = 0x200u;   // experiment: shaded pixels stored straight from registers (12-byte strided stores)
 constexpr unsigned FLAG_OUT_TMA = 0x100u;   // internal Frame.flags bit: shaded colour / normal rows leave through TMA boxes
-constexpr int CH = 128;         // triangles staged in shared memory per pass of the tile rasterizer
+#ifndef CRB_CH
+#define CRB_CH 128
+#endif
+constexpr int CH = CRB_CH;         // triangles staged in shared memory per pass of the tile rasterizer
 constexpr unsigned SPLIT_N = 48;  // single-view launches: tiles with more triangles than this are rasterized by SPLIT_BANDS CTAs, 8 rows each
 constexpr int SPLIT_BANDS = 4;
 #ifndef CRB_CLEAR_EVERY
@@ -55,7 +58,10 @@ constexpr int SPLIT_BANDS = 4;
 #endif
 constexpr unsigned CE = CRB_CLEAR_EVERY;  // every CE-th CTA of k_raster is a clear CTA (power of two)
 constexpr unsigned HEAVY_N = 64;  // tiles with more triangles than this are rasterized first (longest first: shorter kernel tail)
-constexpr int FQ = 256;          // fragments a warp compacts per round (8 per row)
+#ifndef CRB_FQ
+#define CRB_FQ 256
+#endif
+constexpr int FQ = CRB_FQ;          // fragments a warp compacts per round (8 per row)
 #ifndef CRB_KEY_STRIDE
 #define CRB_KEY_STRIDE 35
 #endif
@@ -68,6 +74,10 @@ constexpr float Z_INIT = 1e6f;  // pyx:67
 constexpr float REJ_EPS = 1e-6f;      // fast-reject guard band on barycentric numerators (see tri_fast_setup)
 constexpr float L3_MIN = 1e-30f, L3_MAX = 1e30f;
 constexpr int MAX_DIM = 65535;  // bbox corners are packed in 16 bits
+#ifndef CRB_CLEAR_ROWS
+#define CRB_CLEAR_ROWS 32
+#endif
+constexpr int CLEAR_ROWS = CRB_CLEAR_ROWS;   // rows per TMA box of the fused clear (TH: one box per array and tile)
 constexpr int BOX_ROWS = 8;       // rows per TMA box (clear pattern and shaded rows go out 8 tile rows at a time)
 constexpr int PROF_MAX = 8192;  // k_raster launches that can be timed between two crb_profile_read calls
 
@@ -586,14 +596,16 @@ struct __align__(128) TileSmem {
             float4 slot[NT / 32][2][32];   // per warp: the 32 rows of the current trip, [0] A1 A2 A3 l02, [1] l12 l22 tri info
             unsigned short fq[NT / 32][FQ];  // per warp: compacted fragments of the trip (lane | x << 5)
         } st;
+#ifndef CRB_NO_OUT_STAGE
         struct {
             float col[TH * TW * 3];
             float nrm[TH * TW * 3];
         } out;
+#endif
         struct {                              // clear CTAs only: the constant pattern their TMA boxes are stored from
-            float z[TH * TW];                 //   Z_INIT
-            float c[TH * TW * 3];             //   background colour
-            float n[TH * TW * 3];             //   0
+            float z[CLEAR_ROWS * TW];         //   Z_INIT
+            float c[CLEAR_ROWS * TW * 3];     //   background colour
+            float n[CLEAR_ROWS * TW * 3];     //   0
         } pat;
     } u;
     unsigned long long keys[TH * KEY_STRIDE];
@@ -859,8 +871,16 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
 
     // ---- deferred shading of the winners, staged so that colour / normals leave as whole rows ---------------
     const long long slab = (long long)view * F.slabPixels;
+#ifdef CRB_NO_OUT_STAGE
+    const bool tma = false;
+#else
     const bool tma = clear && M.use != 0u && (F.flags & FLAG_OUT_TMA);     // colour / normal rows leave through TMA boxes
+#endif
+#ifdef CRB_NO_OUT_STAGE
+    const bool vec = false;
+#else
     const bool vec = clear && !tma && (tw == TW) && ((F.W & 3) == 0) && !(F.flags & FLAG_OUT_DIRECT);   // ... or as 16-byte vector stores
+#endif
     const bool stage = tma || vec;
     const float bg = background_color(F);
     for (int p = threadIdx.x; p < TH * TW; p += NT) {
@@ -882,11 +902,14 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
                 }
             }
         }
+#ifndef CRB_NO_OUT_STAGE
         if (stage) {
             S.u.out.col[p * 3] = c[0]; S.u.out.col[p * 3 + 1] = c[1]; S.u.out.col[p * 3 + 2] = c[2];
             S.u.out.nrm[p * 3] = nn[0]; S.u.out.nrm[p * 3 + 1] = nn[1]; S.u.out.nrm[p * 3 + 2] = nn[2];
             if (F.z && !DBG(F, FLAG_DBG_NOOUT)) F.z[pix] = z;
-        } else if (write) {
+        } else
+#endif
+        if (write) {
             if (F.z) F.z[pix] = z;
             if (F.color) { F.color[pix * 3] = c[0]; F.color[pix * 3 + 1] = c[1]; F.color[pix * 3 + 2] = c[2]; }
             if (F.normals) { F.normals[pix * 3] = nn[0]; F.normals[pix * 3 + 1] = nn[1]; F.normals[pix * 3 + 2] = nn[2]; }
@@ -899,6 +922,7 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
     }
     PH(7);
     if (DBG(F, FLAG_DBG_NOOUT)) return;
+#ifndef CRB_NO_OUT_STAGE
     if (tma) {
         fence_async_smem();
         __syncthreads();
@@ -928,6 +952,7 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
             }
         }
     }
+#endif
     PH(9);
 }
 
@@ -936,9 +961,12 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
 __device__ __forceinline__ void tma_clear_tile(const TMaps &M, const TileSmem &S, unsigned t)
 {
     const int view = (int)(t >> 22), yl0 = (int)((t >> 11) & 2047u) * TH, x0 = (int)(t & 2047u) * TW;
-    if (M.use & CRB_BUF_Z) tma_store_box(&M.zt, S.u.pat.z, x0, yl0, view);
-    if (M.use & CRB_BUF_COLOR) tma_store_box(&M.ct, S.u.pat.c, x0 * 3, yl0, view);
-    if (M.use & CRB_BUF_NORMALS) tma_store_box(&M.nt, S.u.pat.n, x0 * 3, yl0, view);
+#pragma unroll
+    for (int r = 0; r < TH; r += CLEAR_ROWS) {
+        if (M.use & CRB_BUF_Z) tma_store_box(&M.zt, S.u.pat.z, x0, yl0 + r, view);
+        if (M.use & CRB_BUF_COLOR) tma_store_box(&M.ct, S.u.pat.c, x0 * 3, yl0 + r, view);
+        if (M.use & CRB_BUF_NORMALS) tma_store_box(&M.nt, S.u.pat.n, x0 * 3, yl0 + r, view);
+    }
 }
 
 // Grid roles.  Busy tiles: one CTA each when the grid is large enough (it is sized from the busy-tile count the host
@@ -971,10 +999,10 @@ __global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame 
             const unsigned ne = (unsigned)F.total[3];
             if (pairs > (unsigned long long)F.pairCap || DBG(F, FLAG_DBG_NOCLEAR)) return;     // frame skipped: buffers stay untouched
             const float bg = background_color(F);
-            for (int i = threadIdx.x; i < TH * TW * 3 / 4; i += NT) {
+            for (int i = threadIdx.x; i < CLEAR_ROWS * TW * 3 / 4; i += NT) {
                 reinterpret_cast<float4 *>(S.u.pat.c)[i] = make_float4(bg, bg, bg, bg);
                 reinterpret_cast<float4 *>(S.u.pat.n)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (i < TH * TW / 4) reinterpret_cast<float4 *>(S.u.pat.z)[i] = make_float4(Z_INIT, Z_INIT, Z_INIT, Z_INIT);
+                if (i < CLEAR_ROWS * TW / 4) reinterpret_cast<float4 *>(S.u.pat.z)[i] = make_float4(Z_INIT, Z_INIT, Z_INIT, Z_INIT);
             }
             fence_async_smem();
             __syncthreads();
@@ -1447,9 +1475,9 @@ bool encode_map(CUtensorMap *m, float *base, int comps, const Frame &F, int box_
 unsigned encode_maps(TMaps *M, const Frame &F)
 {
     unsigned use = 0;
-    if (F.z) { if (!encode_map(&M->z, F.z, 1, F, BOX_ROWS) || !encode_map(&M->zt, F.z, 1, F, TH)) return 0u; use |= CRB_BUF_Z; }
-    if (F.color) { if (!encode_map(&M->c, F.color, 3, F, BOX_ROWS) || !encode_map(&M->ct, F.color, 3, F, TH)) return 0u; use |= CRB_BUF_COLOR; }
-    if (F.normals) { if (!encode_map(&M->n, F.normals, 3, F, BOX_ROWS) || !encode_map(&M->nt, F.normals, 3, F, TH)) return 0u; use |= CRB_BUF_NORMALS; }
+    if (F.z) { if (!encode_map(&M->z, F.z, 1, F, BOX_ROWS) || !encode_map(&M->zt, F.z, 1, F, CLEAR_ROWS)) return 0u; use |= CRB_BUF_Z; }
+    if (F.color) { if (!encode_map(&M->c, F.color, 3, F, BOX_ROWS) || !encode_map(&M->ct, F.color, 3, F, CLEAR_ROWS)) return 0u; use |= CRB_BUF_COLOR; }
+    if (F.normals) { if (!encode_map(&M->n, F.normals, 3, F, BOX_ROWS) || !encode_map(&M->nt, F.normals, 3, F, CLEAR_ROWS)) return 0u; use |= CRB_BUF_NORMALS; }
     return use;
 }
 
