@@ -883,13 +883,14 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
 #endif
     const bool stage = tma || vec;
     const float bg = background_color(F);
+    const long long tilebase = slab + (long long)yl0 * F.W + x0;          // first pixel of the tile in its slab
     for (int p = threadIdx.x; p < TH * TW; p += NT) {
         const int yy = p / TW, xx = p % TW;
         if (yy < rowLo || yy >= th || xx >= tw) continue;
         const unsigned long long key = S.keys[yy * KEY_STRIDE + xx];
         float z = Z_INIT, c[3] = {bg, bg, bg}, nn[3] = {0.f, 0.f, 0.f};
         bool write = clear;
-        const long long pix = slab + (long long)(yl0 + yy) * F.W + x0 + xx;
+        const long long pix = tilebase + (unsigned)(yy * F.W + xx);       // yy < 32, W < 65536: 32-bit offset inside the tile
         if (key != KEY_EMPTY && !DBG(F, FLAG_DBG_NOSHADE)) {
             const unsigned tri = ~(unsigned)(key & 0xFFFFFFFFull);
             const long long ridx = (long long)view * F.T + tri;
