@@ -44,6 +44,7 @@ constexpr int NT = 256;         // threads per CTA in every kernel
 #else
 #define DBG(F, bit) ((void)(bit), false)
 #endif
+constexpr unsigned FLAG_DBG_ONEREC = 0x100000u;   // ablation: every pixel shades from record 0 (measures the cost of the gathers; wrong image)
 constexpr unsigned FLAG_DBG_NOCLEAR = 0x10000u, FLAG_DBG_NOSHADE = 0x20000u, FLAG_DBG_NOROWS = 0x40000u, FLAG_DBG_NOOUT = 0x80000u;  // ablation switches (CRB_DEBUG_SKIP)
 constexpr unsigned FLAG_OUT_DIRECT = 0x200u;   // experiment: shaded pixels stored straight from registers (12-byte strided stores)
 constexpr unsigned FLAG_OUT_TMA = 0x100u;   // internal Frame.flags bit: shaded colour / normal rows leave through TMA boxes
@@ -259,7 +260,7 @@ __device__ __forceinline__ bool fdiv_ok(float n1, float n2, float n3)
 // that won, kept as a guard.  All operands come from the triangle's 128-byte shade record.
 __device__ __forceinline__ bool shade_fragment(const Frame &F, long long ridx, float px, float py, float &z, float c[3], float n[3])
 {
-    const float4 *R = F.shrec + ridx * SREC;
+    const float4 *R = F.shrec + (DBG(F, FLAG_DBG_ONEREC) ? 0ll : ridx) * SREC;
     const float4 A = R[S_A], B = R[S_B], C = R[S_C];
     // x0=A.x y0=A.y x1=A.z y1=A.w x2=B.x y2=B.y z0=B.z z1=B.w z2=C.x  l03=C.y l13=C.z l23=C.w
     const float n1 = (A.z - B.x) * (py - B.y) - (A.w - B.y) * (px - B.x);
@@ -1697,7 +1698,7 @@ int crb_create(int h, int w, float fov, float z_near, float z_far, int device, c
         if (const char *e = getenv("CRB_NO_TMA")) f->use_tma = atoi(e) ? 0 : 1;
         f->out_tma = 1;
         if (const char *e = getenv("CRB_OUT_TMA")) f->out_tma = atoi(e);   // 1 TMA boxes, 0 vector stores, 2 direct stores (experiment)
-        if (const char *e = getenv("CRB_DEBUG_SKIP")) f->dbg_flags = ((unsigned)atoi(e) & 15u) << 16;
+        if (const char *e = getenv("CRB_DEBUG_SKIP")) f->dbg_flags = ((unsigned)atoi(e) & 31u) << 16;
         void *hp = nullptr, *dp = nullptr;
         if (cudaHostAlloc(&hp, 128, cudaHostAllocMapped) == cudaSuccess && cudaHostGetDevicePointer(&dp, hp, 0) == cudaSuccess) {
             memset(hp, 0, 128);

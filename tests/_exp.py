@@ -39,8 +39,6 @@ def run(label, env, zz=z, cc=c, nn=n):
 
 
 run("default", {})
-for k in (2, 3, 4, 8):
-    run(f"{k} tiles per CTA", {"CRB_TILES_PER_CTA": str(k)})
-run("only staging (15)", {"CRB_DEBUG_SKIP": "15"})
-run("only staging, 2 tiles per CTA", {"CRB_DEBUG_SKIP": "15", "CRB_TILES_PER_CTA": "2"})
-run("only staging, 4 tiles per CTA", {"CRB_DEBUG_SKIP": "15", "CRB_TILES_PER_CTA": "4"})
+run("shade from record 0 (no gathers)", {"CRB_DEBUG_SKIP": "16"})
+run("no shading", {"CRB_DEBUG_SKIP": "2"})
+run("no rows", {"CRB_DEBUG_SKIP": "4"})
