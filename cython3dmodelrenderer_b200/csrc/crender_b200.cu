@@ -341,15 +341,15 @@ __global__ void __launch_bounds__(NT) k_setup(const Frame F)
     }
     stage_floats(F.v, first * 9, cnt * 9, sv);
     stage_floats(F.n, first * 9, cnt * 9, sn);
-    stage_floats(F.c, first * 9, cnt * 9, sc);
     if (F.views && threadIdx.x < 16) sM[threadIdx.x] = F.views[view * 16 + threadIdx.x];
     __syncthreads();
-    if (threadIdx.x >= cnt) return;
+    const bool valid = threadIdx.x < cnt;
     const long long tri = first + threadIdx.x;
     const long long ridx = (long long)view * F.T + tri;
     float x[3], y[3], z[3], nx[3], ny[3], nz[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
+        if (!valid) { x[k] = y[k] = z[k] = nx[k] = ny[k] = nz[k] = 1.0f; continue; }
         x[k] = sv[threadIdx.x * 9 + k * 3 + 0];
         y[k] = sv[threadIdx.x * 9 + k * 3 + 1];
         z[k] = sv[threadIdx.x * 9 + k * 3 + 2];
@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(NT) k_setup(const Frame F)
 
     // pyx:202-204: (n0z + n1z + n2z)/3 >= 0 in double -- only the sign of the float sum matters (NaN: not culled)
     const float nsum = (nz[0] + nz[1]) + nz[2];
-    bool drawn = !(nsum >= 0.0f);
+    bool drawn = valid && !(nsum >= 0.0f);
 
     // pyx:132-175: running min from (w,h), running max from 0; NaN never wins a comparison
     float fxl = (float)F.W, fxr = 0.0f, fyt = (float)F.H, fyb = 0.0f;
@@ -384,7 +384,12 @@ __global__ void __launch_bounds__(NT) k_setup(const Frame F)
     const unsigned bx = drawn ? ((unsigned)xl | ((unsigned)xr << 16)) : 0u;
     const unsigned by = drawn ? ((unsigned)yt | ((unsigned)yb << 16)) : 0u;
 
-    F.recE[ridx] = make_float4(__uint_as_float(bx), __uint_as_float(by), 0.0f, 0.0f);
+    if (valid) F.recE[ridx] = make_float4(__uint_as_float(bx), __uint_as_float(by), 0.0f, 0.0f);
+    // the vertex colours are only needed for triangles that are drawn: a CTA without any (culled, off screen, or -- for a
+    // band-sharded filler -- outside the band, which is 7 of 8 CTAs at N=8) never reads them
+    if (!__syncthreads_or(drawn ? 1 : 0)) return;
+    stage_floats(F.c, first * 9, cnt * 9, sc);
+    __syncthreads();
     if (!drawn) return;
     // denominators of mu:12-21 -- pure functions of the triangle, hoisted out of the per-pixel code (same bits)
     const float l03 = (x[1] - x[2]) * (y[0] - y[2]) - (y[1] - y[2]) * (x[0] - x[2]);
