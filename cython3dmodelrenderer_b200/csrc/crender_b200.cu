@@ -1862,8 +1862,8 @@ int crb_render(crb_filler *f, const float *v, const float *c, const float *n, in
     return (flags & CRB_PATH_ATOMIC) ? run_atomic(f, F, (cudaStream_t)stream) : run_tiled(f, F, (cudaStream_t)stream);
 }
 
-int crb_render_host(crb_filler *f, const float *v, const float *c, const float *n, int64_t T, unsigned flags,
-                    unsigned download_mask, float *z_out, float *color_out, float *normals_out, void *stream)
+static int render_host_once(crb_filler *f, const float *v, const float *c, const float *n, int64_t T, unsigned flags,
+                            unsigned download_mask, float *z_out, float *color_out, float *normals_out, void *stream)
 {
     if (check_filler(f)) return CRB_ERR_INVALID;
     if (!f->ws) return fail(CRB_ERR_STATE, "workspace not bound");
@@ -1923,6 +1923,24 @@ int crb_render_host(crb_filler *f, const float *v, const float *c, const float *
     }
     if (!(flags & CRB_NO_SYNC)) CU(cudaStreamSynchronize(st));
     return CRB_OK;
+}
+
+int crb_render_host(crb_filler *f, const float *v, const float *c, const float *n, int64_t T, unsigned flags,
+                    unsigned download_mask, float *z_out, float *color_out, float *normals_out, void *stream)
+{
+    for (int attempt = 0;; ++attempt) {
+        int rc = render_host_once(f, v, c, n, T, flags, download_mask, z_out, color_out, normals_out, stream);
+        if (rc || (flags & CRB_NO_SYNC) || (flags & CRB_PATH_ATOMIC)) return rc;   // asynchronous callers check crb_status themselves
+        // the call is synchronous: a frame the pair list could not hold must not pass silently
+        int64_t need = 0, cap = 0;
+        rc = crb_status(f, &need, &cap, stream);
+        if (rc != CRB_ERR_OVERFLOW) return rc;
+        if (!f->own_ws || attempt >= 3) return rc;          // caller-owned workspace: report, the caller re-binds a larger one
+        const long long maxT = f->maxT;
+        const int maxViews = f->maxViews;
+        rc = crb_alloc_owned(f, maxT, maxViews, need + need / 4 + 1024);   // library-owned: grow and draw the frame again
+        if (rc) return rc;
+    }
 }
 
 int crb_render_views(crb_filler *f, const float *v, const float *c, const float *n, int64_t T, const float *views,

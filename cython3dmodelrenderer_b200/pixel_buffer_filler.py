@@ -224,8 +224,11 @@ class AdvancedPixelBufferFiller:
                 s[1, :T] = c
                 s[2, :T] = n
                 st = self._stage
+                # CRB_NO_SYNC: the overflow check / regrow loop below does the synchronising crb_status itself
                 check(self._L.crb_render_host(self._handle, st[0].data_ptr(), st[1].data_ptr(), st[2].data_ptr(), T,
-                                              flags, 0, None, None, None, self._stream()))
+                                              flags | _lib.CRB_NO_SYNC, 0, None, None, None, self._stream()))
+                if not check_status:
+                    torch.cuda.current_stream(self._dev).synchronize()     # the pinned staging is reused by the next call
             if not check_status:
                 break
             need, cap = ctypes.c_int64(), ctypes.c_int64()

@@ -124,7 +124,10 @@ int crb_render(crb_filler *f, const float *v, const float *c, const float *n, in
 
 /* Same, all pointers HOST memory (pinned recommended): H2D of the three arrays, render, D2H of the buffers named in
  * `download_mask` (CRB_BUF_*; NULL pointers allowed for buffers not requested), then a stream synchronize (unless
- * CRB_NO_SYNC).  This is the call that replaces the body of render_model for a host-resident caller. */
+ * CRB_NO_SYNC).  This is the call that replaces the body of render_model for a host-resident caller.  In the synchronous
+ * form a frame that did not fit the (triangle,tile) pair list never passes silently: a library-owned workspace
+ * (crb_alloc_owned) is grown and the frame drawn again, a caller-owned one returns CRB_ERR_OVERFLOW with the buffers
+ * untouched (see crb_status).  With CRB_NO_SYNC the caller checks crb_status itself. */
 int crb_render_host(crb_filler *f, const float *v, const float *c, const float *n, int64_t T, unsigned flags,
                     unsigned download_mask, float *z_out, float *color_out, float *normals_out, void *stream);
 

@@ -674,3 +674,42 @@ def test_screen_filling_triangles_and_one_crowded_tile(Filler, O):
     o.render_model(m)
     assert int((o.get_z_buffer() < 1e5).sum()) > h * w // 2
     assert_same(buffers(g), buffers(o), "big + crowded")
+
+
+def test_render_host_overflow_is_never_silent(O, trex):
+    """Synchronous crb_render_host: with a library-owned workspace an undersized pair list is grown and the frame drawn
+    again; with a caller-owned workspace the call returns CRB_ERR_OVERFLOW and leaves the buffers untouched."""
+    import ctypes
+    import torch
+    from cython3dmodelrenderer_b200 import _lib
+    L = _lib.load_library()
+    h, w = 160, 200
+    v, c, n = (np.ascontiguousarray(a) for a in (trex._vertices_by_triangles, trex._colors_by_triangles, trex._normals_by_triangles))
+    T = v.shape[0]
+    o = O.OracleFiller(h, w, fov=45.0)
+    o.render_arrays(v, c, n)
+    z = np.empty((h, w), np.float32); col = np.empty((h, w, 3), np.float32); nrm = np.empty((h, w, 3), np.float32)
+    f = ctypes.c_void_p()
+    _lib.check(L.crb_create(h, w, 45.0, 0.1, 1000.0, 0, ctypes.byref(f)))
+    try:
+        _lib.check(L.crb_alloc_owned(f, T, 1, 64))                    # room for 64 pairs: far too small
+        _lib.check(L.crb_render_host(f, v.ctypes.data, c.ctypes.data, n.ctypes.data, T, _lib.CRB_CLEAR_FIRST, _lib.CRB_BUF_ALL,
+                                     z.ctypes.data, col.ctypes.data, nrm.ctypes.data, None))
+        assert_same((z, col, nrm), buffers(o), "library-owned workspace grown")
+    finally:
+        L.crb_destroy(f)
+    g = ctypes.c_void_p()
+    _lib.check(L.crb_create(h, w, 45.0, 0.1, 1000.0, 0, ctypes.byref(g)))
+    try:
+        bz = torch.full((h, w), 7.0, device="cuda"); bc = torch.full((h, w, 3), 7.0, device="cuda"); bn = torch.full((h, w, 3), 7.0, device="cuda")
+        _lib.check(L.crb_bind_buffers(g, bz.data_ptr(), bc.data_ptr(), bn.data_ptr()))
+        nbytes = L.crb_workspace_bytes(g, T, 1, 64)
+        ws = torch.empty(nbytes + 256, dtype=torch.uint8, device="cuda")
+        _lib.check(L.crb_bind_workspace(g, (ws.data_ptr() + 255) // 256 * 256, nbytes, T, 1, 64, None))
+        rc = L.crb_render_host(g, v.ctypes.data, c.ctypes.data, n.ctypes.data, T, _lib.CRB_CLEAR_FIRST, 0, None, None, None, None)
+        assert rc == _lib.CRB_ERR_OVERFLOW
+        assert b"pairs" in L.crb_last_error()
+        torch.cuda.synchronize()
+        assert float(bz.min()) == 7.0 and float(bc.max()) == 7.0       # frame not drawn, not even cleared
+    finally:
+        L.crb_destroy(g)
