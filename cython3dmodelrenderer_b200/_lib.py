@@ -12,9 +12,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libcrender_b200.so")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "crender_b200.h")
+HEADERS = [HEADER, os.path.join(os.path.dirname(_HERE), "include", "crender_ingest_b200.h")]
+SOURCES = [os.path.join(CSRC, "crender_b200.cu"), os.path.join(CSRC, "ingest_b200.cu")]
 
 CRB_OK = 0
 CRB_ERR_INVALID, CRB_ERR_CUDA, CRB_ERR_ZERODIV, CRB_ERR_STATE, CRB_ERR_OVERFLOW = -1, -2, -3, -4, -5
+CRB_ERR_SYNTAX, CRB_ERR_RANGE = -6, -7
 CRB_CLEAR_FIRST, CRB_PATH_ATOMIC, CRB_GURO, CRB_NO_SYNC, CRB_DL_SPARSE, CRB_DEFER_JOIN = 1, 2, 4, 8, 16, 32
 CRB_OPT_CHUNK_PIPELINE, CRB_OPT_TMA, CRB_OPT_TMA_ROWS = 1, 2, 3
 CRB_BUF_Z, CRB_BUF_COLOR, CRB_BUF_NORMALS, CRB_BUF_ALL = 1, 2, 4, 7
@@ -61,6 +64,17 @@ SIGNATURES = {
     "crb_phase_cycles": (_i, [ctypes.POINTER(ctypes.c_uint64), _i]),
     "crb_profile": (_i, [_vp, _i]),
     "crb_profile_read": (_i, [_vp, _ip, ctypes.POINTER(ctypes.c_double)]),
+    # include/crender_ingest_b200.h (model ingest)
+    "crb_obj_parse": (_i, [ctypes.c_char_p, _sz, _vpp]),
+    "crb_obj_free": (None, [_vp]),
+    "crb_obj_counts": (_i, [_vp, _i64p]),
+    "crb_obj_copy": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "crb_obj_mtllib": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(_sz)]),
+    "crb_model_normals_workspace_bytes": (_sz, [_i64, _i64]),
+    "crb_model_vertex_normals": (_i, [_vp, _i64, _vp, _i64, _i, _vp, _vp, _sz, _vp]),
+    "crb_model_vertex_colors": (_i, [_vp, _i64, _i, _vp, _i, _i, _vp, _vp]),
+    "crb_model_gather": (_i, [_vp, _vp, _i64, _vp, _vp]),
+    "crb_model_launch_count": (_i64, []),
 }
 
 _lib = None
@@ -74,9 +88,8 @@ class CrenderError(RuntimeError):
 
 def build(force=False, verbose=False):
     """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false ... (cross-compiles without a GPU)."""
-    src = os.path.join(CSRC, "crender_b200.cu")
     stale = (not os.path.exists(LIB_PATH)
-             or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(src), os.path.getmtime(HEADER)))
+             or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(p) for p in SOURCES + HEADERS))
     if force or stale:
         cmd = ["make", "-C", CSRC, "libcrender_b200.so"] + (["-B"] if force else [])
         subprocess.run(cmd, check=True, stdout=None if verbose else subprocess.DEVNULL)
@@ -108,6 +121,10 @@ def check(rc):
     msg = load_library().crb_last_error().decode("utf-8", "replace")
     if rc == CRB_ERR_ZERODIV:
         raise ZeroDivisionError(msg)
+    if rc == CRB_ERR_RANGE:
+        raise OverflowError(msg)
+    if rc == CRB_ERR_SYNTAX:
+        raise ValueError(msg)
     raise CrenderError(rc, msg)
 
 

@@ -1289,6 +1289,9 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace
 
+// for the library's other translation unit (ingest_b200.cu); not exported
+int crb_internal_fail(int code, const char *msg) { return fail(code, "%s", msg); }
+
 struct crb_filler {
     int h, w, device;
     int row0, row1;

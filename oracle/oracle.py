@@ -21,8 +21,8 @@ _lib = None
 
 def build(force=False):
     """Compile liboracle.so with gcc (seconds).  Building the checker is not using it."""
-    src = os.path.join(_HERE, "crender_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    newest = max(os.path.getmtime(os.path.join(_HERE, s)) for s in ("crender_oracle.c", "ingest_oracle.c"))
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < newest:
         subprocess.check_call(["make", "-s", "-B", "-C", _HERE, "liboracle.so"])
     return _LIB_PATH
 

@@ -55,6 +55,15 @@ def bits_equal(a, b):
     return a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
 
+def same_f32(a, b):
+    """Bit-equal except that any NaN matches any NaN: NaN sign / payload bits depend on the instruction set (x86 SSE makes
+    0xFFC00000, the GPU 0x7FFFFFFF) and mean nothing to NumPy code.  Used by the model-ingest tests."""
+    a, b = np.ascontiguousarray(a, dtype=np.float32), np.ascontiguousarray(b, dtype=np.float32)
+    if a.shape != b.shape:
+        return False
+    return bool(np.all((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))))
+
+
 @pytest.fixture(scope="session")
 def trex():
     return load_indexed("trex")

@@ -19,7 +19,8 @@ def lib():
 
 
 def declared_symbols():
-    text = open(os.path.join(ROOT, "include", "crender_b200.h")).read()
+    text = "".join(open(h).read() for h in _lib.HEADERS)   # every include/*.h
+    assert sorted(os.path.basename(h) for h in _lib.HEADERS) == sorted(os.listdir(os.path.join(ROOT, "include")))
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(crb_[a-z0-9_]+)\s*\(", text)))
 
@@ -28,7 +29,7 @@ def test_header_symbols_all_exported_and_bound(lib):
     names = declared_symbols()
     assert len(names) >= 20
     for name in names:
-        assert hasattr(lib, name), f"{name} declared in crender_b200.h but not exported"
+        assert hasattr(lib, name), f"{name} declared in include/*.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes prototype"
     assert sorted(_lib.SIGNATURES) == names
 
