@@ -5,6 +5,7 @@
 // Built with -fmad=false like the rest of the library: NumPy rounds after every multiply and add.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <charconv>
 #include <cmath>
@@ -507,15 +508,42 @@ __global__ void __launch_bounds__(256) k_fill_incidence(const int32_t *__restric
 // distinct), then walked in that order: a face normal is kept unless a kept one has dot >= 1 with it.  The first 32
 // kept normals live in registers (lane j holds the j-th), later ones in the `kept` scratch.  The mean adds the kept
 // normals in order, starting from +0.0 like np.add.reduce.
+// Vertices met by more than HEAVY_VALENCE corners are handed to k_vertex_normals_heavy (one CTA each).
+constexpr int HEAVY_VALENCE = 512;
+
+__device__ __forceinline__ void finish_vertex(float sx, float sy, float sz, int m, int invert, float *out)
+{
+    if (m > 0) {
+        double dm = (double)m;
+        sx = __double2float_rn(__ddiv_rn((double)sx, dm));
+        sy = __double2float_rn(__ddiv_rn((double)sy, dm));
+        sz = __double2float_rn(__ddiv_rn((double)sz, dm));
+        normalize3(sx, sy, sz);
+    }
+    if (invert) {   // model.py:168-169  `self._normals *= -1`
+        sx = __fmul_rn(sx, -1.0f);
+        sy = __fmul_rn(sy, -1.0f);
+        sz = __fmul_rn(sz, -1.0f);
+    }
+    out[0] = sx;
+    out[1] = sy;
+    out[2] = sz;
+}
+
 __global__ void __launch_bounds__(256) k_vertex_normals(const float4 *__restrict__ faceN, const int *__restrict__ off,
                                                         const int *__restrict__ inc, int *__restrict__ sorted,
                                                         float *__restrict__ kept, int64_t V, int invert,
-                                                        float *__restrict__ out)
+                                                        float *__restrict__ out, int *__restrict__ heavy_count,
+                                                        int *__restrict__ heavy_list)
 {
     int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (v >= V) return;
     int base = off[v], k = off[v + 1] - base;
+    if (k > HEAVY_VALENCE) {
+        if (lane == 0) heavy_list[atomicAdd(heavy_count, 1)] = (int)v;
+        return;
+    }
     for (int i = lane; i < k; i += 32) {
         int e = inc[base + i], r = 0;
         for (int j = 0; j < k; ++j) r += inc[base + j] < e;
@@ -549,22 +577,97 @@ __global__ void __launch_bounds__(256) k_vertex_normals(const float4 *__restrict
         sz = __fadd_rn(sz, n.z);
         __syncwarp();
     }
-    if (lane != 0) return;
-    if (m > 0) {
-        double dm = (double)m;
-        sx = __double2float_rn(__ddiv_rn((double)sx, dm));
-        sy = __double2float_rn(__ddiv_rn((double)sy, dm));
-        sz = __double2float_rn(__ddiv_rn((double)sz, dm));
-        normalize3(sx, sy, sz);
+    if (lane == 0) finish_vertex(sx, sy, sz, m, invert, out + 3 * v);
+}
+
+// One CTA per heavy vertex (a fan centre, a sphere pole): the same walk as above with the work of each step spread over
+// 1024 threads.  Entries are put in file order by a rank sort through shared-memory tiles; the walk keeps the kept
+// normals in shared memory (HEAVY_KEPT_SMEM of them, later ones in the `kept` scratch) and costs one block barrier per
+// entry: the normal appended by the previous step is compared from registers, so its store need not be visible yet.
+constexpr int HEAVY_THREADS = 1024, HEAVY_TILE = 4096, HEAVY_STAGE = 1024, HEAVY_KEPT_SMEM = 12288;
+constexpr size_t HEAVY_SMEM_BYTES = sizeof(float) * 3 * (HEAVY_KEPT_SMEM + HEAVY_STAGE);
+
+__global__ void __launch_bounds__(HEAVY_THREADS) k_vertex_normals_heavy(
+    const float4 *__restrict__ faceN, const int *__restrict__ off, const int *__restrict__ inc, int *__restrict__ sorted,
+    float *__restrict__ kept, int invert, float *__restrict__ out, const int *__restrict__ heavy_count,
+    const int *__restrict__ heavy_list)
+{
+    extern __shared__ float smem[];
+    float *skept = smem;                                   // [HEAVY_KEPT_SMEM][3]
+    float *stage = smem + 3 * HEAVY_KEPT_SMEM;             // [HEAVY_STAGE][3]
+    int *tile = reinterpret_cast<int *>(smem);             // rank-sort tiles alias the kept area (used before the walk)
+    const int tid = threadIdx.x;
+    const int n_heavy = *heavy_count;
+    for (int h = blockIdx.x; h < n_heavy; h += gridDim.x) {
+        const int v = heavy_list[h];
+        const int base = off[v], k = off[v + 1] - base;
+        // ---- file order: rank of every entry among the vertex's entries
+        for (int i0 = 0; i0 < k; i0 += HEAVY_THREADS) {
+            int i = i0 + tid, e = i < k ? inc[base + i] : 0, r = 0;
+            for (int j0 = 0; j0 < k; j0 += HEAVY_TILE) {
+                int nt = min(HEAVY_TILE, k - j0);
+                __syncthreads();
+                for (int j = tid; j < nt; j += HEAVY_THREADS) tile[j] = inc[base + j0 + j];
+                __syncthreads();
+                if (i < k)
+                    for (int j = 0; j < nt; ++j) r += tile[j] < e;
+            }
+            if (i < k) sorted[base + r] = e;
+        }
+        __syncthreads();
+        // ---- the walk
+        float sx = 0.f, sy = 0.f, sz = 0.f, lx = 0.f, ly = 0.f, lz = 0.f;
+        int m = 0;
+        bool pending = false;   // kept[m-1] was stored by thread 0 after the last barrier: compare `l` instead
+        for (int i0 = 0; i0 < k; i0 += HEAVY_STAGE) {
+            int ns = min(HEAVY_STAGE, k - i0);
+            __syncthreads();
+            if (tid < ns) {
+                float4 n = faceN[sorted[base + i0 + tid] / 3];
+                stage[3 * tid] = n.x;
+                stage[3 * tid + 1] = n.y;
+                stage[3 * tid + 2] = n.z;
+            }
+            __syncthreads();
+            for (int i = 0; i < ns; ++i) {
+                const float nx = stage[3 * i], ny = stage[3 * i + 1], nz = stage[3 * i + 2];
+                const int lim = m - (pending ? 1 : 0);
+                bool dup = false;
+                for (int j = tid; j < lim; j += HEAVY_THREADS) {
+                    float qx, qy, qz;
+                    if (j < HEAVY_KEPT_SMEM) {
+                        qx = skept[3 * j], qy = skept[3 * j + 1], qz = skept[3 * j + 2];
+                    } else {
+                        const float *q = kept + 3 * ((int64_t)base + j);
+                        qx = __ldcg(q), qy = __ldcg(q + 1), qz = __ldcg(q + 2);
+                    }
+                    dup |= dot3(qx, qy, qz, nx, ny, nz) >= 1.0f;
+                }
+                if (pending && tid == 0) dup |= dot3(lx, ly, lz, nx, ny, nz) >= 1.0f;
+                const int any = __syncthreads_or(dup);
+                pending = false;
+                if (any) continue;
+                if (tid == 0) {
+                    if (m < HEAVY_KEPT_SMEM) {
+                        skept[3 * m] = nx, skept[3 * m + 1] = ny, skept[3 * m + 2] = nz;
+                    } else {
+                        float *q = kept + 3 * ((int64_t)base + m);
+                        __stcg(q, nx);
+                        __stcg(q + 1, ny);
+                        __stcg(q + 2, nz);
+                    }
+                }
+                lx = nx, ly = ny, lz = nz;
+                pending = true;
+                ++m;
+                sx = __fadd_rn(sx, nx);
+                sy = __fadd_rn(sy, ny);
+                sz = __fadd_rn(sz, nz);
+            }
+        }
+        if (tid == 0) finish_vertex(sx, sy, sz, m, invert, out + 3 * (int64_t)v);
+        __syncthreads();
     }
-    if (invert) {   // model.py:168-169  `self._normals *= -1`
-        sx = __fmul_rn(sx, -1.0f);
-        sy = __fmul_rn(sy, -1.0f);
-        sz = __fmul_rn(sz, -1.0f);
-    }
-    out[3 * v] = sx;
-    out[3 * v + 1] = sy;
-    out[3 * v + 2] = sz;
 }
 
 // astype('int32') of a float32 on x86-64 (cvttps2dq): INT32_MIN for NaN and out-of-range values.
@@ -605,7 +708,7 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct NormalsWs {
     float4 *faceN;
-    int *cnt, *off, *cursor, *inc, *sorted, *sums, *grand;
+    int *cnt, *off, *cursor, *inc, *sorted, *sums, *grand, *heavy_count, *heavy_list;
     float *kept;
     size_t bytes;
 };
@@ -629,6 +732,8 @@ NormalsWs carve(char *p, int64_t V, int64_t T)
     w.kept = (float *)take(sizeof(float) * (size_t)(9 * T + 3));
     w.sums = (int *)take(sizeof(int) * (size_t)(nb + 1));
     w.grand = (int *)take(sizeof(int));
+    w.heavy_count = (int *)take(sizeof(int));
+    w.heavy_list = (int *)take(sizeof(int) * (size_t)(3 * T / HEAVY_VALENCE + 1));
     w.bytes = o;
     return w;
 }
@@ -671,9 +776,19 @@ extern "C" int crb_model_vertex_normals(const float *vertices, int64_t V, const 
         k_fill_incidence<<<blocks_for(3 * T, 256), 256, 0, s>>>(tri, 3 * T, w.cursor, w.inc);
         ++launches;
     }
+    CU(cudaMemsetAsync(w.heavy_count, 0, sizeof(int), s));
     k_vertex_normals<<<blocks_for(V * 32, 256), 256, 0, s>>>(w.faceN, w.off, w.inc, w.sorted, w.kept, V, invert ? 1 : 0,
-                                                            normals_out);
+                                                            normals_out, w.heavy_count, w.heavy_list);
     ++launches;
+    if (3 * T > HEAVY_VALENCE) {   // otherwise no vertex can be heavy
+        CU(cudaFuncSetAttribute(k_vertex_normals_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)HEAVY_SMEM_BYTES));   // per device, cheap
+        unsigned grid = (unsigned)std::min<int64_t>(3 * T / HEAVY_VALENCE, 148);
+        k_vertex_normals_heavy<<<grid, HEAVY_THREADS, HEAVY_SMEM_BYTES, s>>>(w.faceN, w.off, w.inc, w.sorted, w.kept,
+                                                                             invert ? 1 : 0, normals_out, w.heavy_count,
+                                                                             w.heavy_list);
+        ++launches;
+    }
     CU(cudaGetLastError());
     g_launches += launches;
     return CRB_OK;

@@ -66,7 +66,7 @@ int crb_obj_mtllib(const crb_obj *o, int k, const char **data, size_t *len);
  * that before upload).  For every (triangle, corner) in file order the triangle's unit normal
  * -cross(t1-t0, t1-t2)/|.| joins the corner vertex's list unless a normal already in the list has dot >= 1 with it;
  * normals_out[v] = normalise(mean(list)), zeros for an unreferenced vertex, times -1 if `invert`.
- * Workspace: crb_model_normals_workspace_bytes(V,T) bytes of DEVICE scratch (76 B/triangle + 12 B/vertex). */
+ * Workspace: crb_model_normals_workspace_bytes(V,T) bytes of DEVICE scratch (about 76 B/triangle + 12 B/vertex). */
 size_t crb_model_normals_workspace_bytes(int64_t V, int64_t T);
 int crb_model_vertex_normals(const float *vertices, int64_t V, const int32_t *tri, int64_t T, int invert,
                              float *normals_out, void *workspace, size_t workspace_bytes, void *stream);

@@ -98,6 +98,21 @@ def test_vertex_normals_long_lists_and_determinism(dev):
     assert bits_equal(runs[1], runs[0]) and bits_equal(runs[2], runs[0])
 
 
+def test_vertex_normals_kept_list_beyond_shared_memory(dev):
+    """14 000 distinct normals around one vertex: the heavy-vertex kernel's kept list spills from shared memory
+    (12 288 normals) into its global scratch; a second heavy vertex shares the launch."""
+    from oracle import ingest as I
+    rng = np.random.default_rng(6)
+    n = 14000
+    a = np.sort(rng.uniform(0, 2 * np.pi, n + 1))
+    ring = np.stack([np.cos(a), np.sin(a), 2 + 0.2 * rng.standard_normal(n + 1)], 1)
+    v = np.concatenate([[[0, 0, 2.5]], ring, [[0, 0, 1.0]]]).astype(np.float32)
+    tri = np.stack([np.zeros(n, int), np.arange(1, n + 1), np.arange(2, n + 2)], 1)
+    low = np.stack([np.full(900, n + 2), np.arange(1, 901), np.arange(2, 902)], 1)
+    tri = np.concatenate([tri, low, tri[::3]]).astype(np.int32)
+    assert bits_equal(gpu_normals(dev, v, tri), I.vertex_normals(v, tri))
+
+
 def test_vertex_normals_sphere_scale(dev):
     """A 2 M-triangle UV sphere (the C4 mesh family at 1/5 scale): indexed, poles of valence 1 600."""
     from oracle import ingest as I
@@ -232,7 +247,7 @@ def test_model_on_the_reference_assets_and_render(trex):
     chk = json.load(open(os.path.join(GOLDEN, "checksums.json")))
     z = f.get_z_buffer()
     assert int((z < 1e5).sum()) == 252539
-    assert hashlib.sha256(z.tobytes()).hexdigest() == chk["trex_1024x1024_fov45"]["z"]   # the reference's own frame
+    assert hashlib.sha256(z.tobytes()).hexdigest() == chk["cases"]["trex_1024x1024_fov45"]["z"]   # the reference's own frame
     g = AdvancedPixelBufferFiller(1024, 1024, fov=45)
     g.render_arrays(*m.device_triangles())           # device-resident twins: no host round trip
     assert bits_equal(g.get_z_buffer(), z) and bits_equal(g.get_color_buffer(), f.get_color_buffer())
