@@ -584,10 +584,18 @@ def run_extra_workload(args):
         scale = res / 8192.0
         model = synthetic.uv_sphere(max(8, int(3200 * scale)), max(3, int(1564 * scale)))
         band = sharding.band_shard(res, rank, world)
+        bands = [sharding.band_shard(res, r, world) for r in range(world)]
     T = int(model._vertices_by_triangles.shape[0])
-    f = AdvancedPixelBufferFiller(res, res, fov=FOV, device=local, band=band)
     dv, dc, dn = (torch.from_numpy(a).to(dev) for a in
                   (model._vertices_by_triangles, model._colors_by_triangles, model._normals_by_triangles))
+    if band is not None and world > 1 and args.bands == "balanced":
+        # cut the frame where the estimated cost (triangles per 32-row strip) balances, not into equal row counts: the
+        # sphere's poles hold far more triangles per row than its equator.  Rank 0 decides, everybody follows.
+        box = [sharding.balanced_bands(sharding.tile_row_costs(dv, dn, res, res, FOV), world, res) if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        bands = box[0]
+        band = bands[rank]
+    f = AdvancedPixelBufferFiller(res, res, fov=FOV, device=local, band=band)
     light = -np.asarray([0, 0, 1], dtype="float32")
     light = light / np.linalg.norm(light)
 
@@ -637,11 +645,11 @@ def run_extra_workload(args):
         if args.gather != "none":     # final NCCL all-gather of the row bands (north_star: "a final NCCL gather over NVLink")
             z, c, n = f.device_buffers()
             for b in (z, c, n):                     # first use of the communicator / buffers is not what is being timed
-                sharding.gather_bands(b, res)
+                sharding.gather_bands(b, res, bands=bands)
             barrier()
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             g0.record()
-            full = [sharding.gather_bands(b, res) for b in (z, c, n)]
+            full = [sharding.gather_bands(b, res, bands=bands) for b in (z, c, n)]
             g1.record()
             barrier()
             gms = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
@@ -664,7 +672,7 @@ def run_extra_workload(args):
             "scaling": "strong" if band is not None else "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic UV sphere (SURVEY 8d C4)" if band is not None else "bunny fixture + igor texture (tests/golden/bunny_fit.npz)",
             "config": {"workload": args.workload, "res": res, "fov": FOV, "triangles": T,
-                       "sharding": "screen-row bands, tile aligned" if band is not None else "none",
+                       "sharding": (f"screen-row bands, tile aligned, {args.bands}: {bands}") if band is not None else "none",
                        "l2": "frame buffers %.2f GB per GPU vs 126 MB L2" % (28 * rows * res / 1e9)},
             "gtri_per_s": fps * T / 1e9, "clocks": clocks.summary(), "gpu_launches": f.launch_count - launches0,
             "roofline": {"bound": "hbm", "kernel": "k_raster", "achieved": alg / (k_avg / 1000.0) / 1e9 if k_avg else None,
@@ -710,6 +718,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--workload", default="trex_1024_orbit",
                     choices=["trex_1024_orbit", "bunny_4096_guro", "sphere_8192_bands"])
+    ap.add_argument("--bands", default="balanced", choices=["balanced", "uniform"],
+                    help="sphere_8192_bands only: rows per rank equal (uniform) or cut where the estimated cost balances")
     ap.add_argument("--res", type=int, default=0, help="sphere_8192_bands only: override the resolution (scaled sphere)")
     ap.add_argument("--gather", default="none", choices=["none", "bands", "u8", "z", "all"],
                     help="also time the final NCCL gather (reported beside, never inside, the headline value)")

@@ -114,6 +114,7 @@ struct Frame {
     // per-(view,triangle) records (see enum ShadeRec)
     float4 *shrec;              // [nViews*T*8] shade records
     float4 *recD, *recE;        // [nViews*T]
+    unsigned char *alive;       // [nViews*ceil(T/NT)] 1 = this k_setup CTA has a drawn triangle (its recE / records are valid)
     unsigned *count;            // [nViews*nTiles] triangles per tile, accumulated by k_setup, returned to zero by k_alloc
     uint4 *busy;                // [nViews*nTiles] compacted busy tiles: (view:10 ty:11 tx:11, triangles, list offset, -); count in total[2]
     uint4 *busyH;               // [nViews*nTiles] the same for tiles with more than HEAVY_N triangles; count in total[4]
@@ -339,8 +340,13 @@ __global__ void __launch_bounds__(NT) k_setup(const Frame F)
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {  // k_alloc (next launch) accumulates
         F.total[0] = 0ull; F.total[2] = 0ull; F.total[3] = 0ull; F.total[4] = 0ull;
     }
+    // A band-sharded filler sees every triangle of the frame but draws only those that reach its rows: there
+    // the vertices are staged and tested first, and a CTA whose 256 triangles all miss the band stops before it has read
+    // a normal or written a record (7 of 8 CTAs at N = 8).  A full-frame filler stages both arrays behind one barrier.
+    const bool banded = F.row0 > 0 || F.row1 < F.H;
+    unsigned char *alive = F.alive + (long long)view * gridDim.x + blockIdx.x;
     stage_floats(F.v, first * 9, cnt * 9, sv);
-    stage_floats(F.n, first * 9, cnt * 9, sn);
+    if (!banded) stage_floats(F.n, first * 9, cnt * 9, sn);
     if (F.views && threadIdx.x < 16) sM[threadIdx.x] = F.views[view * 16 + threadIdx.x];
     __syncthreads();
     const bool valid = threadIdx.x < cnt;
@@ -349,23 +355,13 @@ __global__ void __launch_bounds__(NT) k_setup(const Frame F)
     float x[3], y[3], z[3], nx[3], ny[3], nz[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        if (!valid) { x[k] = y[k] = z[k] = nx[k] = ny[k] = nz[k] = 1.0f; continue; }
+        if (!valid) { x[k] = y[k] = z[k] = 1.0f; continue; }
         x[k] = sv[threadIdx.x * 9 + k * 3 + 0];
         y[k] = sv[threadIdx.x * 9 + k * 3 + 1];
         z[k] = sv[threadIdx.x * 9 + k * 3 + 2];
-        nx[k] = sn[threadIdx.x * 9 + k * 3 + 0];
-        ny[k] = sn[threadIdx.x * 9 + k * 3 + 1];
-        nz[k] = sn[threadIdx.x * 9 + k * 3 + 2];
-        if (F.views) {
-            view_point(sM, x[k], y[k], z[k]);
-            view_normal(sM, nx[k], ny[k], nz[k]);
-        }
+        if (F.views) view_point(sM, x[k], y[k], z[k]);
         project_vertex(F.proj, x[k], y[k], z[k]);
     }
-
-    // pyx:202-204: (n0z + n1z + n2z)/3 >= 0 in double -- only the sign of the float sum matters (NaN: not culled)
-    const float nsum = (nz[0] + nz[1]) + nz[2];
-    bool drawn = valid && !(nsum >= 0.0f);
 
     // pyx:132-175: running min from (w,h), running max from 0; NaN never wins a comparison
     float fxl = (float)F.W, fxr = 0.0f, fyt = (float)F.H, fyb = 0.0f;
@@ -380,14 +376,35 @@ __global__ void __launch_bounds__(NT) k_setup(const Frame F)
     int yt = clipi(ceil_to_int_ref(fyt), 0, F.H), yb = clipi(ceil_to_int_ref(fyb), 0, F.H);
     yt = max(yt, F.row0);  // band sharding: rows outside [row0,row1) belong to another filler
     yb = min(yb, F.row1);
-    drawn = drawn && (xl < xr) && (yt < yb);  // pyx:209-211 and the empty range() cases
+    bool drawn = valid && (xl < xr) && (yt < yb);  // pyx:209-211 and the empty range() cases
+    if (banded) {
+        if (!__syncthreads_or(drawn ? 1 : 0)) {
+            if (threadIdx.x == 0) *alive = 0;
+            return;
+        }
+        stage_floats(F.n, first * 9, cnt * 9, sn);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (!valid) { nx[k] = ny[k] = nz[k] = 1.0f; continue; }
+        nx[k] = sn[threadIdx.x * 9 + k * 3 + 0];
+        ny[k] = sn[threadIdx.x * 9 + k * 3 + 1];
+        nz[k] = sn[threadIdx.x * 9 + k * 3 + 2];
+        if (F.views) view_normal(sM, nx[k], ny[k], nz[k]);
+    }
+    // pyx:202-204: (n0z + n1z + n2z)/3 >= 0 in double -- only the sign of the float sum matters (NaN: not culled)
+    const float nsum = (nz[0] + nz[1]) + nz[2];
+    drawn = drawn && !(nsum >= 0.0f);
     const unsigned bx = drawn ? ((unsigned)xl | ((unsigned)xr << 16)) : 0u;
     const unsigned by = drawn ? ((unsigned)yt | ((unsigned)yb << 16)) : 0u;
 
     if (valid) F.recE[ridx] = make_float4(__uint_as_float(bx), __uint_as_float(by), 0.0f, 0.0f);
     // the vertex colours are only needed for triangles that are drawn: a CTA without any (culled, off screen, or -- for a
     // band-sharded filler -- outside the band, which is 7 of 8 CTAs at N=8) never reads them
-    if (!__syncthreads_or(drawn ? 1 : 0)) return;
+    const int any_drawn = __syncthreads_or(drawn ? 1 : 0);
+    if (threadIdx.x == 0) *alive = any_drawn ? 1 : 0;   // k_fill (and the atomic path) skip the CTA's triangles otherwise
+    if (!any_drawn) return;
     stage_floats(F.c, first * 9, cnt * 9, sc);
     __syncthreads();
     if (!drawn) return;
@@ -509,6 +526,7 @@ __global__ void __launch_bounds__(NT) k_fill(const Frame F)
 {
     if (*F.total > (unsigned long long)F.pairCap) return;  // overflow: frame is skipped, host is told via crb_status
     const int view = blockIdx.y;
+    if (!F.alive[(long long)view * gridDim.x + blockIdx.x]) return;   // same CTA -> triangle mapping as k_setup
     const long long tri = (long long)blockIdx.x * NT + threadIdx.x;
     if (tri >= F.T) return;
     const long long ridx = (long long)view * F.T + tri;
@@ -1080,7 +1098,7 @@ __global__ void __launch_bounds__(NT) k_raster_atomic(const Frame F, unsigned lo
 {
     const long long tri = ((long long)blockIdx.x * NT + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (tri >= F.T) return;
+    if (tri >= F.T || !F.alive[tri / NT]) return;
     const float4 r2 = F.recE[tri];
     const unsigned bx = __float_as_uint(r2.x), by = __float_as_uint(r2.y);
     if ((bx >> 16) == 0) return;
@@ -1308,6 +1326,7 @@ struct crb_filler {
     int maxViews;
     long long pairCap;
     float4 *shrec, *recD, *recE;
+    unsigned char *alive;
     unsigned *count, *offset, *cursor, *empty;
     uint4 *busy, *busyH;
     float4 *ls0, *ls1, *ls2;
@@ -1349,7 +1368,7 @@ struct crb_filler {
 namespace {
 
 struct WsLayout {
-    size_t shrec, recD, recE, count, offset, cursor, busy, busyH, empty, ls0, ls1, ls2, ls3, ls4, total, set_bytes, sv, sc, sn, bytes;
+    size_t shrec, recD, recE, alive, count, offset, cursor, busy, busyH, empty, ls0, ls1, ls2, ls3, ls4, total, set_bytes, sv, sc, sn, bytes;
 };
 
 long long default_pair_cap(const crb_filler *f, long long T, int views)
@@ -1369,6 +1388,7 @@ WsLayout ws_layout(const crb_filler *f, long long T, int views, long long pairCa
     L.shrec = take(recs * SREC * sizeof(float4));
     L.recD = take(recs * sizeof(float4));
     L.recE = take(recs * sizeof(float4));
+    L.alive = take((size_t)((T > 0 ? T : 1) + NT - 1) / NT * views);
     L.count = take((size_t)tiles * views * 4);
     L.offset = take((size_t)tiles * views * 4);
     L.cursor = take((size_t)tiles * views * 4);
@@ -1429,7 +1449,7 @@ void fill_frame(const crb_filler *f, Frame *F, int set = 0)
     F->nTiles = F->tilesX * F->tilesY;
     const size_t so = set ? f->set_bytes : 0;     // the second workspace set lies set_bytes behind the first
     auto at = [so](auto *p) { return reinterpret_cast<decltype(p)>(reinterpret_cast<char *>(p) + so); };
-    F->shrec = at(f->shrec); F->recD = at(f->recD); F->recE = at(f->recE);
+    F->shrec = at(f->shrec); F->recD = at(f->recD); F->recE = at(f->recE); F->alive = at(f->alive);
     F->count = at(f->count); F->offset = at(f->offset); F->cursor = at(f->cursor);
     F->busy = at(f->busy); F->busyH = at(f->busyH); F->empty = at(f->empty);
     F->ls0 = at(f->ls0); F->ls1 = at(f->ls1); F->ls2 = at(f->ls2); F->ls3 = at(f->ls3); F->ls4 = at(f->ls4);
@@ -1618,6 +1638,7 @@ int bind_ws_pointers(crb_filler *f, void *ws, size_t bytes, long long T, int vie
     f->ws = ws; f->ws_bytes = bytes;
     f->maxT = T; f->maxViews = views; f->pairCap = pairCap;
     f->shrec = (float4 *)(b + L.shrec); f->recD = (float4 *)(b + L.recD); f->recE = (float4 *)(b + L.recE);
+    f->alive = (unsigned char *)(b + L.alive);
     f->count = (unsigned *)(b + L.count); f->offset = (unsigned *)(b + L.offset); f->cursor = (unsigned *)(b + L.cursor);
     f->busy = (uint4 *)(b + L.busy); f->busyH = (uint4 *)(b + L.busyH); f->empty = (unsigned *)(b + L.empty);
     f->ls0 = (float4 *)(b + L.ls0); f->ls1 = (float4 *)(b + L.ls1); f->ls2 = (float4 *)(b + L.ls2); f->ls3 = (uint4 *)(b + L.ls3); f->ls4 = (float4 *)(b + L.ls4);

@@ -39,6 +39,61 @@ def band_shard(h, rank, world, align=TILE_ROWS):
     return min(t0 * align, h), min(t1 * align, h)
 
 
+def tile_row_costs(v_by_tri, n_by_tri, h, w, fov=90.0, align=TILE_ROWS, per_row=2.0, per_kilo_triangle=0.57):
+    """Estimated cost (microseconds on a B200) of every `align`-row strip of an h x w frame of the [T,3,3] camera-space
+    arrays: `per_kilo_triangle` per 1000 drawn triangles whose bounding rows touch the strip + `per_row` for its pixels
+    (measured on the 10 M-triangle sphere at 8192^2: the work that depends on the band is dominated by the triangles in
+    it).  A load-balancing heuristic only -- float32 torch arithmetic on whatever device the tensors live on, not the
+    reference's rounding; the rendered result never depends on where the bands are cut."""
+    import math
+    v = torch.as_tensor(v_by_tri)
+    n = torch.as_tensor(n_by_tri)
+    f = 1.0 / math.tan(float(fov) / 2.0 / 180.0 * math.pi)
+    y = (v[..., 1] * f / v[..., 2] + 1.0) * (h / 2.0)                       # [T,3] screen rows (pyx:116-130)
+    x = (v[..., 0] * (f * h / w) / v[..., 2] + 1.0) * (w / 2.0)
+    drawn = ~(n[..., 2].sum(dim=1) >= 0)                                      # pyx:202-204
+    drawn &= (x.amin(dim=1) < w) & (x.amax(dim=1) > 0) & (y.amin(dim=1) < h) & (y.amax(dim=1) > 0)
+    strips = (int(h) + align - 1) // align
+    lo = (y.amin(dim=1).clamp(0, h - 1) / align).floor().long()[drawn]
+    hi = (y.amax(dim=1).clamp(0, h - 1) / align).floor().long()[drawn]
+    diff = torch.zeros(strips + 1, dtype=torch.float64, device=v.device)
+    diff.index_add_(0, lo, torch.ones_like(lo, dtype=torch.float64))
+    diff.index_add_(0, hi + 1, -torch.ones_like(hi, dtype=torch.float64))
+    tris = diff.cumsum(0)[:strips]
+    return (tris * (per_kilo_triangle / 1000.0) + per_row).cpu()
+
+
+def balanced_bands(costs, world, h, align=TILE_ROWS):
+    """Cuts the strips of `costs` (one entry per `align` rows, e.g. tile_row_costs) into `world` contiguous row bands of
+    nearly equal summed cost: [(row0,row1)] * world, partitioning [0,h) exactly, every cut on a strip boundary.  With
+    more ranks than strips the last ranks get empty bands."""
+    costs = [float(c) for c in costs]
+    strips = len(costs)
+    assert strips == (int(h) + align - 1) // align
+    parts = min(int(world), strips)
+    pre = [0.0]
+    for c in costs:
+        pre.append(pre[-1] + c)
+    # linear partition: best[k][i] = smallest possible maximum band cost when the first i strips form k non-empty bands
+    INF = float("inf")
+    best = [[INF] * (strips + 1) for _ in range(parts + 1)]
+    cut = [[0] * (strips + 1) for _ in range(parts + 1)]
+    best[0][0] = 0.0
+    for k in range(1, parts + 1):
+        for i in range(k, strips - (parts - k) + 1):
+            for j in range(k - 1, i):
+                m = max(best[k - 1][j], pre[i] - pre[j])
+                if m < best[k][i]:
+                    best[k][i], cut[k][i] = m, j
+    ends, i = [], strips
+    for k in range(parts, 0, -1):
+        ends.append(i)
+        i = cut[k][i]
+    ends = ends[::-1] + [strips] * (int(world) - parts)
+    starts = [0] + ends[:-1]
+    return [(min(a * align, h), min(b * align, h)) for a, b in zip(starts, ends)]
+
+
 def _world():
     return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
@@ -72,13 +127,14 @@ def gather_views(local, n_views, dst=None):
     return torch.cat([out[r * cmax:r * cmax + counts[r]] for r in range(world)], dim=0)
 
 
-def gather_bands(local, h, dst=None, align=TILE_ROWS):
-    """Gathers per-rank row bands [rows_r, W, ...] (layout of band_shard) into the full [h, W, ...] buffer."""
+def gather_bands(local, h, dst=None, align=TILE_ROWS, bands=None):
+    """Gathers per-rank row bands [rows_r, W, ...] into the full [h, W, ...] buffer.  `bands` = the [(row0,row1)] list
+    every rank used (e.g. balanced_bands); default: the uniform layout of band_shard."""
     world = _world()
     if world == 1:
         return local
     rank = dist.get_rank()
-    rows = [band_shard(h, r, world, align) for r in range(world)]
+    rows = list(bands) if bands is not None else [band_shard(h, r, world, align) for r in range(world)]
     rmax = max(b - a for a, b in rows)
     if local.shape[0] != rmax:
         pad = torch.zeros((rmax - local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)

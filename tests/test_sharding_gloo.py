@@ -38,6 +38,35 @@ def test_band_shard_partitions_exactly_and_tile_aligned():
     assert sharding.band_shard(8192, 1, 8) == (1024, 2048)
 
 
+def test_balanced_bands_partition_exactly_and_minimise_the_heaviest_band():
+    rng = np.random.default_rng(0)
+    for h in (1, 31, 64, 300, 1024, 8192):
+        strips = (h + 31) // 32
+        for world in (1, 2, 3, 8):
+            costs = rng.uniform(0.1, 10.0, strips) ** 3
+            bands = sharding.balanced_bands(costs, world, h)
+            assert len(bands) == world and bands[0][0] == 0 and bands[-1][1] == h
+            for (a0, a1), (b0, b1) in zip(bands, bands[1:]):
+                assert a1 == b0 and a0 <= a1
+            assert all(a % 32 == 0 or a == h for a, _ in bands)
+            if strips >= world:
+                assert all(b > a for a, b in bands)      # nobody idles while there are strips to hand out
+            heaviest = max(costs[a // 32:(b + 31) // 32].sum() for a, b in bands)
+            uniform = max(costs[a // 32:(b + 31) // 32].sum() for a, b in (sharding.band_shard(h, r, world) for r in range(world)))
+            assert heaviest <= uniform * (1 + 1e-12)
+    assert sharding.balanced_bands([10, 1, 1, 1, 1, 1, 1, 10], 4, 256) == [(0, 32), (32, 64), (64, 224), (224, 256)]
+
+
+def test_tile_row_costs_follow_the_triangles():
+    from cython3dmodelrenderer_b200 import synthetic
+    m = synthetic.uv_sphere(200, 98)
+    c = sharding.tile_row_costs(m._vertices_by_triangles, m._normals_by_triangles, 512, 512, 45.0, per_row=0.0,
+                                per_kilo_triangle=1000.0)
+    drawn = ~(m._normals_by_triangles[..., 2].sum(axis=1) >= 0)
+    assert c.shape == (16,) and float(c.sum()) >= drawn.sum()          # every drawn triangle counted in >= 1 strip
+    assert float(c[0]) == 0.0 and float(c[8]) > 0.0                      # nothing above the sphere, plenty at the equator
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -74,6 +103,11 @@ def _worker(rank, world, port, out_dir):
         nb = torch.from_numpy(full.get_normals_buffer()[r0:r1].copy())
         z_band = sharding.gather_bands(zb, H)
         n_band = sharding.gather_bands(nb, H, dst=0)
+        # ---- the same with bands cut by cost (unequal heights) -------------------------------------------------------
+        bands = sharding.balanced_bands([1.0, 5.0, 1.0, 0.5], world, H)
+        b0, b1 = bands[rank]
+        z_bal = sharding.gather_bands(torch.from_numpy(full.get_z_buffer()[b0:b1].copy()), H, bands=bands)
+        assert bits_equal(z_bal.numpy(), full.get_z_buffer())
         if rank == 0:
             np.savez(os.path.join(out_dir, "r0.npz"), z_all=z_all.numpy(), col_0=col_0.numpy(), z_band=z_band.numpy(),
                      n_band=n_band.numpy(), z_full=full.get_z_buffer(), n_full=full.get_normals_buffer())
