@@ -430,8 +430,8 @@ def run_gpu_arm(args):
     # buffers land in host memory before its slot is reused.
     from cython3dmodelrenderer_b200.pipeline import HostFramePipeline
 
-    def run_pipeline(sparse):
-        pipe = HostFramePipeline(RES, RES, fov=FOV, depth=args.e2e_depth, device=local, sparse=sparse)
+    def run_pipeline(sparse, want=("z", "color", "normals")):
+        pipe = HostFramePipeline(RES, RES, fov=FOV, depth=args.e2e_depth, device=local, sparse=sparse, want=want)
         for i in range(2 * args.e2e_depth):
             pipe.submit(*host_in[i % 4])
         pipe.drain()
@@ -445,16 +445,18 @@ def run_gpu_arm(args):
             last = pipe.submit(*host_in[i % 4])
         pipe.drain()
         dt = time.perf_counter() - t0
-        cov = int((pipe.result(last)["z"] < 1e5).sum())
+        res = pipe.result(last)
+        cov = int((res["z"] < 1e5).sum()) if "z" in res else int((res["color"].sum(axis=-1) > 0).sum())
         tiles = pipe.readback_tiles() if sparse else None
         return dt, cov, pipe.launch_count - l0, tiles
 
     dense_s, dense_cov, dense_launches, _ = run_pipeline(False)
     e2e_s, e2e_cov, e2e_launches, tiles_copied = run_pipeline(True)
+    col_s, col_cov, _, col_tiles = run_pipeline(True, want=("color",))
     if world > 1:
-        t = torch.tensor([e2e_s, sync_s, dense_s], dtype=torch.float64, device=dev)
+        t = torch.tensor([e2e_s, sync_s, dense_s, col_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s, sync_s, dense_s = (float(x) for x in t.tolist())
+        e2e_s, sync_s, dense_s, col_s = (float(x) for x in t.tolist())
     d2h_sparse = tiles_copied * 32 * 32 * 28 / e2e_frames
     e2e = {"value": world * e2e_frames / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": 108 * T,
            "d2h_bytes_per_step": d2h_sparse, "frames_timed": e2e_frames, "pipeline_depth": args.e2e_depth,
@@ -465,6 +467,10 @@ def run_gpu_arm(args):
                   "clock over all frames incl. the final drain",
            "dense_value": world * e2e_frames / dense_s, "dense_d2h_bytes_per_step": 28 * RES * RES,
            "dense_api": "same pipeline with sparse=False: cudaMemcpy of all three buffers (29.4 MB) every frame",
+           "color_only_value": world * e2e_frames / col_s, "color_only_d2h_bytes_per_step": col_tiles * 32 * 32 * 12 / e2e_frames,
+           "color_only_api": "the same pipeline fetching only the colour buffer (want=('color',)): what Renderer.render returns "
+                             "and run.py consumes (renderer.py:49); z and normals stay on the device, as they do for a drop-in "
+                             "caller that never calls get_z_buffer()/get_normals_buffer()", "color_only_lit_pixels": col_cov,
            "synchronous_value": world * e2e_frames / sync_s,
            "synchronous_api": "crb_render_host, one frame per call, full download, stream-synchronised before returning",
            "pcie_floor_note": "a full 29.4 MB download per frame bounds the dense variants at ~1.9 k frames/s on a 55 GB/s link"}

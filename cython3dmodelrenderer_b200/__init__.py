@@ -3,10 +3,13 @@
 
     from cython3dmodelrenderer_b200 import AdvancedPixelBufferFiller   # instead of crender.cy.pixel_buffer_filler
 
-Everything else of the reference (Model, Renderer, illumination, run.py) is used unchanged.
+    from cython3dmodelrenderer_b200 import Model                       # optionally, instead of crender.cy.data_structures
+
+Everything else of the reference (Renderer, illumination, run.py) is used unchanged.
 """
 from ._lib import CrenderError, build, load_library, projection_matrix  # noqa: F401
 from .pixel_buffer_filler import AdvancedPixelBufferFiller  # noqa: F401
 from .pipeline import HostFramePipeline  # noqa: F401
+from .model import Model  # noqa: F401   (SURVEY 8f N4: drop-in for crender.cy.data_structures.Model)
 
-__all__ = ["AdvancedPixelBufferFiller", "HostFramePipeline", "CrenderError", "build", "load_library", "projection_matrix"]
+__all__ = ["AdvancedPixelBufferFiller", "HostFramePipeline", "Model", "CrenderError", "build", "load_library", "projection_matrix"]
