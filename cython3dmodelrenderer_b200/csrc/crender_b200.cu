@@ -1164,37 +1164,71 @@ __global__ void __launch_bounds__(NT) k_init_buffers(float *z, float *color, flo
 }
 
 // Sparse read-back (crb_render_host + CRB_DL_SPARSE).  The host copy of the three buffers persists between calls, every
-// call renders a FRESH frame, and a tile no triangle touches holds fresh-filler values both before and after -- so only
-// tiles that are busy now, or were busy in the frame the host copy currently shows, need to cross PCIe.  One CTA per
-// tile copies the tile's rows from the device buffers straight into the mapped pinned host arrays (16-byte stores,
-// 128 / 384-byte runs) and records the tile's state for the next call; everything else exits at once.  The host arrays
-// end up bit-identical to a full download (tests/test_gpu_parity.py::test_sparse_readback_*).
-__global__ void __launch_bounds__(NT) k_readback(const Frame F, unsigned char *shown_busy, float *hz, float *hc, float *hn,
-                                                  unsigned long long *tiles_copied)
+// call renders a FRESH frame, and a pixel row no fragment was written to holds fresh-filler values both before and after --
+// so only the 32-pixel tile rows that hold something now, or held something in the frame the host copy currently shows,
+// need to cross PCIe.  One CTA per tile that is busy now or has rows to take back: warp w compares rows w, w+8, ... of the
+// tile with the fresh pattern (z 1e6, colour / normals 0) as it reads them, copies the rows that differ now or differed
+// before straight into the mapped pinned host arrays (16-byte stores, 128 / 384-byte runs), and the tile's new row mask is
+// kept for the next call; everything else exits at once.  The host arrays end up bit-identical to a full download
+// (tests/test_gpu_parity.py::test_sparse_readback_*).  `rows_copied` counts tile rows (32 pixels x 28 bytes when all
+// three buffers are wanted).
+__global__ void __launch_bounds__(NT) k_readback(const Frame F, unsigned *shown_rows, float *hz, float *hc, float *hn,
+                                                  unsigned long long *rows_copied)
 {
+    __shared__ unsigned s_now, s_copied;
     if (F.total[0] > (unsigned long long)F.pairCap) return;      // frame skipped: the host copy stays as it is
     const unsigned t = blockIdx.x;
     const bool busy = F.cursor[t] != 0u;                          // k_fill left the tile's pair count here
-    const bool dirty = busy || shown_busy[t] != 0;
+    const unsigned before = shown_rows[t];
+    if (threadIdx.x == 0) { s_now = 0u; s_copied = 0u; }
     __syncthreads();
-    if (!dirty) return;
-    if (threadIdx.x == 0) {
-        shown_busy[t] = busy ? 1 : 0;
-        atomicAdd(tiles_copied, 1ull);
-    }
+    if (!busy && before == 0u) return;
     const int tx = (int)(t % (unsigned)F.tilesX), ty = (int)(t / (unsigned)F.tilesX);
     const int x0 = tx * TW, yl0 = ty * TH;
     const int tw = min(TW, F.W - x0), th = min(TH, F.row1 - F.row0 - yl0);
+    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     if (tw == TW && !(F.W & 3)) {
-        // 56 float4 per tile row: 8 of z, 24 of colour, 24 of normals
-        for (int i = threadIdx.x; i < th * 56; i += NT) {
-            const int r = i / 56, q = i % 56;
+        // a tile row is 56 float4: 8 of z, 24 of colour, 24 of normals; lane l takes float4 l and l + 32 of the row
+        const float bg = background_color(F);
+        unsigned now = 0u, copied = 0u;
+        for (int r = (int)wid; r < th; r += NT / 32) {
             const long long rowpix = (long long)(yl0 + r) * F.W + x0;
-            if (q < 8) { if (hz) reinterpret_cast<float4 *>(hz + rowpix)[q] = reinterpret_cast<const float4 *>(F.z + rowpix)[q]; }
-            else if (q < 32) { if (hc) reinterpret_cast<float4 *>(hc + rowpix * 3)[q - 8] = reinterpret_cast<const float4 *>(F.color + rowpix * 3)[q - 8]; }
-            else if (hn) reinterpret_cast<float4 *>(hn + rowpix * 3)[q - 32] = reinterpret_cast<const float4 *>(F.normals + rowpix * 3)[q - 32];
+            const float4 *src0, *src1 = nullptr;
+            float4 *dst0, *dst1 = nullptr;
+            float f0, f1 = 0.0f;                                   // fresh value of the lane's two float4
+            if (lane < 8u) {
+                src0 = reinterpret_cast<const float4 *>(F.z + rowpix) + lane;
+                dst0 = hz ? reinterpret_cast<float4 *>(hz + rowpix) + lane : nullptr;
+                f0 = Z_INIT;
+            } else {
+                src0 = reinterpret_cast<const float4 *>(F.color + rowpix * 3) + (lane - 8u);
+                dst0 = hc ? reinterpret_cast<float4 *>(hc + rowpix * 3) + (lane - 8u) : nullptr;
+                f0 = bg;
+            }
+            if (lane < 24u) {                                      // float4 32..55 of the row: the normals
+                src1 = reinterpret_cast<const float4 *>(F.normals + rowpix * 3) + lane;
+                dst1 = hn ? reinterpret_cast<float4 *>(hn + rowpix * 3) + lane : nullptr;
+            }
+            const float4 a = *src0;
+            const float4 b = src1 ? *src1 : make_float4(0.f, 0.f, 0.f, 0.f);
+            // bit comparison: -0.0 or NaN in a written pixel is not "fresh"
+            const bool differs = __float_as_uint(a.x) != __float_as_uint(f0) || __float_as_uint(a.y) != __float_as_uint(f0) ||
+                                 __float_as_uint(a.z) != __float_as_uint(f0) || __float_as_uint(a.w) != __float_as_uint(f0) ||
+                                 (__float_as_uint(b.x) | __float_as_uint(b.y) | __float_as_uint(b.z) | __float_as_uint(b.w)) != __float_as_uint(f1);
+            const bool holds = __any_sync(0xFFFFFFFFu, differs);
+            if (holds) now |= 1u << r;
+            if (holds || ((before >> r) & 1u)) {
+                if (dst0) *dst0 = a;
+                if (dst1) *dst1 = b;
+                ++copied;
+            }
+        }
+        if (lane == 0u) {
+            if (now) atomicOr(&s_now, now);
+            if (copied) atomicAdd(&s_copied, copied);
         }
     } else {
+        // ragged tiles (image edge, widths that are not a multiple of 4): whole tile, element by element
         for (int i = threadIdx.x; i < th * tw; i += NT) {
             const int r = i / tw, xx = i % tw;
             const long long p = (long long)(yl0 + r) * F.W + x0 + xx;
@@ -1202,6 +1236,15 @@ __global__ void __launch_bounds__(NT) k_readback(const Frame F, unsigned char *s
             if (hc) { hc[p * 3] = F.color[p * 3]; hc[p * 3 + 1] = F.color[p * 3 + 1]; hc[p * 3 + 2] = F.color[p * 3 + 2]; }
             if (hn) { hn[p * 3] = F.normals[p * 3]; hn[p * 3 + 1] = F.normals[p * 3 + 1]; hn[p * 3 + 2] = F.normals[p * 3 + 2]; }
         }
+        if (threadIdx.x == 0) {
+            s_now = busy ? 0xFFFFFFFFu : 0u;
+            s_copied = (unsigned)th;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        shown_rows[t] = s_now;
+        if (s_copied) atomicAdd(rows_copied, (unsigned long long)s_copied);
     }
 }
 
@@ -1342,7 +1385,7 @@ struct crb_filler {
     int raster_ctas;       // experiments: fixed k_raster grid (0 = automatic)
     int sm_count;
     int use_tma;           // tensor maps are built where the layout allows (CRB_NO_TMA=1 disables): k_clear stores TMA boxes
-    unsigned char *shown_busy;   // sparse read-back: per tile, was it busy in the frame the caller's host arrays show
+    unsigned *shown_busy;        // sparse read-back: per tile, mask of the 32 rows that hold something in the frame the caller's host arrays show
     long long shown_tiles;
     unsigned long long *tiles_copied;   // device counter behind crb_readback_stats
     const void *map_host[3];     // host pointers already resolved to device-visible addresses
@@ -1929,8 +1972,8 @@ static int render_host_once(crb_filler *f, const float *v, const float *c, const
         if (f->shown_tiles != F.nTiles) {
             if (f->shown_busy) cudaFree(f->shown_busy);
             f->shown_busy = nullptr;
-            CU(cudaMalloc(&f->shown_busy, (size_t)(F.nTiles > 0 ? F.nTiles : 1)));
-            CU(cudaMemsetAsync(f->shown_busy, 0, (size_t)(F.nTiles > 0 ? F.nTiles : 1), st));
+            CU(cudaMalloc(&f->shown_busy, 4 * (size_t)(F.nTiles > 0 ? F.nTiles : 1)));
+            CU(cudaMemsetAsync(f->shown_busy, 0, 4 * (size_t)(F.nTiles > 0 ? F.nTiles : 1), st));
             f->shown_tiles = F.nTiles;
         }
         if (!f->tiles_copied) {
@@ -2163,7 +2206,7 @@ int crb_readback_stats(crb_filler *f, int64_t *tiles_copied, int reset, void *st
         CU(cudaStreamSynchronize((cudaStream_t)stream));
         if (reset) CU(cudaMemsetAsync(f->tiles_copied, 0, 8, (cudaStream_t)stream));
     }
-    *tiles_copied = (int64_t)n;
+    *tiles_copied = (int64_t)((n + TH - 1) / TH);   // the device counter counts 32-pixel tile rows
     return CRB_OK;
 }
 
@@ -2171,7 +2214,7 @@ int crb_readback_reset(crb_filler *f, void *stream)
 {
     if (check_filler(f)) return CRB_ERR_INVALID;
     CU(cudaSetDevice(f->device));
-    if (f->shown_busy) CU(cudaMemsetAsync(f->shown_busy, 0, (size_t)(f->shown_tiles > 0 ? f->shown_tiles : 1), (cudaStream_t)stream));
+    if (f->shown_busy) CU(cudaMemsetAsync(f->shown_busy, 0, 4 * (size_t)(f->shown_tiles > 0 ? f->shown_tiles : 1), (cudaStream_t)stream));
     return CRB_OK;
 }
 

@@ -90,10 +90,8 @@ class Model:
         texture = Model._read_texture_file(external_texture_filename) if external_texture_filename is not None else None
         with open(filename.strip(), 'rb') as f:
             raw = f.read()
-        try:
-            raw.decode('utf-8')   # upstream reads in text mode: undecodable bytes raise there too
-        except UnicodeDecodeError:
-            raise
+        if not raw.isascii():
+            raw.decode('utf-8')   # upstream reads in text mode: undecodable bytes raise UnicodeDecodeError there too
         parsed = parse_obj_text(raw)
         if not silent and parsed["bad_lines"]:
             raise RuntimeError(f'Error occurred while parsing line #{parsed["first_bad_line"]} of "{filename}"')

@@ -58,7 +58,7 @@ extern "C" {
                                   output arrays still hold what the previous CRB_DL_SPARSE call of this filler left in them
                                   (fresh-filler values -- z 1e6, colour 0, normals 0 -- before the first call, or after
                                   crb_readback_reset).  Only tiles that are busy now or were busy in that previous frame are
-                                  then copied, by a kernel writing into the pinned + mapped host arrays; the arrays end up
+                                  then copied (at the granularity of 32-pixel tile rows), by a kernel writing into the pinned + mapped host arrays; the arrays end up
                                   bit-identical to a full download.  The arrays must come from cudaHostAlloc /
                                   cudaHostRegister (e.g. torch pin_memory). */
 
@@ -180,8 +180,10 @@ int crb_upload(crb_filler *f, unsigned mask, const float *z_host, const float *c
  * value is CRB_ERR_OVERFLOW -- re-bind a workspace with pair_capacity >= pairs_needed and render again. */
 int crb_status(crb_filler *f, int64_t *pairs_needed, int64_t *pair_capacity, void *stream);
 
-/* Sparse read-back bookkeeping: tiles (32x32 pixels, 28 KB for all three buffers) copied since the last reset of the
- * counter; crb_readback_reset declares that the caller's host arrays hold fresh-filler values again. */
+/* Sparse read-back bookkeeping.  The read-back works on 32-pixel tile rows (896 bytes for all three buffers): a row crosses
+ * PCIe when it holds something now or held something in the frame the host arrays show.  *tiles_copied = rows copied since the
+ * last reset of the counter / 32, rounded up (tile equivalents of 32x32 pixels, 28 KB); crb_readback_reset declares that the
+ * caller's host arrays hold fresh-filler values again. */
 int crb_readback_stats(crb_filler *f, int64_t *tiles_copied, int reset, void *stream);
 int crb_readback_reset(crb_filler *f, void *stream);
 
