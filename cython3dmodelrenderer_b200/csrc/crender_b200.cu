@@ -115,6 +115,8 @@ struct Frame {
     float4 *shrec;              // [nViews*T*8] shade records
     float4 *recD, *recE;        // [nViews*T]
     unsigned char *alive;       // [nViews*ceil(T/NT)] 1 = this k_setup CTA has a drawn triangle (its recE / records are valid)
+    unsigned *chunks;           // band-sharded single view: [0] = number of 256-triangle chunks that may reach the band,
+                                // [1..] their indices (k_band_chunks); nullptr = every chunk is visited (grid = chunks)
     unsigned *count;            // [nViews*nTiles] triangles per tile, accumulated by k_setup, returned to zero by k_alloc
     uint4 *busy;                // [nViews*nTiles] compacted busy tiles: (view:10 ty:11 tx:11, triangles, list offset, -); count in total[2]
     uint4 *busyH;               // [nViews*nTiles] the same for tiles with more than HEAVY_N triangles; count in total[4]
@@ -328,23 +330,18 @@ __device__ __forceinline__ void tile_span(const Frame &F, unsigned bx, unsigned 
     ty1 = (yb - 1 - F.row0) / TH;
 }
 
-__global__ void __launch_bounds__(NT) k_setup(const Frame F)
+// One chunk of NT consecutive triangles of one view.  Every early exit below is taken by the whole CTA or lies behind
+// the last barrier, so the function can be called in a loop (chunk-list mode).
+__device__ __forceinline__ void setup_chunk(const Frame &F, const int view, const long long chunk, const long long chunksPerView,
+                                            float *sv, float *sn, float *sc, float *sM)
 {
-    __shared__ __align__(16) float sv[NT * 9];
-    __shared__ __align__(16) float sn[NT * 9];
-    __shared__ __align__(16) float sc[NT * 9];
-    __shared__ float sM[16];
-    const int view = blockIdx.y;
-    const long long first = (long long)blockIdx.x * NT;
+    const long long first = chunk * NT;
     const long long cnt = min((long long)NT, F.T - first);
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {  // k_alloc (next launch) accumulates
-        F.total[0] = 0ull; F.total[2] = 0ull; F.total[3] = 0ull; F.total[4] = 0ull;
-    }
     // A band-sharded filler sees every triangle of the frame but draws only those that reach its rows: there
     // the vertices are staged and tested first, and a CTA whose 256 triangles all miss the band stops before it has read
     // a normal or written a record (7 of 8 CTAs at N = 8).  A full-frame filler stages both arrays behind one barrier.
     const bool banded = F.row0 > 0 || F.row1 < F.H;
-    unsigned char *alive = F.alive + (long long)view * gridDim.x + blockIdx.x;
+    unsigned char *alive = F.alive + (long long)view * chunksPerView + chunk;
     stage_floats(F.v, first * 9, cnt * 9, sv);
     if (!banded) stage_floats(F.n, first * 9, cnt * 9, sn);
     if (F.views && threadIdx.x < 16) sM[threadIdx.x] = F.views[view * 16 + threadIdx.x];
@@ -450,6 +447,86 @@ __global__ void __launch_bounds__(NT) k_setup(const Frame F)
         for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(cnt_view + ty * F.tilesX + tx, 1u);
 }
 
+__global__ void __launch_bounds__(NT) k_setup(const Frame F)
+{
+    __shared__ __align__(16) float sv[NT * 9];
+    __shared__ __align__(16) float sn[NT * 9];
+    __shared__ __align__(16) float sc[NT * 9];
+    __shared__ float sM[16];
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {  // k_alloc (next launch) accumulates
+        F.total[0] = 0ull; F.total[2] = 0ull; F.total[3] = 0ull; F.total[4] = 0ull;
+    }
+    const long long chunksPerView = (F.T + NT - 1) / NT;
+    if (!F.chunks) {
+        setup_chunk(F, blockIdx.y, blockIdx.x, chunksPerView, sv, sn, sc, sM);
+        return;
+    }
+    // chunk-list mode (band-sharded filler): a grid of a few CTAs per SM walks the chunks k_band_chunks listed
+    const unsigned n = F.chunks[0];
+    for (unsigned i = blockIdx.x; i < n; i += gridDim.x) {
+        __syncthreads();
+        setup_chunk(F, 0, F.chunks[1 + i], chunksPerView, sv, sn, sc, sM);
+    }
+}
+
+// Band-sharded fillers see every triangle of the frame but draw only those that reach their rows.  This
+// pre-pass lists the 256-triangle chunks with at least one triangle whose pixel rectangle meets the band (same projection and
+// rectangle code as k_setup, before the cull), so that k_setup and k_fill visit only those: one CTA per SM slot streams
+// the vertex array through a double-buffered shared-memory stage (16-byte cp.async), i.e. at memory speed rather than
+// at the rate at which 39 075 load -> barrier -> project -> exit CTAs can be launched and retired.
+__device__ __forceinline__ void cp_async16(float *smem_dst, const float *gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+
+__global__ void __launch_bounds__(NT) k_band_chunks(const Frame F)
+{
+    __shared__ __align__(16) float sv[2][NT * 9];
+    const long long nFull = F.T / NT;                 // a ragged last chunk is listed unconditionally (by CTA 0, below)
+    if (blockIdx.x == 0 && threadIdx.x == 0 && nFull * NT < F.T) F.chunks[1 + atomicAdd(F.chunks, 1u)] = (unsigned)nFull;
+    auto fetch = [&](long long chunk, int buf) {
+        const float *src = F.v + chunk * (NT * 9);
+        for (int i = threadIdx.x; i < NT * 9 / 4; i += NT) cp_async16(&sv[buf][i * 4], src + i * 4);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    long long chunk = blockIdx.x;
+    int buf = 0;
+    if (chunk < nFull) fetch(chunk, 0);
+    for (; chunk < nFull; chunk += gridDim.x, buf ^= 1) {
+        const long long next = chunk + gridDim.x;
+        if (next < nFull) {
+            fetch(next, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        float x[3], y[3], z[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            x[k] = sv[buf][threadIdx.x * 9 + k * 3 + 0];
+            y[k] = sv[buf][threadIdx.x * 9 + k * 3 + 1];
+            z[k] = sv[buf][threadIdx.x * 9 + k * 3 + 2];
+            project_vertex(F.proj, x[k], y[k], z[k]);
+        }
+        float fxl = (float)F.W, fxr = 0.0f, fyt = (float)F.H, fyb = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (x[k] < fxl) fxl = x[k];
+            if (x[k] > fxr) fxr = x[k];
+            if (y[k] < fyt) fyt = y[k];
+            if (y[k] > fyb) fyb = y[k];
+        }
+        const int xl = clipi(ceil_to_int_ref(fxl), 0, F.W), xr = clipi(ceil_to_int_ref(fxr), 0, F.W);
+        int yt = clipi(ceil_to_int_ref(fyt), 0, F.H), yb = clipi(ceil_to_int_ref(fyb), 0, F.H);
+        yt = max(yt, F.row0);
+        yb = min(yb, F.row1);
+        const int any = __syncthreads_or((xl < xr) && (yt < yb));   // also: everybody is done with sv[buf]
+        if (any && threadIdx.x == 0) F.chunks[1 + atomicAdd(F.chunks, 1u)] = (unsigned)chunk;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // K2b: list space for every tile.  Block-wide exclusive scan (warp shuffles) of the tile counts, one bump
 // allocation per CTA.  List order in memory is irrelevant: the packed key makes the result order-independent.
@@ -522,12 +599,10 @@ __global__ void __launch_bounds__(NT) k_alloc(const Frame F)
 }
 
 // K2c: scatter the prepared setups into the tile lists (sign-normalised form the row loop wants).
-__global__ void __launch_bounds__(NT) k_fill(const Frame F)
+__device__ __forceinline__ void fill_chunk(const Frame &F, const int view, const long long chunk, const long long chunksPerView)
 {
-    if (*F.total > (unsigned long long)F.pairCap) return;  // overflow: frame is skipped, host is told via crb_status
-    const int view = blockIdx.y;
-    if (!F.alive[(long long)view * gridDim.x + blockIdx.x]) return;   // same CTA -> triangle mapping as k_setup
-    const long long tri = (long long)blockIdx.x * NT + threadIdx.x;
+    if (!F.alive[(long long)view * chunksPerView + chunk]) return;   // k_setup found nothing to draw in this chunk
+    const long long tri = chunk * NT + threadIdx.x;
     if (tri >= F.T) return;
     const long long ridx = (long long)view * F.T + tri;
     const float4 E = F.recE[ridx];
@@ -550,6 +625,18 @@ __global__ void __launch_bounds__(NT) k_fill(const Frame F)
             const unsigned at = F.offset[t] + atomicAdd(F.cursor + t, 1u);
             F.ls0[at] = a; F.ls1[at] = b; F.ls2[at] = s2; F.ls3[at] = s3; F.ls4[at] = s4;
         }
+}
+
+__global__ void __launch_bounds__(NT) k_fill(const Frame F)
+{
+    if (*F.total > (unsigned long long)F.pairCap) return;  // overflow: frame is skipped, host is told via crb_status
+    const long long chunksPerView = (F.T + NT - 1) / NT;
+    if (!F.chunks) {
+        fill_chunk(F, blockIdx.y, blockIdx.x, chunksPerView);   // same CTA -> triangle mapping as k_setup
+        return;
+    }
+    const unsigned n = F.chunks[0];
+    for (unsigned i = blockIdx.x; i < n; i += gridDim.x) fill_chunk(F, 0, F.chunks[1 + i], chunksPerView);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1370,6 +1457,7 @@ struct crb_filler {
     long long pairCap;
     float4 *shrec, *recD, *recE;
     unsigned char *alive;
+    unsigned *chunks;
     unsigned *count, *offset, *cursor, *empty;
     uint4 *busy, *busyH;
     float4 *ls0, *ls1, *ls2;
@@ -1398,6 +1486,7 @@ struct crb_filler {
     int set_used[2];       // the set has a rasterizer launch whose completion is recorded in ev_raster[set]
     int pending_join;      // 1 + set of the last pipelined launch the caller's stream has not been made to wait for (CRB_DEFER_JOIN)
     int split_heavy;       // single-view launches cut heavy tiles into row bands (CRB_SPLIT_HEAVY=0 disables)
+    int band_prepass;      // band-sharded fillers list the chunks that reach the band first (CRB_OPT_BAND_PREPASS)
     int tiles_per_cta;     // k_raster grid = estimated busy tiles / this (CRB_TILES_PER_CTA)
     unsigned dbg_flags;    // ablation switches (CRB_DEBUG_SKIP), never set in production
     int out_tma;           // ... and so does k_raster for the shaded colour / normal rows (CRB_OUT_TMA=0 disables)
@@ -1411,7 +1500,7 @@ struct crb_filler {
 namespace {
 
 struct WsLayout {
-    size_t shrec, recD, recE, alive, count, offset, cursor, busy, busyH, empty, ls0, ls1, ls2, ls3, ls4, total, set_bytes, sv, sc, sn, bytes;
+    size_t shrec, recD, recE, alive, chunks, count, offset, cursor, busy, busyH, empty, ls0, ls1, ls2, ls3, ls4, total, set_bytes, sv, sc, sn, bytes;
 };
 
 long long default_pair_cap(const crb_filler *f, long long T, int views)
@@ -1432,6 +1521,7 @@ WsLayout ws_layout(const crb_filler *f, long long T, int views, long long pairCa
     L.recD = take(recs * sizeof(float4));
     L.recE = take(recs * sizeof(float4));
     L.alive = take((size_t)((T > 0 ? T : 1) + NT - 1) / NT * views);
+    L.chunks = take(4 * ((size_t)((T > 0 ? T : 1) + NT - 1) / NT + 2));
     L.count = take((size_t)tiles * views * 4);
     L.offset = take((size_t)tiles * views * 4);
     L.cursor = take((size_t)tiles * views * 4);
@@ -1559,7 +1649,20 @@ unsigned encode_maps(TMaps *M, const Frame &F)
 int run_prep(crb_filler *f, Frame &F, cudaStream_t st)
 {
     int rc;
-    const unsigned gT = (unsigned)((F.T + NT - 1) / NT);
+    unsigned gT = (unsigned)((F.T + NT - 1) / NT);
+    // band-sharded single view: list the chunks that can reach the band first, then walk only those (persistent grids)
+    const bool banded = F.row0 > 0 || F.row1 < F.H;
+    F.chunks = nullptr;
+    if (banded && f->band_prepass && F.nViews == 1 && !F.views && F.T >= 8 * NT && !(F.flags & CRB_PATH_ATOMIC) &&
+        !(reinterpret_cast<uintptr_t>(F.v) & 15u)) {
+        const size_t so = (size_t)(reinterpret_cast<const char *>(F.alive) - reinterpret_cast<const char *>(f->alive));   // workspace set in use
+        F.chunks = reinterpret_cast<unsigned *>(reinterpret_cast<char *>(f->chunks) + so);
+        CU(cudaMemsetAsync(F.chunks, 0, 4, st));
+        const unsigned gP = (unsigned)min((long long)gT, (long long)f->sm_count * 6);
+        k_band_chunks<<<gP, NT, 0, st>>>(F);
+        if ((rc = launch_check(f, "k_band_chunks"))) return rc;
+        gT = gP;
+    }
     if (F.T > 0) {
         k_setup<<<dim3(gT, F.nViews), NT, 0, st>>>(F);
         if ((rc = launch_check(f, "k_setup"))) return rc;
@@ -1682,6 +1785,7 @@ int bind_ws_pointers(crb_filler *f, void *ws, size_t bytes, long long T, int vie
     f->maxT = T; f->maxViews = views; f->pairCap = pairCap;
     f->shrec = (float4 *)(b + L.shrec); f->recD = (float4 *)(b + L.recD); f->recE = (float4 *)(b + L.recE);
     f->alive = (unsigned char *)(b + L.alive);
+    f->chunks = (unsigned *)(b + L.chunks);
     f->count = (unsigned *)(b + L.count); f->offset = (unsigned *)(b + L.offset); f->cursor = (unsigned *)(b + L.cursor);
     f->busy = (uint4 *)(b + L.busy); f->busyH = (uint4 *)(b + L.busyH); f->empty = (unsigned *)(b + L.empty);
     f->ls0 = (float4 *)(b + L.ls0); f->ls1 = (float4 *)(b + L.ls1); f->ls2 = (float4 *)(b + L.ls2); f->ls3 = (uint4 *)(b + L.ls3); f->ls4 = (float4 *)(b + L.ls4);
@@ -1749,6 +1853,8 @@ int crb_create(int h, int w, float fov, float z_near, float z_far, int device, c
         if (const char *e = getenv("CRB_RASTER_CTAS")) f->raster_ctas = atoi(e);   // experiments: >0 fixed grid, <0 one CTA per tile
         f->use_tma = 1;
         f->split_heavy = 1;
+        f->band_prepass = 1;
+        if (const char *e = getenv("CRB_BAND_PREPASS")) f->band_prepass = atoi(e) ? 1 : 0;
         if (const char *e = getenv("CRB_SPLIT_HEAVY")) f->split_heavy = atoi(e) ? 1 : 0;
         f->chunk_pipeline = 1;
         if (const char *e = getenv("CRB_CHUNK_PIPELINE")) f->chunk_pipeline = atoi(e) ? 1 : 0;
@@ -2183,6 +2289,7 @@ int crb_set_option(crb_filler *f, int option, int value)
     case CRB_OPT_CHUNK_PIPELINE: f->chunk_pipeline = value ? 1 : 0; return CRB_OK;
     case CRB_OPT_TMA: f->use_tma = value ? 1 : 0; return CRB_OK;
     case CRB_OPT_TMA_ROWS: f->out_tma = value ? 1 : 0; return CRB_OK;
+    case CRB_OPT_BAND_PREPASS: f->band_prepass = value ? 1 : 0; return CRB_OK;
     default: return fail(CRB_ERR_INVALID, "unknown option %d", option);
     }
 }

@@ -133,10 +133,12 @@ int crb_render_host(crb_filler *f, const float *v, const float *c, const float *
 
 /* Tuning switches (defaults: all on).  CRB_OPT_CHUNK_PIPELINE: crb_render_views runs the setup / binning kernels of launch
  * i+1 on an internal stream beside the rasterizer of launch i (two workspace sets).  CRB_OPT_TMA: tensor-map (TMA box) stores
- * for the fused clear and the shaded rows where the layout allows.  Results do not depend on either. */
+ * for the fused clear and the shaded rows where the layout allows.  Results do not depend on any of them. */
 #define CRB_OPT_CHUNK_PIPELINE 1
 #define CRB_OPT_TMA 2
 #define CRB_OPT_TMA_ROWS 3   /* shaded colour / normal rows of busy tiles as TMA boxes (1) or 16-byte vector stores (0) */
+#define CRB_OPT_BAND_PREPASS 4   /* band-sharded fillers (crb_set_band): a streaming pre-pass lists the 256-triangle chunks that
+                                    can reach the band, and the setup / binning kernels visit only those (1, default) */
 int crb_set_option(crb_filler *f, int option, int value);
 
 /* Orders `stream` behind rasterizer work left in flight by CRB_DEFER_JOIN (no host synchronisation). */

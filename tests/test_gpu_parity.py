@@ -244,6 +244,35 @@ def test_band_sharded_fillers_concatenate_to_full_frame(Filler, O, trex):
     assert_same(got, buffers(o), "bands")
 
 
+@pytest.mark.parametrize("prepass", [1, 0])
+def test_band_prepass_switch_changes_nothing(Filler, O, bunny, prepass):
+    """CRB_OPT_BAND_PREPASS: with the chunk pre-pass (k_band_chunks + list-walking k_setup / k_fill) or without it, every band
+    equals the oracle's rows -- including empty bands, a ragged last chunk, device-resident inputs and repeated frames."""
+    import torch
+    from cython3dmodelrenderer_b200 import _lib
+    h, w = 640, 512
+    o = O.OracleFiller(h, w, fov=45.0)
+    o.render_model(bunny)
+    want = buffers(o)
+    dv, dc, dn = (torch.from_numpy(a).cuda() for a in
+                  (bunny._vertices_by_triangles, bunny._colors_by_triangles, bunny._normals_by_triangles))
+    for r0, r1 in [(0, 32), (32, 288), (288, 320), (320, 608), (608, 640)]:
+        f = Filler(h, w, fov=45.0, band=(r0, r1))
+        _lib.check(f._L.crb_set_option(f._handle, _lib.CRB_OPT_BAND_PREPASS, prepass))
+        for rep in range(2):
+            f.clear()
+            f.render_arrays(dv, dc, dn)
+            assert_same(buffers(f), tuple(a[r0:r1] for a in want), f"band {r0}:{r1} prepass={prepass} frame {rep}")
+    # composite of two models into one band (no clear in between)
+    f = Filler(h, w, fov=45.0, band=(128, 416))
+    _lib.check(f._L.crb_set_option(f._handle, _lib.CRB_OPT_BAND_PREPASS, prepass))
+    m2 = random_scene(3, T=5000)
+    f.render_arrays(dv, dc, dn)
+    f.render_model(m2)
+    o.render_model(m2)
+    assert_same(buffers(f), tuple(a[128:416] for a in buffers(o)), "band composite")
+
+
 def test_guro_on_device_and_u8_output(Filler, O, trex):
     f, o = Filler(200, 200, fov=45.0), O.OracleFiller(200, 200, fov=45.0)
     f.render_model(trex)
