@@ -471,59 +471,87 @@ __global__ void __launch_bounds__(NT) k_setup(const Frame F)
 
 // Band-sharded fillers see every triangle of the frame but draw only those that reach their rows.  This
 // pre-pass lists the 256-triangle chunks with at least one triangle whose pixel rectangle meets the band (same projection and
-// rectangle code as k_setup, before the cull), so that k_setup and k_fill visit only those: one CTA per SM slot streams
-// the vertex array through a double-buffered shared-memory stage (16-byte cp.async), i.e. at memory speed rather than
-// at the rate at which 39 075 load -> barrier -> project -> exit CTAs can be launched and retired.
-__device__ __forceinline__ void cp_async16(float *smem_dst, const float *gmem_src)
+// rectangle code as k_setup, before the cull), so that k_setup and k_fill visit only those.  A few CTAs per SM stream the
+// vertex array through a ring of BC_STAGES shared-memory buffers filled by 1-D bulk copies (cp.async.bulk, one 9 216-byte
+// copy per chunk issued by one thread, completion counted on an mbarrier), i.e. at memory speed rather than at the rate at
+// which 39 075 load -> barrier -> project -> exit CTAs can be launched and retired.
+constexpr int BC_STAGES = 4;
+constexpr unsigned BC_BYTES = NT * 9 * 4;
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
 {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned phase)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(a), "r"(phase) : "memory");
+}
+// one bulk copy global -> shared of `bytes` (16-byte multiple, both addresses 16-byte aligned), completion on `bar`
+__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst), m = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(m), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(gmem_src),
+                 "r"(bytes), "r"(m) : "memory");
 }
 
 __global__ void __launch_bounds__(NT) k_band_chunks(const Frame F)
 {
-    __shared__ __align__(16) float sv[2][NT * 9];
+    __shared__ __align__(128) float sv[BC_STAGES][NT * 9];
+    __shared__ __align__(8) unsigned long long bar[BC_STAGES];
     const long long nFull = F.T / NT;                 // a ragged last chunk is listed unconditionally (by CTA 0, below)
     if (blockIdx.x == 0 && threadIdx.x == 0 && nFull * NT < F.T) F.chunks[1 + atomicAdd(F.chunks, 1u)] = (unsigned)nFull;
-    auto fetch = [&](long long chunk, int buf) {
-        const float *src = F.v + chunk * (NT * 9);
-        for (int i = threadIdx.x; i < NT * 9 / 4; i += NT) cp_async16(&sv[buf][i * 4], src + i * 4);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    long long chunk = blockIdx.x;
-    int buf = 0;
-    if (chunk < nFull) fetch(chunk, 0);
-    for (; chunk < nFull; chunk += gridDim.x, buf ^= 1) {
-        const long long next = chunk + gridDim.x;
-        if (next < nFull) {
-            fetch(next, buf ^ 1);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
-        __syncthreads();
-        float x[3], y[3], z[3];
+    // this CTA's chunks: blockIdx.x + j * gridDim.x, j < nMine
+    const long long nMine = nFull > blockIdx.x ? (nFull - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < BC_STAGES; ++s) mbar_init(&bar[s], 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int j = 0; j < BC_STAGES && j < nMine; ++j)
+            bulk_load(sv[j], F.v + (blockIdx.x + (long long)j * gridDim.x) * (NT * 9), BC_BYTES, &bar[j]);
+    }
+    __syncthreads();
+    for (long long j = 0; j < nMine; ++j) {
+        const int s = (int)(j % BC_STAGES);
+        mbar_wait(&bar[s], (unsigned)((j / BC_STAGES) & 1));
+        // Conservative row test: a chunk listed without need costs a k_setup visit, a chunk missed would cost pixels.  The
+        // screen y of each vertex is formed like project_vertex forms it, except that the division is a multiplication by
+        // rcp.approx (relative difference < 3e-7, i.e. < 0.01 pixel on screen); the band is widened by far more than that,
+        // and anything non-finite or beyond 1e9 (where the reference's (int)ceil wraps to INT_MIN) lists the chunk.
+        // The x extent is not tested here (k_setup does that exactly).
+        float ylo = 3.0e38f, yhi = -3.0e38f;
+        bool odd = false;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            x[k] = sv[buf][threadIdx.x * 9 + k * 3 + 0];
-            y[k] = sv[buf][threadIdx.x * 9 + k * 3 + 1];
-            z[k] = sv[buf][threadIdx.x * 9 + k * 3 + 2];
-            project_vertex(F.proj, x[k], y[k], z[k]);
+            const float vx = sv[s][threadIdx.x * 9 + k * 3 + 0];
+            const float vy = sv[s][threadIdx.x * 9 + k * 3 + 1];
+            const float vz = sv[s][threadIdx.x * 9 + k * 3 + 2];
+            const float X = ((vx * F.proj.p[0] + vy * F.proj.p[4]) + vz * F.proj.p[8]) + F.proj.p[12];
+            const float Y = ((X * F.proj.p[1] + vy * F.proj.p[5]) + vz * F.proj.p[9]) + F.proj.p[13];
+            float r;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(vz));
+            const float ysc = (Y * r + 1.0f) * F.proj.ys;
+            if (!(fabsf(ysc) < 1.0e9f)) odd = true;
+            ylo = fminf(ylo, ysc);
+            yhi = fmaxf(yhi, ysc);
         }
-        float fxl = (float)F.W, fxr = 0.0f, fyt = (float)F.H, fyb = 0.0f;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            if (x[k] < fxl) fxl = x[k];
-            if (x[k] > fxr) fxr = x[k];
-            if (y[k] < fyt) fyt = y[k];
-            if (y[k] > fyb) fyb = y[k];
+        // rows drawn are the integers r with ymin <= r < ymax inside [row0, row1)
+        const bool reach = odd || ((ylo - (0.25f + 1.0e-5f * fabsf(ylo)) <= (float)(F.row1 - 1)) &&
+                                   (yhi + (0.25f + 1.0e-5f * fabsf(yhi)) > (float)F.row0));
+        const int any = __syncthreads_or(reach);   // also: everybody is done with sv[s]
+        if (threadIdx.x == 0) {
+            const long long chunk = blockIdx.x + j * gridDim.x;
+            if (j + BC_STAGES < nMine) bulk_load(sv[s], F.v + (chunk + (long long)BC_STAGES * gridDim.x) * (NT * 9), BC_BYTES, &bar[s]);
+            if (any) F.chunks[1 + atomicAdd(F.chunks, 1u)] = (unsigned)chunk;
         }
-        const int xl = clipi(ceil_to_int_ref(fxl), 0, F.W), xr = clipi(ceil_to_int_ref(fxr), 0, F.W);
-        int yt = clipi(ceil_to_int_ref(fyt), 0, F.H), yb = clipi(ceil_to_int_ref(fyb), 0, F.H);
-        yt = max(yt, F.row0);
-        yb = min(yb, F.row1);
-        const int any = __syncthreads_or((xl < xr) && (yt < yb));   // also: everybody is done with sv[buf]
-        if (any && threadIdx.x == 0) F.chunks[1 + atomicAdd(F.chunks, 1u)] = (unsigned)chunk;
     }
 }
 
@@ -1658,10 +1686,11 @@ int run_prep(crb_filler *f, Frame &F, cudaStream_t st)
         const size_t so = (size_t)(reinterpret_cast<const char *>(F.alive) - reinterpret_cast<const char *>(f->alive));   // workspace set in use
         F.chunks = reinterpret_cast<unsigned *>(reinterpret_cast<char *>(f->chunks) + so);
         CU(cudaMemsetAsync(F.chunks, 0, 4, st));
-        const unsigned gP = (unsigned)min((long long)gT, (long long)f->sm_count * 6);
+        static const int bcPerSm = getenv("CRB_BC_CTAS") ? atoi(getenv("CRB_BC_CTAS")) : 4;   // 4 x 36 KB rings per SM
+        const unsigned gP = (unsigned)min((long long)gT, (long long)f->sm_count * bcPerSm);
         k_band_chunks<<<gP, NT, 0, st>>>(F);
         if ((rc = launch_check(f, "k_band_chunks"))) return rc;
-        gT = gP;
+        gT = (unsigned)min((long long)gT, (long long)f->sm_count * 6);
     }
     if (F.T > 0) {
         k_setup<<<dim3(gT, F.nViews), NT, 0, st>>>(F);

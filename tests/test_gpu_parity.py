@@ -273,6 +273,31 @@ def test_band_prepass_switch_changes_nothing(Filler, O, bunny, prepass):
     assert_same(buffers(f), tuple(a[128:416] for a in buffers(o)), "band composite")
 
 
+@pytest.mark.parametrize("seed", [0, 5, 7, 11])
+def test_band_prepass_is_conservative_on_odd_vertices(Filler, O, seed):
+    """The chunk pre-pass decides with an approximate reciprocal and a widened band; it must never drop a chunk that k_setup
+    would draw from.  Random scenes (some behind the camera, some snapped to the pixel grid) salted with vertices that are
+    huge, tiny in z, infinite or NaN, cut into thin bands with boundaries the triangles straddle."""
+    import torch
+    h, w = 256, 192
+    m = random_scene(seed, T=6000, span=1.5)
+    v = m._vertices_by_triangles
+    rng = np.random.default_rng(100 + seed)
+    idx = rng.choice(v.shape[0], 60, replace=False)
+    odd = np.array([1e30, -1e30, 3e9, -3e9, 1e-30, -1e-30, np.inf, -np.inf, np.nan, 1e-42], dtype=np.float32)
+    for j, t in enumerate(idx):
+        v[t, j % 3, (j // 3) % 3] = odd[j % len(odd)]
+    v[v[..., 2] == 0] += np.float32(0.01)
+    o = O.OracleFiller(h, w, fov=60.0)
+    o.render_model(m)
+    want = buffers(o)
+    dv, dc, dn = (torch.from_numpy(a).cuda() for a in (v, m._colors_by_triangles, m._normals_by_triangles))
+    for r0, r1 in [(0, 32), (32, 64), (64, 160), (160, 224), (224, 256)]:
+        f = Filler(h, w, fov=60.0, band=(r0, r1))
+        f.render_arrays(dv, dc, dn)
+        assert_same(buffers(f), tuple(a[r0:r1] for a in want), f"seed {seed} band {r0}:{r1}")
+
+
 def test_guro_on_device_and_u8_output(Filler, O, trex):
     f, o = Filler(200, 200, fov=45.0), O.OracleFiller(200, 200, fov=45.0)
     f.render_model(trex)
