@@ -400,7 +400,8 @@ def run_gpu_arm(args):
     # ---- e2e: host buffers through the C ABI, H2D + render + D2H of all three buffers per frame -------------------
     e2e_frames = args.e2e_frames
     host_in = []
-    for k in range(4):
+    NIN = 5     # distinct host inputs, coprime with the pipeline depth: every slot keeps seeing different views
+    for k in range(NIN):
         vk, nk = VW.transform_arrays_host(views_np[k % V], model._vertices_by_triangles, model._normals_by_triangles)
         st = torch.empty((3, T, 3, 3), dtype=torch.float32).pin_memory()
         st[0].copy_(torch.from_numpy(vk)); st[1].copy_(torch.from_numpy(model._colors_by_triangles)); st[2].copy_(torch.from_numpy(nk))
@@ -412,7 +413,7 @@ def run_gpu_arm(args):
     L, h = f._L, f._handle
 
     def e2e_frame(i):
-        st = host_in[i % 4]
+        st = host_in[i % NIN]
         _lib.check(L.crb_render_host(h, st[0].data_ptr(), st[1].data_ptr(), st[2].data_ptr(), T, _lib.CRB_CLEAR_FIRST,
                                      _lib.CRB_BUF_ALL, hz.data_ptr(), hc.data_ptr(), hn.data_ptr(), f._stream()))
     for i in range(3):
@@ -433,7 +434,7 @@ def run_gpu_arm(args):
     def run_pipeline(sparse, want=("z", "color", "normals")):
         pipe = HostFramePipeline(RES, RES, fov=FOV, depth=args.e2e_depth, device=local, sparse=sparse, want=want)
         for i in range(2 * args.e2e_depth):
-            pipe.submit(*host_in[i % 4])
+            pipe.submit(*host_in[i % NIN])
         pipe.drain()
         if sparse:
             pipe.readback_tiles()
@@ -442,7 +443,7 @@ def run_gpu_arm(args):
         t0 = time.perf_counter()
         last = 0
         for i in range(e2e_frames):
-            last = pipe.submit(*host_in[i % 4])
+            last = pipe.submit(*host_in[i % NIN])
         pipe.drain()
         dt = time.perf_counter() - t0
         res = pipe.result(last)
@@ -719,7 +720,7 @@ def main():
     ap.add_argument("--views", type=int, default=128, help="views per GPU per step")
     ap.add_argument("--chunk", type=int, default=128, help="views per kernel launch (larger launches amortise the kernel tail: 32 -> 93 k, 128 -> 98 k frames/s)")
     ap.add_argument("--e2e-frames", type=int, default=200)
-    ap.add_argument("--e2e-depth", type=int, default=3, help="fillers in flight in the pipelined e2e measurement")
+    ap.add_argument("--e2e-depth", type=int, default=4, help="fillers in flight in the pipelined e2e measurement")
     ap.add_argument("--cpu-frames", type=int, default=60)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--workload", default="trex_1024_orbit",

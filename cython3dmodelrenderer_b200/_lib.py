@@ -62,6 +62,7 @@ SIGNATURES = {
     "crb_launch_count": (_i64, [_vp]),
     "crb_selftest_fdiv": (_i, [_i, ctypes.c_uint64, _u, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint32)]),
     "crb_phase_cycles": (_i, [ctypes.POINTER(ctypes.c_uint64), _i]),
+    "crb_trace_dump": (_i, [ctypes.c_char_p]),
     "crb_profile": (_i, [_vp, _i]),
     "crb_profile_read": (_i, [_vp, _ip, ctypes.POINTER(ctypes.c_double)]),
     # include/crender_ingest_b200.h (model ingest)

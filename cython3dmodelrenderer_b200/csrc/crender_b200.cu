@@ -28,6 +28,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "crender_b200.h"
 
@@ -1287,80 +1288,103 @@ __global__ void __launch_bounds__(NT) k_init_buffers(float *z, float *color, flo
 // kept for the next call; everything else exits at once.  The host arrays end up bit-identical to a full download
 // (tests/test_gpu_parity.py::test_sparse_readback_*).  `rows_copied` counts tile rows (32 pixels x 28 bytes when all
 // three buffers are wanted).
-__global__ void __launch_bounds__(NT) k_readback(const Frame F, unsigned *shown_rows, float *hz, float *hc, float *hn,
-                                                  unsigned long long *rows_copied)
+// One tile of the sparse read-back, by one warp; returns the tile rows it copied.
+__device__ __forceinline__ unsigned readback_tile(const Frame &F, const unsigned t, unsigned *shown_rows, float *hz, float *hc, float *hn)
 {
-    __shared__ unsigned s_now, s_copied;
-    if (F.total[0] > (unsigned long long)F.pairCap) return;      // frame skipped: the host copy stays as it is
-    const unsigned t = blockIdx.x;
     const bool busy = F.cursor[t] != 0u;                          // k_fill left the tile's pair count here
     const unsigned before = shown_rows[t];
-    if (threadIdx.x == 0) { s_now = 0u; s_copied = 0u; }
-    __syncthreads();
-    if (!busy && before == 0u) return;
     const int tx = (int)(t % (unsigned)F.tilesX), ty = (int)(t / (unsigned)F.tilesX);
     const int x0 = tx * TW, yl0 = ty * TH;
     const int tw = min(TW, F.W - x0), th = min(TH, F.row1 - F.row0 - yl0);
-    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned now = 0u, copied = 0u;
     if (tw == TW && !(F.W & 3)) {
-        // a tile row is 56 float4: 8 of z, 24 of colour, 24 of normals; lane l takes float4 l and l + 32 of the row
-        const float bg = background_color(F);
-        unsigned now = 0u, copied = 0u;
-        for (int r = (int)wid; r < th; r += NT / 32) {
-            const long long rowpix = (long long)(yl0 + r) * F.W + x0;
-            const float4 *src0, *src1 = nullptr;
-            float4 *dst0, *dst1 = nullptr;
-            float f0, f1 = 0.0f;                                   // fresh value of the lane's two float4
-            if (lane < 8u) {
-                src0 = reinterpret_cast<const float4 *>(F.z + rowpix) + lane;
-                dst0 = hz ? reinterpret_cast<float4 *>(hz + rowpix) + lane : nullptr;
-                f0 = Z_INIT;
-            } else {
-                src0 = reinterpret_cast<const float4 *>(F.color + rowpix * 3) + (lane - 8u);
-                dst0 = hc ? reinterpret_cast<float4 *>(hc + rowpix * 3) + (lane - 8u) : nullptr;
-                f0 = bg;
+        // a tile row is 56 float4: 8 of z, 24 of colour, 24 of normals; lane l takes float4 l and l + 32 of the row.
+        // Four rows are read before any is written, so that a few warps keep the link busy.
+        constexpr int RB = 4;
+        const float f0 = lane < 8u ? Z_INIT : background_color(F);   // fresh value of the lane's first float4 (z | colour)
+        for (int r0 = 0; r0 < th; r0 += RB) {
+            float4 a[RB], b[RB];
+#pragma unroll
+            for (int j = 0; j < RB; ++j) {
+                a[j] = b[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r0 + j < th) {
+                    const long long rowpix = (long long)(yl0 + r0 + j) * F.W + x0;
+                    a[j] = lane < 8u ? reinterpret_cast<const float4 *>(F.z + rowpix)[lane]
+                                     : reinterpret_cast<const float4 *>(F.color + rowpix * 3)[lane - 8u];
+                    if (lane < 24u) b[j] = reinterpret_cast<const float4 *>(F.normals + rowpix * 3)[lane];   // float4 32..55: the normals
+                }
             }
-            if (lane < 24u) {                                      // float4 32..55 of the row: the normals
-                src1 = reinterpret_cast<const float4 *>(F.normals + rowpix * 3) + lane;
-                dst1 = hn ? reinterpret_cast<float4 *>(hn + rowpix * 3) + lane : nullptr;
+#pragma unroll
+            for (int j = 0; j < RB; ++j) {
+                const int r = r0 + j;
+                if (r >= th) break;
+                const long long rowpix = (long long)(yl0 + r) * F.W + x0;
+                // bit comparison: -0.0 or NaN in a written pixel is not "fresh"
+                const bool differs = __float_as_uint(a[j].x) != __float_as_uint(f0) || __float_as_uint(a[j].y) != __float_as_uint(f0) ||
+                                     __float_as_uint(a[j].z) != __float_as_uint(f0) || __float_as_uint(a[j].w) != __float_as_uint(f0) ||
+                                     (__float_as_uint(b[j].x) | __float_as_uint(b[j].y) | __float_as_uint(b[j].z) | __float_as_uint(b[j].w)) != 0u;
+                const bool holds = __any_sync(0xFFFFFFFFu, differs);
+                if (holds) now |= 1u << r;
+                if (holds || ((before >> r) & 1u)) {
+                    if (lane < 8u) { if (hz) reinterpret_cast<float4 *>(hz + rowpix)[lane] = a[j]; }
+                    else if (hc) reinterpret_cast<float4 *>(hc + rowpix * 3)[lane - 8u] = a[j];
+                    if (lane < 24u && hn) reinterpret_cast<float4 *>(hn + rowpix * 3)[lane] = b[j];
+                    ++copied;
+                }
             }
-            const float4 a = *src0;
-            const float4 b = src1 ? *src1 : make_float4(0.f, 0.f, 0.f, 0.f);
-            // bit comparison: -0.0 or NaN in a written pixel is not "fresh"
-            const bool differs = __float_as_uint(a.x) != __float_as_uint(f0) || __float_as_uint(a.y) != __float_as_uint(f0) ||
-                                 __float_as_uint(a.z) != __float_as_uint(f0) || __float_as_uint(a.w) != __float_as_uint(f0) ||
-                                 (__float_as_uint(b.x) | __float_as_uint(b.y) | __float_as_uint(b.z) | __float_as_uint(b.w)) != __float_as_uint(f1);
-            const bool holds = __any_sync(0xFFFFFFFFu, differs);
-            if (holds) now |= 1u << r;
-            if (holds || ((before >> r) & 1u)) {
-                if (dst0) *dst0 = a;
-                if (dst1) *dst1 = b;
-                ++copied;
-            }
-        }
-        if (lane == 0u) {
-            if (now) atomicOr(&s_now, now);
-            if (copied) atomicAdd(&s_copied, copied);
         }
     } else {
         // ragged tiles (image edge, widths that are not a multiple of 4): whole tile, element by element
-        for (int i = threadIdx.x; i < th * tw; i += NT) {
+        for (int i = (int)lane; i < th * tw; i += 32) {
             const int r = i / tw, xx = i % tw;
             const long long p = (long long)(yl0 + r) * F.W + x0 + xx;
             if (hz) hz[p] = F.z[p];
             if (hc) { hc[p * 3] = F.color[p * 3]; hc[p * 3 + 1] = F.color[p * 3 + 1]; hc[p * 3 + 2] = F.color[p * 3 + 2]; }
             if (hn) { hn[p * 3] = F.normals[p * 3]; hn[p * 3 + 1] = F.normals[p * 3 + 1]; hn[p * 3 + 2] = F.normals[p * 3 + 2]; }
         }
-        if (threadIdx.x == 0) {
-            s_now = busy ? 0xFFFFFFFFu : 0u;
-            s_copied = (unsigned)th;
-        }
+        now = busy ? 0xFFFFFFFFu : 0u;
+        copied = (unsigned)th;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        shown_rows[t] = s_now;
-        if (s_copied) atomicAdd(rows_copied, (unsigned long long)s_copied);
+    if (lane == 0u) shown_rows[t] = now;
+    return copied;
+}
+
+// Sparse read-back (crb_render_host + CRB_DL_SPARSE).  The host copy of the three buffers persists between calls, every
+// call renders a FRESH frame, and a pixel row no fragment was written to holds fresh-filler values both before and after --
+// so only the 32-pixel tile rows that hold something now, or held something in the frame the host copy currently shows,
+// need to cross PCIe.  A SMALL grid does it (READBACK_CTAS): the copy is bound by the link, a few dozen warps saturate it,
+// and a larger grid only deepens the queue of posted writes that the next frame's upload and kernel launches (whose read
+// requests share the upstream link) have to wait behind -- measured on the T-Rex orbit, three frames in flight: 1 024
+// CTAs 5 170, 8 CTAs 5 450 frames/s (colour only: 8 200 -> 9 800).  CTA b looks at the tiles b, b + G, b + 2G, ... (busy
+// tiles cluster in space; the interleave spreads them over the CTAs), lists those that are busy now or have rows to take
+// back, and its warps take one listed tile each: a warp compares the tile's rows with the fresh pattern (z 1e6, colour /
+// normals 0) as it reads them, copies the rows that differ now or differed before straight into the mapped pinned host
+// arrays (16-byte stores, 128 / 384-byte runs), and keeps the tile's new row mask for the next call.  The host arrays end
+// up bit-identical to a full download (tests/test_gpu_parity.py::test_sparse_readback_*).  `rows_copied` counts tile
+// rows (32 pixels x 28 bytes when all three buffers are wanted).
+constexpr int READBACK_CTAS = 8;
+
+__global__ void __launch_bounds__(NT) k_readback(const Frame F, unsigned *shown_rows, float *hz, float *hc, float *hn,
+                                                  unsigned long long *rows_copied)
+{
+    __shared__ unsigned s_list[NT];
+    __shared__ unsigned s_n;
+    if (F.total[0] > (unsigned long long)F.pairCap) return;      // frame skipped: the host copy stays as it is
+    const unsigned G = gridDim.x, nT = (unsigned)F.nTiles, perCta = (nT + G - 1u) / G;
+    unsigned copied = 0u;
+    for (unsigned k0 = 0; k0 < perCta; k0 += NT) {
+        if (threadIdx.x == 0) s_n = 0u;
+        __syncthreads();
+        const unsigned k = k0 + threadIdx.x;
+        const unsigned long long t = (unsigned long long)k * G + blockIdx.x;
+        if (k < perCta && t < nT && (F.cursor[t] != 0u || shown_rows[t] != 0u)) s_list[atomicAdd(&s_n, 1u)] = (unsigned)t;
+        __syncthreads();
+        const unsigned n = s_n;
+        for (unsigned i = threadIdx.x >> 5; i < n; i += NT / 32) copied += readback_tile(F, s_list[i], shown_rows, hz, hc, hn);
+        __syncthreads();
     }
+    if ((threadIdx.x & 31) == 0 && copied) atomicAdd(rows_copied, (unsigned long long)copied);
 }
 
 // guro_illumination.py:20-27 over the whole buffer, in place
@@ -2064,6 +2088,20 @@ int crb_render(crb_filler *f, const float *v, const float *c, const float *n, in
     return (flags & CRB_PATH_ATOMIC) ? run_atomic(f, F, (cudaStream_t)stream) : run_tiled(f, F, (cudaStream_t)stream);
 }
 
+// Development aid (CRB_TRACE=1 in the environment): CUDA events at the stage boundaries of crb_render_host, dumped as
+// microseconds since the first one by crb_trace_dump -- the only timeline tool on a box without nsys.
+namespace {
+struct TraceRec { cudaEvent_t e[4]; const void *who; };
+std::vector<TraceRec> g_trace;
+const bool g_trace_on = getenv("CRB_TRACE") && atoi(getenv("CRB_TRACE"));
+inline void trace_mark(TraceRec *r, int k, cudaStream_t st)
+{
+    if (!r) return;
+    cudaEventCreate(&r->e[k]);
+    cudaEventRecord(r->e[k], st);
+}
+}  // namespace
+
 static int render_host_once(crb_filler *f, const float *v, const float *c, const float *n, int64_t T, unsigned flags,
                             unsigned download_mask, float *z_out, float *color_out, float *normals_out, void *stream)
 {
@@ -2074,13 +2112,30 @@ static int render_host_once(crb_filler *f, const float *v, const float *c, const
     CU(cudaSetDevice(f->device));
     { int jrc = join_pending(f, (cudaStream_t)stream); if (jrc) return jrc; }
     cudaStream_t st = (cudaStream_t)stream;
+    TraceRec trec{}, *tr = (g_trace_on && g_trace.size() < 4096) ? &trec : nullptr;
+    trec.who = f;
+    trace_mark(tr, 0, st);
     if (T > 0) {
-        CU(cudaMemcpyAsync(f->stage_v, v, (size_t)T * 36, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(f->stage_c, c, (size_t)T * 36, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(f->stage_n, n, (size_t)T * 36, cudaMemcpyHostToDevice, st));
+        // Equally spaced host arrays (the rows of one [3,T,3,3] block, the usual case) go up as ONE strided copy: under a
+        // pipeline the link is saturated by the read-back of earlier frames and every separate transfer queues behind it.
+        const ptrdiff_t sp = (const char *)c - (const char *)v, dp = (char *)f->stage_c - (char *)f->stage_v;
+        bool one = false;
+        if (sp >= (ptrdiff_t)((size_t)T * 36) && sp == (const char *)n - (const char *)c && sp < (1ll << 30) &&
+            dp == (char *)f->stage_n - (char *)f->stage_c && dp >= (ptrdiff_t)((size_t)T * 36) && dp < (1ll << 30)) {
+            // (rows that lie in separate host allocations are refused by the runtime: three copies then)
+            one = cudaMemcpy2DAsync(f->stage_v, (size_t)dp, v, (size_t)sp, (size_t)T * 36, 3, cudaMemcpyHostToDevice, st) == cudaSuccess;
+            if (!one) cudaGetLastError();
+        }
+        if (!one) {
+            CU(cudaMemcpyAsync(f->stage_v, v, (size_t)T * 36, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(f->stage_c, c, (size_t)T * 36, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(f->stage_n, n, (size_t)T * 36, cudaMemcpyHostToDevice, st));
+        }
     }
+    trace_mark(tr, 1, st);
     int rc = crb_render(f, f->stage_v, f->stage_c, f->stage_n, T, flags, stream);
     if (rc) return rc;
+    trace_mark(tr, 2, st);
     const bool sparse = (flags & CRB_DL_SPARSE) && (flags & CRB_CLEAR_FIRST) && !(flags & CRB_PATH_ATOMIC);
     float *hp[3] = {(download_mask & CRB_BUF_Z) ? z_out : nullptr, (download_mask & CRB_BUF_COLOR) ? color_out : nullptr,
                     (download_mask & CRB_BUF_NORMALS) ? normals_out : nullptr};
@@ -2116,14 +2171,35 @@ static int render_host_once(crb_filler *f, const float *v, const float *c, const
             CU(cudaMemsetAsync(f->tiles_copied, 0, 8, st));
         }
         if (F.nTiles > 0) {
-            k_readback<<<(unsigned)F.nTiles, NT, 0, st>>>(F, f->shown_busy, hp[0], hp[1], hp[2], f->tiles_copied);
+            static const int rbCtas = getenv("CRB_READBACK_CTAS") ? atoi(getenv("CRB_READBACK_CTAS")) : 0;   // experiments
+            const int want = rbCtas > 0 ? rbCtas : READBACK_CTAS;
+            k_readback<<<(unsigned)(F.nTiles < want ? F.nTiles : want), NT, 0, st>>>(F, f->shown_busy, hp[0], hp[1], hp[2], f->tiles_copied);
             if ((rc = launch_check(f, "k_readback"))) return rc;
         }
     } else {
         rc = crb_download(f, download_mask, z_out, color_out, normals_out, stream);
         if (rc) return rc;
     }
+    trace_mark(tr, 3, st);
+    if (tr) g_trace.push_back(trec);
     if (!(flags & CRB_NO_SYNC)) CU(cudaStreamSynchronize(st));
+    return CRB_OK;
+}
+
+int crb_trace_dump(const char *path)
+{
+    if (!path) return fail(CRB_ERR_INVALID, "NULL path");
+    FILE *fp = fopen(path, "w");
+    if (!fp) return fail(CRB_ERR_INVALID, "cannot open %s", path);
+    CU(cudaDeviceSynchronize());
+    for (size_t i = 0; i < g_trace.size(); ++i) {
+        float ms[4] = {0, 0, 0, 0};
+        for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&ms[k], g_trace[0].e[0], g_trace[i].e[k]);
+        fprintf(fp, "%zu %p %.1f %.1f %.1f %.1f\n", i, g_trace[i].who, ms[0] * 1e3, ms[1] * 1e3, ms[2] * 1e3, ms[3] * 1e3);
+    }
+    fclose(fp);
+    for (auto &r : g_trace) for (int k = 0; k < 4; ++k) cudaEventDestroy(r.e[k]);
+    g_trace.clear();
     return CRB_OK;
 }
 

@@ -208,6 +208,11 @@ int crb_profile_read(crb_filler *f, int *launches, double *total_ms);
  * All zeros unless the library was built with -DCRB_PHASE_TIMING (the product build is not). */
 int crb_phase_cycles(uint64_t out[16], int reset);
 
+/* Development aid: with CRB_TRACE=1 in the environment crb_render_host brackets its stages (upload, render, read-back) with
+ * CUDA events; this writes one line per call -- index, filler, four times in microseconds since the first call -- and
+ * forgets them.  Writes an empty file otherwise. */
+int crb_trace_dump(const char *path);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif
