@@ -863,9 +863,17 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
         // stays converged (a per-thread `for (r = tid; ...)` with early `continue`s lets lanes drift apart under
         // independent thread scheduling: measured 7.5 active lanes per instruction).
         if (DBG(F, FLAG_DBG_NOROWS)) totalRows = 0;
-        for (unsigned rb = threadIdx.x & ~31u; rb < totalRows; rb += NT) {
-            const unsigned r = rb + lane;
-            const bool active = r < totalRows;
+        // Tiles of a few large triangles (on average 16+ rows of the tile each: long spans, a full queue round per row)
+        // have too few rows to occupy eight warps 32 at a time: there a trip of fewer than NT rows is dealt out in equal
+        // shares (bunny 4096^2: k_raster 343 -> 304 us).  Tiles of many small triangles keep whole warps: the span pass
+        // costs a warp the same with 8 active lanes as with 32, and those tiles are bound by issue slots, not latency.
+        const bool deal = totalRows >= 16u * m;
+        for (unsigned tb = 0; tb < totalRows; tb += NT) {
+            const unsigned rem = totalRows - tb;
+            const unsigned share = (rem >= (unsigned)NT || !deal) ? 32u : (rem + NT / 32 - 1u) / (NT / 32);
+            if (tb + wid * share >= totalRows) break;          // no rows left for this warp (warp-uniform)
+            const unsigned r = tb + wid * share + lane;
+            const bool active = lane < share && r < totalRows;
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
             bool fdiv = false, span = false;
             float l02 = 0.f, l12 = 0.f, l22 = 0.f, A1 = 0.f, A2 = 0.f, A3 = 0.f;
