@@ -9,9 +9,9 @@ depth = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 frames = int(sys.argv[2]) if len(sys.argv) > 2 else 400
 m = load_indexed("trex")
 T = m._vertices_by_triangles.shape[0]
-views = VW.orbit_views(128, 0, 5)
+views = VW.orbit_views(128, 0, 7)
 host_in = []
-for k in range(5):
+for k in range(7):
     vk, nk = VW.transform_arrays_host(views[k], m._vertices_by_triangles, m._normals_by_triangles)
     st = torch.empty((3, T, 3, 3), dtype=torch.float32).pin_memory()
     st[0].copy_(torch.from_numpy(vk)); st[1].copy_(torch.from_numpy(m._colors_by_triangles)); st[2].copy_(torch.from_numpy(nk))
@@ -19,7 +19,7 @@ for k in range(5):
 for want in (("z", "color", "normals"), ("color",)):
     pipe = HostFramePipeline(1024, 1024, fov=45.0, depth=depth, sparse=True, want=want)
     for i in range(2 * depth):
-        pipe.submit(*host_in[i % 5])
+        pipe.submit(*host_in[i % 7])
     pipe.drain(); pipe.readback_tiles()
     wait = [0.0]
     orig = pipe.result
@@ -28,7 +28,7 @@ for want in (("z", "color", "normals"), ("color",)):
     pipe.result = timed_result
     t0 = time.perf_counter()
     for i in range(frames):
-        pipe.submit(*host_in[i % 5])
+        pipe.submit(*host_in[i % 7])
     t1 = time.perf_counter()
     pipe.drain()
     dt = time.perf_counter() - t0
