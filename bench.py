@@ -602,7 +602,12 @@ def run_extra_workload(args):
         dist.broadcast_object_list(box, src=0)
         bands = box[0]
         band = bands[rank]
-    f = AdvancedPixelBufferFiller(res, res, fov=FOV, device=local, band=band)
+    frame = None
+    if band is not None and args.gather == "peer":
+        frame = sharding.PeerFrame(res, res, dst=0, local_device=local)
+        f = AdvancedPixelBufferFiller(res, res, fov=FOV, device=local, band=band, out_ptrs=frame.band_pointers(band[0]))
+    else:
+        f = AdvancedPixelBufferFiller(res, res, fov=FOV, device=local, band=band)
     light = -np.asarray([0, 0, 1], dtype="float32")
     light = light / np.linalg.norm(light)
 
@@ -649,7 +654,11 @@ def run_extra_workload(args):
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-        if args.gather != "none":     # final NCCL all-gather of the row bands (north_star: "a final NCCL gather over NVLink")
+        if frame is not None:
+            full_z = frame.tensors()[0]
+            gather = {"ms": 0.0, "bytes": 28 * res * res, "what": "none needed: the bands were rendered into rank 0's frame over NVLink (PeerFrame)",
+                      "covered_pixels": int((full_z < 1e5).sum().item()) if rank == 0 else None}
+        elif args.gather != "none":     # final NCCL all-gather of the row bands (north_star: "a final NCCL gather over NVLink")
             z, c, n = f.device_buffers()
             for b in (z, c, n):                     # first use of the communicator / buffers is not what is being timed
                 sharding.gather_bands(b, res, bands=bands)
@@ -664,7 +673,7 @@ def run_extra_workload(args):
             gather = {"ms": float(gms.item()), "bytes": 28 * res * res, "what": "all_gather of z+colour+normal row bands",
                       "covered_pixels": int((full[0] < 1e5).sum().item())}
     z = f.device_buffers()[0]
-    cov = torch.tensor([int((z < 1e5).sum().item())], dtype=torch.int64, device=dev)
+    cov = torch.tensor([int((z < 1e5).sum().item())], dtype=torch.int64, device=dev)   # (PeerFrame: read over NVLink)
     if world > 1:
         dist.all_reduce(cov)
     fps = args.steps / (ms / 1000.0)
@@ -689,6 +698,9 @@ def run_extra_workload(args):
             "gather": gather, "checks": {"covered_pixels": int(cov.item())},
         }
         emit(line)
+    if frame is not None:
+        del f
+        frame.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -728,8 +740,10 @@ def main():
     ap.add_argument("--bands", default="balanced", choices=["balanced", "uniform"],
                     help="sphere_8192_bands only: rows per rank equal (uniform) or cut where the estimated cost balances")
     ap.add_argument("--res", type=int, default=0, help="sphere_8192_bands only: override the resolution (scaled sphere)")
-    ap.add_argument("--gather", default="none", choices=["none", "bands", "u8", "z", "all"],
-                    help="also time the final NCCL gather (reported beside, never inside, the headline value)")
+    ap.add_argument("--gather", default="none", choices=["none", "bands", "u8", "z", "all", "peer"],
+                    help="also time the final NCCL gather (reported beside, never inside, the headline value); "
+                         "peer (sphere_8192_bands only): no gather at all -- every rank's filler renders its band straight into "
+                         "rank 0's frame over NVLink (sharding.PeerFrame), and the value is frames/s complete on rank 0")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -1879,6 +1879,52 @@ int crb_device_count(int *count)
     return CRB_OK;
 }
 
+// ---- frame memory shared between the ranks of one node (band-sharded fillers write their rows straight into the
+// destination rank's frame over NVLink; the "gather" is the rasterizer's own stores) --------------------------------
+static_assert(sizeof(cudaIpcMemHandle_t) == CRB_SHARED_HANDLE_BYTES, "handle size");
+
+int crb_shared_alloc(int device, size_t bytes, void **ptr, unsigned char handle[CRB_SHARED_HANDLE_BYTES])
+{
+    if (!ptr || !handle || bytes == 0) return fail(CRB_ERR_INVALID, "NULL argument or zero size");
+    CU(cudaSetDevice(device));
+    CU(cudaMalloc(ptr, bytes));
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, *ptr);
+    if (e != cudaSuccess) {
+        cudaFree(*ptr);
+        *ptr = nullptr;
+        return fail(CRB_ERR_CUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle, &h, sizeof(h));
+    return CRB_OK;
+}
+
+int crb_shared_open(int device, const unsigned char handle[CRB_SHARED_HANDLE_BYTES], void **ptr)
+{
+    if (!ptr || !handle) return fail(CRB_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    CU(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return CRB_OK;
+}
+
+int crb_shared_close(int device, void *ptr)
+{
+    if (!ptr) return CRB_OK;
+    CU(cudaSetDevice(device));
+    CU(cudaIpcCloseMemHandle(ptr));
+    return CRB_OK;
+}
+
+int crb_shared_free(int device, void *ptr)
+{
+    if (!ptr) return CRB_OK;
+    CU(cudaSetDevice(device));
+    CU(cudaFree(ptr));
+    return CRB_OK;
+}
+
 int crb_projection(int h, int w, float fov, float z_near, float z_far, float proj[16])
 {
     if (!proj) return fail(CRB_ERR_INVALID, "proj is NULL");

@@ -39,14 +39,33 @@ def _check_tri_array(a, name):
     return a
 
 
+class _DevicePointer:
+    """CUDA array interface over a raw device address (memory owned elsewhere, e.g. a frame mapped from another rank)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def wrap_device_pointer(torch, ptr, shape, device):
+    """float32 torch tensor of `shape` over the device address `ptr` (no copy, no ownership)."""
+    if any(int(x) == 0 for x in shape):
+        return torch.empty(tuple(shape), dtype=torch.float32, device=device)
+    # no device argument: torch takes the device that owns the memory from the pointer itself (for a frame mapped from
+    # another rank that is the peer GPU; naming the local device here would make as_tensor copy instead of alias)
+    return torch.as_tensor(_DevicePointer(ptr, shape))
+
+
 class AdvancedPixelBufferFiller:
     """B200 implementation of the Version C filler.  `n_threads` is accepted and ignored.
 
-    Extra keyword (not in the reference): `device` -- CUDA device index (default: torch's current device),
-    `band=(row0,row1)` -- own only those rows of the h x w image (screen-band sharding).
+    Extra keywords (not in the reference): `device` -- CUDA device index (default: torch's current device),
+    `band=(row0,row1)` -- own only those rows of the h x w image (screen-band sharding), `out_ptrs=(z, color, normals)` --
+    raw device addresses of existing [rows,w], [rows,w,3], [rows,w,3] float32 buffers to render into instead of buffers of
+    its own (e.g. this band's rows inside another rank's frame, sharding.PeerFrame); their content is taken as it is.
     """
 
-    def __init__(self, h, w, fov=90.0, z_near=0.1, z_far=1000.0, n_threads=1, device=None, band=None):
+    def __init__(self, h, w, fov=90.0, z_near=0.1, z_far=1000.0, n_threads=1, device=None, band=None, out_ptrs=None):
         torch = _require_cuda()
         self._torch = torch
         self._L = _lib.load_library()
@@ -64,12 +83,18 @@ class AdvancedPixelBufferFiller:
         rows = self.row1 - self.row0
         with torch.cuda.device(self._dev):
             # pyx:65-67: normals 0, colour 0, z = 1e6
-            self._z = torch.empty((rows, self.w), dtype=torch.float32, device=self._dev)
-            self._color = torch.empty((rows, self.w, 3), dtype=torch.float32, device=self._dev)
-            self._normals = torch.empty((rows, self.w, 3), dtype=torch.float32, device=self._dev)
+            if out_ptrs is None:
+                self._z = torch.empty((rows, self.w), dtype=torch.float32, device=self._dev)
+                self._color = torch.empty((rows, self.w, 3), dtype=torch.float32, device=self._dev)
+                self._normals = torch.empty((rows, self.w, 3), dtype=torch.float32, device=self._dev)
+            else:
+                self._z = wrap_device_pointer(torch, out_ptrs[0], (rows, self.w), self._dev)
+                self._color = wrap_device_pointer(torch, out_ptrs[1], (rows, self.w, 3), self._dev)
+                self._normals = wrap_device_pointer(torch, out_ptrs[2], (rows, self.w, 3), self._dev)
             check(self._L.crb_bind_buffers(self._handle, self._z.data_ptr(), self._color.data_ptr(),
                                            self._normals.data_ptr()))
-            check(self._L.crb_init_buffers(self._handle, self._stream()))
+            if out_ptrs is None:
+                check(self._L.crb_init_buffers(self._handle, self._stream()))
         self._ws = None
         self._ws_T = -1
         self._ws_views = 1

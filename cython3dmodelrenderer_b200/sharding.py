@@ -7,7 +7,9 @@ The path shards only where it shards naturally -- there is no exchange step insi
     triangles, clamps every bounding box to its band; per-pixel arithmetic does not depend on the band, so the
     concatenated bands equal the single-GPU frame bit for bit.  Row bands are contiguous in row-major [H,W,*] buffers,
     so the gather is a plain concatenation along dim 0.
-Nothing here touches CUDA directly; the gathers work on whatever device the tensors live on (nccl: cuda, gloo: cpu).
+The gathers work on whatever device the tensors live on (nccl: cuda, gloo: cpu).  PeerFrame is the gather-free variant for
+one node: the destination rank's frame is mapped into every rank (CUDA IPC through the C ABI's crb_shared_*), each rank's
+filler renders its band straight into it over NVLink, and the "gather" is the rasterizer's own stores.
 """
 import torch
 import torch.distributed as dist
@@ -150,3 +152,68 @@ def gather_bands(local, h, dst=None, align=TILE_ROWS, bands=None):
             return None
         out = torch.cat(parts, dim=0)
     return torch.cat([out[r * rmax:r * rmax + (b - a)] for r, (a, b) in enumerate(rows)], dim=0)
+
+
+class PeerFrame:
+    """One h x w frame (z [h,w], colour [h,w,3], normals [h,w,3], float32) in the memory of rank `dst`, mapped into every
+    rank of the node.  Rank r builds its filler with `AdvancedPixelBufferFiller(h, w, ..., band=(row0,row1),
+    out_ptrs=frame.band_pointers(row0))` and renders; after `frame.complete()` (stream synchronisation + barrier) the
+    tensors of `frame.tensors()` on rank `dst` hold the whole frame -- bit-identical to a single-GPU render, with no
+    collective and no staging copy.  Collective constructor: every rank of the process group must call it.
+    `local_device`: CUDA device of this rank; ranks may share a device (CPU-side tests of the plumbing use gloo)."""
+
+    def __init__(self, h, w, dst=0, local_device=None):
+        import ctypes
+        from . import _lib
+        self._L = _lib.load_library()
+        self._check = _lib.check
+        self.h, self.w, self.dst = int(h), int(w), int(dst)
+        self.world = _world()
+        self.rank = dist.get_rank() if self.world > 1 else 0
+        self.device = torch.cuda.current_device() if local_device is None else int(local_device)
+        pix = self.h * self.w
+        self._off_c = (4 * pix + 255) // 256 * 256
+        self._off_n = self._off_c + (12 * pix + 255) // 256 * 256
+        self.nbytes = self._off_n + 12 * pix
+        self.owner = self.rank == self.dst
+        ptr = ctypes.c_void_p()
+        box = [None]
+        if self.owner:
+            handle = ctypes.create_string_buffer(64)
+            self._check(self._L.crb_shared_alloc(self.device, max(self.nbytes, 256), ctypes.byref(ptr), handle))
+            box = [handle.raw]
+        if self.world > 1:
+            dist.broadcast_object_list(box, src=self.dst)
+        if not self.owner:
+            self._check(self._L.crb_shared_open(self.device, ctypes.create_string_buffer(box[0], 64), ctypes.byref(ptr)))
+        self.base = int(ptr.value)
+
+    def band_pointers(self, row0):
+        """Device addresses of row `row0` in the three arrays: what a band filler takes as `out_ptrs`."""
+        r = int(row0) * self.w
+        return self.base + 4 * r, self.base + self._off_c + 12 * r, self.base + self._off_n + 12 * r
+
+    def tensors(self):
+        """(z, colour, normals) torch views of the whole frame (any rank; on other ranks than `dst` they read over NVLink)."""
+        from .pixel_buffer_filler import wrap_device_pointer
+        dev = torch.device("cuda", self.device)
+        return (wrap_device_pointer(torch, self.base, (self.h, self.w), dev),
+                wrap_device_pointer(torch, self.base + self._off_c, (self.h, self.w, 3), dev),
+                wrap_device_pointer(torch, self.base + self._off_n, (self.h, self.w, 3), dev))
+
+    def complete(self):
+        """Every rank's stores have landed in the frame when this returns on all ranks."""
+        torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            dist.barrier()
+
+    def close(self):
+        """Collective: unmaps on the other ranks first, then the owner frees."""
+        if self.base:
+            if not self.owner:
+                self._check(self._L.crb_shared_close(self.device, self.base))
+            if self.world > 1:
+                dist.barrier()
+            if self.owner:
+                self._check(self._L.crb_shared_free(self.device, self.base))
+            self.base = 0

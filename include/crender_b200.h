@@ -75,6 +75,20 @@ int crb_version(void);
 const char *crb_last_error(void);
 int crb_device_count(int *count);
 
+/* ---- frame memory shared between the ranks (processes) of one node -------------------------------------------------
+ * No reference counterpart (the reference is one process).  SURVEY 8e / BASELINE north_star: screen-row bands over N GPUs
+ * "with a final gather over NVLink".  Here the gather is the rasterizer's own stores: the destination rank allocates the
+ * whole frame (crb_shared_alloc: cudaMalloc + CUDA IPC handle), sends the 64-byte handle to the other ranks through
+ * whatever channel it has (torch.distributed in the Python host), they map it (crb_shared_open: peer access over
+ * NVLink / NVSwitch is enabled by the mapping) and bind the rows of their band inside it as their output buffers
+ * (crb_bind_buffers with pointers into the mapped frame).  After a stream synchronisation on every rank and a barrier the
+ * destination rank holds the complete frame.  crb_shared_close unmaps (other ranks), crb_shared_free releases (owner). */
+#define CRB_SHARED_HANDLE_BYTES 64
+int crb_shared_alloc(int device, size_t bytes, void **ptr, unsigned char handle[CRB_SHARED_HANDLE_BYTES]);
+int crb_shared_open(int device, const unsigned char handle[CRB_SHARED_HANDLE_BYTES], void **ptr);
+int crb_shared_close(int device, void *ptr);
+int crb_shared_free(int device, void *ptr);
+
 /* ---- constructor pieces: pyx:39-77 (__cinit__) and pyx:83-90 (_init_projection_matrix) ------------------- */
 
 /* Host only.  proj = row-major 4x4 float32 identical to the reference's proj_mat:

@@ -1,0 +1,65 @@
+"""PeerFrame: band-sharded fillers of several PROCESSES render straight into the frame of rank 0, mapped into
+every rank through CUDA IPC (crb_shared_*).  The frame on rank 0 must equal the oracle's single frame bit for bit.  Ranks are
+placed on cuda:(rank % device_count), so the test runs on a one-GPU box as well (the mapping then crosses processes, not
+GPUs); torch.distributed (gloo) only carries the 64-byte handle and the barriers."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import bits_equal, load_indexed, random_scene
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir, balanced):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from cython3dmodelrenderer_b200 import AdvancedPixelBufferFiller, sharding
+        dev = rank % torch.cuda.device_count()
+        torch.cuda.set_device(dev)
+        h, w = 320, 256
+        m, m2 = load_indexed("bunny"), random_scene(3, T=3000)
+        if balanced:
+            bands = sharding.balanced_bands([1.0, 1.0, 6.0, 6.0, 2.0, 1.0, 1.0, 1.0, 1.0, 1.0], world, h)
+        else:
+            bands = [sharding.band_shard(h, r, world) for r in range(world)]
+        frame = sharding.PeerFrame(h, w, dst=0, local_device=dev)
+        r0, r1 = bands[rank]
+        f = AdvancedPixelBufferFiller(h, w, fov=45.0, device=dev, band=(r0, r1), out_ptrs=frame.band_pointers(r0))
+        for rep in range(2):                       # a fresh frame (fused clear through TMA boxes where the layout allows) ...
+            f.clear()
+            f.render_model(m)
+        f.render_model(m2)                         # ... and a second model composited into it (plain stores, z read back)
+        frame.complete()
+        if rank == 0:
+            z, c, n = (t.cpu().numpy() for t in frame.tensors())
+            np.savez(os.path.join(out_dir, "frame.npz"), z=z, c=c, n=n)
+        del f
+        frame.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,balanced", [(2, False), (3, True)])
+def test_band_fillers_render_into_rank0_frame(world, balanced, tmp_path):
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), balanced), nprocs=world, join=True)
+    from oracle import oracle as O
+    o = O.OracleFiller(320, 256, fov=45.0)
+    o.render_model(load_indexed("bunny"))
+    o.render_model(random_scene(3, T=3000))
+    got = np.load(tmp_path / "frame.npz")
+    assert bits_equal(got["z"], o.get_z_buffer())
+    assert bits_equal(got["c"], o.get_color_buffer())
+    assert bits_equal(got["n"], o.get_normals_buffer())
