@@ -448,7 +448,10 @@ __device__ __forceinline__ void setup_chunk(const Frame &F, const int view, cons
         for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(cnt_view + ty * F.tilesX + tx, 1u);
 }
 
-__global__ void __launch_bounds__(NT) k_setup(const Frame F)
+#ifndef CRB_SETUP_MIN_CTAS
+#define CRB_SETUP_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(NT, CRB_SETUP_MIN_CTAS) k_setup(const Frame F)
 {
     __shared__ __align__(16) float sv[NT * 9];
     __shared__ __align__(16) float sn[NT * 9];
@@ -656,7 +659,10 @@ __device__ __forceinline__ void fill_chunk(const Frame &F, const int view, const
         }
 }
 
-__global__ void __launch_bounds__(NT) k_fill(const Frame F)
+#ifndef CRB_FILL_MIN_CTAS
+#define CRB_FILL_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(NT, CRB_FILL_MIN_CTAS) k_fill(const Frame F)
 {
     if (*F.total > (unsigned long long)F.pairCap) return;  // overflow: frame is skipped, host is told via crb_status
     const long long chunksPerView = (F.T + NT - 1) / NT;
