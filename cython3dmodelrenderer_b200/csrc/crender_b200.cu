@@ -312,7 +312,17 @@ __device__ __forceinline__ unsigned char to_u8(float c) { return (unsigned char)
 __device__ __forceinline__ void stage_floats(const float *__restrict__ g, long long first, long long count, float *s)
 {
     const float *src = g + first;
-    if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+    if (count == (long long)NT * 9 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+        // a full chunk (the usual case): 576 float4, every thread's two or three loads in flight together, 32-bit indices
+        const float4 *s4 = reinterpret_cast<const float4 *>(src);
+        const unsigned t = threadIdx.x;
+        const float4 a = __ldg(s4 + t), b = __ldg(s4 + t + NT);
+        float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t < NT * 9 / 4 - 2 * NT) c = __ldg(s4 + t + 2 * NT);
+        reinterpret_cast<float4 *>(s)[t] = a;
+        reinterpret_cast<float4 *>(s)[t + NT] = b;
+        if (t < NT * 9 / 4 - 2 * NT) reinterpret_cast<float4 *>(s)[t + 2 * NT] = c;
+    } else if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
         const long long n4 = count >> 2;
         const float4 *s4 = reinterpret_cast<const float4 *>(src);
         for (long long i = threadIdx.x; i < n4; i += NT) reinterpret_cast<float4 *>(s)[i] = __ldg(s4 + i);
@@ -449,7 +459,7 @@ __device__ __forceinline__ void setup_chunk(const Frame &F, const int view, cons
 }
 
 #ifndef CRB_SETUP_MIN_CTAS
-#define CRB_SETUP_MIN_CTAS 1
+#define CRB_SETUP_MIN_CTAS 3
 #endif
 __global__ void __launch_bounds__(NT, CRB_SETUP_MIN_CTAS) k_setup(const Frame F)
 {
@@ -631,13 +641,15 @@ __global__ void __launch_bounds__(NT) k_alloc(const Frame F)
 }
 
 // K2c: scatter the prepared setups into the tile lists (sign-normalised form the row loop wants).
-__device__ __forceinline__ void fill_chunk(const Frame &F, const int view, const long long chunk, const long long chunksPerView)
+__device__ __forceinline__ void fill_chunk(const Frame &F, const int view, const long long chunk, const long long chunksPerView, const bool skip)
 {
-    if (!F.alive[(long long)view * chunksPerView + chunk]) return;   // k_setup found nothing to draw in this chunk
     const long long tri = chunk * NT + threadIdx.x;
-    if (tri >= F.T) return;
     const long long ridx = (long long)view * F.T + tri;
-    const float4 E = F.recE[ridx];
+    // speculative: the rectangle flies with the flags that decide whether it is looked at (recE is allocated for every
+    // (view, triangle); in a chunk k_setup left dead it holds stale values, which are then not used)
+    const float4 E = tri < F.T ? F.recE[ridx] : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (skip || !F.alive[(long long)view * chunksPerView + chunk]) return;   // frame skipped / nothing to draw in this chunk
+    if (tri >= F.T) return;
     const unsigned bx = __float_as_uint(E.x), by = __float_as_uint(E.y);
     if ((bx >> 16) == 0) return;  // not drawn (x_right >= 1 for every drawn triangle)
     const float4 *R = F.shrec + ridx * SREC;
@@ -660,18 +672,19 @@ __device__ __forceinline__ void fill_chunk(const Frame &F, const int view, const
 }
 
 #ifndef CRB_FILL_MIN_CTAS
-#define CRB_FILL_MIN_CTAS 1
+#define CRB_FILL_MIN_CTAS 4
 #endif
 __global__ void __launch_bounds__(NT, CRB_FILL_MIN_CTAS) k_fill(const Frame F)
 {
-    if (*F.total > (unsigned long long)F.pairCap) return;  // overflow: frame is skipped, host is told via crb_status
     const long long chunksPerView = (F.T + NT - 1) / NT;
     if (!F.chunks) {
-        fill_chunk(F, blockIdx.y, blockIdx.x, chunksPerView);   // same CTA -> triangle mapping as k_setup
+        // overflow: frame is skipped (host is told via crb_status); the test rides with the first loads instead of before them
+        fill_chunk(F, blockIdx.y, blockIdx.x, chunksPerView, *F.total > (unsigned long long)F.pairCap);   // same CTA -> triangle mapping as k_setup
         return;
     }
+    if (*F.total > (unsigned long long)F.pairCap) return;
     const unsigned n = F.chunks[0];
-    for (unsigned i = blockIdx.x; i < n; i += gridDim.x) fill_chunk(F, 0, F.chunks[1 + i], chunksPerView);
+    for (unsigned i = blockIdx.x; i < n; i += gridDim.x) fill_chunk(F, 0, F.chunks[1 + i], chunksPerView, false);
 }
 
 // ------------------------------------------------------------------------------------------------------------
