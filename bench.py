@@ -451,13 +451,32 @@ def run_gpu_arm(args):
         tiles = pipe.readback_tiles() if sparse else None
         return dt, cov, pipe.launch_count - l0, tiles
 
+    # run.py's product: the flipped uint8 image (N3), 3 bytes per pixel over PCIe, nothing else produced
+    from cython3dmodelrenderer_b200.pipeline import HostImagePipeline
+
+    def run_image_pipeline():
+        pipe = HostImagePipeline(RES, RES, fov=FOV, depth=args.e2e_depth, device=local)
+        for i in range(2 * args.e2e_depth):
+            pipe.submit(host_in[i % NIN])
+        pipe.drain()
+        barrier()
+        t0 = time.perf_counter()
+        last = 0
+        for i in range(e2e_frames):
+            last = pipe.submit(host_in[i % NIN])
+        pipe.drain()
+        dt = time.perf_counter() - t0
+        img = pipe.result(last)
+        return dt, int((img.sum(axis=-1) > 0).sum())
+
+    img_s, img_cov = run_image_pipeline()
     dense_s, dense_cov, dense_launches, _ = run_pipeline(False)
     e2e_s, e2e_cov, e2e_launches, tiles_copied = run_pipeline(True)
     col_s, col_cov, _, col_tiles = run_pipeline(True, want=("color",))
     if world > 1:
-        t = torch.tensor([e2e_s, sync_s, dense_s, col_s], dtype=torch.float64, device=dev)
+        t = torch.tensor([e2e_s, sync_s, dense_s, col_s, img_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s, sync_s, dense_s, col_s = (float(x) for x in t.tolist())
+        e2e_s, sync_s, dense_s, col_s, img_s = (float(x) for x in t.tolist())
     d2h_sparse = tiles_copied * 32 * 32 * 28 / e2e_frames
     e2e = {"value": world * e2e_frames / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": 108 * T,
            "d2h_bytes_per_step": d2h_sparse, "frames_timed": e2e_frames, "pipeline_depth": args.e2e_depth,
@@ -468,6 +487,9 @@ def run_gpu_arm(args):
                   "clock over all frames incl. the final drain",
            "dense_value": world * e2e_frames / dense_s, "dense_d2h_bytes_per_step": 28 * RES * RES,
            "dense_api": "same pipeline with sparse=False: cudaMemcpy of all three buffers (29.4 MB) every frame",
+           "image_u8_value": world * e2e_frames / img_s, "image_u8_d2h_bytes_per_step": 3 * RES * RES,
+           "image_u8_api": "HostImagePipeline.submit: pinned [3,T,3,3] block in, run.py:26's flipped uint8 image (3 B/pixel) in pinned "
+                           "host memory out; the rasterizer writes the uint8 image itself, no float32 buffer is produced",
            "color_only_value": world * e2e_frames / col_s, "color_only_d2h_bytes_per_step": col_tiles * 32 * 32 * 12 / e2e_frames,
            "color_only_api": "the same pipeline fetching only the colour buffer (want=('color',)): what Renderer.render returns "
                              "and run.py consumes (renderer.py:49); z and normals stay on the device, as they do for a drop-in "
@@ -555,7 +577,7 @@ def run_gpu_arm(args):
                        "the 1.5 MB mesh is re-read per view by design" % (V * 28 * RES * RES / 1e9)},
             "gtri_per_s": fps * T / 1e9, "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cpu, "single_frame": single, "drop_in": drop_in, "gather": gather,
-            "checks": {"covered_pixels_view0": covered0, "e2e_covered_pixels": e2e_cov, "e2e_dense_covered_pixels": dense_cov, "e2e_sync_covered_pixels": sync_cov, "pairs_last_launch": int(need.value),
+            "checks": {"covered_pixels_view0": covered0, "e2e_covered_pixels": e2e_cov, "e2e_image_u8_lit_pixels": img_cov, "e2e_dense_covered_pixels": dense_cov, "e2e_sync_covered_pixels": sync_cov, "pairs_last_launch": int(need.value),
                        "pair_capacity": int(cap.value)},
         }
         emit(line)

@@ -9,7 +9,7 @@ Everything else of the reference (Renderer, illumination, run.py) is used unchan
 """
 from ._lib import CrenderError, build, load_library, projection_matrix  # noqa: F401
 from .pixel_buffer_filler import AdvancedPixelBufferFiller  # noqa: F401
-from .pipeline import HostFramePipeline  # noqa: F401
+from .pipeline import HostFramePipeline, HostImagePipeline  # noqa: F401
 from .model import Model  # noqa: F401   (drop-in for crender.cy.data_structures.Model)
 
-__all__ = ["AdvancedPixelBufferFiller", "HostFramePipeline", "Model", "CrenderError", "build", "load_library", "projection_matrix"]
+__all__ = ["AdvancedPixelBufferFiller", "HostFramePipeline", "HostImagePipeline", "Model", "CrenderError", "build", "load_library", "projection_matrix"]

@@ -63,6 +63,8 @@ SIGNATURES = {
     "crb_selftest_fdiv": (_i, [_i, ctypes.c_uint64, _u, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint32)]),
     "crb_phase_cycles": (_i, [ctypes.POINTER(ctypes.c_uint64), _i]),
     "crb_trace_dump": (_i, [ctypes.c_char_p]),
+    "crb_status_async": (_i, [_vp, _vp, _vp]),
+    "crb_render_image_host": (_i, [_vp, _vp, _vp, _vp, _i64, _u, _fp, _vp, _vp, _vp, _vp]),
     "crb_shared_alloc": (_i, [_i, _sz, ctypes.POINTER(_vp), ctypes.c_char_p]),
     "crb_shared_open": (_i, [_i, ctypes.c_char_p, ctypes.POINTER(_vp)]),
     "crb_shared_close": (_i, [_i, _vp]),

@@ -2163,6 +2163,29 @@ int crb_render(crb_filler *f, const float *v, const float *c, const float *n, in
     return (flags & CRB_PATH_ATOMIC) ? run_atomic(f, F, (cudaStream_t)stream) : run_tiled(f, F, (cudaStream_t)stream);
 }
 
+// H2D of the three [T,3,3] arrays into the filler's staging area.
+static int upload_inputs(crb_filler *f, const float *v, const float *c, const float *n, int64_t T, cudaStream_t st)
+{
+    if (T > 0) {
+        // Equally spaced host arrays (the rows of one [3,T,3,3] block, the usual case) go up as ONE strided copy: under a
+        // pipeline the link is saturated by the read-back of earlier frames and every separate transfer queues behind it.
+        const ptrdiff_t sp = (const char *)c - (const char *)v, dp = (char *)f->stage_c - (char *)f->stage_v;
+        bool one = false;
+        if (sp >= (ptrdiff_t)((size_t)T * 36) && sp == (const char *)n - (const char *)c && sp < (1ll << 30) &&
+            dp == (char *)f->stage_n - (char *)f->stage_c && dp >= (ptrdiff_t)((size_t)T * 36) && dp < (1ll << 30)) {
+            // (rows that lie in separate host allocations are refused by the runtime: three copies then)
+            one = cudaMemcpy2DAsync(f->stage_v, (size_t)dp, v, (size_t)sp, (size_t)T * 36, 3, cudaMemcpyHostToDevice, st) == cudaSuccess;
+            if (!one) cudaGetLastError();
+        }
+        if (!one) {
+            CU(cudaMemcpyAsync(f->stage_v, v, (size_t)T * 36, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(f->stage_c, c, (size_t)T * 36, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(f->stage_n, n, (size_t)T * 36, cudaMemcpyHostToDevice, st));
+        }
+    }
+    return CRB_OK;
+}
+
 // Development aid (CRB_TRACE=1 in the environment): CUDA events at the stage boundaries of crb_render_host, dumped as
 // microseconds since the first one by crb_trace_dump -- the only timeline tool on a box without nsys.
 namespace {
@@ -2190,23 +2213,7 @@ static int render_host_once(crb_filler *f, const float *v, const float *c, const
     TraceRec trec{}, *tr = (g_trace_on && g_trace.size() < 4096) ? &trec : nullptr;
     trec.who = f;
     trace_mark(tr, 0, st);
-    if (T > 0) {
-        // Equally spaced host arrays (the rows of one [3,T,3,3] block, the usual case) go up as ONE strided copy: under a
-        // pipeline the link is saturated by the read-back of earlier frames and every separate transfer queues behind it.
-        const ptrdiff_t sp = (const char *)c - (const char *)v, dp = (char *)f->stage_c - (char *)f->stage_v;
-        bool one = false;
-        if (sp >= (ptrdiff_t)((size_t)T * 36) && sp == (const char *)n - (const char *)c && sp < (1ll << 30) &&
-            dp == (char *)f->stage_n - (char *)f->stage_c && dp >= (ptrdiff_t)((size_t)T * 36) && dp < (1ll << 30)) {
-            // (rows that lie in separate host allocations are refused by the runtime: three copies then)
-            one = cudaMemcpy2DAsync(f->stage_v, (size_t)dp, v, (size_t)sp, (size_t)T * 36, 3, cudaMemcpyHostToDevice, st) == cudaSuccess;
-            if (!one) cudaGetLastError();
-        }
-        if (!one) {
-            CU(cudaMemcpyAsync(f->stage_v, v, (size_t)T * 36, cudaMemcpyHostToDevice, st));
-            CU(cudaMemcpyAsync(f->stage_c, c, (size_t)T * 36, cudaMemcpyHostToDevice, st));
-            CU(cudaMemcpyAsync(f->stage_n, n, (size_t)T * 36, cudaMemcpyHostToDevice, st));
-        }
-    }
+    { int urc = upload_inputs(f, v, c, n, T, st); if (urc) return urc; }
     trace_mark(tr, 1, st);
     int rc = crb_render(f, f->stage_v, f->stage_c, f->stage_n, T, flags, stream);
     if (rc) return rc;
@@ -2303,7 +2310,7 @@ int crb_render_views(crb_filler *f, const float *v, const float *c, const float 
     if (check_filler(f)) return CRB_ERR_INVALID;
     if (T < 0 || n_views < 0) return fail(CRB_ERR_INVALID, "negative size");
     if (T > 0 && (!v || !c || !n)) return fail(CRB_ERR_INVALID, "NULL triangle array");
-    if (n_views > 0 && !views) return fail(CRB_ERR_INVALID, "views is NULL");
+    if (n_views > 0 && !views && n_views != 1) return fail(CRB_ERR_INVALID, "views is NULL (allowed for one untransformed view only)");
     if (!f->ws) return fail(CRB_ERR_STATE, "workspace not bound");
     if (T > f->maxT) return fail(CRB_ERR_STATE, "T=%lld exceeds the workspace's max_triangles=%lld", (long long)T, f->maxT);
     if (flags & CRB_PATH_ATOMIC) return fail(CRB_ERR_INVALID, "CRB_PATH_ATOMIC supports single-view renders only");
@@ -2337,7 +2344,7 @@ int crb_render_views(crb_filler *f, const float *v, const float *c, const float 
         F.T = T; F.nViews = (n_views - v0 < f->maxViews) ? n_views - v0 : f->maxViews;
         F.flags = (flags & CRB_GURO) | CRB_CLEAR_FIRST;
         F.v = v; F.c = c; F.n = n;
-        F.views = views + (size_t)v0 * 16;
+        F.views = views ? views + (size_t)v0 * 16 : nullptr;
         F.z = z_out ? z_out + (size_t)v0 * slab : nullptr;
         F.color = color_out ? color_out + (size_t)v0 * slab * 3 : nullptr;
         F.normals = normals_out ? normals_out + (size_t)v0 * slab * 3 : nullptr;
@@ -2370,6 +2377,33 @@ int crb_join(crb_filler *f, void *stream)
     if (check_filler(f)) return CRB_ERR_INVALID;
     CU(cudaSetDevice(f->device));
     return join_pending(f, (cudaStream_t)stream);
+}
+
+int crb_render_image_host(crb_filler *f, const float *v, const float *c, const float *n, int64_t T, unsigned flags,
+                          const float light[3], uint8_t *image_dev, uint8_t *image_host, uint64_t status_pinned[4], void *stream)
+{
+    if (check_filler(f)) return CRB_ERR_INVALID;
+    if (!f->ws) return fail(CRB_ERR_STATE, "workspace not bound");
+    if (T < 0 || T > f->maxT) return fail(CRB_ERR_STATE, "T=%lld outside the workspace's [0,%lld]", (long long)T, f->maxT);
+    if (T > 0 && (!v || !c || !n)) return fail(CRB_ERR_INVALID, "NULL triangle array");
+    if (!image_dev || !image_host) return fail(CRB_ERR_INVALID, "NULL image buffer");
+    CU(cudaSetDevice(f->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    { int jrc = join_pending(f, st); if (jrc) return jrc; }
+    int rc = upload_inputs(f, v, c, n, T, st);
+    if (rc) return rc;
+    // one untransformed view, no float32 output: the rasterizer writes the flipped uint8 image itself
+    rc = crb_render_views(f, f->stage_v, f->stage_c, f->stage_n, T, nullptr, 1, nullptr, nullptr, nullptr, image_dev,
+                          flags & CRB_GURO, light, stream);
+    if (rc) return rc;
+    const size_t bytes = (size_t)(f->row1 - f->row0) * f->w * 3;
+    if (bytes) CU(cudaMemcpyAsync(image_host, image_dev, bytes, cudaMemcpyDeviceToHost, st));
+    if (status_pinned) {
+        rc = crb_status_async(f, status_pinned, stream);
+        if (rc) return rc;
+    }
+    if (!(flags & CRB_NO_SYNC)) CU(cudaStreamSynchronize(st));
+    return CRB_OK;
 }
 
 int crb_transform_view(crb_filler *f, const float *v, const float *n, int64_t T, const float *view, float *v_out,
@@ -2459,6 +2493,18 @@ int crb_status(crb_filler *f, int64_t *pairs_needed, int64_t *pair_capacity, voi
                     f->pairCap);
     }
     if (pairs_needed) *pairs_needed = (int64_t)t[0];
+    return CRB_OK;
+}
+
+int crb_status_async(crb_filler *f, uint64_t pinned[4], void *stream)
+{
+    if (check_filler(f) || !pinned) return fail(CRB_ERR_INVALID, "NULL argument");
+    if (!f->ws) return fail(CRB_ERR_STATE, "workspace not bound");
+    CU(cudaSetDevice(f->device));
+    { int jrc = join_pending(f, (cudaStream_t)stream); if (jrc) return jrc; }
+    unsigned long long *total1 = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(f->total) + f->set_bytes);
+    CU(cudaMemcpyAsync(pinned, f->total, 16, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU(cudaMemcpyAsync(pinned + 2, total1, 16, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     return CRB_OK;
 }
 

@@ -132,3 +132,102 @@ class HostFramePipeline:
     @property
     def launch_count(self):
         return sum(s.filler.launch_count for s in self.slots)
+
+
+class HostImagePipeline:
+    """run.py's product -- the uint8 image `image[::-1].astype('uint8')` (run.py:26), optionally lit by GuroIllumination
+    (renderer.py:48) -- from host triangle arrays to host memory, with only 3 bytes per pixel crossing PCIe.
+
+    Per frame, on the slot's own stream, ONE C-ABI call (crb_render_image_host): one H2D copy of the [3,T,3,3] block, one
+    fused launch sequence (fresh-filler clear + rasterizer + shading with the light applied + truncation to uint8 + row
+    flip, written by the rasterizer itself: no float32 buffer is produced at all), one D2H copy of h*w*3 bytes and of the
+    status words.  `depth` frames are in flight.  Inputs: a pinned float32 tensor [3,T,3,3] = (vertices, colours, normals)
+    by triangles, not to be modified before `result`.  (The per-frame host work matters: at 10 k images/s the submitting
+    thread is the bottleneck if a frame costs it more than a few dozen microseconds.)"""
+
+    def __init__(self, h, w, fov=90.0, z_near=0.1, z_far=1000.0, depth=3, device=None, light=None):
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        self._flags, self._light = 0, None
+        if light is not None:
+            # GuroIllumination.__init__ (guro_illumination.py:17-18): negate, then normalise, in float32
+            l = -np.asarray(light, dtype="float32")
+            l = l / np.linalg.norm(l)
+            self._light = (ctypes.c_float * 3)(*[float(x) for x in l])
+            self._flags = _lib.CRB_GURO
+        self.slots = []
+        for _ in range(depth):
+            s = _Slot()
+            s.filler = AdvancedPixelBufferFiller(h, w, fov=fov, z_near=z_near, z_far=z_far, device=device)
+            torch = s.filler._torch
+            dev = s.filler._dev
+            s.stream = torch.cuda.Stream(device=dev)
+            s.stream_ptr = ctypes.c_void_p(s.stream.cuda_stream)
+            s.dev_u8 = torch.empty((h, w, 3), dtype=torch.uint8, device=dev)
+            s.host_u8 = torch.empty((h, w, 3), dtype=torch.uint8, pin_memory=True)
+            s.host_np = s.host_u8.numpy()
+            s.status = torch.zeros(4, dtype=torch.int64, pin_memory=True)
+            s.status_np = s.status.numpy()
+            s.dev_u8_ptr, s.host_u8_ptr, s.status_ptr = s.dev_u8.data_ptr(), s.host_u8.data_ptr(), s.status.data_ptr()
+            s.done = torch.cuda.Event()
+            s.busy = False
+            self.slots.append(s)
+        self._torch = torch
+        self._L = self.slots[0].filler._L
+        self._next = 0
+
+    def submit(self, block):
+        torch = self._torch
+        if not isinstance(block, torch.Tensor) or block.is_cuda or block.dtype != torch.float32 or block.dim() != 4 or \
+                tuple(block.shape[0:1] + block.shape[2:]) != (3, 3, 3) or not block.is_contiguous():
+            raise ValueError("input must be a contiguous CPU float32 tensor [3,T,3,3] (pinned for asynchronous copies)")
+        i = self._next
+        self._next = (i + 1) % len(self.slots)
+        s = self.slots[i]
+        if s.busy:
+            self.result(i)
+        T = int(block.shape[1])
+        if T > s.filler._ws_T or s.filler._ws is None:
+            with torch.cuda.stream(s.stream):
+                s.filler._ensure_workspace(T, views=1)
+        s.T = T
+        s.keep = block
+        base = block.data_ptr()
+        s.args = (base, base + 36 * T, base + 72 * T)
+        self._launch(s)
+        s.busy = True
+        return i
+
+    def _launch(self, s):
+        # one C call: upload, fused clear + raster + shade (+ light) + uint8 + flip, download of the image and the status words
+        check(self._L.crb_render_image_host(s.filler._handle, s.args[0], s.args[1], s.args[2], s.T, self._flags | _lib.CRB_NO_SYNC,
+                                            self._light, s.dev_u8_ptr, s.host_u8_ptr, s.status_ptr, s.stream_ptr))
+        s.done.record(s.stream)
+
+    def result(self, i):
+        """Waits for slot i's frame; returns the uint8 [h,w,3] image (pinned memory, valid until the slot is resubmitted)."""
+        s = self.slots[i]
+        while s.busy:
+            s.done.synchronize()
+            f = s.filler
+            if max(int(s.status_np[1]), int(s.status_np[3])) > f._pair_cap:
+                # the frame was skipped (pair list too small): take the report, enlarge the list and draw it again
+                need, cap = ctypes.c_int64(), ctypes.c_int64()
+                rc = self._L.crb_status(f._handle, ctypes.byref(need), ctypes.byref(cap), s.stream_ptr)
+                if rc != _lib.CRB_ERR_OVERFLOW:
+                    check(rc)
+                with self._torch.cuda.stream(s.stream):
+                    f._ensure_workspace(s.T, f._ws_views, int(max(need.value, s.status_np[1], s.status_np[3]) * 1.25) + 1024)
+                self._launch(s)
+                continue
+            s.busy = False
+            s.keep = None
+        return s.host_np
+
+    def drain(self):
+        for i in range(len(self.slots)):
+            self.result(i)
+
+    @property
+    def launch_count(self):
+        return sum(s.filler.launch_count for s in self.slots)

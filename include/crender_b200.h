@@ -168,9 +168,18 @@ int crb_sync(crb_filler *f, void *stream);
  * normals_out [n_views,rows,w,3] (DEVICE).  Any of the three output pointers may be NULL (buffer not wanted).
  * color_u8_out, if not NULL, additionally receives run.py:26's output stage on device: [n_views,rows,w,3] uint8,
  * rows flipped (image[::-1]) and truncated like .astype('uint8'). */
-int crb_render_views(crb_filler *f, const float *v, const float *c, const float *n, int64_t T, const float *views,
+int crb_render_views(crb_filler *f, const float *v, const float *c, const float *n, int64_t T, const float *views /* NULL: one untransformed view */,
                      int n_views, float *z_out, float *color_out, float *normals_out, uint8_t *color_u8_out,
                      unsigned flags, const float light[3], void *stream);
+
+/* run.py's product from host arrays in one call: H2D of the three arrays, a fresh-filler frame whose only
+ * output is run.py:26's `image[::-1].astype('uint8')` -- written by the rasterizer itself, lit like GuroIllumination
+ * (renderer.py:48, guro_illumination.py:20-27) when flags has CRB_GURO and `light` is the normalised, negated direction --
+ * and D2H of those (rows x w x 3) bytes into `image_host`.  `image_dev`: device scratch of the same size.  `status_pinned`
+ * (optional): crb_status_async behind the frame.  CRB_NO_SYNC returns without waiting.  The filler's float32 buffers are
+ * not touched. */
+int crb_render_image_host(crb_filler *f, const float *v, const float *c, const float *n, int64_t T, unsigned flags,
+                          const float light[3], uint8_t *image_dev, uint8_t *image_host, uint64_t status_pinned[4], void *stream);
 
 /* Writes the camera-space arrays a view produces ([T,3,3] each, DEVICE) -- what the reference would be handed as
  * model._vertices_by_triangles / _normals_by_triangles for that view.  Used to feed the oracle in parity tests. */
@@ -195,6 +204,13 @@ int crb_upload(crb_filler *f, unsigned mask, const float *z_host, const float *c
  * produced; if it exceeded the workspace's pair capacity the frame was NOT drawn (buffers untouched) and the return
  * value is CRB_ERR_OVERFLOW -- re-bind a workspace with pair_capacity >= pairs_needed and render again. */
 int crb_status(crb_filler *f, int64_t *pairs_needed, int64_t *pair_capacity, void *stream);
+
+/* The same without blocking: queues the copy of the four status words of the two workspace sets (pairs of the last frame,
+ * largest overflowing demand; per set) into `pinned` (page-locked host memory) behind the work already on `stream`.
+ * Once the stream has passed that point the caller tests max(pinned[1], pinned[3]) > pair capacity itself (frame skipped:
+ * call crb_status for the report and the reset) -- pipelined callers poll an event instead of paying a synchronous round
+ * trip per frame. */
+int crb_status_async(crb_filler *f, uint64_t pinned[4], void *stream);
 
 /* Sparse read-back bookkeeping.  The read-back works on 32-pixel tile rows (896 bytes for all three buffers): a row crosses
  * PCIe when it holds something now or held something in the frame the host arrays show.  *tiles_copied = rows copied since the

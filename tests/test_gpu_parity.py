@@ -493,6 +493,53 @@ def test_host_frame_pipeline_matches_oracle(sparse, O, trex):
         assert_same(got[k], want[k], f"pipelined frame {k}")
 
 
+@pytest.mark.parametrize("lit", [False, True])
+def test_host_image_pipeline_matches_run_py(lit, O, trex):
+    """HostImagePipeline (N3): pinned [3,T,3,3] block in, run.py:26's `image[::-1].astype('uint8')` out (with
+    GuroIllumination, renderer.py:48, when a light is given) -- equal to the oracle's frame converted the reference's way,
+    for a sequence of different views through three slots."""
+    import torch
+    from cython3dmodelrenderer_b200 import HostImagePipeline, views as VW
+    h, w = 160, 224
+    pipe = HostImagePipeline(h, w, fov=45.0, depth=3, light=[0, 0, 1] if lit else None)
+    views = VW.orbit_views(7)
+    frames, want = [], []
+    for k in range(7):
+        vk, nk = VW.transform_arrays_host(views[k], trex._vertices_by_triangles, trex._normals_by_triangles)
+        frames.append(torch.from_numpy(np.stack([vk, trex._colors_by_triangles, nk])).pin_memory())
+        o = O.OracleFiller(h, w, fov=45.0)
+        o.render_arrays(vk, trex._colors_by_triangles, nk)
+        if lit:
+            O.guro(o.get_color_buffer(), o.get_normals_buffer(), [0, 0, 1])
+        want.append(o.get_color_buffer()[::-1].astype("uint8"))
+    pending, got = [], [None] * 7
+    for k in range(7):
+        pending.append((k, pipe.submit(frames[k])))
+        if len(pending) == 3:
+            kk, slot = pending.pop(0)
+            got[kk] = pipe.result(slot).copy()
+    for kk, slot in pending:
+        got[kk] = pipe.result(slot).copy()
+    for k in range(7):
+        assert np.array_equal(got[k], want[k]), f"image {k}"
+    # a frame whose (triangle,tile) pairs do not fit the default list: detected from the status words that come back with
+    # the image, the list is grown and the frame drawn again
+    T = 600
+    v = np.tile(np.array([[[-30, -30, 1.0], [30, -30, 1.0], [0.0, 30, 1.0]]], np.float32), (T, 1, 1))
+    v[:, :, 2] += np.linspace(0, 0.5, T, dtype=np.float32)[:, None]
+    n = -np.ones((T, 3, 3), np.float32)
+    c = np.random.default_rng(0).random((T, 3, 3)).astype(np.float32) * 255
+    big = HostImagePipeline(512, 512, fov=90.0, depth=2, light=[0, 0, 1] if lit else None)
+    o = O.OracleFiller(512, 512, fov=90.0)
+    o.render_arrays(v, c, n)
+    if lit:
+        O.guro(o.get_color_buffer(), o.get_normals_buffer(), [0, 0, 1])
+    block = torch.from_numpy(np.stack([v, c, n])).pin_memory()
+    for rep in range(3):
+        img = big.result(big.submit(block))
+        assert np.array_equal(img, o.get_color_buffer()[::-1].astype("uint8")), f"overflowing frame, pass {rep}"
+
+
 @pytest.mark.parametrize("size", [(96, 128), (100, 76), (50, 37), (257, 388)])
 def test_sparse_readback_equals_full_download(size, O):
     """CRB_DL_SPARSE: a sequence of unrelated fresh frames through ONE slot (so every frame's host arrays start from the
