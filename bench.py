@@ -348,7 +348,46 @@ def run_gpu_arm(args):
 
     # optional: the final NCCL gather of the view-sharded result to rank 0 (reported beside, never inside, `value`)
     gather = None
-    if world > 1 and args.gather != "none":
+    if world > 1 and args.gather == "u8":
+        # run.py's uint8 images of all N*V views delivered to rank 0: each rank renders its views in chunks (uint8 image only,
+        # written by the rasterizer) and the NCCL gather of chunk i travels while chunk i+1 is rendered
+        from cython3dmodelrenderer_b200 import sharding
+        u8 = torch.empty((V, RES, RES, 3), dtype=torch.uint8, device=dev)
+        gchunk = min(args.chunk, 32)
+
+        def produce(first, count):
+            f.render_views(dv, dc, dn, dviews[first:first + count], want=(), color_u8_out=u8[first:first + count], chunk=count,
+                           check_status=False)
+            return u8[first:first + count]
+
+        def render_only():
+            for first in range(0, V, gchunk):
+                produce(first, min(gchunk, V - first))
+
+        allu8 = sharding.gather_views_overlapped(produce, V, gchunk, dst=0)       # warm-up: communicator, buffers
+        res_ms = {}
+        for name, fn in (("render_u8_only", render_only),
+                         ("render_u8_and_overlapped_gather", lambda: sharding.gather_views_overlapped(produce, V, gchunk, dst=0, out=allu8))):
+            fn()
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(3):
+                fn()
+            g1.record()
+            barrier()
+            t_ = torch.tensor([g0.elapsed_time(g1) / 3], dtype=torch.float64, device=dev)
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+            res_ms[name] = float(t_.item())
+        nbytes = u8.numel() * world
+        gather = {"what": f"uint8 images (run.py:26) of all views gathered to rank 0 by NCCL in chunks of {gchunk} views beside the rendering",
+                  "ms": res_ms, "bytes": nbytes,
+                  "frames_per_s_delivered_to_rank0": n_total / (res_ms["render_u8_and_overlapped_gather"] / 1000.0),
+                  "frames_per_s_render_u8_only": n_total / (res_ms["render_u8_only"] / 1000.0)}
+        if rank == 0:
+            gather["lit_pixels_view0_of_last_rank"] = int((allu8[world - 1, 0].sum(dim=-1) > 0).sum().item())
+        del allu8, u8
+    elif world > 1 and args.gather != "none":
         from cython3dmodelrenderer_b200 import sharding
         parts = {"z": z} if args.gather == "z" else {"z": z, "color": col, "normals": nrm}
         for t_ in parts.values():

@@ -129,6 +129,36 @@ def gather_views(local, n_views, dst=None):
     return torch.cat([out[r * cmax:r * cmax + counts[r]] for r in range(world)], dim=0)
 
 
+def gather_views_overlapped(produce, n_local, chunk, dst=0, out=None):
+    """View-sharded render with the gather running beside it ("chunk the gather so it overlaps rendering").
+
+    `produce(first, count)` renders the local views [first, first+count) and returns them as one contiguous tensor
+    [count, ...] (queued on the current stream).  After every chunk an asynchronous gather to rank `dst` is started: the
+    collective waits for that chunk only, and the next chunk is rendered while it travels (NCCL runs on its own stream;
+    gloo on its worker thread).  Every rank must hold the same n_local.  Returns, on `dst`, a tensor [world, n_local, ...]
+    (rank-major: entry [r, i] is local view i of rank r; pass `out` to reuse it) and None elsewhere -- after all
+    collectives have completed on the current stream."""
+    world = _world()
+    rank = dist.get_rank() if world > 1 else 0
+    works, first = [], 0
+    while first < n_local:
+        count = min(int(chunk), n_local - first)
+        part = produce(first, count)
+        if world == 1:
+            if out is None:
+                out = torch.empty((1, n_local) + tuple(part.shape[1:]), dtype=part.dtype, device=part.device)
+            out[0, first:first + count].copy_(part)
+        else:
+            if rank == dst and out is None:
+                out = torch.empty((world, n_local) + tuple(part.shape[1:]), dtype=part.dtype, device=part.device)
+            dests = [out[r, first:first + count] for r in range(world)] if rank == dst else None
+            works.append((dist.gather(part.contiguous(), dests, dst=dst, async_op=True), part))   # `part` stays alive until done
+        first += count
+    for w, _ in works:
+        w.wait()
+    return out if rank == dst else None
+
+
 def gather_bands(local, h, dst=None, align=TILE_ROWS, bands=None):
     """Gathers per-rank row bands [rows_r, W, ...] into the full [h, W, ...] buffer.  `bands` = the [(row0,row1)] list
     every rank used (e.g. balanced_bands); default: the uniform layout of band_shard."""

@@ -108,6 +108,20 @@ def _worker(rank, world, port, out_dir):
         b0, b1 = bands[rank]
         z_bal = sharding.gather_bands(torch.from_numpy(full.get_z_buffer()[b0:b1].copy()), H, bands=bands)
         assert bits_equal(z_bal.numpy(), full.get_z_buffer())
+        # ---- the chunked gather that runs beside the producer: 5 local "views" per rank in chunks of 2 ------------------
+        made = []
+        def produce(first, count):
+            made.append((first, count))
+            return torch.arange(first, first + count, dtype=torch.float32)[:, None, None].repeat(1, 3, 4) + 100.0 * rank
+        ov = sharding.gather_views_overlapped(produce, 5, 2, dst=0)
+        assert made == [(0, 2), (2, 2), (4, 1)]
+        if rank == 0:
+            assert ov.shape == (world, 5, 3, 4)
+            for r in range(world):
+                for i in range(5):
+                    assert bool((ov[r, i] == 100.0 * r + i).all())
+        else:
+            assert ov is None
         if rank == 0:
             np.savez(os.path.join(out_dir, "r0.npz"), z_all=z_all.numpy(), col_0=col_0.numpy(), z_band=z_band.numpy(),
                      n_band=n_band.numpy(), z_full=full.get_z_buffer(), n_full=full.get_normals_buffer())
