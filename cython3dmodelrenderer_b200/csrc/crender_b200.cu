@@ -804,7 +804,16 @@ __device__ __forceinline__ void write_clear_tile(const Frame &F, unsigned skip, 
             if (wn) { F.normals[p * 3] = 0.f; F.normals[p * 3 + 1] = 0.f; F.normals[p * 3 + 2] = 0.f; }
         }
     }
-    if (F.color_u8) {
+    if (F.color_u8 && tw == TW && !(F.W & 15) && !(reinterpret_cast<uintptr_t>(F.color_u8) & 15u)) {
+        // a tile row of the uint8 image is 96 bytes = six 16-byte stores (rows are 16-byte multiples: W % 16 == 0)
+        const int rows = F.row1 - F.row0;
+        const unsigned w4 = (unsigned)to_u8(bg) * 0x01010101u;
+        const uint4 val = make_uint4(w4, w4, w4, w4);
+        for (int i = threadIdx.x; i < th * 6; i += NTH) {
+            const int r = i / 6, q = i - r * 6;
+            reinterpret_cast<uint4 *>(F.color_u8 + ((long long)view * F.slabPixels + (long long)(rows - 1 - (yl0 + r)) * F.W + x0) * 3)[q] = val;
+        }
+    } else if (F.color_u8) {
         const int rows = F.row1 - F.row0;
         const unsigned char b8 = to_u8(bg);
         for (int i = threadIdx.x; i < th * tw * 3; i += NTH) {
