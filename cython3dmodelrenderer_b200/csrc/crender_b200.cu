@@ -895,7 +895,10 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
         // have too few rows to occupy eight warps 32 at a time: there a trip of fewer than NT rows is dealt out in equal
         // shares (bunny 4096^2: k_raster 343 -> 304 us).  Tiles of many small triangles keep whole warps: the span pass
         // costs a warp the same with 8 active lanes as with 32, and those tiles are bound by issue slots, not latency.
-        const bool deal = totalRows >= 16u * m;
+#ifndef CRB_DEAL_ROWS
+#define CRB_DEAL_ROWS 16
+#endif
+        const bool deal = totalRows >= (unsigned)CRB_DEAL_ROWS * m;
         for (unsigned tb = 0; tb < totalRows; tb += NT) {
             const unsigned rem = totalRows - tb;
             const unsigned share = (rem >= (unsigned)NT || !deal) ? 32u : (rem + NT / 32 - 1u) / (NT / 32);
