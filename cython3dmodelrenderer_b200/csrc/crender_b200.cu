@@ -691,11 +691,14 @@ __global__ void __launch_bounds__(NT, CRB_FILL_MIN_CTAS) k_fill(const Frame F)
 // K3+K4: tile rasterizer + deferred shading
 // ------------------------------------------------------------------------------------------------------------
 
-// shared-memory 64-bit min.  There is no native 64-bit ATOMS.MIN; most fragments lose the depth test and leave after
-// the plain load, winners pay one CAS (retry only when two lanes hit the same pixel in the same instant).
+// shared-memory 64-bit min.  There is no native 64-bit ATOMS.MIN.  The first attempt is a CAS against the empty key: with a
+// depth complexity of ~1.25 most fragments find their pixel still empty and are done with one shared-memory transaction
+// (instead of a load and a CAS: bunny 4096^2 -2.8 %, T-Rex unchanged); the others continue from the value it returned --
+// losers leave at once, winners retry only when two lanes hit the same pixel in the same instant.
 __device__ __forceinline__ void smem_key_min(unsigned long long *p, unsigned long long key)
 {
-    unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(p);
+    unsigned long long cur = atomicCAS(p, KEY_EMPTY, key);
+    if (cur == KEY_EMPTY) return;
     while (key < cur) {
         const unsigned long long old = atomicCAS(p, cur, key);
         if (old == cur) break;
