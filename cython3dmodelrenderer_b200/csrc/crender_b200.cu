@@ -341,10 +341,40 @@ __device__ __forceinline__ void tile_span(const Frame &F, unsigned bx, unsigned 
     ty1 = (yb - 1 - F.row0) / TH;
 }
 
+// ---- 1-D bulk copies global -> shared (TMA without a tensor map) and the mbarrier they complete on ----------------
+constexpr int BC_STAGES = 4;
+constexpr unsigned BC_BYTES = NT * 9 * 4;
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned phase)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(a), "r"(phase) : "memory");
+}
+// one bulk copy global -> shared of `bytes` (16-byte multiple, both addresses 16-byte aligned), completion on `bar`
+__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst), m = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(m), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(gmem_src),
+                 "r"(bytes), "r"(m) : "memory");
+}
+
 // One chunk of NT consecutive triangles of one view.  Every early exit below is taken by the whole CTA or lies behind
 // the last barrier, so the function can be called in a loop (chunk-list mode).
 __device__ __forceinline__ void setup_chunk(const Frame &F, const int view, const long long chunk, const long long chunksPerView,
-                                            float *sv, float *sn, float *sc, float *sM)
+                                            float *sv, float *sn, float *sc, float *sM, unsigned long long *bar = nullptr)
 {
     const long long first = chunk * NT;
     const long long cnt = min((long long)NT, F.T - first);
@@ -353,10 +383,22 @@ __device__ __forceinline__ void setup_chunk(const Frame &F, const int view, cons
     // a normal or written a record (7 of 8 CTAs at N = 8).  A full-frame filler stages both arrays behind one barrier.
     const bool banded = F.row0 > 0 || F.row1 < F.H;
     unsigned char *alive = F.alive + (long long)view * chunksPerView + chunk;
-    stage_floats(F.v, first * 9, cnt * 9, sv);
-    if (!banded) stage_floats(F.n, first * 9, cnt * 9, sn);
+    // A full chunk of a full-frame filler arrives as two bulk copies (one thread issues them, everybody waits on the
+    // mbarrier: no per-thread load / store instructions, no registers in flight); anything else is staged by the threads.
+    const bool bulk = bar && !banded && cnt == NT &&
+                      !((reinterpret_cast<uintptr_t>(F.v + first * 9) | reinterpret_cast<uintptr_t>(F.n + first * 9)) & 15u);
+    if (bulk) {
+        if (threadIdx.x == 0) {
+            bulk_load(sv, F.v + first * 9, BC_BYTES, bar);
+            bulk_load(sn, F.n + first * 9, BC_BYTES, bar);
+        }
+    } else {
+        stage_floats(F.v, first * 9, cnt * 9, sv);
+        if (!banded) stage_floats(F.n, first * 9, cnt * 9, sn);
+    }
     if (F.views && threadIdx.x < 16) sM[threadIdx.x] = F.views[view * 16 + threadIdx.x];
     __syncthreads();
+    if (bulk) mbar_wait(bar, 0u);
     const bool valid = threadIdx.x < cnt;
     const long long tri = first + threadIdx.x;
     const long long ridx = (long long)view * F.T + tri;
@@ -472,7 +514,12 @@ __global__ void __launch_bounds__(NT, CRB_SETUP_MIN_CTAS) k_setup(const Frame F)
     }
     const long long chunksPerView = (F.T + NT - 1) / NT;
     if (!F.chunks) {
-        setup_chunk(F, blockIdx.y, blockIdx.x, chunksPerView, sv, sn, sc, sM);
+        __shared__ __align__(8) unsigned long long bar;
+        if (threadIdx.x == 0) {
+            mbar_init(&bar, 2u);      // two bulk copies (vertices, normals), one arrival each
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        setup_chunk(F, blockIdx.y, blockIdx.x, chunksPerView, sv, sn, sc, sM, &bar);
         return;
     }
     // chunk-list mode (band-sharded filler): a grid of a few CTAs per SM walks the chunks k_band_chunks listed
@@ -489,35 +536,6 @@ __global__ void __launch_bounds__(NT, CRB_SETUP_MIN_CTAS) k_setup(const Frame F)
 // vertex array through a ring of BC_STAGES shared-memory buffers filled by 1-D bulk copies (cp.async.bulk, one 9 216-byte
 // copy per chunk issued by one thread, completion counted on an mbarrier), i.e. at memory speed rather than at the rate at
 // which 39 075 load -> barrier -> project -> exit CTAs can be launched and retired.
-constexpr int BC_STAGES = 4;
-constexpr unsigned BC_BYTES = NT * 9 * 4;
-
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned phase)
-{
-    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(a), "r"(phase) : "memory");
-}
-// one bulk copy global -> shared of `bytes` (16-byte multiple, both addresses 16-byte aligned), completion on `bar`
-__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar)
-{
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst), m = (unsigned)__cvta_generic_to_shared(bar);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(m), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(gmem_src),
-                 "r"(bytes), "r"(m) : "memory");
-}
-
 __global__ void __launch_bounds__(NT) k_band_chunks(const Frame F)
 {
     __shared__ __align__(128) float sv[BC_STAGES][NT * 9];
