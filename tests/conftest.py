@@ -32,6 +32,23 @@ def load_indexed(name):
     return TriModel(v, c, n)
 
 
+def case_model(info):
+    """The model a golden case of checksums.json was rendered from (tests/golden/make_golden.py): a fixture as it is, a
+    view of the T-Rex orbit (camera-space arrays of views.transform_arrays_host, config C5), or the full-size UV sphere
+    of config C4.  Returns (model, n_threads for the CPU oracle)."""
+    if "orbit" in info:
+        from cython3dmodelrenderer_b200 import views as VW
+        base = load_indexed("trex")
+        view = VW.orbit_views(info["orbit"], first=info["view"], count=1)[0]
+        vk, nk = VW.transform_arrays_host(view, base._vertices_by_triangles, base._normals_by_triangles)
+        return TriModel(vk, base._colors_by_triangles, nk), 1
+    if info["model"].startswith("uv_sphere"):
+        from cython3dmodelrenderer_b200 import synthetic
+        m = synthetic.uv_sphere(3200, 1564)
+        return TriModel(m._vertices_by_triangles, m._colors_by_triangles, m._normals_by_triangles), os.cpu_count() or 1
+    return load_indexed(info["model"]), 1
+
+
 def random_scene(seed, T=None, span=1.0):
     """SURVEY 8d property-test scenes: mixed sizes, depths 0.2..5, some behind the camera, some snapped to a grid."""
     rng = np.random.default_rng(seed)

@@ -97,12 +97,34 @@ def main():
     # Renderer.render with GuroIllumination (crender/cy/renderer.py:47-49, guro_illumination.py:20-27): the lit colour buffer
     from crender.cy.illumination import GuroIllumination
     for name, h, w, fov, light in [("trex", 1024, 1024, 45.0, [0, 0, 1]), ("bunny", 2048, 2048, 45.0, [0, 0, 1]),
-                                   ("basketball", 777, 555, 60.0, [0.3, -0.5, 1.0])]:
+                                   ("basketball", 777, 555, 60.0, [0.3, -0.5, 1.0]),
+                                   ("bunny", 4096, 4096, 45.0, [0, 0, 1])]:       # config C2: 4096^2 "with lighting"
         z, c, n = render(models[name], h, w, fov)
         c = c.copy()
         GuroIllumination(light).draw_illumination(c, n)
         cases[f"{name}_{h}x{w}_fov{fov:g}_guro"] = dict(model=name, h=h, w=w, fov=fov, light=light, color_lit=sha(c),
                                                         covered=int((z < 1e5).sum()))
+    # config C5: views of the 1024^2 T-Rex orbit; the reference is fed the camera-space arrays the view transform
+    # produces (views.transform_arrays_host restates the GPU transform in NumPy float32)
+    from cython3dmodelrenderer_b200 import views as VW
+    for n_total, ks in [(128, (0, 32, 64, 96)), (1024, (100, 611))]:
+        for k in ks:
+            view = VW.orbit_views(n_total, first=k, count=1)[0]
+            vk, nk = VW.transform_arrays_host(view, trex._vertices_by_triangles, trex._normals_by_triangles)
+            z, c, n = render(type("M", (), dict(_vertices_by_triangles=vk, _colors_by_triangles=trex._colors_by_triangles,
+                                                _normals_by_triangles=nk))(), 1024, 1024, 45.0)
+            cases[f"trex_orbit{n_total}_view{k}_1024x1024_fov45"] = dict(
+                model="trex", h=1024, w=1024, fov=45.0, orbit=n_total, view=k, z=sha(z), color=sha(c), normals=sha(n),
+                covered=int((z < 1e5).sum()), v_in=sha(vk), n_in=sha(nk))
+    # config C4 at full size: the 10 003 200-triangle UV sphere at 8192^2, rendered by the reference itself
+    from cython3dmodelrenderer_b200 import synthetic
+    sph = synthetic.uv_sphere(3200, 1564)
+    z, c, n = render(sph, 8192, 8192, 45.0)
+    cases["sphere10m_8192x8192_fov45"] = dict(
+        model="uv_sphere(3200,1564)", h=8192, w=8192, fov=45.0, z=sha(z), color=sha(c), normals=sha(n),
+        covered=int((z < 1e5).sum()), T=int(sph._vertices_by_triangles.shape[0]),
+        v_in=sha(sph._vertices_by_triangles), c_in=sha(sph._colors_by_triangles), n_in=sha(sph._normals_by_triangles))
+    del sph, z, c, n
     inputs = {k: dict(v=sha(m._vertices_by_triangles), c=sha(m._colors_by_triangles), n=sha(m._normals_by_triangles))
               for k, m in models.items()}
     with open(os.path.join(HERE, "checksums.json"), "w") as fo:

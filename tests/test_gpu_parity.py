@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, TriModel, bits_equal, random_scene
+from conftest import GOLDEN, TriModel, bits_equal, case_model, random_scene
 
 pytestmark = pytest.mark.gpu
 CHECKS = json.load(open(os.path.join(GOLDEN, "checksums.json")))
@@ -413,6 +413,73 @@ def test_full_size_sphere_properties(Filler):
         assert torch.equal(cb.view(torch.int32), c[r0:r1].view(torch.int32))
         assert torch.equal(nb.view(torch.int32), n[r0:r1].view(torch.int32))
         del b
+
+
+def _sha_dev(t):
+    """sha256 of a CUDA tensor's bytes (downloaded in one piece)."""
+    return hashlib.sha256(t.contiguous().cpu().numpy().tobytes()).hexdigest()
+
+
+def test_full_size_sphere_equals_reference_golden(Filler):
+    """Config C4 at FULL size (10 003 200 triangles, 8192^2) against the golden the reference build itself rendered
+    (tests/golden/make_golden.py, n_threads=1; the C oracle reproduces it in tests/test_oracle_pinning.py): all three
+    buffers of the single-GPU frame, and of the frame concatenated from four cost-balanced row bands (what the ranks
+    of a band-sharded run hold), bit for bit."""
+    import torch
+    from cython3dmodelrenderer_b200 import sharding
+    info = CHECKS["cases"]["sphere10m_8192x8192_fov45"]
+    m, _ = case_model(info)
+    assert sha(m._vertices_by_triangles) == info["v_in"] and sha(m._colors_by_triangles) == info["c_in"] \
+        and sha(m._normals_by_triangles) == info["n_in"], "the synthetic sphere is not the one the golden was made from"
+    dv, dc, dn = (torch.from_numpy(a).cuda() for a in (m._vertices_by_triangles, m._colors_by_triangles, m._normals_by_triangles))
+    f = Filler(8192, 8192, fov=45.0)
+    f.render_arrays(dv, dc, dn)
+    z, c, n = f.device_buffers()
+    assert int((z < 1e5).sum()) == info["covered"] == 38399961
+    assert (_sha_dev(z), _sha_dev(c), _sha_dev(n)) == (info["z"], info["color"], info["normals"])
+    del f, z, c, n
+    bands = sharding.balanced_bands(sharding.tile_row_costs(dv, dn, 8192, 8192, 45.0), 4, 8192)
+    assert bands[0][0] == 0 and bands[-1][1] == 8192 and all(a[1] == b[0] for a, b in zip(bands, bands[1:]))
+    parts = []
+    for r0, r1 in bands:
+        b = Filler(8192, 8192, fov=45.0, band=(r0, r1))
+        b.render_arrays(dv, dc, dn)
+        parts.append(tuple(t.cpu() for t in b.device_buffers()))
+        del b
+    for k, name in enumerate(("z", "color", "normals")):
+        whole = torch.cat([p[k] for p in parts], dim=0)
+        assert hashlib.sha256(whole.numpy().tobytes()).hexdigest() == info[name], f"band-concatenated {name}"
+
+
+def test_orbit_views_at_1024_equal_reference_goldens(Filler, trex):
+    """Config C5 at its real size: evenly spread views of the 1024^2 T-Rex orbit, rendered the way bench.py renders
+    them (one render_views call, 128 views per launch, GPU view transform), against goldens the reference build rendered
+    from the camera-space arrays of the same views (tests/golden/make_golden.py)."""
+    import torch
+    from cython3dmodelrenderer_b200 import views as VW
+    dv, dc, dn = (torch.from_numpy(a).cuda() for a in
+                  (trex._vertices_by_triangles, trex._colors_by_triangles, trex._normals_by_triangles))
+    f = Filler(1024, 1024, fov=45.0)
+    out = f.render_views(dv, dc, dn, VW.orbit_views(128), chunk=128)
+    checked = 0
+    for key, info in sorted(CHECKS["cases"].items()):
+        if info.get("orbit") != 128:
+            continue
+        k = info["view"]
+        assert int((out["z"][k] < 1e5).sum()) == info["covered"], key
+        assert (_sha_dev(out["z"][k]), _sha_dev(out["color"][k]), _sha_dev(out["normals"][k])) == \
+            (info["z"], info["color"], info["normals"]), key
+        checked += 1
+    assert checked == 4
+    del out
+    # two views of the 1024-view orbit (config C5's own view count), as a rank of an 8-GPU run would render them
+    ks = sorted(info["view"] for info in CHECKS["cases"].values() if info.get("orbit") == 1024)
+    views = np.stack([VW.orbit_views(1024, first=k, count=1)[0] for k in ks])
+    out = f.render_views(dv, dc, dn, views, chunk=2)
+    for i, k in enumerate(ks):
+        info = CHECKS["cases"][f"trex_orbit1024_view{k}_1024x1024_fov45"]
+        assert (_sha_dev(out["z"][i]), _sha_dev(out["color"][i]), _sha_dev(out["normals"][i])) == \
+            (info["z"], info["color"], info["normals"]), k
 
 
 @pytest.mark.parametrize("mode", ["tma", "tma_vec_rows", "tma_direct_rows", "plain", "tiny_grid", "tma_tiny_grid"])
