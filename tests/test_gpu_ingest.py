@@ -116,7 +116,7 @@ def test_vertex_normals_kept_list_beyond_shared_memory(dev):
 def test_vertex_normals_sphere_scale(dev):
     """A 2 M-triangle UV sphere (the C4 mesh family at 1/5 scale): indexed, poles of valence 1 600."""
     from oracle import ingest as I
-    from tests_sphere import indexed_sphere
+    from sphere_mesh import indexed_sphere
     v, tri = indexed_sphere(1600, 626)
     assert bits_equal(gpu_normals(dev, v, tri), I.vertex_normals(v, tri))
 

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Runs on the GPU box: parity tests, quick per-config timing, bench summary.  usage: tools/gpu_check.sh [pytest-args]
 timeout 900 python -m pytest tests -m gpu -x -q "$@" 2>&1 | tail -4
-python tests/_quick_time.py 2>&1 | grep -v Warning
+python tools/scratch/_quick_time.py 2>&1 | grep -v Warning
 timeout 600 python bench.py --steps 10 --no-cpu 2>/dev/null > gpurun_out/bench_quick.json
 python - <<'PY'
 import json

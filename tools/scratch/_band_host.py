@@ -1,6 +1,6 @@
 """Is a band frame host-bound?  Host enqueue time per frame vs device time per frame.  usage: _band_host.py row0 row1"""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, _ROOT); sys.path.insert(0, os.path.join(_ROOT, "tests"))
 import torch
 from cython3dmodelrenderer_b200 import AdvancedPixelBufferFiller, synthetic
 band = (int(sys.argv[1]), int(sys.argv[2]))

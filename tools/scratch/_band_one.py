@@ -1,6 +1,6 @@
 """One band of the C4 frame, a few frames (for an ncu launch list).  usage: _band_one.py row0 row1"""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, _ROOT); sys.path.insert(0, os.path.join(_ROOT, "tests"))
 import torch
 from cython3dmodelrenderer_b200 import AdvancedPixelBufferFiller, synthetic
 band = (int(sys.argv[1]), int(sys.argv[2]))

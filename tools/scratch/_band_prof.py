@@ -1,7 +1,7 @@
 """The C4 frame (10 M-triangle sphere, 8192^2) cut into N row bands, every band rendered in turn on ONE GPU (what rank r
 of N does; bands are independent, so max over bands = the N-GPU frame time).  usage: _band_prof.py N [uniform|balanced]"""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, _ROOT); sys.path.insert(0, os.path.join(_ROOT, "tests"))
 import torch
 from cython3dmodelrenderer_b200 import AdvancedPixelBufferFiller, sharding, synthetic
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 8

@@ -1,6 +1,6 @@
 """Per-config frame time (device-resident, fused clear): T-Rex 1024 batch of 32 views, bunny 2048 / 4096 single frames."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, _ROOT); sys.path.insert(0, os.path.join(_ROOT, "tests"))
 import torch
 from conftest import load_indexed
 from cython3dmodelrenderer_b200 import AdvancedPixelBufferFiller, views as VW

@@ -1,6 +1,6 @@
 """e2e frames/s of HostFramePipeline on the T-Rex orbit (pinned host inputs, sparse read-back).  usage: _e2e_time.py [depth] [frames]"""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, _ROOT); sys.path.insert(0, os.path.join(_ROOT, "tests"))
 import torch
 from conftest import load_indexed
 from cython3dmodelrenderer_b200 import views as VW

@@ -1,8 +1,8 @@
 """A/B timing of k_raster variants selected by environment switches read at filler creation (GPU box only)."""
 import sys, os, ctypes
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, _ROOT); sys.path.insert(0, os.path.join(_ROOT, "tests"))
 if any("CRB_DEBUG_SKIP" in a for a in sys.argv[1:]) or True:
-    _abl = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "cython3dmodelrenderer_b200", "csrc", "libcrender_b200_ablation.so")
+    _abl = os.path.join(_ROOT, "cython3dmodelrenderer_b200", "csrc", "libcrender_b200_ablation.so")
     if os.path.exists(_abl) and "CRB_LIB_OVERRIDE" not in os.environ:
         os.environ["CRB_LIB_OVERRIDE"] = _abl      # the product build has no ablation switches
 import torch

@@ -1,6 +1,6 @@
 """HostImagePipeline rate and where the host time goes.  usage: _img_time.py [depth] [frames]"""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, _ROOT); sys.path.insert(0, os.path.join(_ROOT, "tests"))
 import numpy as np, torch
 from conftest import load_indexed
 from cython3dmodelrenderer_b200 import views as VW, HostImagePipeline

@@ -1,5 +1,5 @@
 """Timing of the model-ingest row (N4) on the GPU box: drop-in Model vs the reference's Model (oracle/_ref copy) on the
-reference's assets.  Prints one JSON object.  Run: python tests/_ingest_time.py"""
+reference's assets.  Prints one JSON object.  Run: python tools/scratch/_ingest_time.py"""
 import json
 import os
 import sys
@@ -8,7 +8,7 @@ import warnings
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 REF = os.path.join(ROOT, "oracle", "_ref")
 OBJ = os.path.join(REF, "objects")
@@ -64,7 +64,7 @@ def main():
             r["reference_rotate_ms"] = timeit(lambda: rm.rotate([10, -80, 0]), 2)
         out[name] = r
     # the C4 mesh family: indexed UV sphere, 10 M triangles
-    from tests_sphere import indexed_sphere
+    from sphere_mesh import indexed_sphere
     v, tri = indexed_sphere(3200, 1564)
     dv, dt = torch.from_numpy(v).cuda(), torch.from_numpy(tri).cuda()
     dn = torch.empty_like(dv)

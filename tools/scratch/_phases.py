@@ -1,6 +1,6 @@
 """Per-phase warp-cycle split of k_raster (needs csrc/libcrender_b200_timing.so = the library built with -DCRB_PHASE_TIMING)."""
 import ctypes, os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 os.environ["CRB_LIB_OVERRIDE"] = os.path.join(ROOT, "cython3dmodelrenderer_b200", "csrc", "libcrender_b200_timing.so")
 import torch

@@ -1,6 +1,6 @@
 """Single-frame latency (one crb_render(CLEAR_FIRST) per CUDA-graph replay) with and without heavy-tile splitting."""
 import sys, os, ctypes
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, _ROOT); sys.path.insert(0, os.path.join(_ROOT, "tests"))
 import torch
 from conftest import load_indexed
 from cython3dmodelrenderer_b200 import AdvancedPixelBufferFiller, _lib

@@ -1,6 +1,6 @@
 """uint8-image-only batched render (N3 fused into the rasterizer): 128 T-Rex views, chunks of 32 / 128."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, _ROOT); sys.path.insert(0, os.path.join(_ROOT, "tests"))
 import torch
 from conftest import load_indexed
 from cython3dmodelrenderer_b200 import AdvancedPixelBufferFiller, views as VW
