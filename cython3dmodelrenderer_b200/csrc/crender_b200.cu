@@ -766,15 +766,17 @@ struct __align__(128) TileSmem {
     // TMA source first (128-byte aligned): shaded colour / normal rows of the tile
     union {
         struct {
-            float4 s0[CH];  // x0 y0 x1 y1
-            float4 s1[CH];  // x2 y2 z0 z1
-            float4 s2[CH];  // z2 d1 d2 d3   (d = sign-normalised denominators l03' l13' l23', see k_fill)
-            uint4 s3[CH];   // bx by tri flags
-            float4 s4[CH];  // 1/d1 1/d2 1/d3 -
-            unsigned rowStart[CH];
+            // per staged triangle (written by its staging thread, see raster_tile): the three edges in the sign-normalised form
+            // the row loop wants, each with the vertex its numerator is measured from -- mu:24-26 with l3' = |l3|
+            float4 e0[CH];  // l01' y2 l02' x2      bar1 numerator = l01'*(py - y2) - l02'*(px - x2)
+            float4 e1[CH];  // l11' y0 l12' x0      bar2
+            float4 e2[CH];  // l21' y1 l22' x1      bar3
+            float4 tz[CH];  // z0 z1 z2 | triangle index
+            float4 td[CH];  // d1 d2 d3 (denominators, > 0 where sane) | PK_* flags and the tile-relative pixel rectangle
+            float4 tr[CH];  // 1/d1 1/d2 1/d3 (correctly rounded) | first row work item of the triangle
             unsigned char owner[CH * TH];  // row work item -> staged triangle
-            float4 slot[NT / 32][2][32];   // per warp: the 32 rows of the current trip, [0] A1 A2 A3 l02, [1] l12 l22 tri info
-            unsigned short fq[NT / 32][FQ];  // per warp: compacted fragments of the trip (lane | x << 5)
+            float4 slot[NT / 32][2][32];   // per warp, per trip parity: the trip's 32 rows (A1 A2 A3 | staged triangle, tile row)
+            unsigned short fq[NT / 32][FQ];  // per warp: queue of fragments (row lane | x << 5 | trip parity << 10)
         } st;
 #ifndef CRB_NO_OUT_STAGE
         struct {
@@ -849,19 +851,31 @@ __device__ __forceinline__ void write_clear_tile(const Frame &F, unsigned skip, 
 // (l1', l2', d' > 0) form, inside => num' >= -REJ_EPS (k_fill).  num' differs from the real-valued
 // E(x) = A - l2'*(x-b) by at most 3*2^-24*(|A| + |l2'|*|x-b|); M below is > 16x that bound plus the guard band, so
 // E(x) < -M proves the reference rejects the pixel.  E is linear in x: the admissible x form a half line whose end is
-// b + (A+M)/l2'.  The end is computed with an approximate reciprocal and widened by one pixel; coordinates are limited
-// to 2^18 (FL_SPAN) so that the float evaluation of the end is accurate to < 1/4 pixel wherever it lies on the screen.
-__device__ __forceinline__ void span_bound(float A, float l2, float b, float wmax, float &lo, float &hi)
+// e = b + (A+M)/l2'.  The end is computed with an approximate reciprocal (relative error < 2^-22) and widened by wd, which
+// exceeds every rounding of that evaluation for coordinates up to 2^18 (FL_SPAN); no walk towards the exact end follows --
+// a pixel admitted without need (1.4 % of the survivors) is rejected by the exact pass like any other.  An edge that is
+// (nearly) horizontal, |l2'| < 1e-20, bounds nothing here: rows on its far side lie outside the triangle's pixel rectangle.
+// tools/scratch/span_test.c checks the bound against the per-pixel test on 16 M random rows.
+__device__ __forceinline__ void span_bound(float A, float l2, float b, float xc, float &lo, float &hi)
 {
-    const float M = 3.814697e-6f * (fabsf(A) + fabsf(l2) * wmax) + 1e-5f;   // 2^-18 * magnitude + guard
-    if (l2 == 0.0f) {
-        if (A < -M) { lo = 1e30f; hi = -1e30f; }   // the whole row is outside this edge
-        return;
+    const float w = fabsf(xc - b) + 16.0f;                                          // >= |x - b| for every x of the tile
+    const float M = __fmaf_rn(__fmaf_rn(fabsf(l2), w, fabsf(A)), 3.814697e-6f, 1e-5f);   // 2^-18 * magnitude + guard
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l2));
+    const float d = (A + M) * r;
+    const float e = d + b;
+    const float wd = __fmaf_rn(fabsf(d), 9.5367431640625e-7f, 0.0078125f);         // 2^-20 |e - b| + 2^-7
+    if (fabsf(l2) >= 1e-20f) {
+        if (l2 > 0.0f) hi = fminf(hi, e + wd);     // x <= e   (fminf / fmaxf ignore a NaN: no tightening)
+        else lo = fmaxf(lo, e - wd);               // x >= e
     }
-    const float e = b + __fdividef(A + M, l2);
-    if (l2 > 0.0f) hi = fminf(hi, e + 1.0f);       // x <= e   (fminf/fmaxf ignore a NaN e: no tightening)
-    else lo = fmaxf(lo, e - 1.0f);                 // x >= e
 }
+
+// bits of a staged triangle's packed word (td[].w)
+constexpr unsigned PK_REJ = 1u;      // bits 0..2: barycentric k may use the division-free rejection
+constexpr unsigned PK_SPAN = 8u;     // FL_SPAN
+constexpr unsigned PK_FAST = 16u;    // FL_SPAN and FL_FDIV: div_rn_by() applies whenever the numerators are >= 2^-40
+constexpr int PK_XA = 8, PK_XB = 14, PK_YT = 20;   // tile-relative rectangle: first x (6 bits), end x (6 bits), first row (5 bits)
 
 // Visibility + deferred shading of one busy tile (n triangles staged at list offset off).
 __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, TileSmem &S, const bool clear, const int view,
@@ -872,7 +886,7 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
     const int tw = min(TW, F.W - x0), th = min(min(TH, F.row1 - y0), rowHi);   // this CTA's rows of the tile: [rowLo, th)
     const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     PH_DECL
-    for (int i = threadIdx.x; i < TH * KEY_STRIDE; i += NT) S.keys[i] = KEY_EMPTY;
+    for (int i = threadIdx.x; i < TH * KEY_STRIDE / 2; i += NT) reinterpret_cast<ulonglong2 *>(S.keys)[i] = make_ulonglong2(KEY_EMPTY, KEY_EMPTY);
 
     // ---- visibility: every (triangle,row) of the tile is one work item -------------------------------------
     for (unsigned base = 0; base < n; base += CH) {
@@ -880,14 +894,12 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
         __syncthreads();  // keys initialised / previous pass finished with the staging area
         PH(2);
         unsigned rows = 0;
-        if (threadIdx.x < m) {   // coalesced copy of the setups k_fill prepared for this tile
+        float4 tr3 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (threadIdx.x < m) {   // the setups k_fill prepared for this tile, brought into the form the row loop wants
             const unsigned at = off + base + threadIdx.x;
             const uint4 d = F.ls3[at];
-            S.u.st.s0[threadIdx.x] = F.ls0[at];
-            S.u.st.s1[threadIdx.x] = F.ls1[at];
-            S.u.st.s2[threadIdx.x] = F.ls2[at];
-            S.u.st.s3[threadIdx.x] = d;
-            S.u.st.s4[threadIdx.x] = F.ls4[at];
+            const float4 a = F.ls0[at], b = F.ls1[at], c = F.ls2[at];
+            tr3 = F.ls4[at];
             {   // the shading pass will want this triangle's 128-byte record: start pulling it into L1 now
                 const char *sr = reinterpret_cast<const char *>(F.shrec + ((long long)view * F.T + d.z) * SREC);
                 asm volatile("prefetch.global.L1 [%0];" :: "l"(sr));
@@ -895,13 +907,27 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
                 asm volatile("prefetch.global.L1 [%0];" :: "l"(sr + 64));
                 asm volatile("prefetch.global.L1 [%0];" :: "l"(sr + 96));
             }
+            // edge vectors, sign-normalised (exact negation: flip the sign bit)
+            const unsigned s1 = (d.w & 1u) << 31, s2 = (d.w & 2u) << 30, s3 = (d.w & 4u) << 29;
+            S.u.st.e0[threadIdx.x] = make_float4(__uint_as_float(__float_as_uint(a.z - b.x) ^ s1), b.y,
+                                                 __uint_as_float(__float_as_uint(a.w - b.y) ^ s1), b.x);
+            S.u.st.e1[threadIdx.x] = make_float4(__uint_as_float(__float_as_uint(b.x - a.x) ^ s2), a.y,
+                                                 __uint_as_float(__float_as_uint(b.y - a.y) ^ s2), a.x);
+            S.u.st.e2[threadIdx.x] = make_float4(__uint_as_float(__float_as_uint(a.x - a.z) ^ s3), a.w,
+                                                 __uint_as_float(__float_as_uint(a.y - a.w) ^ s3), a.z);
+            S.u.st.tz[threadIdx.x] = make_float4(b.z, b.w, c.x, __uint_as_float(d.z));
             const int yt = max((int)(d.y & 0xFFFF), y0 + rowLo), yb = min((int)(d.y >> 16), y0 + th);
             rows = (unsigned)max(yb - yt, 0);
+            const int xa = max((int)(d.x & 0xFFFF), x0) - x0, xb = min((int)(d.x >> 16), x0 + tw) - x0;   // 0 <= xa < xb <= 32
+            const unsigned pk = ((d.w >> 4) & 7u) | ((d.w & FL_SPAN) ? PK_SPAN : 0u) |
+                                ((d.w & (FL_SPAN | FL_FDIV)) == (FL_SPAN | FL_FDIV) ? PK_FAST : 0u) |
+                                ((unsigned)xa << PK_XA) | ((unsigned)max(xb, xa) << PK_XB) | ((unsigned)((yt - y0) & 31) << PK_YT);
+            S.u.st.td[threadIdx.x] = make_float4(c.y, c.z, c.w, __uint_as_float(pk));
         }
         unsigned totalRows;
         const unsigned start = block_exclusive_scan(rows, S.warp_sums, totalRows);
         if (threadIdx.x < m) {
-            S.u.st.rowStart[threadIdx.x] = start;
+            S.u.st.tr[threadIdx.x] = make_float4(tr3.x, tr3.y, tr3.z, __uint_as_float(start));
             for (unsigned j = 0; j < rows; ++j) S.u.st.owner[start + j] = (unsigned char)threadIdx.x;
         }
         PH(3);
@@ -920,149 +946,138 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
 #define CRB_DEAL_ROWS 16
 #endif
         const bool deal = totalRows >= (unsigned)CRB_DEAL_ROWS * m;
-        for (unsigned tb = 0; tb < totalRows; tb += NT) {
-            const unsigned rem = totalRows - tb;
+        // Exact pass.  The surviving pixels of a trip's 32 rows are intervals (first x, count).  In rounds of at most FQ/32 - 1
+        // pixels per row, the rows append one entry per fragment (row lane | x << 5 | trip parity << 10) to the warp's queue at
+        // the positions an exclusive scan of the counts assigns, and the queue is evaluated 32 entries at a time -- whole
+        // batches only: what is left (< 32 entries) moves to the front and heads the first batch of the warp's next trip,
+        // whose rows go into the slot array of the other parity, so that all 32 lanes evaluate a fragment in every step but
+        // the warp's last.  qn: entries in the queue (warp-uniform).
+        unsigned qn = 0, trip = 0;
+        bool finished = false;
+        unsigned short *fq = S.u.st.fq[wid];
+        for (unsigned tb = 0; !finished; tb += NT) {
+            const unsigned rem = tb < totalRows ? totalRows - tb : 0u;
             const unsigned share = (rem >= (unsigned)NT || !deal) ? 32u : (rem + NT / 32 - 1u) / (NT / 32);
-            if (tb + wid * share >= totalRows) break;          // no rows left for this warp (warp-uniform)
+            if (wid * share >= rem) {                        // no rows left for this warp (warp-uniform) ...
+                if (qn == 0u) break;
+                finished = true;                             // ... but fragments of its last trip: one more turn evaluates them
+            }
             const unsigned r = tb + wid * share + lane;
-            const bool active = lane < share && r < totalRows;
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-            bool fdiv = false, span = false;
-            float l02 = 0.f, l12 = 0.f, l22 = 0.f, A1 = 0.f, A2 = 0.f, A3 = 0.f;
-            float thr1 = 0.f, thr2 = 0.f, thr3 = 0.f;
-            unsigned tri = 0, o = 0;
-            int xa = 0, xb = 0, y = y0;
+            const bool active = !finished && lane < share && r < totalRows;
+            const unsigned par = trip & 1u;
+            ++trip;
+            int xa = 0, cnt = 0;              // the row's candidate pixels: tile-relative [xa, xa + cnt)
             if (active) {
-                o = S.u.st.owner[r];
-                a = S.u.st.s0[o]; b = S.u.st.s1[o];
-                const uint4 d = S.u.st.s3[o];
-                tri = d.z;
-                fdiv = (d.w & FL_FDIV) != 0;
-                span = (d.w & FL_SPAN) != 0;
-                y = max((int)(d.y & 0xFFFF), y0 + rowLo) + (int)(r - S.u.st.rowStart[o]);
-                xa = max((int)(d.x & 0xFFFF), x0);
-                xb = min((int)(d.x >> 16), x0 + tw);
-                const unsigned s1 = (d.w & 1u) << 31, s2 = (d.w & 2u) << 30, s3 = (d.w & 4u) << 29;
-                // edge vectors, sign-normalised (exact negation: flip the sign bit)
-                const float l01 = __uint_as_float(__float_as_uint(a.z - b.x) ^ s1);
-                const float l11 = __uint_as_float(__float_as_uint(b.x - a.x) ^ s2);
-                const float l21 = __uint_as_float(__float_as_uint(a.x - a.z) ^ s3);
-                l02 = __uint_as_float(__float_as_uint(a.w - b.y) ^ s1);
-                l12 = __uint_as_float(__float_as_uint(b.y - a.y) ^ s2);
-                l22 = __uint_as_float(__float_as_uint(a.y - a.w) ^ s3);
-                thr1 = (d.w & 16u) ? -REJ_EPS : -INFINITY;
-                thr2 = (d.w & 32u) ? -REJ_EPS : -INFINITY;
-                thr3 = (d.w & 64u) ? -REJ_EPS : -INFINITY;
-                const float py = (float)y;
-                A1 = l01 * (py - b.y); A2 = l11 * (py - a.y); A3 = l21 * (py - a.w);
-            }
-            // pass 1: which pixels of the row need the exact path.  A pixel is certainly outside (bar_k < 0) when a
-            // numerator is below its threshold; each numerator is a monotone function of x (every rounding in
-            // A - l2*(px - b) is monotone), so the pixels that survive all three tests form ONE interval.
-            unsigned mask = 0;
-            if (span) {
-                // analytic, conservative interval first, then its two ends are walked inwards with the very test the
-                // per-pixel loop applies until they rest on surviving pixels: same mask as testing every pixel
-                float lo = (float)xa, hi = (float)(xb - 1);
-                const float fa = lo, fb = hi;
-                span_bound(A1, l02, b.x, fmaxf(fabsf(fa - b.x), fabsf(fb - b.x)), lo, hi);
-                span_bound(A2, l12, a.x, fmaxf(fabsf(fa - a.x), fabsf(fb - a.x)), lo, hi);
-                span_bound(A3, l22, a.z, fmaxf(fabsf(fa - a.z), fabsf(fb - a.z)), lo, hi);
-                if (lo <= hi) {
-                    xa = max(xa, (int)ceilf(lo));      // lo, hi lie within [xa-2, xb+1]: the conversions are exact
-                    xb = min(xb, (int)floorf(hi) + 1);
-                } else {
-                    xb = xa;
-                }
-                while (xa < xb) {
-                    const float px = (float)xa;
-                    if (!(A1 - l02 * (px - b.x) < thr1 || A2 - l12 * (px - a.x) < thr2 || A3 - l22 * (px - a.z) < thr3)) break;
-                    ++xa;
-                }
-                while (xa < xb) {
-                    const float px = (float)(xb - 1);
-                    if (!(A1 - l02 * (px - b.x) < thr1 || A2 - l12 * (px - a.x) < thr2 || A3 - l22 * (px - a.z) < thr3)) break;
-                    --xb;
-                }
-                if (xa < xb) mask = (0xFFFFFFFFu >> (32 - (xb - xa))) << (xa - x0);
-            }
-            if (__any_sync(0xFFFFFFFFu, active && !span)) {
-                // rows of triangles without the analytic bound (huge / non-finite coordinates or denominators): every
-                // pixel of the rectangle row is tested
-                const int len = (active && !span) ? max(xb - xa, 0) : 0;
-                const int maxlen = __reduce_max_sync(0xFFFFFFFFu, len);
-                for (int i = 0; i < maxlen; ++i) {
-                    const float px = (float)(xa + i);
-                    const float n1 = A1 - l02 * (px - b.x);
-                    const float n2 = A2 - l12 * (px - a.x);
-                    const float n3 = A3 - l22 * (px - a.z);
-                    const bool keep = (i < len) && !(n1 < thr1 || n2 < thr2 || n3 < thr3);   // else: certainly bar < 0
-                    mask |= (keep ? 1u : 0u) << ((xa + i - x0) & 31);
-                }
-            }
-            // pass 2 (exact): the surviving pixels of the warp's 32 rows are compacted into a per-warp queue, so that
-            // every lane then evaluates one fragment per step whatever the spread of span lengths (the per-row loop this
-            // replaces ran at 13 of 32 lanes).  A fragment finds its row through the slot its owner lane published.
-            S.u.st.slot[wid][0][lane] = make_float4(A1, A2, A3, l02);
-            S.u.st.slot[wid][1][lane] = make_float4(l12, l22, __uint_as_float(tri),
-                                                    __uint_as_float(o | ((unsigned)(y - y0) << 8) | (fdiv ? 65536u : 0u) | (span ? 131072u : 0u)));
-            unsigned short *fq = S.u.st.fq[wid];
-            while (__any_sync(0xFFFFFFFFu, mask != 0u)) {   // one round unless some row has more than 8 survivors
-                const int cnt = min(__popc(mask), FQ / 32);
-                int inc = cnt;
-#pragma unroll
-                for (int dd = 1; dd < 32; dd <<= 1) {
-                    const int t = __shfl_up_sync(0xFFFFFFFFu, inc, dd);
-                    if ((int)lane >= dd) inc += t;
-                }
-                const int total = __shfl_sync(0xFFFFFFFFu, inc, 31), pre = inc - cnt;
-                const int maxc = __reduce_max_sync(0xFFFFFFFFu, cnt);
-                if (__all_sync(0xFFFFFFFFu, span || mask == 0u)) {
-                    // every mask is one interval (the usual case): its first cnt pixels are first, first + 1, ...
-                    const unsigned firstbit = (unsigned)__ffs(mask) - 1u;
-                    const unsigned entry = lane | (firstbit << 5);
-                    for (int j = 0; j < maxc; ++j)
-                        if (j < cnt) fq[pre + j] = (unsigned short)(entry + ((unsigned)j << 5));
-                    if (cnt) mask = (cnt + (int)firstbit >= 32) ? 0u : (mask >> (cnt + firstbit)) << (cnt + firstbit);
-                } else {
-                    for (int j = 0; j < maxc; ++j) {
-                        if (j < cnt) {
-                            const int bit = __ffs(mask) - 1;
-                            mask &= mask - 1;
-                            fq[pre + j] = (unsigned short)(lane | ((unsigned)bit << 5));
-                        }
+                const unsigned o = S.u.st.owner[r];
+                const float4 E0 = S.u.st.e0[o], E1 = S.u.st.e1[o], E2 = S.u.st.e2[o];
+                const unsigned pk = __float_as_uint(S.u.st.td[o].w);
+                const unsigned yl = ((pk >> PK_YT) & 31u) + (r - __float_as_uint(S.u.st.tr[o].w));   // row inside the tile
+                const float py = (float)(y0 + (int)yl);
+                const float A1 = E0.x * (py - E0.y), A2 = E1.x * (py - E1.y), A3 = E2.x * (py - E2.y);
+                xa = (int)((pk >> PK_XA) & 63u);
+                int xb = (int)((pk >> PK_XB) & 63u);
+                S.u.st.slot[wid][par][lane] = make_float4(A1, A2, A3, __uint_as_float(o | (yl << 8)));
+                // pass 1: which pixels of the row need the exact path.  A pixel is certainly outside (bar_k < 0) when a
+                // numerator is below its threshold; each numerator is a monotone function of x (every rounding in
+                // A - l2*(px - b) is monotone), so the pixels that survive all three tests form ONE interval.
+                if (pk & PK_SPAN) {
+                    // analytic, conservative interval (span_bound)
+                    float lo = (float)(x0 + xa), hi = (float)(x0 + xb - 1);
+                    const float xc = (float)(x0 + TW / 2);
+                    span_bound(A1, E0.z, E0.w, xc, lo, hi);
+                    span_bound(A2, E1.z, E1.w, xc, lo, hi);
+                    span_bound(A3, E2.z, E2.w, xc, lo, hi);
+                    if (lo <= hi) {
+                        xa = max(xa, (int)ceilf(lo) - x0);       // lo, hi lie within [x0 + xa - 1, x0 + xb]: the conversions are exact
+                        xb = min(xb, (int)floorf(hi) + 1 - x0);
+                    } else {
+                        xb = xa;
                     }
+                } else {
+                    // triangles without the analytic bound (huge / non-finite coordinates or denominators): every pixel of
+                    // the rectangle row is tested against the thresholds; the hull of the survivors is the interval
+                    const float thr1 = (pk & (PK_REJ << 0)) ? -REJ_EPS : -INFINITY;
+                    const float thr2 = (pk & (PK_REJ << 1)) ? -REJ_EPS : -INFINITY;
+                    const float thr3 = (pk & (PK_REJ << 2)) ? -REJ_EPS : -INFINITY;
+                    unsigned mask = 0;
+#pragma unroll 1
+                    for (int x = xa; x < xb; ++x) {
+                        const float px = (float)(x0 + x);
+                        const float n1 = A1 - E0.z * (px - E0.w);
+                        const float n2 = A2 - E1.z * (px - E1.w);
+                        const float n3 = A3 - E2.z * (px - E2.w);
+                        if (!(n1 < thr1 || n2 < thr2 || n3 < thr3)) mask |= 1u << x;        // else: certainly bar < 0
+                    }
+                    xa = mask ? __ffs(mask) - 1 : 0;
+                    xb = mask ? 32 - __clz(mask) : 0;
                 }
-                __syncwarp();
-                for (int base2 = 0; base2 < total; base2 += 32) {
-                    const int idx = base2 + (int)lane;
-                    if (idx < total) {
-                        const unsigned e = fq[idx];
-                        const unsigned src = e & 31u, bit = e >> 5;
-                        const float4 q0 = S.u.st.slot[wid][0][src], q1 = S.u.st.slot[wid][1][src];
-                        const unsigned info = __float_as_uint(q1.w), o2 = info & 255u;
-                        const float4 pa = S.u.st.s0[o2], pb = S.u.st.s1[o2], pc = S.u.st.s2[o2], pr = S.u.st.s4[o2];
+                cnt = max(xb - xa, 0);
+            }
+            __syncwarp();                     // the slots are published
+            const unsigned old = qn;          // entries of the previous trip still waiting (they sit at the front)
+            unsigned done = 0;
+            unsigned entry = lane | ((unsigned)xa << 5) | (par << 10);
+            for (;;) {
+                const bool more = __any_sync(0xFFFFFFFFu, cnt > 0);
+                if (more) {
+                    const int c = min(cnt, FQ / 32 - 1);
+                    int inc = c;
+#pragma unroll
+                    for (int dd = 1; dd < 32; dd <<= 1) {
+                        const int t = __shfl_up_sync(0xFFFFFFFFu, inc, dd);
+                        if ((int)lane >= dd) inc += t;
+                    }
+                    unsigned short *at = fq + qn + (unsigned)(inc - c);
+#pragma unroll
+                    for (int j = 0; j < FQ / 32 - 1; ++j)
+                        if (j < c) at[j] = (unsigned short)(entry + ((unsigned)j << 5));
+                    entry += (unsigned)c << 5;
+                    cnt -= c;
+                    qn += (unsigned)__shfl_sync(0xFFFFFFFFu, inc, 31);
+                    __syncwarp();
+                }
+                const bool flush = !more && (finished || done < old);     // the slots of the trip before last are about to be reused
+                unsigned b = 0;
+                for (; b + 32u <= qn || (flush && b < qn); b += 32u) {
+                    if (b + lane < qn) {
+                        const unsigned e = fq[b + lane];
+                        const unsigned src = e & 31u, bit = (e >> 5) & 31u;
+                        const float4 q = S.u.st.slot[wid][e >> 10][src];
+                        const unsigned info = __float_as_uint(q.w), o2 = info & 255u;
+                        const float2 h0 = *reinterpret_cast<const float2 *>(&S.u.st.e0[o2].z);
+                        const float2 h1 = *reinterpret_cast<const float2 *>(&S.u.st.e1[o2].z);
+                        const float2 h2 = *reinterpret_cast<const float2 *>(&S.u.st.e2[o2].z);
+                        const float4 Z = S.u.st.tz[o2], D = S.u.st.td[o2], R = S.u.st.tr[o2];
                         const float px = (float)(x0 + (int)bit);
-                        const float n1 = q0.x - q0.w * (px - pb.x);
-                        const float n2 = q0.y - q1.x * (px - pa.x);
-                        const float n3 = q0.z - q1.y * (px - pa.z);
+                        const float n1 = q.x - h0.x * (px - h0.y);
+                        const float n2 = q.y - h1.x * (px - h1.y);
+                        const float n3 = q.z - h2.x * (px - h2.y);
                         float b1, b2, b3;
-                        // FL_SPAN rows have |numerator| < 2^40 by construction (coordinates <= 2^18): only the lower bound is tested
-                        if ((info & 65536u) && ((info & 131072u) ? fdiv_ok_lo(n1, n2, n3) : fdiv_ok(n1, n2, n3))) {
-                            b1 = div_rn_by(n1, pc.y, pr.x); b2 = div_rn_by(n2, pc.z, pr.y); b3 = div_rn_by(n3, pc.w, pr.z);
+                        // PK_FAST triangles have |numerator| < 2^40 by construction (coordinates <= 2^18): only the lower bound is tested
+                        if ((__float_as_uint(D.w) & PK_FAST) && fdiv_ok_lo(n1, n2, n3)) {
+                            b1 = div_rn_by(n1, D.x, R.x); b2 = div_rn_by(n2, D.y, R.y); b3 = div_rn_by(n3, D.z, R.z);
                         } else {
-                            b1 = n1 / pc.y; b2 = n2 / pc.z; b3 = n3 / pc.w;
+                            b1 = n1 / D.x; b2 = n2 / D.y; b3 = n3 / D.z;
                         }
                         if (!(b1 < 0.0f || b2 < 0.0f || b3 < 0.0f)) {                 // pyx:216
-                            const float z = (pb.z * b1 + pb.w * b2) + pc.x * b3;          // pyx:219
+                            const float z = (Z.x * b1 + Z.y * b2) + Z.z * b3;             // pyx:219
                             if (z == z)                                                   // pyx:220 rejects NaN only
-                                smem_key_min(S.keys + ((info >> 8) & 31u) * KEY_STRIDE + bit, pack_key(z, __float_as_uint(q1.z)));
+                                smem_key_min(S.keys + ((info >> 8) & 31u) * KEY_STRIDE + bit, pack_key(z, __float_as_uint(Z.w)));
                         }
                     }
                 }
-                __syncwarp();
+                if (b) {                      // what is left moves to the front
+                    const unsigned left = qn > b ? qn - b : 0u;
+                    unsigned short tmp = 0;
+                    if (lane < left) tmp = fq[b + lane];
+                    __syncwarp();
+                    if (lane < left) fq[lane] = tmp;
+                    done += min(b, qn);
+                    qn = left;
+                    __syncwarp();
+                }
+                if (!more) break;
             }
-            __syncwarp();
         }
         PH(5);
     }
