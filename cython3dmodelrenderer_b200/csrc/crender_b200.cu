@@ -191,9 +191,8 @@ __device__ __forceinline__ int clipi(int a, int lo, int hi) { return a < lo ? lo
 // -0.0 is folded onto +0.0 first (they compare equal in the reference, so the triangle index must break the tie).
 __device__ __forceinline__ unsigned depth_key(float z)
 {
-    unsigned b = __float_as_uint(z);
-    if (b == 0x80000000u) b = 0u;
-    return b ^ ((b & 0x80000000u) ? 0xFFFFFFFFu : 0x80000000u);
+    const unsigned b = __float_as_uint(__fadd_rn(z, 0.0f));        // -0.0 + 0.0 = +0.0, every other value unchanged (z is never NaN here)
+    return b ^ ((unsigned)((int)b >> 31) | 0x80000000u);
 }
 __device__ __forceinline__ unsigned long long pack_key(float z, unsigned tri)
 {
@@ -884,9 +883,13 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
     const int x0 = tx * TW, yl0 = ty * TH;       // yl0: row inside the band's buffers
     const int y0 = F.row0 + yl0;                  // absolute image row
     const int tw = min(TW, F.W - x0), th = min(min(TH, F.row1 - y0), rowHi);   // this CTA's rows of the tile: [rowLo, th)
-    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    // the thread index is read once, through an asm the compiler cannot re-issue: under the 40-register cap it otherwise
+    // re-reads the special register (S2R + the lane / warp arithmetic) inside every loop -- 6 % of the kernel's instructions
+    unsigned tid;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+    const unsigned lane = tid & 31u, wid = tid >> 5;
     PH_DECL
-    for (int i = threadIdx.x; i < TH * KEY_STRIDE / 2; i += NT) reinterpret_cast<ulonglong2 *>(S.keys)[i] = make_ulonglong2(KEY_EMPTY, KEY_EMPTY);
+    for (int i = tid; i < TH * KEY_STRIDE / 2; i += NT) reinterpret_cast<ulonglong2 *>(S.keys)[i] = make_ulonglong2(KEY_EMPTY, KEY_EMPTY);
 
     // ---- visibility: every (triangle,row) of the tile is one work item -------------------------------------
     for (unsigned base = 0; base < n; base += CH) {
@@ -895,8 +898,8 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
         PH(2);
         unsigned rows = 0;
         float4 tr3 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (threadIdx.x < m) {   // the setups k_fill prepared for this tile, brought into the form the row loop wants
-            const unsigned at = off + base + threadIdx.x;
+        if (tid < m) {   // the setups k_fill prepared for this tile, brought into the form the row loop wants
+            const unsigned at = off + base + tid;
             const uint4 d = F.ls3[at];
             const float4 a = F.ls0[at], b = F.ls1[at], c = F.ls2[at];
             tr3 = F.ls4[at];
@@ -909,26 +912,26 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
             }
             // edge vectors, sign-normalised (exact negation: flip the sign bit)
             const unsigned s1 = (d.w & 1u) << 31, s2 = (d.w & 2u) << 30, s3 = (d.w & 4u) << 29;
-            S.u.st.e0[threadIdx.x] = make_float4(__uint_as_float(__float_as_uint(a.z - b.x) ^ s1), b.y,
+            S.u.st.e0[tid] = make_float4(__uint_as_float(__float_as_uint(a.z - b.x) ^ s1), b.y,
                                                  __uint_as_float(__float_as_uint(a.w - b.y) ^ s1), b.x);
-            S.u.st.e1[threadIdx.x] = make_float4(__uint_as_float(__float_as_uint(b.x - a.x) ^ s2), a.y,
+            S.u.st.e1[tid] = make_float4(__uint_as_float(__float_as_uint(b.x - a.x) ^ s2), a.y,
                                                  __uint_as_float(__float_as_uint(b.y - a.y) ^ s2), a.x);
-            S.u.st.e2[threadIdx.x] = make_float4(__uint_as_float(__float_as_uint(a.x - a.z) ^ s3), a.w,
+            S.u.st.e2[tid] = make_float4(__uint_as_float(__float_as_uint(a.x - a.z) ^ s3), a.w,
                                                  __uint_as_float(__float_as_uint(a.y - a.w) ^ s3), a.z);
-            S.u.st.tz[threadIdx.x] = make_float4(b.z, b.w, c.x, __uint_as_float(d.z));
+            S.u.st.tz[tid] = make_float4(b.z, b.w, c.x, __uint_as_float(d.z));
             const int yt = max((int)(d.y & 0xFFFF), y0 + rowLo), yb = min((int)(d.y >> 16), y0 + th);
             rows = (unsigned)max(yb - yt, 0);
             const int xa = max((int)(d.x & 0xFFFF), x0) - x0, xb = min((int)(d.x >> 16), x0 + tw) - x0;   // 0 <= xa < xb <= 32
             const unsigned pk = ((d.w >> 4) & 7u) | ((d.w & FL_SPAN) ? PK_SPAN : 0u) |
                                 ((d.w & (FL_SPAN | FL_FDIV)) == (FL_SPAN | FL_FDIV) ? PK_FAST : 0u) |
                                 ((unsigned)xa << PK_XA) | ((unsigned)max(xb, xa) << PK_XB) | ((unsigned)((yt - y0) & 31) << PK_YT);
-            S.u.st.td[threadIdx.x] = make_float4(c.y, c.z, c.w, __uint_as_float(pk));
+            S.u.st.td[tid] = make_float4(c.y, c.z, c.w, __uint_as_float(pk));
         }
         unsigned totalRows;
         const unsigned start = block_exclusive_scan(rows, S.warp_sums, totalRows);
-        if (threadIdx.x < m) {
-            S.u.st.tr[threadIdx.x] = make_float4(tr3.x, tr3.y, tr3.z, __uint_as_float(start));
-            for (unsigned j = 0; j < rows; ++j) S.u.st.owner[start + j] = (unsigned char)threadIdx.x;
+        if (tid < m) {
+            S.u.st.tr[tid] = make_float4(tr3.x, tr3.y, tr3.z, __uint_as_float(start));
+            for (unsigned j = 0; j < rows; ++j) S.u.st.owner[start + j] = (unsigned char)tid;
         }
         PH(3);
         __syncthreads();
@@ -1099,13 +1102,14 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
     const bool stage = tma || vec;
     const float bg = background_color(F);
     const long long tilebase = slab + (long long)yl0 * F.W + x0;          // first pixel of the tile in its slab
-    for (int p = threadIdx.x; p < TH * TW; p += NT) {
-        const int yy = p / TW, xx = p % TW;
+    const unsigned rowStep = (unsigned)(NT / TW) * (unsigned)F.W;
+    long long pix = tilebase + (unsigned)((int)wid * F.W + (int)lane);    // this thread's pixels: column lane, rows wid, wid + 8, ...
+    for (int p = tid; p < TH * TW; p += NT, pix += rowStep) {
+        const int yy = p / TW, xx = (int)lane;
         if (yy < rowLo || yy >= th || xx >= tw) continue;
         const unsigned long long key = S.keys[yy * KEY_STRIDE + xx];
         float z = Z_INIT, c[3] = {bg, bg, bg}, nn[3] = {0.f, 0.f, 0.f};
         bool write = clear;
-        const long long pix = tilebase + (unsigned)(yy * F.W + xx);       // yy < 32, W < 65536: 32-bit offset inside the tile
         if (key != KEY_EMPTY && !DBG(F, FLAG_DBG_NOSHADE)) {
             const unsigned tri = ~(unsigned)(key & 0xFFFFFFFFull);
             const long long ridx = (long long)view * F.T + tri;
@@ -1153,8 +1157,8 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
         }
     } else if (vec) {
         __syncthreads();
-        const int q = threadIdx.x & 7;
-        for (int r = rowLo + (threadIdx.x >> 3); r < th; r += NT / 8) {
+        const int q = tid & 7;
+        for (int r = rowLo + (tid >> 3); r < th; r += NT / 8) {
             const long long o = (slab + (long long)(yl0 + r) * F.W + x0) * 3;
             if (F.color) {
                 float4 *g = reinterpret_cast<float4 *>(F.color + o);
