@@ -1195,10 +1195,12 @@ __device__ __forceinline__ void tma_clear_tile(const TMaps &M, const TileSmem &S
 // frame) -- a few thousand cycles of queueing, no arithmetic -- so those stores drain beside the rasterizing CTAs that
 // share its SM for the whole length of the kernel.  Launches without tensor maps clear with plain stores up front,
 // every CTA adopting its share of the empty tiles.
-// 6 resident CTAs per SM (40 registers, 35.7 KB shared memory each): measured 4 % faster than 5 with 48 registers
+// 6 resident CTAs per SM (40 registers, 36.9 KB shared memory each -- 0.7 KB below the limit): 5 with 48 registers measured
+// 8.7 % slower (profiles/history/r02_probe_variants.json)
 #ifndef CRB_RASTER_MIN_CTAS
 #define CRB_RASTER_MIN_CTAS 6
 #endif
+static_assert(sizeof(TileSmem) + 1024 <= 233472 / CRB_RASTER_MIN_CTAS, "k_raster: shared memory per CTA exceeds the residency its launch bounds assume");
 __global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame F, const __grid_constant__ TMaps M)
 {
     __shared__ TileSmem S;
@@ -1358,15 +1360,6 @@ __global__ void __launch_bounds__(NT) k_init_buffers(float *z, float *color, flo
     }
 }
 
-// Sparse read-back (crb_render_host + CRB_DL_SPARSE).  The host copy of the three buffers persists between calls, every
-// call renders a FRESH frame, and a pixel row no fragment was written to holds fresh-filler values both before and after --
-// so only the 32-pixel tile rows that hold something now, or held something in the frame the host copy currently shows,
-// need to cross PCIe.  One CTA per tile that is busy now or has rows to take back: warp w compares rows w, w+8, ... of the
-// tile with the fresh pattern (z 1e6, colour / normals 0) as it reads them, copies the rows that differ now or differed
-// before straight into the mapped pinned host arrays (16-byte stores, 128 / 384-byte runs), and the tile's new row mask is
-// kept for the next call; everything else exits at once.  The host arrays end up bit-identical to a full download
-// (tests/test_gpu_parity.py::test_sparse_readback_*).  `rows_copied` counts tile rows (32 pixels x 28 bytes when all
-// three buffers are wanted).
 // One tile of the sparse read-back, by one warp; returns the tile rows it copied.
 __device__ __forceinline__ unsigned readback_tile(const Frame &F, const unsigned t, unsigned *shown_rows, float *hz, float *hc, float *hn)
 {
@@ -1680,6 +1673,18 @@ int check_filler(const crb_filler *f)
     return CRB_OK;
 }
 
+// Shared by every render entry point: triangle indices are packed into 32 bits (the ~tri half of the visibility key, the
+// staged triangle's index word), so a larger T would silently alias winners.
+int check_triangles(const crb_filler *f, int64_t T, const float *v, const float *c, const float *n)
+{
+    if (T < 0) return fail(CRB_ERR_INVALID, "T < 0");
+    if (T > 0 && (!v || !c || !n)) return fail(CRB_ERR_INVALID, "NULL triangle array");
+    if (!f->ws) return fail(CRB_ERR_STATE, "workspace not bound");
+    if (T > f->maxT) return fail(CRB_ERR_STATE, "T=%lld exceeds the workspace's max_triangles=%lld", (long long)T, f->maxT);
+    if (T > 0xFFFFFFF0ll) return fail(CRB_ERR_INVALID, "T exceeds 32-bit triangle indices");
+    return CRB_OK;
+}
+
 int host_projection(int h, int w, float fov, float z_near, float z_far, ProjC *P)
 {
     if (w == 0) return fail(CRB_ERR_ZERODIV, "division by zero");  // pyx:59 h / w
@@ -1791,7 +1796,7 @@ int run_prep(crb_filler *f, Frame &F, cudaStream_t st)
         const size_t so = (size_t)(reinterpret_cast<const char *>(F.alive) - reinterpret_cast<const char *>(f->alive));   // workspace set in use
         F.chunks = reinterpret_cast<unsigned *>(reinterpret_cast<char *>(f->chunks) + so);
         CU(cudaMemsetAsync(F.chunks, 0, 4, st));
-        static const int bcPerSm = getenv("CRB_BC_CTAS") ? atoi(getenv("CRB_BC_CTAS")) : 4;   // 4 x 36 KB rings per SM
+        constexpr int bcPerSm = 4;   // 4 x 36 KB rings per SM
         const unsigned gP = (unsigned)min((long long)gT, (long long)f->sm_count * bcPerSm);
         k_band_chunks<<<gP, NT, 0, st>>>(F);
         if ((rc = launch_check(f, "k_band_chunks"))) return rc;
@@ -1936,6 +1941,86 @@ int bind_ws_pointers(crb_filler *f, void *ws, size_t bytes, long long T, int vie
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------------------
+// The expensive, size-independent part of a filler -- two streams, five events and a mapped page-locked statistics block
+// (cudaHostAlloc / cudaFreeHost alone cost milliseconds and synchronise the device) -- is recycled through a process-wide
+// free list: the reference's only idiom is a NEW filler per frame (run.py:21), so crb_create / crb_destroy must be cheap.
+// ------------------------------------------------------------------------------------------------------------
+#include <mutex>
+namespace {
+struct Shell {
+    int device;
+    cudaStream_t s_prep, s_raster;
+    cudaEvent_t ev_start, ev_fill[2], ev_raster[2];
+    unsigned long long *hstats, *hstats_dev;
+};
+std::mutex g_shell_mu;
+std::vector<Shell> g_shells;
+constexpr size_t SHELL_POOL_MAX = 64;
+
+int shell_acquire(int device, Shell *out)
+{
+    {
+        std::lock_guard<std::mutex> lk(g_shell_mu);
+        for (size_t i = 0; i < g_shells.size(); ++i)
+            if (g_shells[i].device == device) {
+                *out = g_shells[i];
+                g_shells.erase(g_shells.begin() + (long)i);
+                if (out->hstats) memset(out->hstats, 0, 128);
+                return CRB_OK;
+            }
+    }
+    Shell sh;
+    memset(&sh, 0, sizeof(sh));
+    sh.device = device;
+    int lo = 0, hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    // equal priorities measured best (a high-priority front end costs the rasterizer more than it gains)
+    CU(cudaStreamCreateWithPriority(&sh.s_prep, cudaStreamNonBlocking, lo));
+    CU(cudaStreamCreateWithPriority(&sh.s_raster, cudaStreamNonBlocking, lo));
+    CU(cudaEventCreateWithFlags(&sh.ev_start, cudaEventDisableTiming));
+    for (int k = 0; k < 2; ++k) {
+        CU(cudaEventCreateWithFlags(&sh.ev_fill[k], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&sh.ev_raster[k], cudaEventDisableTiming));
+    }
+    void *hp = nullptr, *dp = nullptr;
+    if (cudaHostAlloc(&hp, 128, cudaHostAllocMapped) == cudaSuccess && cudaHostGetDevicePointer(&dp, hp, 0) == cudaSuccess) {
+        memset(hp, 0, 128);
+        sh.hstats = (unsigned long long *)hp;
+        sh.hstats_dev = (unsigned long long *)dp;
+    } else {
+        if (hp) cudaFreeHost(hp);
+        cudaGetLastError();
+    }
+    *out = sh;
+    return CRB_OK;
+}
+
+void shell_destroy(Shell &sh)
+{
+    if (sh.hstats) cudaFreeHost(sh.hstats);
+    if (sh.s_prep) cudaStreamDestroy(sh.s_prep);
+    if (sh.s_raster) cudaStreamDestroy(sh.s_raster);
+    if (sh.ev_start) cudaEventDestroy(sh.ev_start);
+    for (int k = 0; k < 2; ++k) {
+        if (sh.ev_fill[k]) cudaEventDestroy(sh.ev_fill[k]);
+        if (sh.ev_raster[k]) cudaEventDestroy(sh.ev_raster[k]);
+    }
+}
+
+void shell_release(Shell &sh)
+{
+    {
+        std::lock_guard<std::mutex> lk(g_shell_mu);
+        if (g_shells.size() < SHELL_POOL_MAX) {
+            g_shells.push_back(sh);
+            return;
+        }
+    }
+    shell_destroy(sh);
+}
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------------------
 extern "C" {
@@ -2030,42 +2115,27 @@ int crb_create(int h, int w, float fov, float z_near, float z_far, int device, c
         CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
         f->sm_count = sms > 0 ? sms : 148;
         f->raster_ctas = 0;
-        if (const char *e = getenv("CRB_RASTER_CTAS")) f->raster_ctas = atoi(e);   // experiments: >0 fixed grid, <0 one CTA per tile
         f->use_tma = 1;
         f->split_heavy = 1;
         f->band_prepass = 1;
-        if (const char *e = getenv("CRB_BAND_PREPASS")) f->band_prepass = atoi(e) ? 1 : 0;
-        if (const char *e = getenv("CRB_SPLIT_HEAVY")) f->split_heavy = atoi(e) ? 1 : 0;
         f->chunk_pipeline = 1;
-        if (const char *e = getenv("CRB_CHUNK_PIPELINE")) f->chunk_pipeline = atoi(e) ? 1 : 0;
         {
-            int lo = 0, hi = 0;
-            CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-            int pp = lo;           // equal priorities measured best (a high-priority front end costs the rasterizer more than it gains)
-            if (const char *e = getenv("CRB_PREP_PRIORITY")) pp = atoi(e) ? hi : lo;
-            CU(cudaStreamCreateWithPriority(&f->s_prep, cudaStreamNonBlocking, pp));
-            CU(cudaStreamCreateWithPriority(&f->s_raster, cudaStreamNonBlocking, lo));
-        }
-        CU(cudaEventCreateWithFlags(&f->ev_start, cudaEventDisableTiming));
-        for (int k = 0; k < 2; ++k) {
-            CU(cudaEventCreateWithFlags(&f->ev_fill[k], cudaEventDisableTiming));
-            CU(cudaEventCreateWithFlags(&f->ev_raster[k], cudaEventDisableTiming));
+            Shell sh;
+            int src = shell_acquire(device, &sh);
+            if (src) { delete f; return src; }
+            f->s_prep = sh.s_prep; f->s_raster = sh.s_raster; f->ev_start = sh.ev_start;
+            for (int k = 0; k < 2; ++k) { f->ev_fill[k] = sh.ev_fill[k]; f->ev_raster[k] = sh.ev_raster[k]; }
+            f->hstats = sh.hstats; f->hstats_dev = sh.hstats_dev;
         }
         f->tiles_per_cta = 1;
+        f->out_tma = 1;
+#ifdef CRB_ABLATION     // development builds only (make variants): switches read from the environment
+        if (const char *e = getenv("CRB_RASTER_CTAS")) f->raster_ctas = atoi(e);
         if (const char *e = getenv("CRB_TILES_PER_CTA")) { int k = atoi(e); if (k >= 1 && k <= 64) f->tiles_per_cta = k; }
         if (const char *e = getenv("CRB_NO_TMA")) f->use_tma = atoi(e) ? 0 : 1;
-        f->out_tma = 1;
-        if (const char *e = getenv("CRB_OUT_TMA")) f->out_tma = atoi(e);   // 1 TMA boxes, 0 vector stores, 2 direct stores (experiment)
+        if (const char *e = getenv("CRB_OUT_TMA")) f->out_tma = atoi(e);
         if (const char *e = getenv("CRB_DEBUG_SKIP")) f->dbg_flags = ((unsigned)atoi(e) & 31u) << 16;
-        void *hp = nullptr, *dp = nullptr;
-        if (cudaHostAlloc(&hp, 128, cudaHostAllocMapped) == cudaSuccess && cudaHostGetDevicePointer(&dp, hp, 0) == cudaSuccess) {
-            memset(hp, 0, 128);
-            f->hstats = (unsigned long long *)hp;
-            f->hstats_dev = (unsigned long long *)dp;
-        } else {
-            if (hp) cudaFreeHost(hp);
-            cudaGetLastError();
-        }
+#endif
     }
     *out = f;
     return CRB_OK;
@@ -2080,13 +2150,14 @@ void crb_destroy(crb_filler *f)
     if (f->keybuf) cudaFree(f->keybuf);
     if (f->s_prep) cudaStreamSynchronize(f->s_prep);        // nothing of ours may still be running when the caller frees memory
     if (f->s_raster) cudaStreamSynchronize(f->s_raster);
-    if (f->hstats) cudaFreeHost(f->hstats);
-    if (f->s_prep) cudaStreamDestroy(f->s_prep);
-    if (f->s_raster) cudaStreamDestroy(f->s_raster);
-    if (f->ev_start) cudaEventDestroy(f->ev_start);
-    for (int k = 0; k < 2; ++k) {
-        if (f->ev_fill[k]) cudaEventDestroy(f->ev_fill[k]);
-        if (f->ev_raster[k]) cudaEventDestroy(f->ev_raster[k]);
+    {
+        Shell sh;
+        memset(&sh, 0, sizeof(sh));
+        sh.device = f->device;
+        sh.s_prep = f->s_prep; sh.s_raster = f->s_raster; sh.ev_start = f->ev_start;
+        for (int k = 0; k < 2; ++k) { sh.ev_fill[k] = f->ev_fill[k]; sh.ev_raster[k] = f->ev_raster[k]; }
+        sh.hstats = f->hstats; sh.hstats_dev = f->hstats_dev;
+        shell_release(sh);
     }
     if (f->shown_busy) cudaFree(f->shown_busy);
     if (f->tiles_copied) cudaFree(f->tiles_copied);
@@ -2198,12 +2269,8 @@ int crb_init_buffers(crb_filler *f, void *stream)
 int crb_render(crb_filler *f, const float *v, const float *c, const float *n, int64_t T, unsigned flags, void *stream)
 {
     if (check_filler(f)) return CRB_ERR_INVALID;
-    if (T < 0) return fail(CRB_ERR_INVALID, "T < 0");
-    if (T > 0 && (!v || !c || !n)) return fail(CRB_ERR_INVALID, "NULL triangle array");
     if (!f->z || !f->color || !f->normals) return fail(CRB_ERR_STATE, "buffers not bound");
-    if (!f->ws) return fail(CRB_ERR_STATE, "workspace not bound");
-    if (T > f->maxT) return fail(CRB_ERR_STATE, "T=%lld exceeds the workspace's max_triangles=%lld", (long long)T, f->maxT);
-    if (T > 0xFFFFFFF0ll) return fail(CRB_ERR_INVALID, "T exceeds 32-bit triangle indices");
+    { int trc = check_triangles(f, T, v, c, n); if (trc) return trc; }
     CU(cudaSetDevice(f->device));
     { int jrc = join_pending(f, (cudaStream_t)stream); if (jrc) return jrc; }
     if ((long long)(f->row1 - f->row0) * f->w == 0) return CRB_OK;
@@ -2256,9 +2323,7 @@ static int render_host_once(crb_filler *f, const float *v, const float *c, const
                             unsigned download_mask, float *z_out, float *color_out, float *normals_out, void *stream)
 {
     if (check_filler(f)) return CRB_ERR_INVALID;
-    if (!f->ws) return fail(CRB_ERR_STATE, "workspace not bound");
-    if (T < 0 || T > f->maxT) return fail(CRB_ERR_STATE, "T=%lld outside the workspace's [0,%lld]", (long long)T, f->maxT);
-    if (T > 0 && (!v || !c || !n)) return fail(CRB_ERR_INVALID, "NULL triangle array");
+    { int trc = check_triangles(f, T, v, c, n); if (trc) return trc; }
     CU(cudaSetDevice(f->device));
     { int jrc = join_pending(f, (cudaStream_t)stream); if (jrc) return jrc; }
     cudaStream_t st = (cudaStream_t)stream;
@@ -2305,8 +2370,7 @@ static int render_host_once(crb_filler *f, const float *v, const float *c, const
             CU(cudaMemsetAsync(f->tiles_copied, 0, 8, st));
         }
         if (F.nTiles > 0) {
-            static const int rbCtas = getenv("CRB_READBACK_CTAS") ? atoi(getenv("CRB_READBACK_CTAS")) : 0;   // experiments
-            const int want = rbCtas > 0 ? rbCtas : READBACK_CTAS;
+            const int want = READBACK_CTAS;
             k_readback<<<(unsigned)(F.nTiles < want ? F.nTiles : want), NT, 0, st>>>(F, f->shown_busy, hp[0], hp[1], hp[2], f->tiles_copied);
             if ((rc = launch_check(f, "k_readback"))) return rc;
         }
@@ -2360,11 +2424,9 @@ int crb_render_views(crb_filler *f, const float *v, const float *c, const float 
                      unsigned flags, const float light[3], void *stream)
 {
     if (check_filler(f)) return CRB_ERR_INVALID;
-    if (T < 0 || n_views < 0) return fail(CRB_ERR_INVALID, "negative size");
-    if (T > 0 && (!v || !c || !n)) return fail(CRB_ERR_INVALID, "NULL triangle array");
+    if (n_views < 0) return fail(CRB_ERR_INVALID, "negative size");
+    { int trc = check_triangles(f, T, v, c, n); if (trc) return trc; }
     if (n_views > 0 && !views && n_views != 1) return fail(CRB_ERR_INVALID, "views is NULL (allowed for one untransformed view only)");
-    if (!f->ws) return fail(CRB_ERR_STATE, "workspace not bound");
-    if (T > f->maxT) return fail(CRB_ERR_STATE, "T=%lld exceeds the workspace's max_triangles=%lld", (long long)T, f->maxT);
     if (flags & CRB_PATH_ATOMIC) return fail(CRB_ERR_INVALID, "CRB_PATH_ATOMIC supports single-view renders only");
     if ((flags & CRB_GURO) && !light) return fail(CRB_ERR_INVALID, "CRB_GURO needs a light direction");
     if ((reinterpret_cast<uintptr_t>(z_out) | reinterpret_cast<uintptr_t>(color_out) | reinterpret_cast<uintptr_t>(normals_out)) & 15u)
@@ -2435,9 +2497,7 @@ int crb_render_image_host(crb_filler *f, const float *v, const float *c, const f
                           const float light[3], uint8_t *image_dev, uint8_t *image_host, uint64_t status_pinned[4], void *stream)
 {
     if (check_filler(f)) return CRB_ERR_INVALID;
-    if (!f->ws) return fail(CRB_ERR_STATE, "workspace not bound");
-    if (T < 0 || T > f->maxT) return fail(CRB_ERR_STATE, "T=%lld outside the workspace's [0,%lld]", (long long)T, f->maxT);
-    if (T > 0 && (!v || !c || !n)) return fail(CRB_ERR_INVALID, "NULL triangle array");
+    { int trc = check_triangles(f, T, v, c, n); if (trc) return trc; }
     if (!image_dev || !image_host) return fail(CRB_ERR_INVALID, "NULL image buffer");
     CU(cudaSetDevice(f->device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -2548,6 +2608,8 @@ int crb_status(crb_filler *f, int64_t *pairs_needed, int64_t *pair_capacity, voi
     return CRB_OK;
 }
 
+int64_t crb_pair_capacity(const crb_filler *f) { return (f && f->ws) ? (int64_t)f->pairCap : 0; }
+
 int crb_status_async(crb_filler *f, uint64_t pinned[4], void *stream)
 {
     if (check_filler(f) || !pinned) return fail(CRB_ERR_INVALID, "NULL argument");
@@ -2566,7 +2628,9 @@ int crb_set_option(crb_filler *f, int option, int value)
     switch (option) {
     case CRB_OPT_CHUNK_PIPELINE: f->chunk_pipeline = value ? 1 : 0; return CRB_OK;
     case CRB_OPT_TMA: f->use_tma = value ? 1 : 0; return CRB_OK;
-    case CRB_OPT_TMA_ROWS: f->out_tma = value ? 1 : 0; return CRB_OK;
+    case CRB_OPT_TMA_ROWS: f->out_tma = (value == 2) ? 2 : (value ? 1 : 0); return CRB_OK;
+    case CRB_OPT_RASTER_CTAS: f->raster_ctas = value > 0 ? value : 0; return CRB_OK;
+    case CRB_OPT_SPLIT_HEAVY: f->split_heavy = value ? 1 : 0; return CRB_OK;
     case CRB_OPT_BAND_PREPASS: f->band_prepass = value ? 1 : 0; return CRB_OK;
     default: return fail(CRB_ERR_INVALID, "unknown option %d", option);
     }
@@ -2585,6 +2649,7 @@ int crb_readback_stats(crb_filler *f, int64_t *tiles_copied, int reset, void *st
 {
     if (check_filler(f) || !tiles_copied) return fail(CRB_ERR_INVALID, "NULL argument");
     CU(cudaSetDevice(f->device));
+    { int jrc = join_pending(f, (cudaStream_t)stream); if (jrc) return jrc; }
     unsigned long long n = 0;
     if (f->tiles_copied) {
         CU(cudaMemcpyAsync(&n, f->tiles_copied, 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
@@ -2599,6 +2664,7 @@ int crb_readback_reset(crb_filler *f, void *stream)
 {
     if (check_filler(f)) return CRB_ERR_INVALID;
     CU(cudaSetDevice(f->device));
+    { int jrc = join_pending(f, (cudaStream_t)stream); if (jrc) return jrc; }
     if (f->shown_busy) CU(cudaMemsetAsync(f->shown_busy, 0, 4 * (size_t)(f->shown_tiles > 0 ? f->shown_tiles : 1), (cudaStream_t)stream));
     return CRB_OK;
 }

@@ -194,6 +194,8 @@ class Model:
         """attr[tri] on the device -> (host array [T,3,3], device tensor kept under `key`)."""
         torch = self._torch
         tri = _wrap_indices(host_tri, n_rows)
+        if tri.size == 0:      # a mesh without faces: upstream's np.array([], int32) indexes to an empty (0,3) gather
+            tri = tri.reshape(0, 3)
         if tri.ndim != 2 or tri.shape[1] != 3:
             raise ValueError(f"triangle index array must be [T,3], got {tuple(tri.shape)}")
         d_tri = self._to_device(tri)

@@ -93,8 +93,6 @@ class AdvancedPixelBufferFiller:
                 self._normals = wrap_device_pointer(torch, out_ptrs[2], (rows, self.w, 3), self._dev)
             check(self._L.crb_bind_buffers(self._handle, self._z.data_ptr(), self._color.data_ptr(),
                                            self._normals.data_ptr()))
-            if out_ptrs is None:
-                check(self._L.crb_init_buffers(self._handle, self._stream()))
         self._ws = None
         self._ws_T = -1
         self._ws_views = 1
@@ -104,7 +102,13 @@ class AdvancedPixelBufferFiller:
         self._host_np = {}
         self._stale = {"z": True, "color": True, "normals": True}   # device newer than host mirror
         self._exposed = set()         # mirrors handed to the caller (may have been written through)
-        self._pending_clear = False
+        # pyx:65-67 (normals 0, colour 0, z = 1e6): the fresh-filler values are not stored here -- they materialise fused into
+        # the first render's tile pass, or with the first read if nothing was rendered (a new filler per frame is the
+        # reference's idiom, run.py:21, so the constructor queues no kernel at all)
+        self._pending_clear = out_ptrs is None
+        self._status = None           # pinned status words of the last frame (crb_status_async)
+        self._unchecked = None        # the last render, until its status words have been looked at (see _validate)
+        self._deferred_keep = None    # inputs of a batch issued with defer_join (see render_views)
 
     # ------------------------------------------------------------------------------------------------ plumbing
     def __del__(self):
@@ -134,10 +138,7 @@ class AdvancedPixelBufferFiller:
         ptr = (ws.data_ptr() + 255) // 256 * 256
         check(self._L.crb_bind_workspace(self._handle, ptr, nbytes, T, views, pair_cap, self._stream()))
         self._ws, self._ws_T, self._ws_views = ws, T, views
-        cap = ctypes.c_int64()
-        need = ctypes.c_int64()
-        check(self._L.crb_status(self._handle, ctypes.byref(need), ctypes.byref(cap), self._stream()))
-        self._pair_cap = cap.value
+        self._pair_cap = int(self._L.crb_pair_capacity(self._handle))
 
     def _mirror(self, name):
         if name not in self._host:
@@ -165,14 +166,43 @@ class AdvancedPixelBufferFiller:
             check(self._L.crb_init_buffers(self._handle, self._stream()))
             self._pending_clear = False
 
+    def _validate(self):
+        """The overflow check of the last render, deferred to the first point that looks at its result: the status words
+        came back asynchronously (crb_status_async); a frame whose (triangle, tile) pairs did not fit the workspace was
+        skipped as a whole (buffers untouched) and is drawn again with the room it asked for."""
+        u = self._unchecked
+        if u is None:
+            return
+        self._unchecked = None
+        self._torch.cuda.current_stream(self._dev).synchronize()
+        st = self._status_np
+        while max(int(st[1]), int(st[3])) > self._pair_cap:
+            need, cap = ctypes.c_int64(), ctypes.c_int64()
+            rc = self._L.crb_status(self._handle, ctypes.byref(need), ctypes.byref(cap), self._stream())   # report + reset
+            if rc != _lib.CRB_ERR_OVERFLOW:
+                check(rc)
+                break
+            self._ensure_workspace(u[4], self._ws_views, int(need.value * 1.25) + 1024)
+            self._queue_render(*u)
+            self._torch.cuda.current_stream(self._dev).synchronize()
+
     def _get(self, name, bit):
         t = self._mirror(name)
         self._materialize_clear()
         if self._stale[name]:
             args = {"z": None, "color": None, "normals": None}
             args[name] = t.data_ptr()
-            check(self._L.crb_download(self._handle, bit, args["z"], args["color"], args["normals"], self._stream()))
-            self._torch.cuda.current_stream(self._dev).synchronize()
+            for attempt in range(2):
+                check(self._L.crb_download(self._handle, bit, args["z"], args["color"], args["normals"], self._stream()))
+                if self._unchecked is None:
+                    self._torch.cuda.current_stream(self._dev).synchronize()
+                    break
+                # first read after a render: one synchronisation serves the download and the frame's status words; only a
+                # frame that had to be drawn again is fetched twice
+                cap = self._pair_cap
+                self._validate()
+                if self._pair_cap == cap:
+                    break
             self._stale[name] = False
         self._exposed.add(name)
         return self._host_np[name]
@@ -209,6 +239,7 @@ class AdvancedPixelBufferFiller:
         """Fresh-filler state (pyx:65-67).  The reference has no reset (a new filler per frame is its idiom,
         run.py:21); here the clear is fused into the next frame's tile pass instead of a separate memset."""
         self._pending_clear = True
+        self._unchecked = None    # whatever the last frame was, nothing of it remains
         for name in self._stale:
             self._stale[name] = True
         self._exposed.clear()   # arrays handed out earlier are detached until fetched again
@@ -226,44 +257,32 @@ class AdvancedPixelBufferFiller:
             v, c, n = v.contiguous(), c.contiguous(), n.contiguous()
             T = v.shape[0]
         else:
+            # (a vertex with camera z == 0: the reference build trips Cython's division check inside a nogil block, prints an
+            # unraisable ZeroDivisionError, abandons the projection loop and rasterizes half-projected garbage, pyx:122; here
+            # that vertex simply gets IEEE inf / NaN coordinates like on the device-resident path -- stated divergence)
             v, c, n = (np.asarray(a) for a in (v, c, n))
             T = v.shape[0]
-            if T and bool((v[:, :, 2] == 0).any()):
-                # pyx:122 `buff / z` with Cython's division check: a vertex at z == 0 raises upstream
-                raise ZeroDivisionError("float division")
+        self._validate()                 # an earlier frame this one composites onto must have been drawn
         if self._pending_clear:
             flags |= _lib.CRB_CLEAR_FIRST
         else:
             self._push_exposed()
         self._ensure_workspace(T)
-        while True:
-            if on_device:
-                check(self._L.crb_render(self._handle, v.data_ptr(), c.data_ptr(), n.data_ptr(), T, flags,
-                                         self._stream()))
-            else:
-                if self._stage is None or self._stage.shape[1] < T:
-                    self._stage = torch.empty((3, max(T, 1), 3, 3), dtype=torch.float32, pin_memory=True)
-                    self._stage_np = self._stage.numpy()
-                s = self._stage_np
-                s[0, :T] = v
-                s[1, :T] = c
-                s[2, :T] = n
-                st = self._stage
-                # CRB_NO_SYNC: the overflow check / regrow loop below does the synchronising crb_status itself
-                check(self._L.crb_render_host(self._handle, st[0].data_ptr(), st[1].data_ptr(), st[2].data_ptr(), T,
-                                              flags | _lib.CRB_NO_SYNC, 0, None, None, None, self._stream()))
-                if not check_status:
-                    torch.cuda.current_stream(self._dev).synchronize()     # the pinned staging is reused by the next call
-            if not check_status:
-                break
-            need, cap = ctypes.c_int64(), ctypes.c_int64()
-            rc = self._L.crb_status(self._handle, ctypes.byref(need), ctypes.byref(cap), self._stream())
-            if rc == _lib.CRB_ERR_OVERFLOW:
-                # the frame was not drawn; give the pair list the room it asked for and draw it again
-                self._ensure_workspace(T, self._ws_views, int(need.value * 1.25) + 1024)
-                continue
-            check(rc)
-            break
+        if not on_device:
+            if self._stage is None or self._stage.shape[1] < T:
+                self._stage = torch.empty((3, max(T, 1), 3, 3), dtype=torch.float32, pin_memory=True)
+                self._stage_np = self._stage.numpy()
+            s = self._stage_np
+            s[0, :T] = v
+            s[1, :T] = c
+            s[2, :T] = n
+            v = c = n = None
+        args = (on_device, v, c, n, T, flags)
+        self._queue_render(*args)
+        if check_status:
+            self._unchecked = args       # (device inputs stay referenced until the frame is known to have been drawn)
+        elif not on_device:
+            torch.cuda.current_stream(self._dev).synchronize()     # the pinned staging is reused by the next call
         self._pending_clear = False
         for name in self._stale:
             self._stale[name] = True
@@ -272,14 +291,33 @@ class AdvancedPixelBufferFiller:
             if name in self._exposed:
                 self._get(name, bit)
 
+    def _queue_render(self, on_device, v, c, n, T, flags):
+        """Queues one frame (upload of the staged host arrays if any, kernels, status words) on the current stream."""
+        if on_device:
+            check(self._L.crb_render(self._handle, v.data_ptr(), c.data_ptr(), n.data_ptr(), T, flags, self._stream()))
+        else:
+            st = self._stage
+            check(self._L.crb_render_host(self._handle, st[0].data_ptr(), st[1].data_ptr(), st[2].data_ptr(), T,
+                                          flags | _lib.CRB_NO_SYNC, 0, None, None, None, self._stream()))
+        if self._status is None:
+            self._status = self._torch.zeros(4, dtype=self._torch.int64, pin_memory=True)
+            self._status_np = self._status.numpy()
+        check(self._L.crb_status_async(self._handle, self._status.data_ptr(), self._stream()))
+
+    def set_option(self, option, value):
+        """crb_set_option: tuning switches (_lib.CRB_OPT_*), e.g. the store path of the fused clear or a fixed k_raster grid."""
+        check(self._L.crb_set_option(self._handle, int(option), int(value)))
+
     def device_buffers(self):
         """(z, color, normals) torch CUDA tensors -- the device-resident truth (no copy)."""
+        self._validate()
         self._materialize_clear()
         self._push_exposed()
         return self._z, self._color, self._normals
 
     def illuminate_guro(self, light_direction):
         """GuroIllumination.draw_illumination on the device buffers, in place (guro_illumination.py:20-27)."""
+        self._validate()
         self._materialize_clear()
         self._push_exposed()
         arr = (ctypes.c_float * 3)(*[float(x) for x in light_direction])
@@ -288,6 +326,7 @@ class AdvancedPixelBufferFiller:
 
     def color_u8_flipped(self):
         """run.py:26 `image[::-1].astype('uint8')` computed on device; returns a torch CUDA uint8 tensor."""
+        self._validate()
         self._materialize_clear()
         self._push_exposed()
         out = self._torch.empty((self.row1 - self.row0, self.w, 3), dtype=self._torch.uint8, device=self._dev)
@@ -342,6 +381,9 @@ class AdvancedPixelBufferFiller:
             flags |= _lib.CRB_GURO
         if defer_join and not check_status:
             flags |= _lib.CRB_DEFER_JOIN
+            # the front end may still be queued on the filler's internal stream when this call returns: torch's allocator orders
+            # the reuse of freed memory on the CALLER's stream only, so temporaries made above stay referenced until join()
+            self._deferred_keep = (views, v, c, n)
         self._ensure_workspace(T, views=min(int(chunk), max(V, 1)))
         ptr = lambda t: None if t is None else t.data_ptr()
         while True:
@@ -362,6 +404,7 @@ class AdvancedPixelBufferFiller:
     def join(self):
         """Orders the current stream behind batches issued with defer_join=True."""
         check(self._L.crb_join(self._handle, self._stream()))
+        self._deferred_keep = None
 
     def transform_view(self, v, n, view):
         """The camera-space [T,3,3] arrays one view produces (what the reference would be handed for that view)."""

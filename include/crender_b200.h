@@ -150,9 +150,14 @@ int crb_render_host(crb_filler *f, const float *v, const float *c, const float *
  * for the fused clear and the shaded rows where the layout allows.  Results do not depend on any of them. */
 #define CRB_OPT_CHUNK_PIPELINE 1
 #define CRB_OPT_TMA 2
-#define CRB_OPT_TMA_ROWS 3   /* shaded colour / normal rows of busy tiles as TMA boxes (1) or 16-byte vector stores (0) */
+#define CRB_OPT_TMA_ROWS 3   /* shaded colour / normal rows of busy tiles as TMA boxes (1), staged 16-byte vector stores (0) or
+                                12-byte stores straight from registers (2) */
 #define CRB_OPT_BAND_PREPASS 4   /* band-sharded fillers (crb_set_band): a streaming pre-pass lists the 256-triangle chunks that
                                     can reach the band, and the setup / binning kernels visit only those (1, default) */
+#define CRB_OPT_RASTER_CTAS 5    /* > 0: fixed k_raster grid (a grid smaller than the busy tiles makes every CTA walk several tiles);
+                                    0 (default): sized from the busy-tile count the previous launch reported */
+#define CRB_OPT_SPLIT_HEAVY 6    /* single-view launches cut tiles with many triangles into four row bands rasterized by
+                                    different CTAs (default 1) */
 int crb_set_option(crb_filler *f, int option, int value);
 
 /* Orders `stream` behind rasterizer work left in flight by CRB_DEFER_JOIN (no host synchronisation). */
@@ -204,6 +209,9 @@ int crb_upload(crb_filler *f, unsigned mask, const float *z_host, const float *c
  * produced; if it exceeded the workspace's pair capacity the frame was NOT drawn (buffers untouched) and the return
  * value is CRB_ERR_OVERFLOW -- re-bind a workspace with pair_capacity >= pairs_needed and render again. */
 int crb_status(crb_filler *f, int64_t *pairs_needed, int64_t *pair_capacity, void *stream);
+
+/* Pair capacity of the bound workspace (0 if none); no device interaction. */
+int64_t crb_pair_capacity(const crb_filler *f);
 
 /* The same without blocking: queues the copy of the four status words of the two workspace sets (pairs of the last frame,
  * largest overflowing demand; per set) into `pinned` (page-locked host memory) behind the work already on `stream`.

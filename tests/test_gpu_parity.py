@@ -198,10 +198,16 @@ def test_api_contract_matches_reference(Filler, trex):
         f.render_model(TriModel(v0.astype(np.float64), trex._colors_by_triangles, trex._normals_by_triangles))
     with pytest.raises(AttributeError):
         f.render_model(TriModel(v0, None, trex._normals_by_triangles))
+    # a vertex with camera z == 0 (stated divergence, DESIGN 2: the reference build prints an unraisable ZeroDivisionError
+    # and rasterizes half-projected garbage): that vertex gets IEEE inf / NaN here, host and device inputs alike, and the
+    # frame is the one the C oracle (same IEEE arithmetic, no division check) draws
     bad = v0.copy()
     bad[7, 1, 2] = 0.0
-    with pytest.raises(ZeroDivisionError):
-        f.render_model(TriModel(bad, trex._colors_by_triangles, trex._normals_by_triangles))
+    from oracle import oracle as O
+    g, o = Filler(1024, 1024, fov=45.0), O.OracleFiller(1024, 1024, fov=45.0)
+    g.render_model(TriModel(bad, trex._colors_by_triangles, trex._normals_by_triangles))
+    o.render_arrays(bad, trex._colors_by_triangles, trex._normals_by_triangles)
+    assert_same(buffers(g), buffers(o), "vertex at z == 0")
 
 
 def test_host_writes_through_live_views_persist(Filler, O, trex):
@@ -484,18 +490,19 @@ def test_orbit_views_at_1024_equal_reference_goldens(Filler, trex):
 
 @pytest.mark.parametrize("mode", ["tma", "tma_vec_rows", "tma_direct_rows", "plain", "tiny_grid", "tma_tiny_grid"])
 @pytest.mark.parametrize("size", [(96, 128), (100, 76), (50, 36), (257, 388), (64, 30)])
-def test_fused_clear_store_paths(mode, size, Filler, O, monkeypatch):
+def test_fused_clear_store_paths(mode, size, Filler, O):
     """clear()+render takes the store path the layout allows: TMA boxes (rows that are 16-byte multiples), clipped by
-    the hardware on partial tiles, or plain stores (W % 4 != 0, CRB_NO_TMA=1); a grid smaller than the number of busy
-    tiles makes k_raster walk several tiles per CTA (CRB_RASTER_CTAS).  All of them must give the oracle's bits."""
-    monkeypatch.setenv("CRB_NO_TMA", "1" if mode in ("plain", "tiny_grid") else "0")
-    monkeypatch.setenv("CRB_OUT_TMA", {"tma_vec_rows": "0", "tma_direct_rows": "2"}.get(mode, "1"))
-    if "tiny_grid" in mode:
-        monkeypatch.setenv("CRB_RASTER_CTAS", "3")
+    the hardware on partial tiles, or plain stores (W % 4 != 0, CRB_OPT_TMA off); a grid smaller than the number of busy
+    tiles makes k_raster walk several tiles per CTA (CRB_OPT_RASTER_CTAS).  All of them must give the oracle's bits."""
+    from cython3dmodelrenderer_b200 import _lib
     h, w = size
     for seed in (3, 5, 8):
         m = random_scene(seed, T=300)
         g, o = Filler(h, w, fov=60.0), O.OracleFiller(h, w, fov=60.0)
+        g.set_option(_lib.CRB_OPT_TMA, 0 if mode in ("plain", "tiny_grid") else 1)
+        g.set_option(_lib.CRB_OPT_TMA_ROWS, {"tma_vec_rows": 0, "tma_direct_rows": 2}.get(mode, 1))
+        if "tiny_grid" in mode:
+            g.set_option(_lib.CRB_OPT_RASTER_CTAS, 3)
         g.render_model(random_scene(seed + 50, T=40))      # stale contents the fused clear must wipe
         g.clear()
         for _ in range(2):                                 # second frame: grid sized from the first frame's statistics
@@ -683,13 +690,14 @@ def test_integration_stub_flow_without_torch(O, trex):
 
 
 @pytest.mark.parametrize("split", ["1", "0"])
-def test_single_view_heavy_tile_split(split, Filler, O, monkeypatch):
+def test_single_view_heavy_tile_split(split, Filler, O):
     """Single-view launches cut tiles with many triangles into four 8-row bands rasterized by different CTAs
-    (CRB_SPLIT_HEAVY); fresh and compositing renders, partial tiles at the image edge."""
-    monkeypatch.setenv("CRB_SPLIT_HEAVY", split)
+    (CRB_OPT_SPLIT_HEAVY); fresh and compositing renders, partial tiles at the image edge."""
+    from cython3dmodelrenderer_b200 import _lib
     for (h, w), seed in (((96, 128), 21), ((75, 100), 22), ((40, 33), 23)):
         m = random_scene(200 + seed, T=5000, span=0.5)          # hundreds of triangles per tile
         g, o = Filler(h, w, fov=70.0), O.OracleFiller(h, w, fov=70.0)
+        g.set_option(_lib.CRB_OPT_SPLIT_HEAVY, int(split))
         g.clear()
         g.render_model(m)                                       # fused clear, TMA where the layout allows
         o.render_model(m)
