@@ -144,11 +144,12 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the reference's own Version C on the host cores
 # --------------------------------------------------------------------------------------------------------------------
-def cpu_reference_runner(n_threads=None):
+def cpu_reference_runner(n_threads=None, res=None, fov=FOV):
     """Returns (kind, cores, render(v, c, n) -> seconds).  A fresh filler per frame (Version C has no buffer reset),
     constructor and lock-grid initialisation outside the timed part, stdout silenced (the reference printf()s)."""
     from conftest import TriModel
     from oracle import build_ref
+    res = RES if res is None else int(res)
     cores = n_threads or os.cpu_count() or 1
     if build_ref.built():
         sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
@@ -161,7 +162,7 @@ def cpu_reference_runner(n_threads=None):
             os.dup2(saved, 1)
 
         def render(v, c, n):
-            f = Ref(RES, RES, fov=FOV, n_threads=cores)
+            f = Ref(res, res, fov=fov, n_threads=cores)
             f.get_z_buffer()[...] += 0  # pre-touch all three buffers (np.zeros pages are mapped lazily)
             f.get_color_buffer()[...] = 0
             f.get_normals_buffer()[...] = 0
@@ -179,7 +180,7 @@ def cpu_reference_runner(n_threads=None):
     from oracle import oracle as O
 
     def render(v, c, n):
-        f = O.OracleFiller(RES, RES, fov=FOV, n_threads=cores)
+        f = O.OracleFiller(res, res, fov=fov, n_threads=cores)
         t0 = time.perf_counter()
         f.render_arrays(v, c, n)
         return time.perf_counter() - t0
@@ -187,15 +188,15 @@ def cpu_reference_runner(n_threads=None):
 
 
 def best_cpu_threads(arrays, colors):
-    """The reference's OpenMP path does not scale monotonically (dynamic schedule + per-pixel locks): give it its best
-    thread count among {8, 16, 32, nproc/2, nproc} (median of 4 frames each) instead of blindly using nproc."""
+    """The reference's OpenMP path does not scale monotonically (dynamic schedule + per-pixel locks): it gets its best
+    thread count among {8, 16, 32, nproc/2, nproc} (median of 8 frames each after a warm-up) instead of blindly nproc."""
     nproc = os.cpu_count() or 1
     cands = sorted({c for c in (8, 16, 32, nproc // 2, nproc) if 1 <= c <= nproc} or {1})
     best = None
     for c in cands:
         _, _, render = cpu_reference_runner(c)
         ts = []
-        for i in range(5):
+        for i in range(9):
             v, n = arrays[i % len(arrays)]
             ts.append(render(v, colors, n))
         med = statistics.median(ts[1:])
@@ -204,13 +205,24 @@ def best_cpu_threads(arrays, colors):
     return best[1]
 
 
-def cpu_frames(model, views_np, frames, warm=2):
+def sample_view_indices(n_total, count=8):
+    """Views k * n_total / count: an evenly spread sample of the orbit (frames of different view angles cost differently)."""
+    return [(k * n_total) // count for k in range(count)]
+
+
+def orbit_sample_arrays(model, n_total, count=8):
     from cython3dmodelrenderer_b200 import views as VW
-    arrays0 = [VW.transform_arrays_host(views_np[k % len(views_np)], model._vertices_by_triangles, model._normals_by_triangles)
-               for k in range(2)]
-    kind, cores, render = cpu_reference_runner(best_cpu_threads(arrays0, model._colors_by_triangles))
-    arrays = [VW.transform_arrays_host(views_np[k % len(views_np)], model._vertices_by_triangles, model._normals_by_triangles)
-              for k in range(min(frames, 8))]
+    out = []
+    for k in sample_view_indices(n_total, count):
+        view = VW.orbit_views(n_total, first=k, count=1)[0]
+        out.append(VW.transform_arrays_host(view, model._vertices_by_triangles, model._normals_by_triangles))
+    return out
+
+
+def cpu_frames(model, n_total, frames, warm=2):
+    """Host Version C on `frames` frames cycling through 8 evenly spread views of the n_total-view orbit."""
+    arrays = orbit_sample_arrays(model, n_total, 8)
+    kind, cores, render = cpu_reference_runner(best_cpu_threads(arrays, model._colors_by_triangles))
     times = []
     for i in range(warm + frames):
         v, n = arrays[i % len(arrays)]
@@ -224,13 +236,12 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from cython3dmodelrenderer_b200 import views as VW
     model = load_trex()
     T = model._vertices_by_triangles.shape[0]
-    views_np = VW.orbit_views(args.gpus * args.views, first=0, count=8)
-    sample = 16  # frames per step: a bounded sample of the orbit
-    arrays = [VW.transform_arrays_host(views_np[k], model._vertices_by_triangles, model._normals_by_triangles) for k in range(8)]
+    n_total = args.gpus * args.views
+    arrays = orbit_sample_arrays(model, n_total, 8)           # views k * n_total / 8: the whole orbit, not one pose
     kind, cores, render = cpu_reference_runner(best_cpu_threads(arrays, model._colors_by_triangles))
+    sample = 16  # frames per step: a bounded sample of the orbit (each of the 8 views twice)
     step_s = []
     for s in range(args.warmup + args.steps):
         t = 0.0
@@ -246,11 +257,13 @@ def run_reference_arm(args):
         "warmup": args.warmup, "ms_per_step": 1000.0 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic orbit of the T-Rex fixture (tests/golden/trex_fit.npz)",
         "config": {"workload": "trex_1024_orbit", "res": RES, "fov": FOV, "triangles": int(T), "illumination": False,
-                   "sample_frames_per_step": sample},
+                   "sample_frames_per_step": sample, "orbit_views_total": n_total,
+                   "sample_views": sample_view_indices(n_total, 8)},
         "gtri_per_s": fps * T / 1e9,
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
-                         "sample": f"{sample} orbit frames per step x {args.steps} steps, render_model only, fresh filler "
-                                   f"per frame, n_threads={cores} (best of 8/16/32/nproc/2/nproc, nproc={os.cpu_count()})"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "host_cores": os.cpu_count(), "kind": kind,
+                         "sample": f"{sample} frames per step x {args.steps} steps cycling through 8 evenly spread views "
+                                   f"(k * {n_total} / 8) of the orbit, render_model only, fresh filler per frame, n_threads={cores} "
+                                   f"(the fastest of 8/16/32/nproc/2/nproc on this host, nproc={os.cpu_count()})"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -266,14 +279,7 @@ def run_gpu_arm(args):
     from cython3dmodelrenderer_b200 import AdvancedPixelBufferFiller, _lib
     from cython3dmodelrenderer_b200 import views as VW
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+    world, rank, local, dev = init_dist()
 
     model = load_trex()
     T = int(model._vertices_by_triangles.shape[0])
@@ -346,67 +352,78 @@ def run_gpu_arm(args):
     f.profile(False)
     _lib.check(f._L.crb_set_option(f._handle, _lib.CRB_OPT_CHUNK_PIPELINE, 1))
 
-    # optional: the final NCCL gather of the view-sharded result to rank 0 (reported beside, never inside, `value`)
+    # ---- delivery of the view-sharded result over NVLink (reported beside `value`, which is the rendering rate) ----
     gather = None
-    if world > 1 and args.gather == "u8":
-        # run.py's uint8 images of all N*V views delivered to rank 0: each rank renders its views in chunks (uint8 image only,
-        # written by the rasterizer) and the NCCL gather of chunk i travels while chunk i+1 is rendered
+    if world > 1 and args.gather != "none":
         from cython3dmodelrenderer_b200 import sharding
-        u8 = torch.empty((V, RES, RES, 3), dtype=torch.uint8, device=dev)
+        NVLINK_IN = 900.0e9        # NVLink 5 / NVSwitch: bytes per second into one GPU (nominal, per direction)
         gchunk = min(args.chunk, 32)
+        u8 = torch.empty((V, RES, RES, 3), dtype=torch.uint8, device=dev)
 
-        def produce(first, count):
+        def produce_u8(first, count):
             f.render_views(dv, dc, dn, dviews[first:first + count], want=(), color_u8_out=u8[first:first + count], chunk=count,
                            check_status=False)
             return u8[first:first + count]
 
-        def render_only():
-            for first in range(0, V, gchunk):
-                produce(first, min(gchunk, V - first))
+        def produce_z(first, count):
+            f.render_views(dv, dc, dn, dviews[first:first + count], want=("z",), z_out=z[first:first + count], chunk=count,
+                           check_status=False)
+            return z[first:first + count]
 
-        allu8 = sharding.gather_views_overlapped(produce, V, gchunk, dst=0)       # warm-up: communicator, buffers
-        res_ms = {}
-        for name, fn in (("render_u8_only", render_only),
-                         ("render_u8_and_overlapped_gather", lambda: sharding.gather_views_overlapped(produce, V, gchunk, dst=0, out=allu8))):
+        def timed(fn, reps=3):
             fn()
             barrier()
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             g0.record()
-            for _ in range(3):
+            for _ in range(reps):
                 fn()
             g1.record()
             barrier()
-            t_ = torch.tensor([g0.elapsed_time(g1) / 3], dtype=torch.float64, device=dev)
+            t_ = torch.tensor([g0.elapsed_time(g1) / reps], dtype=torch.float64, device=dev)
             dist.all_reduce(t_, op=dist.ReduceOp.MAX)
-            res_ms[name] = float(t_.item())
-        nbytes = u8.numel() * world
-        gather = {"what": f"uint8 images (run.py:26) of all views gathered to rank 0 by NCCL in chunks of {gchunk} views beside the rendering",
-                  "ms": res_ms, "bytes": nbytes,
-                  "frames_per_s_delivered_to_rank0": n_total / (res_ms["render_u8_and_overlapped_gather"] / 1000.0),
-                  "frames_per_s_render_u8_only": n_total / (res_ms["render_u8_only"] / 1000.0)}
-        if rank == 0:
-            gather["lit_pixels_view0_of_last_rank"] = int((allu8[world - 1, 0].sum(dim=-1) > 0).sum().item())
-        del allu8, u8
-    elif world > 1 and args.gather != "none":
-        from cython3dmodelrenderer_b200 import sharding
-        parts = {"z": z} if args.gather == "z" else {"z": z, "color": col, "normals": nrm}
-        for t_ in parts.values():
-            sharding.gather_views(t_[:8].contiguous(), 8 * world, dst=0)      # communicator / buffer warm-up
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        got = {k: sharding.gather_views(t_, n_total, dst=0) for k, t_ in parts.items()}
-        g1.record()
-        barrier()
-        gms = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
-        dist.all_reduce(gms, op=dist.ReduceOp.MAX)
-        nbytes = sum(t_.numel() * t_.element_size() for t_ in parts.values()) * world
-        gather = {"what": "gather of the per-rank view slabs to rank 0 (NCCL over NVLink): " + "+".join(parts), "ms": float(gms.item()),
-                  "bytes": nbytes, "gb_per_s": nbytes / float(gms.item()) / 1e6,
-                  "frames_per_s_including_gather": n_total / ((ms / args.steps + float(gms.item())) / 1000.0)}
-        if rank == 0:
-            gather["covered_pixels_view0_of_rank1"] = int((got["z"][V] < 1e5).sum().item())
-        del got
+            return float(t_.item())
+
+        def render_only(produce):
+            for first in range(0, V, gchunk):
+                produce(first, min(gchunk, V - first))
+
+        gather = {"note": "`value` is the rendering rate with every rank's views left in its own HBM; the entries below add the "
+                          "delivery.  One GPU takes 900 GB/s from NVLink while eight produce 2-3 TB/s of frames, so everything "
+                          "gathered into ONE rank is bound by that rank's ingress (ingress_bound_frames_per_s); the row exchange "
+                          "(all-to-all: every rank ends with its row band of ALL views) spreads the ingress over the ranks and "
+                          "scales", "chunk_views": gchunk}
+        want_modes = ("u8", "z", "exchange") if args.gather in ("auto", "all") else (args.gather,)
+        for mode in want_modes:
+            if mode == "u8":
+                produce, bpf, what = produce_u8, 3 * RES * RES, "run.py:26's uint8 images of all views gathered to rank 0 (NCCL gather per chunk, travelling while the next chunk is rendered)"
+            elif mode == "z":
+                produce, bpf, what = produce_z, 4 * RES * RES, "the float32 z buffers of all views gathered to rank 0 (NCCL gather per chunk beside the rendering)"
+            elif mode == "exchange":
+                produce, bpf, what = produce_u8, 3 * RES * RES, ("row exchange of the uint8 images (NCCL all-to-all per chunk beside the rendering): rank r ends "
+                                                                "with rows [r*H/N, (r+1)*H/N) of all N*V views -- the delivery layout whose ingress is spread over the ranks")
+            else:
+                continue
+            try:
+                if mode == "exchange":
+                    res_buf = sharding.exchange_rows_overlapped(produce, V, gchunk)
+                    both = timed(lambda: sharding.exchange_rows_overlapped(produce, V, gchunk, out=res_buf))
+                    bound = NVLINK_IN * world * world / (bpf * max(world - 1, 1))   # a rank receives its 1/N row band of the (N-1)/N frames other ranks render
+                    check_px = int((res_buf[world - 1, 0].sum(dim=-1) > 0).sum().item())
+                else:
+                    res_buf = sharding.gather_views_overlapped(produce, V, gchunk, dst=0)
+                    both = timed(lambda: sharding.gather_views_overlapped(produce, V, gchunk, dst=0, out=res_buf))
+                    bound = NVLINK_IN / bpf * world / max(world - 1, 1)     # rank 0 receives the frames of the other N-1 ranks
+                    check_px = int((res_buf[world - 1, 0].reshape(RES * RES, -1).abs().sum(dim=-1) > 0).sum().item()) if rank == 0 else None
+                only = timed(lambda: render_only(produce))
+                delivered = n_total / (both / 1000.0)
+                gather[mode] = {"what": what, "bytes_per_frame": bpf, "ms_render_only": only, "ms_render_and_delivery": both,
+                                "frames_per_s_render_only": n_total / (only / 1000.0), "frames_per_s_delivered": delivered,
+                                "ingress_bound_frames_per_s": bound, "frac_of_ingress_bound": delivered / bound,
+                                "delivery_efficiency": only / both, "check_pixels": check_px}
+                del res_buf
+            except Exception as ex:     # a delivery variant must never take the headline line down
+                gather[mode] = {"error": repr(ex)[:300]}
+        del u8
 
     # sanity: the timed output is a real frame (covered pixel count of view 0 of rank 0 is the reference's 252 539)
     covered0 = int((z[0] < 1e5).sum().item())
@@ -593,17 +610,47 @@ def run_gpu_arm(args):
             fr.clear()
             fr.render_model(mk)
             return fr.get_color_buffer(), fr.get_normals_buffer(), fr.get_z_buffer()
+        def new_filler_color_only():
+            ff = AdvancedPixelBufferFiller(RES, RES, fov=FOV, n_threads=8, device=local)
+            ff.render_model(mk)
+            return ff.get_color_buffer()
         drop_in = {"new_filler_per_frame_ms": per_frame(new_filler), "one_filler_clear_render_get3_ms": per_frame(reused),
+                   "new_filler_color_only_ms": per_frame(new_filler_color_only),
+                   "pcie_floor_ms": {"three_buffers": 28 * RES * RES / 55e6, "color_only": 12 * RES * RES / 55e6,
+                                     "note": "dense float32 download at the ~55 GB/s this link sustains"},
                    "what": "AdvancedPixelBufferFiller(...).render_model(model) + the three get_*_buffer() calls on host NumPy data, "
                            "synchronous, full 29.4 MB download (the unmodified run.py flow with the import swapped)"}
         del fr
 
-    cpu = None
+    cpu, cpu_threads = None, None
     if rank == 0 and world == 1 and not args.no_cpu:
-        kind, cores, times = cpu_frames(model, views_np, frames=args.cpu_frames)
-        cpu = {"value": len(times) / sum(times), "unit": "frames/s", "cores": cores, "kind": kind,
-               "sample": f"{len(times)} orbit frames (views 0..7 cycled) after 2 warm-ups, render_model only, fresh "
-                         f"filler per frame, n_threads={cores} (best of 8/16/32/nproc/2/nproc, nproc={os.cpu_count()})", "median_ms": 1000 * statistics.median(times)}
+        kind, cores, times = cpu_frames(model, n_total, frames=args.cpu_frames)
+        cpu = {"value": len(times) / sum(times), "unit": "frames/s", "cores": cores, "host_cores": os.cpu_count(), "kind": kind,
+               "sample": f"{len(times)} frames cycling through 8 evenly spread views (k * {n_total} / 8) of the orbit after 2 warm-ups, "
+                         f"render_model only, fresh filler per frame, n_threads={cores} (the fastest of 8/16/32/nproc/2/nproc on this "
+                         f"host, nproc={os.cpu_count()})", "median_ms": 1000 * statistics.median(times)}
+        cpu_threads = cores
+
+    # ---- the other BASELINE.json configs, measured in the same run (C2, C3: one GPU; C4: row bands over the N ranks) ----------
+    secondary = None
+    if not args.no_secondary:
+        del z, col, nrm, f
+        torch.cuda.empty_cache()
+        secondary = {}
+        for wl in (("bunny_4096_guro", "basketball_2048", "sphere_8192_bands") if world == 1 else ("sphere_8192_bands",)):
+            try:
+                if world > 1:
+                    # the frame twice: bands left where they are rendered, and the complete frame on rank 0 (PeerFrame)
+                    for mode in ("none", "peer"):
+                        a2 = argparse.Namespace(**vars(args)); a2.gather = mode
+                        ln = measure_workload(a2, wl, world, rank, local, dev, cpu_threads, with_cpu=False)
+                        if rank == 0:
+                            secondary[wl + ("" if mode == "none" else "_complete_on_rank0")] = ln
+                else:
+                    secondary[wl] = measure_workload(args, wl, world, rank, local, dev, cpu_threads)
+            except Exception as ex:
+                secondary[wl] = {"error": repr(ex)[:300]}
+            torch.cuda.empty_cache()
 
     if rank == 0:
         line = {
@@ -615,7 +662,7 @@ def run_gpu_arm(args):
                        "buffers": "z+color+normals f32, fresh per view", "l2": "outputs %.2f GB/step per GPU >> 126 MB L2; "
                        "the 1.5 MB mesh is re-read per view by design" % (V * 28 * RES * RES / 1e9)},
             "gtri_per_s": fps * T / 1e9, "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches,
-            "roofline": roofline, "cpu_baseline": cpu, "single_frame": single, "drop_in": drop_in, "gather": gather,
+            "roofline": roofline, "cpu_baseline": cpu, "single_frame": single, "drop_in": drop_in, "gather": gather, "secondary": secondary,
             "checks": {"covered_pixels_view0": covered0, "e2e_covered_pixels": e2e_cov, "e2e_image_u8_lit_pixels": img_cov, "e2e_dense_covered_pixels": dense_cov, "e2e_sync_covered_pixels": sync_cov, "pairs_last_launch": int(need.value),
                        "pair_capacity": int(cap.value)},
         }
@@ -626,58 +673,113 @@ def run_gpu_arm(args):
 
 
 # --------------------------------------------------------------------------------------------------------------------
-# secondary workloads (not the headline line): BASELINE.json configs C2 and C4
+# secondary workloads (not the headline line): BASELINE.json configs C2, C3 and C4
 # --------------------------------------------------------------------------------------------------------------------
-def run_extra_workload(args):
-    """bunny_4096_guro (C2: bunny + igor texture, 4096^2, fused clear + render + Guro pass, one GPU) and
-    sphere_8192_bands (C4: 10 M-triangle UV sphere at 8192^2, screen-row bands over N GPUs, optional NCCL all-gather).
-    Same JSON shape as the headline line; `scaling` is "strong" for the band-sharded frame (total work is fixed)."""
+def init_dist():
     import torch
     import torch.distributed as dist
-    from conftest import load_indexed
-    from cython3dmodelrenderer_b200 import AdvancedPixelBufferFiller, sharding, synthetic
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
+    bind_rank_to_cpus(local, int(os.environ.get("LOCAL_WORLD_SIZE", str(world))))
+    if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if args.workload == "bunny_4096_guro":
-        res, model, band = 4096, load_indexed("bunny"), None
-    else:
-        res = args.res or 8192
+    return world, rank, local, torch.device("cuda", local)
+
+
+def bind_rank_to_cpus(local, local_world):
+    """One process per GPU: each rank gets its own slice of the CPUs nearest its GPU (`nvidia-smi topo -m`, column "CPU
+    Affinity"; all allowed CPUs if that cannot be read), BEFORE any pinned buffer is allocated -- page-locked memory is placed on
+    the NUMA node of the thread that touches it first, and eight ranks submitting from the same few cores serialise."""
+    if local_world <= 1 or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+        near = None
+        try:
+            txt = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+            for ln in txt.splitlines():
+                cells = ln.split("\t") if "\t" in ln else ln.split()
+                if cells and cells[0].strip() == f"GPU{local}":
+                    for cell in cells[1:]:
+                        cell = cell.strip()
+                        if cell and all(ch.isdigit() or ch in ",-" for ch in cell) and any(ch.isdigit() for ch in cell) and ("-" in cell or "," in cell):
+                            cpus = set()
+                            for part in cell.split(","):
+                                lo, _, hi = part.partition("-")
+                                cpus.update(range(int(lo), int(hi or lo) + 1))
+                            near = sorted(cpus & set(allowed))
+                            break
+        except Exception:
+            near = None
+        pool = near or allowed
+        # ranks whose GPUs share the same CPU set split it evenly
+        per = max(1, len(pool) // local_world)
+        mine = pool[(local * per) % len(pool):][:per] or pool
+        os.sched_setaffinity(0, mine)
+        return mine
+    except Exception:
+        return None
+
+
+WORKLOADS = {
+    # name: (BASELINE.json config, fixture / generator, resolution, fused Guro light, CPU frames in the cpu_baseline sample)
+    "bunny_4096_guro": ("C2", "bunny", 4096, True, 3),
+    "basketball_2048": ("C3", "basketball", 2048, False, 5),
+    "sphere_8192_bands": ("C4", "sphere", 8192, False, 1),
+}
+
+
+def measure_workload(args, workload, world, rank, local, dev, cpu_threads=None, with_cpu=True):
+    """One frame per step of a secondary config: bunny_4096_guro (C2: bunny + igor texture, 4096^2, fused clear + render + Guro
+    pass), basketball_2048 (C3 substitute: the quad-faced, textured basketball at 2048^2) -- one GPU each (replicas only) -- and
+    sphere_8192_bands (C4: 10 M-triangle UV sphere at 8192^2, screen-row bands over the N ranks, the complete frame either
+    staying where it is rendered, all-gathered by NCCL or written straight into rank 0's memory over NVLink).  Returns, on
+    rank 0, a dict shaped like the headline line (value, roofline of k_raster, cpu_baseline and e2e at N = 1)."""
+    import torch
+    import torch.distributed as dist
+    from conftest import TriModel, load_indexed
+    from cython3dmodelrenderer_b200 import AdvancedPixelBufferFiller, sharding, synthetic
+    from cython3dmodelrenderer_b200 import views as VW
+
+    cfg, source, res0, guro, cpu_n = WORKLOADS[workload]
+    banded = source == "sphere"
+    if banded:
+        res = args.res or res0
         scale = res / 8192.0
         model = synthetic.uv_sphere(max(8, int(3200 * scale)), max(3, int(1564 * scale)))
         band = sharding.band_shard(res, rank, world)
         bands = [sharding.band_shard(res, r, world) for r in range(world)]
+    else:
+        res, model, band, bands = res0, load_indexed(source), None, None
+        if rank != 0:
+            return None              # replicas only: nothing to shard, rank 0 measures
     T = int(model._vertices_by_triangles.shape[0])
     dv, dc, dn = (torch.from_numpy(a).to(dev) for a in
                   (model._vertices_by_triangles, model._colors_by_triangles, model._normals_by_triangles))
-    if band is not None and world > 1 and args.bands == "balanced":
+    if banded and world > 1 and args.bands == "balanced":
         # cut the frame where the estimated cost (triangles per 32-row strip) balances, not into equal row counts: the
         # sphere's poles hold far more triangles per row than its equator.  Rank 0 decides, everybody follows.
         box = [sharding.balanced_bands(sharding.tile_row_costs(dv, dn, res, res, FOV), world, res) if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         bands = box[0]
         band = bands[rank]
+    gather_mode = args.gather if banded and world > 1 else "none"
+    if gather_mode == "auto":
+        gather_mode = "peer"
     frame = None
-    if band is not None and args.gather == "peer":
+    if banded and world > 1 and gather_mode == "peer":
         frame = sharding.PeerFrame(res, res, dst=0, local_device=local)
         f = AdvancedPixelBufferFiller(res, res, fov=FOV, device=local, band=band, out_ptrs=frame.band_pointers(band[0]))
     else:
-        f = AdvancedPixelBufferFiller(res, res, fov=FOV, device=local, band=band)
-    light = -np.asarray([0, 0, 1], dtype="float32")
-    light = light / np.linalg.norm(light)
-
-    from cython3dmodelrenderer_b200 import views as VW
+        f = AdvancedPixelBufferFiller(res, res, fov=FOV, device=local, band=band if (banded and world > 1) else None)
     ident = torch.from_numpy(VW.view_matrix()[None, :]).to(dev)     # identity rotation, zero pivot / translation
     zb, cb, nb_ = f.device_buffers()
 
     def step():
-        if args.workload == "bunny_4096_guro":
+        if guro:
             # one frame = fused clear + raster + shading with the Guro light applied in the shading pass (CRB_GURO),
             # written straight into the filler's own buffers (identity view: x*1 + 0 terms are exact)
             f.render_views(dv, dc, dn, ident, z_out=zb[None], color_out=cb[None], normals_out=nb_[None], guro_light=[0, 0, 1],
@@ -688,12 +790,13 @@ def run_extra_workload(args):
 
     def barrier():
         torch.cuda.synchronize()
-        if world > 1:
+        if world > 1 and banded:
             dist.barrier()
         torch.cuda.synchronize()
 
-    f.clear(); f.render_arrays(dv, dc, dn)        # sizes the workspace, checks the pair list
-    for _ in range(max(args.warmup, 3)):
+    f.clear(); f.render_arrays(dv, dc, dn); f.device_buffers()       # sizes the workspace, checks the pair list
+    steps = max(3, min(args.steps, 20))
+    for _ in range(3):
         step()
     barrier()
     launches0 = f.launch_count
@@ -702,66 +805,117 @@ def run_extra_workload(args):
     with ClockSampler(local) as clocks:
         barrier()
         e0.record()
-        for _ in range(args.steps):
+        for _ in range(steps):
             step()
+        if frame is not None:
+            pass        # (the stores into rank 0's frame are complete when this rank's stream has drained: barrier below)
         e1.record()
         clocks.sample_now()
         barrier()
-    ms = e0.elapsed_time(e1)
+    ms_own = e0.elapsed_time(e1)
+    ms = ms_own
     k_launches, k_ms = f.profile_read()
     f.profile(False)
+    launches = f.launch_count - launches0
     gather = None
-    if world > 1:
+    if banded and world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
         if frame is not None:
             full_z = frame.tensors()[0]
-            gather = {"ms": 0.0, "bytes": 28 * res * res, "what": "none needed: the bands were rendered into rank 0's frame over NVLink (PeerFrame)",
+            gather = {"mode": "peer", "ms": 0.0, "bytes": 28 * res * res,
+                      "what": "none needed: every rank's rasterizer stores its band straight into rank 0's frame over NVLink "
+                              "(sharding.PeerFrame); `value` is complete frames per second on rank 0",
                       "covered_pixels": int((full_z < 1e5).sum().item()) if rank == 0 else None}
-        elif args.gather != "none":     # final NCCL all-gather of the row bands (north_star: "a final NCCL gather over NVLink")
+        elif gather_mode in ("bands", "all"):     # final NCCL all-gather of the row bands (north_star: "a final NCCL gather over NVLink")
             z, c, n = f.device_buffers()
-            for b in (z, c, n):                     # first use of the communicator / buffers is not what is being timed
-                sharding.gather_bands(b, res, bands=bands)
+            for b_ in (z, c, n):                     # first use of the communicator / buffers is not what is being timed
+                sharding.gather_bands(b_, res, bands=bands)
             barrier()
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             g0.record()
-            full = [sharding.gather_bands(b, res, bands=bands) for b in (z, c, n)]
+            full = [sharding.gather_bands(b_, res, bands=bands) for b_ in (z, c, n)]
             g1.record()
             barrier()
             gms = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
             dist.all_reduce(gms, op=dist.ReduceOp.MAX)
-            gather = {"ms": float(gms.item()), "bytes": 28 * res * res, "what": "all_gather of z+colour+normal row bands",
+            gather = {"mode": "nccl_all_gather", "ms": float(gms.item()), "bytes": 28 * res * res,
+                      "what": "all_gather_into_tensor of the z + colour + normal row bands after the frame (every rank ends with the whole frame)",
+                      "frames_per_s_including_gather": 1000.0 / (ms / steps + float(gms.item())),
                       "covered_pixels": int((full[0] < 1e5).sum().item())}
+            del full
     z = f.device_buffers()[0]
     cov = torch.tensor([int((z < 1e5).sum().item())], dtype=torch.int64, device=dev)   # (PeerFrame: read over NVLink)
-    if world > 1:
+    if banded and world > 1:
         dist.all_reduce(cov)
-    fps = args.steps / (ms / 1000.0)
+    fps = steps / (ms / 1000.0)
     peak, peak_src = peaks()
-    rows = res if band is None else band[1] - band[0]
+    rows = res if not (banded and world > 1) else band[1] - band[0]
     alg = 108 * T + 28 * rows * res       # per GPU: every rank reads all triangles, writes its own rows
     k_avg = k_ms / max(k_launches, 1)
+
+    cpu = e2e = None
+    if rank == 0 and world == 1 and with_cpu and not args.no_cpu:
+        # host Version C on the same frame (the reference build where it exists): fresh filler per frame, render_model only --
+        # plus, for C2, the reference's own GuroIllumination pass over the result (renderer.py:48)
+        kind, cores, render = cpu_reference_runner(cpu_threads, res=res, fov=FOV)
+        times = [render(model._vertices_by_triangles, model._colors_by_triangles, model._normals_by_triangles) for _ in range(cpu_n)]
+        cpu = {"value": len(times) / sum(times), "unit": "frames/s", "cores": cores, "host_cores": os.cpu_count(), "kind": kind,
+               "sample": f"{len(times)} frame(s), render_model only, fresh pre-touched filler per frame, n_threads={cores}",
+               "median_ms": 1000 * statistics.median(times)}
+        # e2e: the drop-in idiom on host arrays -- a new filler, render_model, the three get_*_buffer (dense download)
+        m_host = TriModel(model._vertices_by_triangles, model._colors_by_triangles, model._normals_by_triangles)
+
+        def drop_in_frame():
+            ff = AdvancedPixelBufferFiller(res, res, fov=FOV, n_threads=8, device=local)
+            ff.render_model(m_host)
+            if guro:
+                ff.illuminate_guro(np.float32([0, 0, -1]))
+            return ff.get_color_buffer(), ff.get_normals_buffer(), ff.get_z_buffer()
+        nrep = 2 if res >= 8192 else 5
+        drop_in_frame()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(nrep):
+            out = drop_in_frame()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / nrep
+        e2e = {"value": 1.0 / dt, "unit": "frames/s", "h2d_bytes_per_step": 108 * T, "d2h_bytes_per_step": 28 * res * res,
+               "api": "AdvancedPixelBufferFiller(...).render_model(model) + get_color/normals/z_buffer() on host NumPy arrays, a new "
+                      "filler per frame, synchronous" + (" (+ illuminate_guro before the reads)" if guro else ""),
+               "covered_pixels": int((out[2] < 1e5).sum())}
+        del out
+
+    line = None
     if rank == 0:
         line = {
-            "metric": f"{args.workload} frames/s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "strong" if band is not None else "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic UV sphere (SURVEY 8d C4)" if band is not None else "bunny fixture + igor texture (tests/golden/bunny_fit.npz)",
-            "config": {"workload": args.workload, "res": res, "fov": FOV, "triangles": T,
-                       "sharding": (f"screen-row bands, tile aligned, {args.bands}: {bands}") if band is not None else "none",
+            "metric": f"{workload} frames/s", "value": fps, "unit": "frames/s", "n_gpus": world if banded else 1, "steps": steps,
+            "warmup": 3, "ms_per_step": ms / steps, "higher_is_better": True,
+            "scaling": "strong" if (banded and world > 1) else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic UV sphere (SURVEY 8d C4)" if banded else f"{source} fixture + igor texture (tests/golden/{source}_fit.npz)",
+            "config": {"workload": workload, "baseline_config": cfg, "res": res, "fov": FOV, "triangles": T, "illumination": bool(guro),
+                       "sharding": (f"screen-row bands, tile aligned, {args.bands}: {bands}") if (banded and world > 1) else "none (replicas only)",
                        "l2": "frame buffers %.2f GB per GPU vs 126 MB L2" % (28 * rows * res / 1e9)},
-            "gtri_per_s": fps * T / 1e9, "clocks": clocks.summary(), "gpu_launches": f.launch_count - launches0,
+            "gtri_per_s": fps * T / 1e9, "clocks": clocks.summary(), "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "k_raster", "achieved": alg / (k_avg / 1000.0) / 1e9 if k_avg else None,
                          "peak": peak, "unit": "GB/s", "frac": (alg / (k_avg / 1000.0) / 1e9 / peak) if k_avg else None,
                          "traffic": None, "peak_source": peak_src, "avg_launch_ms": k_avg,
-                         "algorithmic_bytes_per_launch": alg, "share_of_step": k_ms / e0.elapsed_time(e1)},
-            "gather": gather, "checks": {"covered_pixels": int(cov.item())},
+                         "algorithmic_bytes_per_launch": alg, "share_of_step": k_ms / ms_own if ms_own else None},
+            "cpu_baseline": cpu, "e2e": e2e, "gather": gather, "checks": {"covered_pixels": int(cov.item())},
         }
-        emit(line)
+    del f
     if frame is not None:
-        del f
         frame.close()
+    return line
+
+
+def run_extra_workload(args):
+    import torch.distributed as dist
+    world, rank, local, dev = init_dist()
+    line = measure_workload(args, args.workload, world, rank, local, dev)
+    if rank == 0 and line is not None:
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -797,11 +951,12 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=60)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--workload", default="trex_1024_orbit",
-                    choices=["trex_1024_orbit", "bunny_4096_guro", "sphere_8192_bands"])
+                    choices=["trex_1024_orbit", "bunny_4096_guro", "basketball_2048", "sphere_8192_bands"])
     ap.add_argument("--bands", default="balanced", choices=["balanced", "uniform"],
                     help="sphere_8192_bands only: rows per rank equal (uniform) or cut where the estimated cost balances")
     ap.add_argument("--res", type=int, default=0, help="sphere_8192_bands only: override the resolution (scaled sphere)")
-    ap.add_argument("--gather", default="none", choices=["none", "bands", "u8", "z", "all", "peer"],
+    ap.add_argument("--no-secondary", action="store_true", help="skip the C2 / C3 / C4 lines measured after the headline")
+    ap.add_argument("--gather", default="auto", choices=["auto", "none", "bands", "u8", "z", "exchange", "all", "peer"],
                     help="also time the final NCCL gather (reported beside, never inside, the headline value); "
                          "peer (sphere_8192_bands only): no gather at all -- every rank's filler renders its band straight into "
                          "rank 0's frame over NVLink (sharding.PeerFrame), and the value is frames/s complete on rank 0")

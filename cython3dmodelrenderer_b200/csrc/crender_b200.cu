@@ -59,6 +59,7 @@ constexpr int SPLIT_BANDS = 4;
 #define CRB_CLEAR_EVERY 4
 #endif
 constexpr unsigned CE = CRB_CLEAR_EVERY;  // every CE-th CTA of k_raster is a clear CTA (power of two)
+constexpr int WIDE_TILES = 12;    // a triangle whose pixel rectangle touches more tiles than this is binned by its whole warp
 constexpr unsigned HEAVY_N = 64;  // tiles with more triangles than this are rasterized first (longest first: shorter kernel tail)
 #ifndef CRB_FQ
 #define CRB_FQ 256
@@ -456,7 +457,7 @@ __device__ __forceinline__ void setup_chunk(const Frame &F, const int view, cons
     if (!any_drawn) return;
     stage_floats(F.c, first * 9, cnt * 9, sc);
     __syncthreads();
-    if (!drawn) return;
+    if (drawn) {
     // denominators of mu:12-21 -- pure functions of the triangle, hoisted out of the per-pixel code (same bits)
     const float l03 = (x[1] - x[2]) * (y[0] - y[2]) - (y[1] - y[2]) * (x[0] - x[2]);
     const float l13 = (x[2] - x[0]) * (y[1] - y[0]) - (y[2] - y[0]) * (x[1] - x[0]);
@@ -490,13 +491,26 @@ __device__ __forceinline__ void setup_chunk(const Frame &F, const int view, cons
     R[S_C1] = make_float4(q[3], q[4], q[5], q[6]);
     R[S_C2] = make_float4(q[7], q[8], __uint_as_float(fl), 0.0f);
     F.recD[ridx] = make_float4(__frcp_rn(l03), __frcp_rn(l13), __frcp_rn(l23), __uint_as_float(fl));
+    }
     if (F.flags & CRB_PATH_ATOMIC) return;
 
-    int tx0, tx1, ty0, ty1;
-    tile_span(F, bx, by, tx0, tx1, ty0, ty1);
+    // per-tile counts.  A triangle that touches a few tiles (the usual case) is counted by its own thread; one that spans many
+    // (a quad of the 2048^2 basketball covers hundreds) is counted by its whole warp, a tile per lane -- left to one thread, a
+    // screen-filling triangle alone kept the kernel busy for a millisecond
+    int tx0 = 0, tx1 = -1, ty0 = 0, ty1 = -1;
+    if (drawn) tile_span(F, bx, by, tx0, tx1, ty0, ty1);
     unsigned *cnt_view = F.count + (long long)view * F.nTiles;
-    for (int ty = ty0; ty <= ty1; ++ty)
-        for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(cnt_view + ty * F.tilesX + tx, 1u);
+    const int nt = drawn ? (tx1 - tx0 + 1) * (ty1 - ty0 + 1) : 0;
+    if (nt <= WIDE_TILES)
+        for (int ty = ty0; ty <= ty1; ++ty)
+            for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(cnt_view + ty * F.tilesX + tx, 1u);
+    for (unsigned wide = __ballot_sync(0xFFFFFFFFu, nt > WIDE_TILES); wide; wide &= wide - 1u) {
+        const int src = __ffs(wide) - 1;
+        const int sx0 = __shfl_sync(0xFFFFFFFFu, tx0, src), sx1 = __shfl_sync(0xFFFFFFFFu, tx1, src);
+        const int sy0 = __shfl_sync(0xFFFFFFFFu, ty0, src), n = __shfl_sync(0xFFFFFFFFu, nt, src);
+        const int wx = sx1 - sx0 + 1;
+        for (int i = (int)(threadIdx.x & 31u); i < n; i += 32) atomicAdd(cnt_view + (sy0 + i / wx) * F.tilesX + sx0 + i % wx, 1u);
+    }
 }
 
 #ifndef CRB_SETUP_MIN_CTAS
@@ -665,27 +679,51 @@ __device__ __forceinline__ void fill_chunk(const Frame &F, const int view, const
     // speculative: the rectangle flies with the flags that decide whether it is looked at (recE is allocated for every
     // (view, triangle); in a chunk k_setup left dead it holds stale values, which are then not used)
     const float4 E = tri < F.T ? F.recE[ridx] : make_float4(0.f, 0.f, 0.f, 0.f);
-    if (skip || !F.alive[(long long)view * chunksPerView + chunk]) return;   // frame skipped / nothing to draw in this chunk
-    if (tri >= F.T) return;
+    if (skip || !F.alive[(long long)view * chunksPerView + chunk]) return;   // frame skipped / nothing to draw in this chunk (CTA-uniform)
     const unsigned bx = __float_as_uint(E.x), by = __float_as_uint(E.y);
-    if ((bx >> 16) == 0) return;  // not drawn (x_right >= 1 for every drawn triangle)
-    const float4 *R = F.shrec + ridx * SREC;
-    const float4 a = R[S_A], b = R[S_B], c = R[S_C], d = F.recD[ridx];
-    const unsigned fl = __float_as_uint(d.w);
-    // |l3| and |1/l3| where the coordinate is negated (RN(1/-x) = -RN(1/x): flipping the sign bit is exact)
-    const float4 s2 = make_float4(c.x, (fl & (FL_NEG << 0)) ? -c.y : c.y, (fl & (FL_NEG << 1)) ? -c.z : c.z, (fl & (FL_NEG << 2)) ? -c.w : c.w);
-    const float4 s4 = make_float4((fl & (FL_NEG << 0)) ? -d.x : d.x, (fl & (FL_NEG << 1)) ? -d.y : d.y, (fl & (FL_NEG << 2)) ? -d.z : d.z, 0.0f);
-    const uint4 s3 = make_uint4(bx, by, (unsigned)tri, fl);
-
-    int tx0, tx1, ty0, ty1;
-    tile_span(F, bx, by, tx0, tx1, ty0, ty1);
+    const bool drawn = tri < F.T && (bx >> 16) != 0;  // (x_right >= 1 for every drawn triangle)
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, s2 = a, s4 = a;
+    uint4 s3 = make_uint4(0u, 0u, 0u, 0u);
+    int tx0 = 0, tx1 = -1, ty0 = 0, ty1 = -1;
+    if (drawn) {
+        const float4 *R = F.shrec + ridx * SREC;
+        const float4 c = R[S_C], d = F.recD[ridx];
+        a = R[S_A]; b = R[S_B];
+        const unsigned fl = __float_as_uint(d.w);
+        // |l3| and |1/l3| where the coordinate is negated (RN(1/-x) = -RN(1/x): flipping the sign bit is exact)
+        s2 = make_float4(c.x, (fl & (FL_NEG << 0)) ? -c.y : c.y, (fl & (FL_NEG << 1)) ? -c.z : c.z, (fl & (FL_NEG << 2)) ? -c.w : c.w);
+        s4 = make_float4((fl & (FL_NEG << 0)) ? -d.x : d.x, (fl & (FL_NEG << 1)) ? -d.y : d.y, (fl & (FL_NEG << 2)) ? -d.z : d.z, 0.0f);
+        s3 = make_uint4(bx, by, (unsigned)tri, fl);
+        tile_span(F, bx, by, tx0, tx1, ty0, ty1);
+    }
     const long long vb = (long long)view * F.nTiles;
-    for (int ty = ty0; ty <= ty1; ++ty)
-        for (int tx = tx0; tx <= tx1; ++tx) {
-            const long long t = vb + ty * F.tilesX + tx;
+    const int nt = drawn ? (tx1 - tx0 + 1) * (ty1 - ty0 + 1) : 0;
+    if (nt <= WIDE_TILES)
+        for (int ty = ty0; ty <= ty1; ++ty)
+            for (int tx = tx0; tx <= tx1; ++tx) {
+                const long long t = vb + ty * F.tilesX + tx;
+                const unsigned at = F.offset[t] + atomicAdd(F.cursor + t, 1u);
+                F.ls0[at] = a; F.ls1[at] = b; F.ls2[at] = s2; F.ls3[at] = s3; F.ls4[at] = s4;
+            }
+    // triangles that span many tiles: the whole warp scatters them, a tile per lane (see setup_chunk)
+    for (unsigned wide = __ballot_sync(0xFFFFFFFFu, nt > WIDE_TILES); wide; wide &= wide - 1u) {
+        const int src = __ffs(wide) - 1;
+        auto bc = [src](float4 v) {
+            return make_float4(__shfl_sync(0xFFFFFFFFu, v.x, src), __shfl_sync(0xFFFFFFFFu, v.y, src), __shfl_sync(0xFFFFFFFFu, v.z, src),
+                               __shfl_sync(0xFFFFFFFFu, v.w, src));
+        };
+        const float4 wa = bc(a), wb = bc(b), w2 = bc(s2), w4 = bc(s4);
+        const uint4 w3 = make_uint4(__shfl_sync(0xFFFFFFFFu, s3.x, src), __shfl_sync(0xFFFFFFFFu, s3.y, src), __shfl_sync(0xFFFFFFFFu, s3.z, src),
+                                    __shfl_sync(0xFFFFFFFFu, s3.w, src));
+        const int sx0 = __shfl_sync(0xFFFFFFFFu, tx0, src), sx1 = __shfl_sync(0xFFFFFFFFu, tx1, src);
+        const int sy0 = __shfl_sync(0xFFFFFFFFu, ty0, src), n = __shfl_sync(0xFFFFFFFFu, nt, src);
+        const int wx = sx1 - sx0 + 1;
+        for (int i = (int)(threadIdx.x & 31u); i < n; i += 32) {
+            const long long t = vb + (sy0 + i / wx) * F.tilesX + sx0 + i % wx;
             const unsigned at = F.offset[t] + atomicAdd(F.cursor + t, 1u);
-            F.ls0[at] = a; F.ls1[at] = b; F.ls2[at] = s2; F.ls3[at] = s3; F.ls4[at] = s4;
+            F.ls0[at] = wa; F.ls1[at] = wb; F.ls2[at] = w2; F.ls3[at] = w3; F.ls4[at] = w4;
         }
+    }
 }
 
 #ifndef CRB_FILL_MIN_CTAS

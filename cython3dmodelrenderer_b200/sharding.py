@@ -159,6 +159,41 @@ def gather_views_overlapped(produce, n_local, chunk, dst=0, out=None):
     return out if rank == dst else None
 
 
+def exchange_rows_overlapped(produce, n_local, chunk, out=None):
+    """View-sharded render delivered ROW-sharded: after every chunk of views an asynchronous all-to-all is started in which
+    rank r receives rows [r*H/N, (r+1)*H/N) of the chunk's views from every rank, and the next chunk is rendered while it
+    travels.  Unlike a gather into one rank, whose NVLink ingress (900 GB/s) caps the whole job, every rank here receives only
+    1/N of the frames' bytes, so the delivery scales with the number of GPUs -- the layout for a consumer that is itself
+    sharded by image region (an encoder or a loss evaluated per row band).  `produce(first, count)` as in
+    gather_views_overlapped; the image height must be divisible by the world size.  Returns, on every rank, a tensor
+    [world, n_local, H/N, ...] (entry [s, i] = this rank's row band of local view i of rank s; pass `out` to reuse it)."""
+    world = _world()
+    rank = dist.get_rank() if world > 1 else 0
+    works, first = [], 0
+    while first < n_local:
+        count = min(int(chunk), n_local - first)
+        part = produce(first, count)                                  # [count, H, ...]
+        H = part.shape[1]
+        if H % world:
+            raise ValueError(f"image height {H} is not divisible by the world size {world}")
+        hb = H // world
+        if out is None:
+            out = torch.empty((world, n_local, hb) + tuple(part.shape[2:]), dtype=part.dtype, device=part.device)
+        if world == 1:
+            out[0, first:first + count].copy_(part)
+        else:
+            # [count, N, hb, ...] -> [N, count, hb, ...]: block d goes to rank d
+            send = part.reshape((count, world, hb) + tuple(part.shape[2:])).transpose(0, 1).contiguous()
+            recv = torch.empty_like(send)
+            w = dist.all_to_all_single(recv, send, async_op=True)
+            works.append((w, send, recv, first, count))
+        first += count
+    for w, _, recv, f0, cnt in works:
+        w.wait()
+        out[:, f0:f0 + cnt].copy_(recv)
+    return out
+
+
 def gather_bands(local, h, dst=None, align=TILE_ROWS, bands=None):
     """Gathers per-rank row bands [rows_r, W, ...] into the full [h, W, ...] buffer.  `bands` = the [(row0,row1)] list
     every rank used (e.g. balanced_bands); default: the uniform layout of band_shard."""

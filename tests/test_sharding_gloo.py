@@ -122,6 +122,19 @@ def _worker(rank, world, port, out_dir):
                     assert bool((ov[r, i] == 100.0 * r + i).all())
         else:
             assert ov is None
+        # ---- the row exchange (all-to-all per chunk): every rank ends with its row band of ALL views --------------------
+        Hx = 6 * world
+
+        def produce_img(first, count):          # value = 1000 * rank + 10 * view + row
+            rows = torch.arange(Hx, dtype=torch.float32)[None, :, None]
+            vs = torch.arange(first, first + count, dtype=torch.float32)[:, None, None]
+            return (1000.0 * rank + 10.0 * vs + rows).repeat(1, 1, 5)
+        ex = sharding.exchange_rows_overlapped(produce_img, 5, 2)
+        assert ex.shape == (world, 5, 6, 5)
+        for src in range(world):
+            for i in range(5):
+                for rr_ in range(6):
+                    assert bool((ex[src, i, rr_] == 1000.0 * src + 10.0 * i + (6 * rank + rr_)).all())
         if rank == 0:
             np.savez(os.path.join(out_dir, "r0.npz"), z_all=z_all.numpy(), col_0=col_0.numpy(), z_band=z_band.numpy(),
                      n_band=n_band.numpy(), z_full=full.get_z_buffer(), n_full=full.get_normals_buffer())
