@@ -392,19 +392,64 @@ def run_gpu_arm(args):
                           "gathered into ONE rank is bound by that rank's ingress (ingress_bound_frames_per_s); the row exchange "
                           "(all-to-all: every rank ends with its row band of ALL views) spreads the ingress over the ranks and "
                           "scales", "chunk_views": gchunk}
-        want_modes = ("u8", "z", "exchange") if args.gather in ("auto", "all") else (args.gather,)
+        want_modes = ("u8", "z", "exchange_nccl", "u8_peer", "exchange") if args.gather in ("auto", "all") else (args.gather,)
+
+        def fused(mode):
+            """Delivery fused into the rasterizer (sharding.RowExchange / crb_set_u8_exchange): k_raster stores the uint8 image
+            row band by row band into the receiving ranks' memory over NVLink -- one launch of all V views, no NCCL call."""
+            xch = sharding.RowExchange(V, RES, RES, local_device=local, gather_to=0 if mode == "u8_peer" else None)
+            try:
+                def both_fn():
+                    f.render_views(dv, dc, dn, dviews, want=(), chunk=args.chunk, check_status=False, u8_exchange=xch.plan(0))
+
+                def only_fn():
+                    f.render_views(dv, dc, dn, dviews, want=(), color_u8_out=u8, chunk=args.chunk, check_status=False)
+                both = timed(both_fn)
+                only = timed(only_fn)
+                t = xch.tensor()
+                check_px = int((t[world - 1, 0].sum(dim=-1) > 0).sum().item()) if t is not None else None
+                same = None
+                if t is not None:      # the delivered bytes are the ones a local render of the same views holds
+                    band = u8[0, :xch.hb] if mode == "exchange" and rank == 0 else (u8[0] if rank == 0 else None)
+                    same = bool(torch.equal(t[rank, 0], band)) if band is not None else None
+                return both, only, check_px, same
+            finally:
+                xch.close()
+
         for mode in want_modes:
+            if mode in ("exchange", "u8_peer"):
+                bpf = 3 * RES * RES
+                try:
+                    both, only, check_px, same = fused(mode)
+                    if mode == "exchange":
+                        bound = NVLINK_IN * world * world / (bpf * max(world - 1, 1))
+                        what = ("row exchange of the uint8 images fused into the rasterizer: k_raster stores each image row band straight into "
+                                "the memory of the rank that owns the band (peer memory over NVLink / NVSwitch, crb_set_u8_exchange); rank r "
+                                "ends with rows [r*H/N, (r+1)*H/N) of all N*V views; no NCCL call, no staging copy")
+                    else:
+                        bound = NVLINK_IN / bpf * world / max(world - 1, 1)
+                        what = ("the uint8 images of all views written by every rank's k_raster straight into rank 0's memory (peer stores "
+                                "over NVLink, crb_set_u8_exchange with one band): a gather without a collective")
+                    delivered = n_total / (both / 1000.0)
+                    gather[mode] = {"what": what, "bytes_per_frame": bpf, "ms_render_only": only, "ms_render_and_delivery": both,
+                                    "frames_per_s_render_only": n_total / (only / 1000.0), "frames_per_s_delivered": delivered,
+                                    "ingress_bound_frames_per_s": bound, "frac_of_ingress_bound": delivered / bound,
+                                    "delivery_efficiency": only / both,
+                                    "check_pixels": check_px, "delivered_equals_local_render": same}
+                except Exception as ex:
+                    gather[mode] = {"error": repr(ex)[:300]}
+                continue
             if mode == "u8":
                 produce, bpf, what = produce_u8, 3 * RES * RES, "run.py:26's uint8 images of all views gathered to rank 0 (NCCL gather per chunk, travelling while the next chunk is rendered)"
             elif mode == "z":
                 produce, bpf, what = produce_z, 4 * RES * RES, "the float32 z buffers of all views gathered to rank 0 (NCCL gather per chunk beside the rendering)"
-            elif mode == "exchange":
-                produce, bpf, what = produce_u8, 3 * RES * RES, ("row exchange of the uint8 images (NCCL all-to-all per chunk beside the rendering): rank r ends "
+            elif mode == "exchange_nccl":
+                produce, bpf, what = produce_u8, 3 * RES * RES, ("row exchange of the uint8 images the library way (NCCL all-to-all per chunk beside the rendering; kept as the baseline of the fused exchange): rank r ends "
                                                                 "with rows [r*H/N, (r+1)*H/N) of all N*V views -- the delivery layout whose ingress is spread over the ranks")
             else:
                 continue
             try:
-                if mode == "exchange":
+                if mode == "exchange_nccl":
                     res_buf = sharding.exchange_rows_overlapped(produce, V, gchunk)
                     both = timed(lambda: sharding.exchange_rows_overlapped(produce, V, gchunk, out=res_buf))
                     bound = NVLINK_IN * world * world / (bpf * max(world - 1, 1))   # a rank receives its 1/N row band of the (N-1)/N frames other ranks render
@@ -956,7 +1001,7 @@ def main():
                     help="sphere_8192_bands only: rows per rank equal (uniform) or cut where the estimated cost balances")
     ap.add_argument("--res", type=int, default=0, help="sphere_8192_bands only: override the resolution (scaled sphere)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the C2 / C3 / C4 lines measured after the headline")
-    ap.add_argument("--gather", default="auto", choices=["auto", "none", "bands", "u8", "z", "exchange", "all", "peer"],
+    ap.add_argument("--gather", default="auto", choices=["auto", "none", "bands", "u8", "z", "exchange", "exchange_nccl", "u8_peer", "all", "peer"],
                     help="also time the final NCCL gather (reported beside, never inside, the headline value); "
                          "peer (sphere_8192_bands only): no gather at all -- every rank's filler renders its band straight into "
                          "rank 0's frame over NVLink (sharding.PeerFrame), and the value is frames/s complete on rank 0")

@@ -50,6 +50,7 @@ SIGNATURES = {
     "crb_render_views": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _i, _vp, _vp, _vp, _vp, _u, _fp, _vp]),
     "crb_set_option": (_i, [_vp, _i, _i]),
     "crb_join": (_i, [_vp, _vp]),
+    "crb_set_u8_exchange": (_i, [_vp, _i, _i, ctypes.POINTER(_vp)]),
     "crb_sync": (_i, [_vp, _vp]),
     "crb_readback_stats": (_i, [_vp, _i64p, _i, _vp]),
     "crb_readback_reset": (_i, [_vp, _vp]),

@@ -137,6 +137,10 @@ struct Frame {
     float *z, *color, *normals;
     unsigned char *color_u8;
     long long slabPixels;       // rows*W
+    // row exchange of the uint8 image (crb_set_u8_exchange): u8xN > 0 = image row r of view k goes to row band d = r / u8xRows,
+    // i.e. to u8x[d] + ((k * u8xRows + r - d * u8xRows) * W + x) * 3 -- u8x[d] is rank d's receive buffer (peer memory)
+    unsigned char *u8x[CRB_MAX_EXCHANGE];
+    int u8xN, u8xRows;
     float light[3];
 };
 
@@ -303,6 +307,18 @@ __device__ __forceinline__ float background_color(const Frame &)
 
 // run.py:26 .astype('uint8'): C truncation toward zero, then the low 8 bits.
 __device__ __forceinline__ unsigned char to_u8(float c) { return (unsigned char)(int)c; }
+
+// Address of pixel (x, image row yl of the band's buffers) of view `view` in the flipped uint8 image (run.py:26 image[::-1]):
+// the caller's [views,rows,W,3] array, or -- row exchange -- the receive buffer of the rank that owns the image row.
+__device__ __forceinline__ unsigned char *u8_pixel(const Frame &F, int view, int yl, int x)
+{
+    const int fr = F.row1 - F.row0 - 1 - yl;
+    if (F.u8xN) {
+        const int d = fr / F.u8xRows;
+        return F.u8x[d] + (((long long)view * F.u8xRows + (fr - d * F.u8xRows)) * F.W + x) * 3;
+    }
+    return F.color_u8 + ((long long)view * F.slabPixels + (long long)fr * F.W + x) * 3;
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // K1+K2: vertex transform + projection, triangle setup, cull, bbox, per-tile counts
@@ -865,20 +881,19 @@ __device__ __forceinline__ void write_clear_tile(const Frame &F, unsigned skip, 
         }
     }
     if (F.color_u8 && tw == TW && !(F.W & 15) && !(reinterpret_cast<uintptr_t>(F.color_u8) & 15u)) {
-        // a tile row of the uint8 image is 96 bytes = six 16-byte stores (rows are 16-byte multiples: W % 16 == 0)
-        const int rows = F.row1 - F.row0;
+        // a tile row of the uint8 image is 96 bytes = six 16-byte stores (rows are 16-byte multiples: W % 16 == 0; the receive
+        // buffers of a row exchange are 256-byte aligned)
         const unsigned w4 = (unsigned)to_u8(bg) * 0x01010101u;
         const uint4 val = make_uint4(w4, w4, w4, w4);
         for (int i = threadIdx.x; i < th * 6; i += NTH) {
             const int r = i / 6, q = i - r * 6;
-            reinterpret_cast<uint4 *>(F.color_u8 + ((long long)view * F.slabPixels + (long long)(rows - 1 - (yl0 + r)) * F.W + x0) * 3)[q] = val;
+            reinterpret_cast<uint4 *>(u8_pixel(F, view, yl0 + r, x0))[q] = val;
         }
     } else if (F.color_u8) {
-        const int rows = F.row1 - F.row0;
         const unsigned char b8 = to_u8(bg);
         for (int i = threadIdx.x; i < th * tw * 3; i += NTH) {
             const int r = i / (tw * 3), xx = i % (tw * 3);
-            F.color_u8[((long long)view * F.slabPixels + (long long)(rows - 1 - (yl0 + r)) * F.W + x0) * 3 + xx] = b8;
+            u8_pixel(F, view, yl0 + r, x0)[xx] = b8;
         }
     }
 }
@@ -1173,8 +1188,7 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
             if (F.normals) { F.normals[pix * 3] = nn[0]; F.normals[pix * 3 + 1] = nn[1]; F.normals[pix * 3 + 2] = nn[2]; }
         }
         if (F.color_u8 && write) {
-            const int rows = F.row1 - F.row0;
-            unsigned char *o = F.color_u8 + (slab + (long long)(rows - 1 - (yl0 + yy)) * F.W + x0 + xx) * 3;
+            unsigned char *o = u8_pixel(F, view, yl0 + yy, x0 + xx);
             o[0] = to_u8(c[0]); o[1] = to_u8(c[1]); o[2] = to_u8(c[2]);
         }
     }
@@ -1657,6 +1671,8 @@ struct crb_filler {
     bool prof_on;
     int prof_n;
     cudaEvent_t *prof_ev;  // 2 * PROF_MAX events, created on first use
+    unsigned char *u8x[CRB_MAX_EXCHANGE];   // crb_set_u8_exchange: receive buffer of every row band (u8x_n == 0: off)
+    int u8x_n, u8x_rows;
 };
 
 namespace {
@@ -2469,6 +2485,8 @@ int crb_render_views(crb_filler *f, const float *v, const float *c, const float 
     if ((flags & CRB_GURO) && !light) return fail(CRB_ERR_INVALID, "CRB_GURO needs a light direction");
     if ((reinterpret_cast<uintptr_t>(z_out) | reinterpret_cast<uintptr_t>(color_out) | reinterpret_cast<uintptr_t>(normals_out)) & 15u)
         return fail(CRB_ERR_INVALID, "output slabs must be 16-byte aligned");
+    if (f->u8x_n && color_u8_out) return fail(CRB_ERR_INVALID, "color_u8_out must be NULL while a row exchange is set (crb_set_u8_exchange)");
+    if (f->u8x_n && f->u8x_n * f->u8x_rows != f->row1 - f->row0) return fail(CRB_ERR_STATE, "row exchange bands do not cover the filler's rows");
     CU(cudaSetDevice(f->device));
     const long long slab = (long long)(f->row1 - f->row0) * f->w;
     if (slab == 0) return CRB_OK;
@@ -2501,6 +2519,11 @@ int crb_render_views(crb_filler *f, const float *v, const float *c, const float 
         F.color = color_out ? color_out + (size_t)v0 * slab * 3 : nullptr;
         F.normals = normals_out ? normals_out + (size_t)v0 * slab * 3 : nullptr;
         F.color_u8 = color_u8_out ? color_u8_out + (size_t)v0 * slab * 3 : nullptr;
+        if (f->u8x_n) {      // row exchange: the uint8 image leaves through the receive buffers of the row bands
+            F.u8xN = f->u8x_n; F.u8xRows = f->u8x_rows;
+            for (int d = 0; d < f->u8x_n; ++d) F.u8x[d] = f->u8x[d] + (size_t)v0 * f->u8x_rows * f->w * 3;
+            F.color_u8 = F.u8x[0];
+        }
         if (light) { F.light[0] = light[0]; F.light[1] = light[1]; F.light[2] = light[2]; }
         int rc;
         if (!pipe) {
@@ -2521,6 +2544,19 @@ int crb_render_views(crb_filler *f, const float *v, const float *c, const float 
         f->pending_join = 1 + last_set;
         if (!defer) return join_pending(f, user);
     }
+    return CRB_OK;
+}
+
+int crb_set_u8_exchange(crb_filler *f, int n_bands, int rows_per_band, void *const *band_base)
+{
+    if (check_filler(f)) return CRB_ERR_INVALID;
+    if (n_bands == 0) { f->u8x_n = 0; return CRB_OK; }
+    if (n_bands < 0 || n_bands > CRB_MAX_EXCHANGE || rows_per_band <= 0 || !band_base) return fail(CRB_ERR_INVALID, "bad row exchange");
+    if ((long long)n_bands * rows_per_band != f->row1 - f->row0) return fail(CRB_ERR_INVALID, "n_bands * rows_per_band must equal the filler's rows");
+    for (int d = 0; d < n_bands; ++d)
+        if (!band_base[d] || (reinterpret_cast<uintptr_t>(band_base[d]) & 15u)) return fail(CRB_ERR_INVALID, "band_base must be non-NULL and 16-byte aligned");
+    for (int d = 0; d < n_bands; ++d) f->u8x[d] = static_cast<unsigned char *>(band_base[d]);
+    f->u8x_n = n_bands; f->u8x_rows = rows_per_band;
     return CRB_OK;
 }
 

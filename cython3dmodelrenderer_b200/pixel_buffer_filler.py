@@ -42,18 +42,19 @@ def _check_tri_array(a, name):
 class _DevicePointer:
     """CUDA array interface over a raw device address (memory owned elsewhere, e.g. a frame mapped from another rank)."""
 
-    def __init__(self, ptr, shape):
-        self.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": "<f4", "data": (int(ptr), False),
+    def __init__(self, ptr, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": typestr, "data": (int(ptr), False),
                                          "version": 3, "strides": None}
 
 
-def wrap_device_pointer(torch, ptr, shape, device):
-    """float32 torch tensor of `shape` over the device address `ptr` (no copy, no ownership)."""
+def wrap_device_pointer(torch, ptr, shape, device, dtype=None):
+    """torch tensor (float32, or uint8 with dtype=torch.uint8) of `shape` over the device address `ptr` (no copy, no ownership)."""
+    dtype = dtype or torch.float32
     if any(int(x) == 0 for x in shape):
-        return torch.empty(tuple(shape), dtype=torch.float32, device=device)
+        return torch.empty(tuple(shape), dtype=dtype, device=device)
     # no device argument: torch takes the device that owns the memory from the pointer itself (for a frame mapped from
     # another rank that is the peer GPU; naming the local device here would make as_tensor copy instead of alias)
-    return torch.as_tensor(_DevicePointer(ptr, shape))
+    return torch.as_tensor(_DevicePointer(ptr, shape, "|u1" if dtype == torch.uint8 else "<f4"))
 
 
 class AdvancedPixelBufferFiller:
@@ -334,7 +335,8 @@ class AdvancedPixelBufferFiller:
         return out
 
     def render_views(self, v, c, n, views, z_out=None, color_out=None, normals_out=None, color_u8_out=None,
-                     want=("z", "color", "normals"), guro_light=None, chunk=32, check_status=True, defer_join=False):
+                     want=("z", "color", "normals"), guro_light=None, chunk=32, check_status=True, defer_join=False,
+                     u8_exchange=None):
         """Batched multi-view render (config C5): every view gets fresh-filler buffers in its own slab.
 
         v, c, n: torch CUDA float32 [T,3,3] (device-resident base mesh);  views: [V,16] float32 (numpy or CUDA tensor,
@@ -343,6 +345,9 @@ class AdvancedPixelBufferFiller:
         `guro_light` = raw light direction (as given to GuroIllumination) fuses the illumination into the shading pass.
         `defer_join=True` (with check_status=False): the call returns without ordering the current stream behind the
         rasterizer, so the next batch's front end overlaps it; call `join()` before using the outputs.
+        `u8_exchange=(rows_per_band, [address, ...])` (sharding.RowExchange.plan): the flipped uint8 images leave the
+        rasterizer row band by row band straight into the listed receive buffers (other GPUs' memory) instead of a
+        local array -- the view-sharded render and its delivery in one kernel (crb_set_u8_exchange).
         Returns a dict of the produced tensors."""
         torch = self._torch
         for a in (v, c, n):
@@ -386,6 +391,21 @@ class AdvancedPixelBufferFiller:
             self._deferred_keep = (views, v, c, n)
         self._ensure_workspace(T, views=min(int(chunk), max(V, 1)))
         ptr = lambda t: None if t is None else t.data_ptr()
+        if u8_exchange is not None:
+            if color_u8_out is not None:
+                raise ValueError("u8_exchange replaces color_u8_out")
+            hb, bases = u8_exchange
+            arr = (ctypes.c_void_p * len(bases))(*[int(b) for b in bases])
+            check(self._L.crb_set_u8_exchange(self._handle, len(bases), int(hb), arr))
+        try:
+            return self._render_views_loop(v, c, n, T, views, V, z_out, color_out, normals_out, color_u8_out, flags, light,
+                                           check_status, out, ptr)
+        finally:
+            if u8_exchange is not None:
+                check(self._L.crb_set_u8_exchange(self._handle, 0, 0, None))
+
+    def _render_views_loop(self, v, c, n, T, views, V, z_out, color_out, normals_out, color_u8_out, flags, light, check_status,
+                           out, ptr):
         while True:
             check(self._L.crb_render_views(self._handle, v.data_ptr(), c.data_ptr(), n.data_ptr(), T, views.data_ptr(), V,
                                            ptr(z_out), ptr(color_out), ptr(normals_out), ptr(color_u8_out), flags, light,

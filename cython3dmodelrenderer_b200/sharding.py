@@ -282,3 +282,87 @@ class PeerFrame:
             if self.owner:
                 self._check(self._L.crb_shared_free(self.device, self.base))
             self.base = 0
+
+
+class RowExchange:
+    """Delivery of a view-sharded batch (config C5) fused into the rasterizer: every rank's k_raster stores the flipped uint8
+    image of its views (run.py:26) row band by row band straight into the receive buffers of the ranks that own the bands --
+    peer memory mapped through CUDA IPC (crb_shared_*), stores over NVLink / NVSwitch while the frame is rasterized, no NCCL
+    call and no staging copy (crb_set_u8_exchange).  Two layouts:
+      * all-to-all (default): rank d receives rows [d*H/N, (d+1)*H/N) of ALL N*V views: `tensor()` = [N, V, H/N, W, 3] uint8,
+        entry [s, i] = this rank's row band of local view i of rank s.  Every rank takes in 1/N of the bytes, so the
+        delivery scales with the number of GPUs (a gather into one rank is capped by that rank's 900 GB/s NVLink ingress);
+      * `gather_to=d`: whole images of all views into rank d: `tensor()` on d = [N, V, H, W, 3].
+    Use: `f.render_views(v, c, n, views, want=(), u8_exchange=xch.plan(first_view))`, then `xch.complete()`.
+    Collective constructor / close (every rank of the process group).  Ranks may share a device (CPU-side plumbing tests)."""
+
+    def __init__(self, n_local_views, h, w, local_device=None, gather_to=None):
+        import ctypes
+        from . import _lib
+        self._L = _lib.load_library()
+        self._check = _lib.check
+        self.world = _world()
+        self.rank = dist.get_rank() if self.world > 1 else 0
+        self.device = torch.cuda.current_device() if local_device is None else int(local_device)
+        self.V, self.h, self.w = int(n_local_views), int(h), int(w)
+        self.gather_to = gather_to
+        self.n_bands = 1 if gather_to is not None else self.world
+        if self.h % self.n_bands:
+            raise ValueError(f"image height {self.h} is not divisible by the {self.n_bands} row bands")
+        if self.n_bands > 8:
+            raise ValueError("at most 8 row bands (CRB_MAX_EXCHANGE)")
+        self.hb = self.h // self.n_bands
+        self.view_bytes = self.hb * self.w * 3
+        self.receives = gather_to is None or self.rank == gather_to
+        self.nbytes = self.world * self.V * self.view_bytes
+        ptr = ctypes.c_void_p()
+        handle = None
+        if self.receives:
+            hb_ = ctypes.create_string_buffer(64)
+            self._check(self._L.crb_shared_alloc(self.device, max(self.nbytes, 256), ctypes.byref(ptr), hb_))
+            handle = hb_.raw
+        self.own = int(ptr.value or 0)
+        handles = [handle]
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, handle)
+        owners = [gather_to] if gather_to is not None else list(range(self.world))
+        self.base, self._opened = [], []
+        for d in owners:
+            if d == self.rank:
+                self.base.append(self.own)
+            else:
+                p = ctypes.c_void_p()
+                self._check(self._L.crb_shared_open(self.device, ctypes.create_string_buffer(handles[d], 64), ctypes.byref(p)))
+                self.base.append(int(p.value))
+                self._opened.append(int(p.value))
+
+    def plan(self, first_view=0):
+        """What render_views takes as `u8_exchange` for a call whose views are this rank's local views [first_view, ...)."""
+        off = (self.rank * self.V + int(first_view)) * self.view_bytes
+        return self.hb, [b + off for b in self.base]
+
+    def tensor(self):
+        """This rank's receive buffer [world, V, rows_per_band, W, 3] uint8 (None on ranks that receive nothing)."""
+        if not self.receives:
+            return None
+        from .pixel_buffer_filler import wrap_device_pointer
+        return wrap_device_pointer(torch, self.own, (self.world, self.V, self.hb, self.w, 3), torch.device("cuda", self.device),
+                                   dtype=torch.uint8)
+
+    def complete(self):
+        """Every rank's stores have landed when this returns on all ranks."""
+        torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            dist.barrier()
+
+    def close(self):
+        """Collective: unmap the peers' buffers, then free the own one."""
+        for p in self._opened:
+            self._check(self._L.crb_shared_close(self.device, p))
+        self._opened = []
+        if self.world > 1:
+            dist.barrier()
+        if self.own:
+            self._check(self._L.crb_shared_free(self.device, self.own))
+            self.own = 0

@@ -177,6 +177,20 @@ int crb_render_views(crb_filler *f, const float *v, const float *c, const float 
                      int n_views, float *z_out, float *color_out, float *normals_out, uint8_t *color_u8_out,
                      unsigned flags, const float light[3], void *stream);
 
+/* Row exchange of the uint8 image (SURVEY 8e, config C5 "view-sharded ... with NCCL gather"; no reference counterpart --
+ * run.py is one process).  While n_bands > 0, crb_render_views writes run.py:26's flipped uint8 image of its views NOT into
+ * color_u8_out (pass NULL there) but row band by row band into other GPUs' memory, from inside the rasterizer: image row r
+ * (after the flip) of the call's view k belongs to band d = r / rows_per_band and is stored at
+ *     band_base[d] + ((k * rows_per_band + (r - d * rows_per_band)) * w + x) * 3
+ * band_base[d] = a device address valid on THIS GPU (own memory, or rank d's receive buffer mapped with crb_shared_open:
+ * the stores then cross NVLink / NVSwitch while the frame is rasterized) -- the collective is the kernel's own stores,
+ * no staging copy and no NCCL call; a stream synchronisation on every rank plus a barrier completes the exchange.
+ * n_bands = 1 with rows_per_band = rows is a gather of whole images into one rank; n_bands = N the all-to-all after which
+ * rank d holds rows [d*rows_per_band, (d+1)*rows_per_band) of every rank's views.  Requirements: 1 <= n_bands <=
+ * CRB_MAX_EXCHANGE, n_bands * rows_per_band == rows of the filler, every band_base 16-byte aligned.  n_bands = 0 ends it. */
+#define CRB_MAX_EXCHANGE 8
+int crb_set_u8_exchange(crb_filler *f, int n_bands, int rows_per_band, void *const *band_base);
+
 /* run.py's product from host arrays in one call: H2D of the three arrays, a fresh-filler frame whose only
  * output is run.py:26's `image[::-1].astype('uint8')` -- written by the rasterizer itself, lit like GuroIllumination
  * (renderer.py:48, guro_illumination.py:20-27) when flags has CRB_GURO and `light` is the normalised, negated direction --

@@ -63,3 +63,52 @@ def test_band_fillers_render_into_rank0_frame(world, balanced, tmp_path):
     assert bits_equal(got["z"], o.get_z_buffer())
     assert bits_equal(got["c"], o.get_color_buffer())
     assert bits_equal(got["n"], o.get_normals_buffer())
+
+
+def _exchange_worker(rank, world, port, out_dir, gather_to):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from cython3dmodelrenderer_b200 import AdvancedPixelBufferFiller, sharding, views as VW
+        dev = rank % torch.cuda.device_count()
+        torch.cuda.set_device(dev)
+        h, w, V = 192, 160, 5            # 192 rows = 2 bands of 96 / 3 bands of 64; 160 = 5 tiles of 32 (W % 16 == 0: vector clear)
+        m = load_indexed("trex")
+        dv, dc, dn = (torch.from_numpy(a).cuda() for a in (m._vertices_by_triangles, m._colors_by_triangles, m._normals_by_triangles))
+        views = VW.orbit_views(world * V, first=rank, count=V, stride=world)       # view k -> rank k mod N, like bench.py
+        f = AdvancedPixelBufferFiller(h, w, fov=45.0, device=dev)
+        xch = sharding.RowExchange(V, h, w, local_device=dev, gather_to=gather_to)
+        # two calls (3 + 2 views), the first split into launches of 2 views: the receive addresses advance with the view index
+        f.render_views(dv, dc, dn, views[:3], want=(), chunk=2, u8_exchange=xch.plan(0))
+        f.render_views(dv, dc, dn, views[3:], want=(), chunk=2, u8_exchange=xch.plan(3))
+        xch.complete()
+        ref = f.render_views(dv, dc, dn, views, want=(), color_u8_out=True, chunk=4)["color_u8"]    # the same images, kept local
+        np.save(os.path.join(out_dir, f"ref{rank}.npy"), ref.cpu().numpy())
+        t = xch.tensor()
+        if t is not None:
+            np.save(os.path.join(out_dir, f"got{rank}.npy"), t.cpu().numpy())
+        dist.barrier()
+        del f
+        xch.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,gather_to", [(2, None), (3, None), (2, 1)])
+def test_row_exchange_from_inside_the_rasterizer(world, gather_to, tmp_path):
+    """sharding.RowExchange / crb_set_u8_exchange: after the exchange rank d holds its row band of every rank's uint8
+    images (or, gather_to=d, the whole images), equal to what each rank renders into a local color_u8 array."""
+    mp.spawn(_exchange_worker, args=(world, _free_port(), str(tmp_path), gather_to), nprocs=world, join=True)
+    refs = [np.load(tmp_path / f"ref{r}.npy") for r in range(world)]            # [V, h, w, 3] per source rank
+    assert all(int((r.sum(axis=-1) > 0).sum()) > 1000 for r in refs)
+    if gather_to is None:
+        hb = refs[0].shape[1] // world
+        for d in range(world):
+            got = np.load(tmp_path / f"got{d}.npy")                              # [world, V, hb, w, 3]
+            for s in range(world):
+                assert np.array_equal(got[s], refs[s][:, d * hb:(d + 1) * hb]), f"band {d} of rank {s}'s views"
+    else:
+        got = np.load(tmp_path / f"got{gather_to}.npy")                           # [world, V, h, w, 3]
+        for s in range(world):
+            assert np.array_equal(got[s], refs[s])
+        assert not (tmp_path / f"got{1 - gather_to}.npy").exists()
