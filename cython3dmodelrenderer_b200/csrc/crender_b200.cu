@@ -92,8 +92,9 @@ static_assert(TW == 32, "a tile row is one warp wide");
 //   prefetched into L1 when a tile stages the triangle):
 //     S_A (x0 y0 x1 y1)  S_B (x2 y2 z0 z1)  S_C (z2 l03 l13 l23)      screen-space vertices + denominators of mu:14,17,20
 //     S_N0 (n0.xyz n1.x)  S_N1 (n1.yz n2.xy)  S_X (n2.z c0.xyz)  S_C1 (c1.xyz c2.x)  S_C2 (c2.yz flags -)
-//   recD (1/l03 1/l13 1/l23 flags)   correctly rounded reciprocals (rcp.rn) + FL_* bits, for k_fill
-//   recE (bbox x, bbox y, -, -)      packed half-open pixel rectangle (0,0 = not drawn)
+//   recE (bbox x, bbox y, local, flags)  packed half-open pixel rectangle of a DRAWN triangle; the entries of a 256-triangle chunk are
+//                                    dense: chunk c of view v has alive[v,c] entries at [v*T + c*256, ...), entry j = triangle
+//                                    c*256 + local (k_fill and the atomic path walk drawn triangles only, with full warps)
 enum ShadeRec { S_A = 0, S_B, S_C, S_N0, S_N1, S_X, S_C1, S_C2, SREC };
 
 struct ProjC {
@@ -115,8 +116,8 @@ struct Frame {
     // scratch
     // per-(view,triangle) records (see enum ShadeRec)
     float4 *shrec;              // [nViews*T*8] shade records
-    float4 *recD, *recE;        // [nViews*T]
-    unsigned char *alive;       // [nViews*ceil(T/NT)] 1 = this k_setup CTA has a drawn triangle (its recE / records are valid)
+    float4 *recE;               // [nViews*T]
+    unsigned short *alive;      // [nViews*ceil(T/NT)] drawn triangles of the chunk (k_setup CTA): recE holds that many entries for it
     unsigned *chunks;           // band-sharded single view: [0] = number of 256-triangle chunks that may reach the band,
                                 // [1..] their indices (k_band_chunks); nullptr = every chunk is visited (grid = chunks)
     unsigned *count;            // [nViews*nTiles] triangles per tile, accumulated by k_setup, returned to zero by k_alloc
@@ -127,9 +128,10 @@ struct Frame {
     unsigned *empty;            // [nViews*nTiles] compacted tiles without triangles (same packing); count in total[3]
     unsigned *offset;           // [nViews*nTiles] start of the tile's list
     unsigned *cursor;           // [nViews*nTiles] fill cursor
-    float4 *ls0, *ls1, *ls2;    // [pairCap] staged triangle setups, tile by tile: (x0 y0 x1 y1) (x2 y2 z0 z1) (z2 d1 d2 d3)
-    uint4 *ls3;                 // [pairCap] (bbox x, bbox y, triangle index, flags)
-    float4 *ls4;                // [pairCap] (1/d1 1/d2 1/d3 -) correctly rounded reciprocals of the denominators
+    float4 *ls;                 // [pairCap*4] staged triangle setups, tile by tile, ONE 64-byte entry (two whole 32-byte sectors, written
+                                // by one thread) per (triangle, tile) pair: (x0 y0 x1 y1) (x2 y2 z0 z1) (z2 d1 d2 d3) (bbox x, bbox y,
+                                // triangle index, flags) -- d = sign-normalised denominators; their reciprocals are formed when a tile
+                                // stages the entry (rcp.rn: three instructions' worth per entry instead of 16 more bytes per pair)
     unsigned long long *total;  // [0] pairs of this frame, [1] sticky max of overflowing totals, [2] busy tiles, [3] empty tiles
     unsigned long long *hstats; // mapped host word: (tiles of the launch << 32 | busy tiles), posted by k_raster for the next launch's grid size
     long long pairCap;
@@ -387,10 +389,31 @@ __device__ __forceinline__ void bulk_load(void *smem_dst, const void *gmem_src, 
                  "r"(bytes), "r"(m) : "memory");
 }
 
+// Positions of the threads whose flag is set, in thread order (warp ballots + one shared-memory word per warp), and their number.
+// Two block barriers; every thread of the CTA must call it.
+__device__ __forceinline__ unsigned block_compact(const bool flag, unsigned *wsum, unsigned &total)
+{
+    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    const unsigned b = __ballot_sync(0xFFFFFFFFu, flag);
+    if (lane == 0) wsum[wid] = __popc(b);
+    __syncthreads();
+    unsigned base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) {
+        const unsigned c = wsum[w];
+        if (w < (int)wid) base += c;
+        tot += c;
+    }
+    total = tot;
+    __syncthreads();
+    return base + __popc(b & ((1u << lane) - 1u));
+}
+
 // One chunk of NT consecutive triangles of one view.  Every early exit below is taken by the whole CTA or lies behind
 // the last barrier, so the function can be called in a loop (chunk-list mode).
 __device__ __forceinline__ void setup_chunk(const Frame &F, const int view, const long long chunk, const long long chunksPerView,
-                                            float *sv, float *sn, float *sc, float *sM, unsigned long long *bar = nullptr)
+                                            float *sv, float *sn, float *sc, float *sM, unsigned char *slist, unsigned *wsum,
+                                            unsigned long long *bar = nullptr)
 {
     const long long first = chunk * NT;
     const long long cnt = min((long long)NT, F.T - first);
@@ -398,15 +421,19 @@ __device__ __forceinline__ void setup_chunk(const Frame &F, const int view, cons
     // the vertices are staged and tested first, and a CTA whose 256 triangles all miss the band stops before it has read
     // a normal or written a record (7 of 8 CTAs at N = 8).  A full-frame filler stages both arrays behind one barrier.
     const bool banded = F.row0 > 0 || F.row1 < F.H;
-    unsigned char *alive = F.alive + (long long)view * chunksPerView + chunk;
+    unsigned short *alive = F.alive + (long long)view * chunksPerView + chunk;
     // A full chunk of a full-frame filler arrives as two bulk copies (one thread issues them, everybody waits on the
     // mbarrier: no per-thread load / store instructions, no registers in flight); anything else is staged by the threads.
     const bool bulk = bar && !banded && cnt == NT &&
-                      !((reinterpret_cast<uintptr_t>(F.v + first * 9) | reinterpret_cast<uintptr_t>(F.n + first * 9)) & 15u);
+                      !((reinterpret_cast<uintptr_t>(F.v + first * 9) | reinterpret_cast<uintptr_t>(F.n + first * 9) |
+                         reinterpret_cast<uintptr_t>(F.c + first * 9)) & 15u);
     if (bulk) {
+        // (the colours come along even though a chunk without a drawn triangle will not look at them: a later staging step
+        // would put another memory round trip and a barrier into every CTA's life, and such chunks are rare in a full frame)
         if (threadIdx.x == 0) {
             bulk_load(sv, F.v + first * 9, BC_BYTES, bar);
             bulk_load(sn, F.n + first * 9, BC_BYTES, bar);
+            bulk_load(sc, F.c + first * 9, BC_BYTES, bar);
         }
     } else {
         stage_floats(F.v, first * 9, cnt * 9, sv);
@@ -415,16 +442,44 @@ __device__ __forceinline__ void setup_chunk(const Frame &F, const int view, cons
     if (F.views && threadIdx.x < 16) sM[threadIdx.x] = F.views[view * 16 + threadIdx.x];
     __syncthreads();
     if (bulk) mbar_wait(bar, 0u);
-    const bool valid = threadIdx.x < cnt;
-    const long long tri = first + threadIdx.x;
+    // `me`: the triangle of the chunk this thread sets up (-1: none).  A full-frame filler culls first (pyx:202-204 needs only
+    // the z of the three view-space normals) and hands the survivors to the first threads, so that the projection, the
+    // denominators and the record stores below run in full warps for the ~half of a closed mesh that faces the camera
+    // instead of in every warp at half occupancy.  (A band-sharded filler tests the rows first, see above.)
+    int me = threadIdx.x < cnt ? (int)threadIdx.x : -1;
+    unsigned kept = 0;
+    if (!banded) {
+        bool keep = false;
+        if (me >= 0) {
+            const float *q = sn + me * 9;
+            float z0 = q[2], z1 = q[5], z2 = q[8];
+            if (F.views) {   // view_normal, z row only
+                z0 = (sM[6] * q[0] + sM[7] * q[1]) + sM[8] * q[2];
+                z1 = (sM[6] * q[3] + sM[7] * q[4]) + sM[8] * q[5];
+                z2 = (sM[6] * q[6] + sM[7] * q[7]) + sM[8] * q[8];
+            }
+            keep = !(((z0 + z1) + z2) >= 0.0f);
+        }
+        const unsigned pos = block_compact(keep, wsum, kept);
+        if (kept == 0) {
+            if (threadIdx.x == 0) *alive = 0;
+            return;
+        }
+        if (keep) slist[pos] = (unsigned char)me;
+        __syncthreads();
+        me = threadIdx.x < kept ? (int)slist[threadIdx.x] : -1;
+    }
+    const bool valid = me >= 0;
+    const int mi = valid ? me : 0;
+    const long long tri = first + mi;
     const long long ridx = (long long)view * F.T + tri;
     float x[3], y[3], z[3], nx[3], ny[3], nz[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         if (!valid) { x[k] = y[k] = z[k] = 1.0f; continue; }
-        x[k] = sv[threadIdx.x * 9 + k * 3 + 0];
-        y[k] = sv[threadIdx.x * 9 + k * 3 + 1];
-        z[k] = sv[threadIdx.x * 9 + k * 3 + 2];
+        x[k] = sv[mi * 9 + k * 3 + 0];
+        y[k] = sv[mi * 9 + k * 3 + 1];
+        z[k] = sv[mi * 9 + k * 3 + 2];
         if (F.views) view_point(sM, x[k], y[k], z[k]);
         project_vertex(F.proj, x[k], y[k], z[k]);
     }
@@ -454,9 +509,9 @@ __device__ __forceinline__ void setup_chunk(const Frame &F, const int view, cons
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         if (!valid) { nx[k] = ny[k] = nz[k] = 1.0f; continue; }
-        nx[k] = sn[threadIdx.x * 9 + k * 3 + 0];
-        ny[k] = sn[threadIdx.x * 9 + k * 3 + 1];
-        nz[k] = sn[threadIdx.x * 9 + k * 3 + 2];
+        nx[k] = sn[mi * 9 + k * 3 + 0];
+        ny[k] = sn[mi * 9 + k * 3 + 1];
+        nz[k] = sn[mi * 9 + k * 3 + 2];
         if (F.views) view_normal(sM, nx[k], ny[k], nz[k]);
     }
     // pyx:202-204: (n0z + n1z + n2z)/3 >= 0 in double -- only the sign of the float sum matters (NaN: not culled)
@@ -465,26 +520,19 @@ __device__ __forceinline__ void setup_chunk(const Frame &F, const int view, cons
     const unsigned bx = drawn ? ((unsigned)xl | ((unsigned)xr << 16)) : 0u;
     const unsigned by = drawn ? ((unsigned)yt | ((unsigned)yb << 16)) : 0u;
 
-    if (valid) F.recE[ridx] = make_float4(__uint_as_float(bx), __uint_as_float(by), 0.0f, 0.0f);
-    // the vertex colours are only needed for triangles that are drawn: a CTA without any (culled, off screen, or -- for a
-    // band-sharded filler -- outside the band, which is 7 of 8 CTAs at N=8) never reads them
-    const int any_drawn = __syncthreads_or(drawn ? 1 : 0);
-    if (threadIdx.x == 0) *alive = any_drawn ? 1 : 0;   // k_fill (and the atomic path) skip the CTA's triangles otherwise
-    if (!any_drawn) return;
-    stage_floats(F.c, first * 9, cnt * 9, sc);
-    __syncthreads();
+    float l03 = 0.f, l13 = 0.f, l23 = 0.f;
+    unsigned fl = 0;
     if (drawn) {
     // denominators of mu:12-21 -- pure functions of the triangle, hoisted out of the per-pixel code (same bits)
-    const float l03 = (x[1] - x[2]) * (y[0] - y[2]) - (y[1] - y[2]) * (x[0] - x[2]);
-    const float l13 = (x[2] - x[0]) * (y[1] - y[0]) - (y[2] - y[0]) * (x[1] - x[0]);
-    const float l23 = (x[0] - x[1]) * (y[2] - y[1]) - (y[0] - y[1]) * (x[2] - x[1]);
+    l03 = (x[1] - x[2]) * (y[0] - y[2]) - (y[1] - y[2]) * (x[0] - x[2]);
+    l13 = (x[2] - x[0]) * (y[1] - y[0]) - (y[2] - y[0]) * (x[1] - x[0]);
+    l23 = (x[0] - x[1]) * (y[2] - y[1]) - (y[0] - y[1]) * (x[2] - x[1]);
     // Division-free rejection (SURVEY 7, K3 obligation).  num/l3 is bit-identical to (-num)/(-l3), and negation commutes
     // with every rounding that produced num, so the rasterizer evaluates each coordinate with l3' = |l3| (edge vector
     // negated when l3 < 0, FL_NEG).  For L3_MIN <= l3' <= L3_MAX a numerator <= -REJ_EPS then gives a quotient that is a
     // negative NON-ZERO float (|q| >= 1e-36), i.e. exactly the reference's `bar < 0` -- no division needed (FL_REJ).
     // Everything else (denominator zero / tiny / huge / non-finite, numerator inside the guard band or NaN) takes the
     // exact division path.
-    unsigned fl = 0;
     const float a03 = fabsf(l03), a13 = fabsf(l13), a23 = fabsf(l23);
     if (a03 >= L3_MIN && a03 <= L3_MAX) fl |= (FL_REJ << 0) | (l03 < 0.f ? (FL_NEG << 0) : 0u);
     if (a13 >= L3_MIN && a13 <= L3_MAX) fl |= (FL_REJ << 1) | (l13 < 0.f ? (FL_NEG << 1) : 0u);
@@ -496,8 +544,32 @@ __device__ __forceinline__ void setup_chunk(const Frame &F, const int view, cons
                            (y[1] - y[1] == 0.f) && (y[2] - y[2] == 0.f);
     if ((fl & (7u * FL_REJ)) == 7u * FL_REJ && finite_xy && cmax <= SPAN_COORD_MAX) fl |= FL_SPAN;
     if (fminf(fminf(a03, a13), a23) >= FDIV_LO && fmaxf(fmaxf(a03, a13), a23) <= FDIV_HI) fl |= FL_FDIV;
+    }
+
+    // the chunk's entries for k_fill and the atomic path, densely at the head of its recE block: the triangles that survived
+    // the cull (a full-frame filler; the rare ones whose rectangle is empty carry bx = 0) or exactly the drawn ones (a
+    // band-sharded filler, where most triangles of a visited chunk still miss the band)
+    unsigned n_entries, dpos;
+    bool entry;
+    if (banded) {
+        dpos = block_compact(drawn, wsum, n_entries);
+        entry = drawn;
+    } else {
+        dpos = threadIdx.x; entry = valid;
+        n_entries = __syncthreads_or(drawn ? 1 : 0) ? kept : 0u;
+    }
+    if (entry && n_entries) F.recE[(long long)view * F.T + first + dpos] = make_float4(__uint_as_float(bx), __uint_as_float(by), __uint_as_float((unsigned)mi), __uint_as_float(fl));
+    if (threadIdx.x == 0) *alive = (unsigned short)n_entries;
+    // the vertex colours are only needed for triangles that are drawn: a CTA without any (culled, off screen, or -- for a
+    // band-sharded filler -- outside the band, which is 7 of 8 CTAs at N=8) never reads them
+    if (n_entries == 0) return;
+    if (!bulk) {
+        stage_floats(F.c, first * 9, cnt * 9, sc);
+        __syncthreads();
+    }
+    if (drawn) {
     float4 *R = F.shrec + ridx * SREC;
-    const float *q = sc + threadIdx.x * 9;
+    const float *q = sc + mi * 9;
     R[S_A] = make_float4(x[0], y[0], x[1], y[1]);
     R[S_B] = make_float4(x[2], y[2], z[0], z[1]);
     R[S_C] = make_float4(z[2], l03, l13, l23);
@@ -506,7 +578,6 @@ __device__ __forceinline__ void setup_chunk(const Frame &F, const int view, cons
     R[S_X] = make_float4(nz[2], q[0], q[1], q[2]);
     R[S_C1] = make_float4(q[3], q[4], q[5], q[6]);
     R[S_C2] = make_float4(q[7], q[8], __uint_as_float(fl), 0.0f);
-    F.recD[ridx] = make_float4(__frcp_rn(l03), __frcp_rn(l13), __frcp_rn(l23), __uint_as_float(fl));
     }
     if (F.flags & CRB_PATH_ATOMIC) return;
 
@@ -538,6 +609,8 @@ __global__ void __launch_bounds__(NT, CRB_SETUP_MIN_CTAS) k_setup(const Frame F)
     __shared__ __align__(16) float sn[NT * 9];
     __shared__ __align__(16) float sc[NT * 9];
     __shared__ float sM[16];
+    __shared__ unsigned char slist[NT];
+    __shared__ unsigned wsum[NT / 32];
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {  // k_alloc (next launch) accumulates
         F.total[0] = 0ull; F.total[2] = 0ull; F.total[3] = 0ull; F.total[4] = 0ull;
     }
@@ -545,17 +618,17 @@ __global__ void __launch_bounds__(NT, CRB_SETUP_MIN_CTAS) k_setup(const Frame F)
     if (!F.chunks) {
         __shared__ __align__(8) unsigned long long bar;
         if (threadIdx.x == 0) {
-            mbar_init(&bar, 2u);      // two bulk copies (vertices, normals), one arrival each
+            mbar_init(&bar, 3u);      // three bulk copies (vertices, normals, colours), one arrival each
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        setup_chunk(F, blockIdx.y, blockIdx.x, chunksPerView, sv, sn, sc, sM, &bar);
+        setup_chunk(F, blockIdx.y, blockIdx.x, chunksPerView, sv, sn, sc, sM, slist, wsum, &bar);
         return;
     }
     // chunk-list mode (band-sharded filler): a grid of a few CTAs per SM walks the chunks k_band_chunks listed
     const unsigned n = F.chunks[0];
     for (unsigned i = blockIdx.x; i < n; i += gridDim.x) {
         __syncthreads();
-        setup_chunk(F, 0, F.chunks[1 + i], chunksPerView, sv, sn, sc, sM);
+        setup_chunk(F, 0, F.chunks[1 + i], chunksPerView, sv, sn, sc, sM, slist, wsum);
     }
 }
 
@@ -688,28 +761,31 @@ __global__ void __launch_bounds__(NT) k_alloc(const Frame F)
 }
 
 // K2c: scatter the prepared setups into the tile lists (sign-normalised form the row loop wants).
-__device__ __forceinline__ void fill_chunk(const Frame &F, const int view, const long long chunk, const long long chunksPerView, const bool skip)
+constexpr int FT = 64;            // threads per k_fill CTA: four CTAs share a chunk, and one whose entries are used up leaves at once
+__device__ __forceinline__ void fill_chunk(const Frame &F, const int view, const long long chunk, const long long chunksPerView, const bool skip,
+                                           const unsigned tix /* position in the chunk, 0..NT-1 */)
 {
-    const long long tri = chunk * NT + threadIdx.x;
+    // the chunk's drawn triangles sit densely at the head of its recE block (setup_chunk): thread j takes entry j, so the warps
+    // that have work are full and the others leave at once.  Speculative: the entry flies with the count that decides whether
+    // it is looked at (recE is allocated for every (view, triangle); entries beyond the count are stale and not used)
+    const long long slot = chunk * NT + tix;
+    const float4 E = slot < F.T ? F.recE[(long long)view * F.T + slot] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const unsigned nd = F.alive[(long long)view * chunksPerView + chunk];
+    if (skip || (tix & ~31u) >= nd) return;   // frame skipped / no entry for this warp (warp-uniform)
+    const unsigned bx = tix < nd ? __float_as_uint(E.x) : 0u, by = tix < nd ? __float_as_uint(E.y) : 0u;
+    const bool drawn = (bx >> 16) != 0;  // (x_right >= 1 for every drawn triangle)
+    const long long tri = chunk * NT + (drawn ? (long long)(__float_as_uint(E.z) & 255u) : 0ll);
     const long long ridx = (long long)view * F.T + tri;
-    // speculative: the rectangle flies with the flags that decide whether it is looked at (recE is allocated for every
-    // (view, triangle); in a chunk k_setup left dead it holds stale values, which are then not used)
-    const float4 E = tri < F.T ? F.recE[ridx] : make_float4(0.f, 0.f, 0.f, 0.f);
-    if (skip || !F.alive[(long long)view * chunksPerView + chunk]) return;   // frame skipped / nothing to draw in this chunk (CTA-uniform)
-    const unsigned bx = __float_as_uint(E.x), by = __float_as_uint(E.y);
-    const bool drawn = tri < F.T && (bx >> 16) != 0;  // (x_right >= 1 for every drawn triangle)
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, s2 = a, s4 = a;
-    uint4 s3 = make_uint4(0u, 0u, 0u, 0u);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, s2 = a, s3 = a;
     int tx0 = 0, tx1 = -1, ty0 = 0, ty1 = -1;
     if (drawn) {
         const float4 *R = F.shrec + ridx * SREC;
-        const float4 c = R[S_C], d = F.recD[ridx];
+        const float4 c = R[S_C];
         a = R[S_A]; b = R[S_B];
-        const unsigned fl = __float_as_uint(d.w);
-        // |l3| and |1/l3| where the coordinate is negated (RN(1/-x) = -RN(1/x): flipping the sign bit is exact)
+        const unsigned fl = __float_as_uint(E.w);
+        // |l3| where the coordinate is negated (flipping the sign bit is exact)
         s2 = make_float4(c.x, (fl & (FL_NEG << 0)) ? -c.y : c.y, (fl & (FL_NEG << 1)) ? -c.z : c.z, (fl & (FL_NEG << 2)) ? -c.w : c.w);
-        s4 = make_float4((fl & (FL_NEG << 0)) ? -d.x : d.x, (fl & (FL_NEG << 1)) ? -d.y : d.y, (fl & (FL_NEG << 2)) ? -d.z : d.z, 0.0f);
-        s3 = make_uint4(bx, by, (unsigned)tri, fl);
+        s3 = make_float4(__uint_as_float(bx), __uint_as_float(by), __uint_as_float((unsigned)tri), __uint_as_float(fl));
         tile_span(F, bx, by, tx0, tx1, ty0, ty1);
     }
     const long long vb = (long long)view * F.nTiles;
@@ -719,7 +795,8 @@ __device__ __forceinline__ void fill_chunk(const Frame &F, const int view, const
             for (int tx = tx0; tx <= tx1; ++tx) {
                 const long long t = vb + ty * F.tilesX + tx;
                 const unsigned at = F.offset[t] + atomicAdd(F.cursor + t, 1u);
-                F.ls0[at] = a; F.ls1[at] = b; F.ls2[at] = s2; F.ls3[at] = s3; F.ls4[at] = s4;
+                float4 *o = F.ls + (size_t)at * 4;     // one 64-byte entry = two whole sectors
+                o[0] = a; o[1] = b; o[2] = s2; o[3] = s3;
             }
     // triangles that span many tiles: the whole warp scatters them, a tile per lane (see setup_chunk)
     for (unsigned wide = __ballot_sync(0xFFFFFFFFu, nt > WIDE_TILES); wide; wide &= wide - 1u) {
@@ -728,34 +805,34 @@ __device__ __forceinline__ void fill_chunk(const Frame &F, const int view, const
             return make_float4(__shfl_sync(0xFFFFFFFFu, v.x, src), __shfl_sync(0xFFFFFFFFu, v.y, src), __shfl_sync(0xFFFFFFFFu, v.z, src),
                                __shfl_sync(0xFFFFFFFFu, v.w, src));
         };
-        const float4 wa = bc(a), wb = bc(b), w2 = bc(s2), w4 = bc(s4);
-        const uint4 w3 = make_uint4(__shfl_sync(0xFFFFFFFFu, s3.x, src), __shfl_sync(0xFFFFFFFFu, s3.y, src), __shfl_sync(0xFFFFFFFFu, s3.z, src),
-                                    __shfl_sync(0xFFFFFFFFu, s3.w, src));
+        const float4 wa = bc(a), wb = bc(b), w2 = bc(s2), w3 = bc(s3);
         const int sx0 = __shfl_sync(0xFFFFFFFFu, tx0, src), sx1 = __shfl_sync(0xFFFFFFFFu, tx1, src);
         const int sy0 = __shfl_sync(0xFFFFFFFFu, ty0, src), n = __shfl_sync(0xFFFFFFFFu, nt, src);
         const int wx = sx1 - sx0 + 1;
-        for (int i = (int)(threadIdx.x & 31u); i < n; i += 32) {
+        for (int i = (int)(tix & 31u); i < n; i += 32) {
             const long long t = vb + (sy0 + i / wx) * F.tilesX + sx0 + i % wx;
             const unsigned at = F.offset[t] + atomicAdd(F.cursor + t, 1u);
-            F.ls0[at] = wa; F.ls1[at] = wb; F.ls2[at] = w2; F.ls3[at] = w3; F.ls4[at] = w4;
+            float4 *o = F.ls + (size_t)at * 4;
+            o[0] = wa; o[1] = wb; o[2] = w2; o[3] = w3;
         }
     }
 }
 
 #ifndef CRB_FILL_MIN_CTAS
-#define CRB_FILL_MIN_CTAS 4
+#define CRB_FILL_MIN_CTAS 16
 #endif
-__global__ void __launch_bounds__(NT, CRB_FILL_MIN_CTAS) k_fill(const Frame F)
+__global__ void __launch_bounds__(FT, CRB_FILL_MIN_CTAS) k_fill(const Frame F)
 {
     const long long chunksPerView = (F.T + NT - 1) / NT;
+    const unsigned tix = (blockIdx.x & (NT / FT - 1)) * FT + threadIdx.x;
     if (!F.chunks) {
         // overflow: frame is skipped (host is told via crb_status); the test rides with the first loads instead of before them
-        fill_chunk(F, blockIdx.y, blockIdx.x, chunksPerView, *F.total > (unsigned long long)F.pairCap);   // same CTA -> triangle mapping as k_setup
+        fill_chunk(F, blockIdx.y, blockIdx.x / (NT / FT), chunksPerView, *F.total > (unsigned long long)F.pairCap, tix);   // same chunk -> triangles mapping as k_setup
         return;
     }
     if (*F.total > (unsigned long long)F.pairCap) return;
     const unsigned n = F.chunks[0];
-    for (unsigned i = blockIdx.x; i < n; i += gridDim.x) fill_chunk(F, 0, F.chunks[1 + i], chunksPerView, false);
+    for (unsigned i = blockIdx.x / (NT / FT); i < n; i += gridDim.x / (NT / FT)) fill_chunk(F, 0, F.chunks[1 + i], chunksPerView, false, tix);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -953,9 +1030,12 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
         float4 tr3 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (tid < m) {   // the setups k_fill prepared for this tile, brought into the form the row loop wants
             const unsigned at = off + base + tid;
-            const uint4 d = F.ls3[at];
-            const float4 a = F.ls0[at], b = F.ls1[at], c = F.ls2[at];
-            tr3 = F.ls4[at];
+            const float4 *en = F.ls + (size_t)at * 4;
+            const float4 a = en[0], b = en[1], c = en[2], d4 = en[3];
+            const uint4 d = make_uint4(__float_as_uint(d4.x), __float_as_uint(d4.y), __float_as_uint(d4.z), __float_as_uint(d4.w));
+            // correctly rounded reciprocals of the (sign-normalised) denominators, for div_rn_by: RN(1/-x) = -RN(1/x), so these are
+            // the bits k_setup's rcp.rn of the signed denominators would give after the same sign flip
+            tr3 = make_float4(__frcp_rn(c.y), __frcp_rn(c.z), __frcp_rn(c.w), 0.0f);
             {   // the shading pass will want this triangle's 128-byte record: start pulling it into L1 now
                 const char *sr = reinterpret_cast<const char *>(F.shrec + ((long long)view * F.T + d.z) * SREC);
                 asm volatile("prefetch.global.L1 [%0];" :: "l"(sr));
@@ -1345,12 +1425,13 @@ __global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame 
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT) k_raster_atomic(const Frame F, unsigned long long *keybuf)
 {
-    const long long tri = ((long long)blockIdx.x * NT + threadIdx.x) >> 5;
+    const long long slot = ((long long)blockIdx.x * NT + threadIdx.x) >> 5;     // entry of a chunk's dense list of drawn triangles
     const int lane = threadIdx.x & 31;
-    if (tri >= F.T || !F.alive[tri / NT]) return;
-    const float4 r2 = F.recE[tri];
+    if (slot >= F.T || (unsigned)(slot % NT) >= F.alive[slot / NT]) return;
+    const float4 r2 = F.recE[slot];
     const unsigned bx = __float_as_uint(r2.x), by = __float_as_uint(r2.y);
-    if ((bx >> 16) == 0) return;
+    if ((bx >> 16) == 0) return;       // an entry whose pixel rectangle is empty
+    const long long tri = slot / NT * NT + (__float_as_uint(r2.z) & 255u);
     const Tri9 t = load_tri9(F, tri);
     const int xl = bx & 0xFFFF, xr = bx >> 16, yt = by & 0xFFFF, yb = by >> 16;
     const int bw = xr - xl;
@@ -1631,14 +1712,12 @@ struct crb_filler {
     long long maxT;
     int maxViews;
     long long pairCap;
-    float4 *shrec, *recD, *recE;
-    unsigned char *alive;
+    float4 *shrec, *recE;
+    unsigned short *alive;
     unsigned *chunks;
     unsigned *count, *offset, *cursor, *empty;
     uint4 *busy, *busyH;
-    float4 *ls0, *ls1, *ls2;
-    uint4 *ls3;
-    float4 *ls4;
+    float4 *ls;
     unsigned long long *total;
     float *stage_v, *stage_c, *stage_n;  // device staging for host-pointer calls
     // differential path scratch (library-owned, lazily allocated)
@@ -1678,7 +1757,7 @@ struct crb_filler {
 namespace {
 
 struct WsLayout {
-    size_t shrec, recD, recE, alive, chunks, count, offset, cursor, busy, busyH, empty, ls0, ls1, ls2, ls3, ls4, total, set_bytes, sv, sc, sn, bytes;
+    size_t shrec, recE, alive, chunks, count, offset, cursor, busy, busyH, empty, ls, total, set_bytes, sv, sc, sn, bytes;
 };
 
 long long default_pair_cap(const crb_filler *f, long long T, int views)
@@ -1696,9 +1775,8 @@ WsLayout ws_layout(const crb_filler *f, long long T, int views, long long pairCa
     auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 256); return at; };
     const size_t recs = (size_t)(T > 0 ? T : 1) * views;
     L.shrec = take(recs * SREC * sizeof(float4));
-    L.recD = take(recs * sizeof(float4));
     L.recE = take(recs * sizeof(float4));
-    L.alive = take((size_t)((T > 0 ? T : 1) + NT - 1) / NT * views);
+    L.alive = take((size_t)((T > 0 ? T : 1) + NT - 1) / NT * views * sizeof(unsigned short));
     L.chunks = take(4 * ((size_t)((T > 0 ? T : 1) + NT - 1) / NT + 2));
     L.count = take((size_t)tiles * views * 4);
     L.offset = take((size_t)tiles * views * 4);
@@ -1706,11 +1784,7 @@ WsLayout ws_layout(const crb_filler *f, long long T, int views, long long pairCa
     L.busy = take((size_t)tiles * views * 16);
     L.busyH = take((size_t)tiles * views * 16 * SPLIT_BANDS);
     L.empty = take((size_t)tiles * views * 4);
-    L.ls0 = take((size_t)pairCap * 16);
-    L.ls1 = take((size_t)pairCap * 16);
-    L.ls2 = take((size_t)pairCap * 16);
-    L.ls3 = take((size_t)pairCap * 16);
-    L.ls4 = take((size_t)pairCap * 16);
+    L.ls = take((size_t)pairCap * 64);
     L.total = take(64);
     L.set_bytes = o;            // everything above exists twice (two launches of a batch in flight, see crb_render_views)
     o = 2 * L.set_bytes;
@@ -1772,10 +1846,10 @@ void fill_frame(const crb_filler *f, Frame *F, int set = 0)
     F->nTiles = F->tilesX * F->tilesY;
     const size_t so = set ? f->set_bytes : 0;     // the second workspace set lies set_bytes behind the first
     auto at = [so](auto *p) { return reinterpret_cast<decltype(p)>(reinterpret_cast<char *>(p) + so); };
-    F->shrec = at(f->shrec); F->recD = at(f->recD); F->recE = at(f->recE); F->alive = at(f->alive);
+    F->shrec = at(f->shrec); F->recE = at(f->recE); F->alive = at(f->alive);
     F->count = at(f->count); F->offset = at(f->offset); F->cursor = at(f->cursor);
     F->busy = at(f->busy); F->busyH = at(f->busyH); F->empty = at(f->empty);
-    F->ls0 = at(f->ls0); F->ls1 = at(f->ls1); F->ls2 = at(f->ls2); F->ls3 = at(f->ls3); F->ls4 = at(f->ls4);
+    F->ls = at(f->ls);
     F->total = at(f->total);
     F->hstats = f->hstats_dev;
     F->pairCap = f->pairCap;
@@ -1870,7 +1944,7 @@ int run_prep(crb_filler *f, Frame &F, cudaStream_t st)
     k_alloc<<<(unsigned)((nAllTiles + NT - 1) / NT), NT, 0, st>>>(F);
     if ((rc = launch_check(f, "k_alloc"))) return rc;
     if (F.T > 0) {
-        k_fill<<<dim3(gT, F.nViews), NT, 0, st>>>(F);
+        k_fill<<<dim3(gT * (NT / FT), F.nViews), FT, 0, st>>>(F);
         if ((rc = launch_check(f, "k_fill"))) return rc;
     }
     return CRB_OK;
@@ -1976,12 +2050,12 @@ int bind_ws_pointers(crb_filler *f, void *ws, size_t bytes, long long T, int vie
     char *b = (char *)ws;
     f->ws = ws; f->ws_bytes = bytes;
     f->maxT = T; f->maxViews = views; f->pairCap = pairCap;
-    f->shrec = (float4 *)(b + L.shrec); f->recD = (float4 *)(b + L.recD); f->recE = (float4 *)(b + L.recE);
-    f->alive = (unsigned char *)(b + L.alive);
+    f->shrec = (float4 *)(b + L.shrec); f->recE = (float4 *)(b + L.recE);
+    f->alive = (unsigned short *)(b + L.alive);
     f->chunks = (unsigned *)(b + L.chunks);
     f->count = (unsigned *)(b + L.count); f->offset = (unsigned *)(b + L.offset); f->cursor = (unsigned *)(b + L.cursor);
     f->busy = (uint4 *)(b + L.busy); f->busyH = (uint4 *)(b + L.busyH); f->empty = (unsigned *)(b + L.empty);
-    f->ls0 = (float4 *)(b + L.ls0); f->ls1 = (float4 *)(b + L.ls1); f->ls2 = (float4 *)(b + L.ls2); f->ls3 = (uint4 *)(b + L.ls3); f->ls4 = (float4 *)(b + L.ls4);
+    f->ls = (float4 *)(b + L.ls);
     f->total = (unsigned long long *)(b + L.total);
     f->stage_v = (float *)(b + L.sv); f->stage_c = (float *)(b + L.sc); f->stage_n = (float *)(b + L.sn);
     f->set_bytes = L.set_bytes;
