@@ -28,6 +28,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <atomic>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "crender_b200.h"
@@ -2433,6 +2436,81 @@ static int upload_inputs(crb_filler *f, const float *v, const float *c, const fl
     return CRB_OK;
 }
 
+// Pageable host arrays -> device (CRB_HOST_PAGEABLE).  cudaMemcpyAsync from pageable memory is staged by the driver on the
+// calling thread at a few GB/s; a reference Model's NumPy arrays are pageable, and for the 10 M-triangle frame (1.08 GB) that
+// copy was 75 ms of a 130 ms frame.  Here `nth` worker threads each own two 8 MB slots of a process-wide pinned ring: copy a
+// chunk into a slot (memcpy), queue its cudaMemcpyAsync, go on with the next chunk while that one travels; a slot is reused
+// once the event recorded behind its copy has fired.  All source bytes have been read when the function returns.
+namespace {
+constexpr size_t PG_CHUNK = 8u << 20;
+constexpr int PG_MAX_THREADS = 8, PG_SLOTS_PER_THREAD = 2;
+struct PageRing {
+    std::mutex mu;                     // one pageable upload at a time
+    int device = -1;
+    char *base = nullptr;
+    cudaEvent_t ev[PG_MAX_THREADS * PG_SLOTS_PER_THREAD] = {};
+    bool used[PG_MAX_THREADS * PG_SLOTS_PER_THREAD] = {};     // the slot's last copy may still be in flight (its event tells)
+};
+PageRing g_ring;
+struct PgSeg { char *dst; const char *src; size_t len; };
+}  // namespace
+
+static int upload_pageable(crb_filler *f, const float *v, const float *c, const float *n, int64_t T, cudaStream_t st)
+{
+    if (T <= 0) return CRB_OK;
+    const size_t bytes = (size_t)T * 36;
+    std::lock_guard<std::mutex> lock(g_ring.mu);
+    if (!g_ring.base || g_ring.device != f->device) {      // first use, or a filler on another device (events belong to a device)
+        if (g_ring.base) {
+            cudaSetDevice(g_ring.device);
+            for (int sl = 0; sl < PG_MAX_THREADS * PG_SLOTS_PER_THREAD; ++sl) {
+                if (g_ring.used[sl]) cudaEventSynchronize(g_ring.ev[sl]);
+                cudaEventDestroy(g_ring.ev[sl]);
+                g_ring.ev[sl] = nullptr; g_ring.used[sl] = false;
+            }
+            cudaFreeHost(g_ring.base);
+            g_ring.base = nullptr;
+            CU(cudaSetDevice(f->device));
+        }
+        CU(cudaHostAlloc((void **)&g_ring.base, PG_CHUNK * PG_MAX_THREADS * PG_SLOTS_PER_THREAD, cudaHostAllocPortable));
+        for (auto &e : g_ring.ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        g_ring.device = f->device;
+    }
+    std::vector<PgSeg> segs;
+    const float *src[3] = {v, c, n};
+    float *dst[3] = {f->stage_v, f->stage_c, f->stage_n};
+    for (int a = 0; a < 3; ++a)
+        for (size_t o = 0; o < bytes; o += PG_CHUNK)
+            segs.push_back({(char *)dst[a] + o, (const char *)src[a] + o, bytes - o < PG_CHUNK ? bytes - o : PG_CHUNK});
+    unsigned hw = std::thread::hardware_concurrency();
+    int nth = (int)(hw ? hw / 2 : 4);
+    nth = nth < 1 ? 1 : (nth > PG_MAX_THREADS ? PG_MAX_THREADS : nth);
+    if ((size_t)nth > segs.size()) nth = (int)segs.size();
+    std::atomic<int> err{0};
+    auto work = [&](int t) {
+        if (cudaSetDevice(f->device) != cudaSuccess) { err = 1; return; }
+        int k = 0;
+        for (size_t i = (size_t)t; i < segs.size(); i += (size_t)nth, ++k) {
+            const int sl = t * PG_SLOTS_PER_THREAD + (k % PG_SLOTS_PER_THREAD);
+            if (g_ring.used[sl] && cudaEventSynchronize(g_ring.ev[sl]) != cudaSuccess) { err = 1; return; }
+            char *slot = g_ring.base + (size_t)sl * PG_CHUNK;
+            memcpy(slot, segs[i].src, segs[i].len);
+            if (cudaMemcpyAsync(segs[i].dst, slot, segs[i].len, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+                cudaEventRecord(g_ring.ev[sl], st) != cudaSuccess) { err = 1; return; }
+            g_ring.used[sl] = true;
+        }
+    };
+    if (nth == 1) work(0);
+    else {
+        std::vector<std::thread> team;
+        for (int t = 1; t < nth; ++t) team.emplace_back(work, t);
+        work(0);
+        for (auto &th : team) th.join();
+    }
+    if (err) { cudaGetLastError(); return fail(CRB_ERR_CUDA, "staged upload of pageable host arrays failed"); }
+    return CRB_OK;     // (copies still in flight keep their slots: the next call waits on the slot's event before it reuses one)
+}
+
 // Development aid (CRB_TRACE=1 in the environment): CUDA events at the stage boundaries of crb_render_host, dumped as
 // microseconds since the first one by crb_trace_dump -- the only timeline tool on a box without nsys.
 namespace {
@@ -2458,9 +2536,9 @@ static int render_host_once(crb_filler *f, const float *v, const float *c, const
     TraceRec trec{}, *tr = (g_trace_on && g_trace.size() < 4096) ? &trec : nullptr;
     trec.who = f;
     trace_mark(tr, 0, st);
-    { int urc = upload_inputs(f, v, c, n, T, st); if (urc) return urc; }
+    { int urc = (flags & CRB_HOST_PAGEABLE) ? upload_pageable(f, v, c, n, T, st) : upload_inputs(f, v, c, n, T, st); if (urc) return urc; }
     trace_mark(tr, 1, st);
-    int rc = crb_render(f, f->stage_v, f->stage_c, f->stage_n, T, flags, stream);
+    int rc = crb_render(f, f->stage_v, f->stage_c, f->stage_n, T, flags & ~CRB_HOST_PAGEABLE, stream);
     if (rc) return rc;
     trace_mark(tr, 2, st);
     const bool sparse = (flags & CRB_DL_SPARSE) && (flags & CRB_CLEAR_FIRST) && !(flags & CRB_PATH_ATOMIC);

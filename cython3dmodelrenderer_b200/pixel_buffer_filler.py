@@ -66,6 +66,8 @@ class AdvancedPixelBufferFiller:
     its own (e.g. this band's rows inside another rank's frame, sharding.PeerFrame); their content is taken as it is.
     """
 
+    PAGEABLE_MIN_BYTES = 8 << 20      # host arrays of at least this size go up through the library's threaded staging ring
+
     def __init__(self, h, w, fov=90.0, z_near=0.1, z_far=1000.0, n_threads=1, device=None, band=None, out_ptrs=None):
         torch = _require_cuda()
         self._torch = torch
@@ -269,7 +271,12 @@ class AdvancedPixelBufferFiller:
         else:
             self._push_exposed()
         self._ensure_workspace(T)
-        if not on_device:
+        if not on_device and T * 36 >= self.PAGEABLE_MIN_BYTES:
+            # large host arrays: the library stages them itself, chunk by chunk through its pinned ring with worker threads
+            # (CRB_HOST_PAGEABLE) -- a single-threaded NumPy copy into pinned memory was 75 ms of the 10 M-triangle frame
+            v, c, n = (np.ascontiguousarray(a) for a in (v, c, n))
+            flags |= _lib.CRB_HOST_PAGEABLE
+        elif not on_device:
             if self._stage is None or self._stage.shape[1] < T:
                 self._stage = torch.empty((3, max(T, 1), 3, 3), dtype=torch.float32, pin_memory=True)
                 self._stage_np = self._stage.numpy()
@@ -296,6 +303,9 @@ class AdvancedPixelBufferFiller:
         """Queues one frame (upload of the staged host arrays if any, kernels, status words) on the current stream."""
         if on_device:
             check(self._L.crb_render(self._handle, v.data_ptr(), c.data_ptr(), n.data_ptr(), T, flags, self._stream()))
+        elif flags & _lib.CRB_HOST_PAGEABLE:
+            check(self._L.crb_render_host(self._handle, v.ctypes.data, c.ctypes.data, n.ctypes.data, T,
+                                          flags | _lib.CRB_NO_SYNC, 0, None, None, None, self._stream()))
         else:
             st = self._stage
             check(self._L.crb_render_host(self._handle, st[0].data_ptr(), st[1].data_ptr(), st[2].data_ptr(), T,

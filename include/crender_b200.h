@@ -54,6 +54,11 @@ extern "C" {
                                   internal stream), so that the NEXT batch's setup / binning kernels overlap this batch's
                                   rasterization.  The outputs may only be used on `stream` after crb_join(); every other
                                   entry point that touches the filler joins by itself. */
+#define CRB_HOST_PAGEABLE 64u   /* crb_render_host only: v / c / n are ordinary (pageable) host memory, e.g. the NumPy arrays of a
+                                  reference Model.  They are staged through a process-wide ring of pinned buffers by a few worker
+                                  threads, chunk by chunk, each chunk's host-to-device copy in flight while the next is being
+                                  staged; the arrays have been read completely when the call returns (CRB_NO_SYNC included).
+                                  Without the flag the three pointers must be page-locked (they are handed to cudaMemcpyAsync). */
 #define CRB_DL_SPARSE 16u      /* crb_render_host + CRB_CLEAR_FIRST only: sparse read-back.  The caller promises that the host
                                   output arrays still hold what the previous CRB_DL_SPARSE call of this filler left in them
                                   (fresh-filler values -- z 1e6, colour 0, normals 0 -- before the first call, or after

@@ -384,6 +384,21 @@ def test_scaled_sphere_matches_oracle(Filler, O):
     assert_same(buffers(f), buffers(o), "sphere 1/16")
 
 
+def test_pageable_host_arrays_through_the_staging_ring(Filler, O, trex, monkeypatch):
+    """CRB_HOST_PAGEABLE (large NumPy inputs are staged by the library's worker threads through its pinned ring): forced on
+    for a small model, two renders composited, arrays mutated right after the call returns (they have been read by then)."""
+    monkeypatch.setattr(Filler, "PAGEABLE_MIN_BYTES", 0)
+    f, o = Filler(320, 256, fov=45.0), O.OracleFiller(320, 256, fov=45.0)
+    v, c, n = (a.copy() for a in (trex._vertices_by_triangles, trex._colors_by_triangles, trex._normals_by_triangles))
+    f.render_arrays(v, c, n)
+    o.render_arrays(v, c, n)
+    v[:] = 0.5; c[:] = 1.0; n[:] = -1.0                 # the frame above must not see this
+    m2 = random_scene(11, T=2000)
+    f.render_model(m2)
+    o.render_model(m2)
+    assert_same(buffers(f), buffers(o), "pageable host arrays")
+
+
 def test_full_size_sphere_properties(Filler):
     """Config C4 at full size (10 003 200 triangles, 8192^2): too big for a CPU compare in seconds, so size-independent
     properties: band-sharded == unsharded (exact), tiled path == atomic path (exact), re-rendering is idempotent, the
