@@ -416,7 +416,7 @@ __device__ __forceinline__ unsigned block_compact(const bool flag, unsigned *wsu
 // the last barrier, so the function can be called in a loop (chunk-list mode).
 __device__ __forceinline__ void setup_chunk(const Frame &F, const int view, const long long chunk, const long long chunksPerView,
                                             float *sv, float *sn, float *sc, float *sM, unsigned char *slist, unsigned *wsum,
-                                            unsigned long long *bar = nullptr)
+                                            const bool staged)
 {
     const long long first = chunk * NT;
     const long long cnt = min((long long)NT, F.T - first);
@@ -425,26 +425,14 @@ __device__ __forceinline__ void setup_chunk(const Frame &F, const int view, cons
     // a normal or written a record (7 of 8 CTAs at N = 8).  A full-frame filler stages both arrays behind one barrier.
     const bool banded = F.row0 > 0 || F.row1 < F.H;
     unsigned short *alive = F.alive + (long long)view * chunksPerView + chunk;
-    // A full chunk of a full-frame filler arrives as two bulk copies (one thread issues them, everybody waits on the
-    // mbarrier: no per-thread load / store instructions, no registers in flight); anything else is staged by the threads.
-    const bool bulk = bar && !banded && cnt == NT &&
-                      !((reinterpret_cast<uintptr_t>(F.v + first * 9) | reinterpret_cast<uintptr_t>(F.n + first * 9) |
-                         reinterpret_cast<uintptr_t>(F.c + first * 9)) & 15u);
-    if (bulk) {
-        // (the colours come along even though a chunk without a drawn triangle will not look at them: a later staging step
-        // would put another memory round trip and a barrier into every CTA's life, and such chunks are rare in a full frame)
-        if (threadIdx.x == 0) {
-            bulk_load(sv, F.v + first * 9, BC_BYTES, bar);
-            bulk_load(sn, F.n + first * 9, BC_BYTES, bar);
-            bulk_load(sc, F.c + first * 9, BC_BYTES, bar);
-        }
-    } else {
+    // `staged`: the chunk's vertices, normals and colours already lie in sv / sn / sc (k_setup's ring of bulk copies: the loads of
+    // this chunk travelled while the previous one was being set up); anything else is staged here by the threads.
+    if (!staged) {
         stage_floats(F.v, first * 9, cnt * 9, sv);
         if (!banded) stage_floats(F.n, first * 9, cnt * 9, sn);
     }
     if (F.views && threadIdx.x < 16) sM[threadIdx.x] = F.views[view * 16 + threadIdx.x];
     __syncthreads();
-    if (bulk) mbar_wait(bar, 0u);
     // `me`: the triangle of the chunk this thread sets up (-1: none).  A full-frame filler culls first (pyx:202-204 needs only
     // the z of the three view-space normals) and hands the survivors to the first threads, so that the projection, the
     // denominators and the record stores below run in full warps for the ~half of a closed mesh that faces the camera
@@ -506,8 +494,10 @@ __device__ __forceinline__ void setup_chunk(const Frame &F, const int view, cons
             if (threadIdx.x == 0) *alive = 0;
             return;
         }
-        stage_floats(F.n, first * 9, cnt * 9, sn);
-        __syncthreads();
+        if (!staged) {
+            stage_floats(F.n, first * 9, cnt * 9, sn);
+            __syncthreads();
+        }
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -566,7 +556,7 @@ __device__ __forceinline__ void setup_chunk(const Frame &F, const int view, cons
     // the vertex colours are only needed for triangles that are drawn: a CTA without any (culled, off screen, or -- for a
     // band-sharded filler -- outside the band, which is 7 of 8 CTAs at N=8) never reads them
     if (n_entries == 0) return;
-    if (!bulk) {
+    if (!staged) {
         stage_floats(F.c, first * 9, cnt * 9, sc);
         __syncthreads();
     }
@@ -606,32 +596,68 @@ __device__ __forceinline__ void setup_chunk(const Frame &F, const int view, cons
 #ifndef CRB_SETUP_MIN_CTAS
 #define CRB_SETUP_MIN_CTAS 3
 #endif
+// Persistent: a few CTAs per SM walk the (view, chunk) work items -- all chunks of all views, or the chunks k_band_chunks listed
+// for a band-sharded filler -- through a ring of SETUP_STAGES shared-memory stages.  One thread issues the three 9 216-byte bulk
+// copies (cp.async.bulk, completion counted on the stage's mbarrier) of the item two turns ahead as soon as the CTA is done
+// with a stage, so a chunk's vertices, normals and colours arrive while the previous chunk is being projected: the memory
+// round trip that headed every one-chunk CTA's life (load -> barrier -> work) is off the critical path.
+constexpr int SETUP_STAGES = 2;
+constexpr size_t SETUP_STAGE_FLOATS = 3 * (size_t)NT * 9;
+constexpr size_t SETUP_DYN_SMEM = SETUP_STAGES * SETUP_STAGE_FLOATS * sizeof(float);
 __global__ void __launch_bounds__(NT, CRB_SETUP_MIN_CTAS) k_setup(const Frame F)
 {
-    __shared__ __align__(16) float sv[NT * 9];
-    __shared__ __align__(16) float sn[NT * 9];
-    __shared__ __align__(16) float sc[NT * 9];
+    extern __shared__ __align__(128) float stg[];          // [SETUP_STAGES][3][NT * 9]
+    __shared__ __align__(8) unsigned long long bar[SETUP_STAGES];
     __shared__ float sM[16];
     __shared__ unsigned char slist[NT];
     __shared__ unsigned wsum[NT / 32];
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {  // k_alloc (next launch) accumulates
+    if (blockIdx.x == 0 && threadIdx.x == 0) {  // k_alloc (next launch) accumulates
         F.total[0] = 0ull; F.total[2] = 0ull; F.total[3] = 0ull; F.total[4] = 0ull;
     }
     const long long chunksPerView = (F.T + NT - 1) / NT;
-    if (!F.chunks) {
-        __shared__ __align__(8) unsigned long long bar;
-        if (threadIdx.x == 0) {
-            mbar_init(&bar, 3u);      // three bulk copies (vertices, normals, colours), one arrival each
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        setup_chunk(F, blockIdx.y, blockIdx.x, chunksPerView, sv, sn, sc, sM, slist, wsum, &bar);
-        return;
+    const long long nItems = F.chunks ? (long long)F.chunks[0] : chunksPerView * F.nViews;
+    const bool banded = F.row0 > 0 || F.row1 < F.H;
+    // bulk copies want 16-byte aligned sources (a chunk is 9 216 bytes, so only the array bases matter) and whole chunks; a
+    // band-sharded filler without a chunk list tests the vertices before it reads anything else (setup_chunk) and stages itself
+    const bool bulk_ok = !((reinterpret_cast<uintptr_t>(F.v) | reinterpret_cast<uintptr_t>(F.n) | reinterpret_cast<uintptr_t>(F.c)) & 15u) &&
+                         (!banded || F.chunks);
+    auto item = [&](long long w, int &view) -> long long {
+        if (F.chunks) { view = 0; return (long long)F.chunks[1 + w]; }
+        view = (int)(w / chunksPerView);
+        return w % chunksPerView;
+    };
+    auto issue = [&](long long w, int s) {            // one thread: the three bulk copies of item w into stage s (if it qualifies)
+        int view;
+        const long long chunk = item(w, view);
+        if (!bulk_ok || (chunk + 1) * NT > F.T) return;
+        float *d = stg + (size_t)s * SETUP_STAGE_FLOATS;
+        bulk_load(d, F.v + chunk * NT * 9, BC_BYTES, &bar[s]);
+        bulk_load(d + NT * 9, F.n + chunk * NT * 9, BC_BYTES, &bar[s]);
+        bulk_load(d + 2 * NT * 9, F.c + chunk * NT * 9, BC_BYTES, &bar[s]);
+    };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < SETUP_STAGES; ++s) mbar_init(&bar[s], 3u);      // three copies, one arrival each
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int s = 0; s < SETUP_STAGES; ++s)
+            if ((long long)blockIdx.x + (long long)s * gridDim.x < nItems) issue((long long)blockIdx.x + (long long)s * gridDim.x, s);
     }
-    // chunk-list mode (band-sharded filler): a grid of a few CTAs per SM walks the chunks k_band_chunks listed
-    const unsigned n = F.chunks[0];
-    for (unsigned i = blockIdx.x; i < n; i += gridDim.x) {
-        __syncthreads();
-        setup_chunk(F, 0, F.chunks[1 + i], chunksPerView, sv, sn, sc, sM, slist, wsum);
+    __syncthreads();
+    unsigned uses = 0;                                  // bit s: parity of the bulk-loaded items stage s has delivered so far
+    int i = 0;
+    for (long long w = blockIdx.x; w < nItems; w += gridDim.x, ++i) {
+        const int s = i % SETUP_STAGES;
+        int view;
+        const long long chunk = item(w, view);
+        const bool staged = bulk_ok && (chunk + 1) * NT <= F.T;
+        if (staged) {
+            mbar_wait(&bar[s], (uses >> s) & 1u);
+            uses ^= 1u << s;
+        }
+        float *d = stg + (size_t)s * SETUP_STAGE_FLOATS;
+        setup_chunk(F, view, chunk, chunksPerView, d, d + NT * 9, d + 2 * NT * 9, sM, slist, wsum, staged);
+        __syncthreads();                                // everybody is done with the stage (and with sM / slist / wsum)
+        const long long w2 = w + (long long)SETUP_STAGES * gridDim.x;
+        if (threadIdx.x == 0 && w2 < nItems) issue(w2, s);
     }
 }
 
@@ -1912,6 +1938,16 @@ unsigned encode_maps(TMaps *M, const Frame &F)
 }
 
 // project/setup/count -> alloc -> fill -> raster+shade for up to maxViews views
+// k_setup's ring of stages needs more than the 48 KB of shared memory a kernel gets by default: opt in once per device
+int setup_smem_attr(int device)
+{
+    static bool done[64] = {};
+    if (device >= 0 && device < 64 && done[device]) return CRB_OK;
+    CU(cudaFuncSetAttribute(k_setup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SETUP_DYN_SMEM));
+    if (device >= 0 && device < 64) done[device] = true;
+    return CRB_OK;
+}
+
 // project/setup/count -> alloc -> fill for up to maxViews views
 int run_prep(crb_filler *f, Frame &F, cudaStream_t st)
 {
@@ -1934,7 +1970,9 @@ int run_prep(crb_filler *f, Frame &F, cudaStream_t st)
         gT = (unsigned)min((long long)gT, (long long)f->sm_count * 6);
     }
     if (F.T > 0) {
-        k_setup<<<dim3(gT, F.nViews), NT, 0, st>>>(F);
+        if ((rc = setup_smem_attr(f->device))) return rc;
+        const long long items = F.chunks ? (long long)gT : (long long)gT * F.nViews;
+        k_setup<<<(unsigned)min(items, (long long)f->sm_count * CRB_SETUP_MIN_CTAS), NT, SETUP_DYN_SMEM, st>>>(F);
         if ((rc = launch_check(f, "k_setup"))) return rc;
     } else {
         CU(cudaMemsetAsync(F.total, 0, 8, st));
@@ -2021,7 +2059,8 @@ int run_atomic(crb_filler *f, Frame &F, cudaStream_t st)
         if ((rc = launch_check(f, "k_fill_u64"))) return rc;
     }
     if (F.T > 0) {
-        k_setup<<<dim3((unsigned)((F.T + NT - 1) / NT), 1), NT, 0, st>>>(F);
+        if ((rc = setup_smem_attr(f->device))) return rc;
+        k_setup<<<(unsigned)min((F.T + NT - 1) / NT, (long long)f->sm_count * CRB_SETUP_MIN_CTAS), NT, SETUP_DYN_SMEM, st>>>(F);
         if ((rc = launch_check(f, "k_setup"))) return rc;
         k_raster_atomic<<<(unsigned)((F.T * 32 + NT - 1) / NT), NT, 0, st>>>(F, f->keybuf);
         if ((rc = launch_check(f, "k_raster_atomic"))) return rc;
