@@ -686,13 +686,16 @@ def run_gpu_arm(args):
             try:
                 if world > 1:
                     # the frame twice: bands left where they are rendered, and the complete frame on rank 0 (PeerFrame)
-                    for mode in ("none", "peer"):
+                    for mode in ("none", "peer", "u8_peer"):
                         a2 = argparse.Namespace(**vars(args)); a2.gather = mode
                         ln = measure_workload(a2, wl, world, rank, local, dev, cpu_threads, with_cpu=False)
                         if rank == 0:
-                            secondary[wl + ("" if mode == "none" else "_complete_on_rank0")] = ln
+                            secondary[wl + {"none": "", "peer": "_complete_on_rank0", "u8_peer": "_u8_image_complete_on_rank0"}[mode]] = ln
                 else:
                     secondary[wl] = measure_workload(args, wl, world, rank, local, dev, cpu_threads)
+                    if wl == "sphere_8192_bands":      # the single-GPU rate of the image-only frame, the base of the N-GPU u8 lines
+                        a2 = argparse.Namespace(**vars(args)); a2.gather = "u8_local"
+                        secondary[wl + "_u8_image"] = measure_workload(a2, wl, world, rank, local, dev, cpu_threads, with_cpu=False)
             except Exception as ex:
                 secondary[wl] = {"error": repr(ex)[:300]}
             torch.cuda.empty_cache()
@@ -811,11 +814,16 @@ def measure_workload(args, workload, world, rank, local, dev, cpu_threads=None, 
         dist.broadcast_object_list(box, src=0)
         bands = box[0]
         band = bands[rank]
-    gather_mode = args.gather if banded and world > 1 else "none"
+    gather_mode = args.gather if banded and (world > 1 or args.gather == "u8_local") else "none"
     if gather_mode == "auto":
         gather_mode = "peer"
-    frame = None
-    if banded and world > 1 and gather_mode == "peer":
+    frame = image = None
+    if banded and world > 1 and gather_mode == "u8_peer":
+        # run.py's product (the flipped uint8 image) complete on rank 0: every rank's rasterizer stores its band's image rows
+        # straight into rank 0's memory (sharding.PeerImage); no float32 buffer is produced
+        image = sharding.PeerImage(res, res, dst=0, local_device=local)
+        f = AdvancedPixelBufferFiller(res, res, fov=FOV, device=local, band=band)
+    elif banded and world > 1 and gather_mode == "peer":
         frame = sharding.PeerFrame(res, res, dst=0, local_device=local)
         f = AdvancedPixelBufferFiller(res, res, fov=FOV, device=local, band=band, out_ptrs=frame.band_pointers(band[0]))
     else:
@@ -823,8 +831,14 @@ def measure_workload(args, workload, world, rank, local, dev, cpu_threads=None, 
     ident = torch.from_numpy(VW.view_matrix()[None, :]).to(dev)     # identity rotation, zero pivot / translation
     zb, cb, nb_ = f.device_buffers()
 
+    u8_local = torch.empty((1, res, res, 3), dtype=torch.uint8, device=dev) if (gather_mode == "u8_local") else None
+
     def step():
-        if guro:
+        if image is not None:
+            f.render_views(dv, dc, dn, ident, want=(), chunk=1, check_status=False, u8_exchange=image.plan(band))
+        elif u8_local is not None:
+            f.render_views(dv, dc, dn, ident, want=(), color_u8_out=u8_local, chunk=1, check_status=False)
+        elif guro:
             # one frame = fused clear + raster + shading with the Guro light applied in the shading pass (CRB_GURO),
             # written straight into the filler's own buffers (identity view: x*1 + 0 terms are exact)
             f.render_views(dv, dc, dn, ident, z_out=zb[None], color_out=cb[None], normals_out=nb_[None], guro_light=[0, 0, 1],
@@ -867,7 +881,13 @@ def measure_workload(args, workload, world, rank, local, dev, cpu_threads=None, 
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-        if frame is not None:
+        if image is not None:
+            gather = {"mode": "u8_peer", "ms": 0.0, "bytes": 3 * res * res,
+                      "what": "none needed: every rank's rasterizer stores its band of run.py's flipped uint8 image straight into rank "
+                              "0's memory over NVLink (sharding.PeerImage, crb_set_u8_exchange); `value` is complete images per second on "
+                              "rank 0; no float32 buffer is produced",
+                      "lit_pixels": int((image.tensor().sum(dim=-1) > 0).sum().item()) if rank == 0 else None}
+        elif frame is not None:
             full_z = frame.tensors()[0]
             gather = {"mode": "peer", "ms": 0.0, "bytes": 28 * res * res,
                       "what": "none needed: every rank's rasterizer stores its band straight into rank 0's frame over NVLink "
@@ -891,13 +911,17 @@ def measure_workload(args, workload, world, rank, local, dev, cpu_threads=None, 
                       "covered_pixels": int((full[0] < 1e5).sum().item())}
             del full
     z = f.device_buffers()[0]
+    if image is not None or u8_local is not None:        # (the timed steps produced no float32 buffer: draw one frame for the check)
+        f.clear(); f.render_arrays(dv, dc, dn)
+        z = f.device_buffers()[0]
     cov = torch.tensor([int((z < 1e5).sum().item())], dtype=torch.int64, device=dev)   # (PeerFrame: read over NVLink)
     if banded and world > 1:
         dist.all_reduce(cov)
     fps = steps / (ms / 1000.0)
     peak, peak_src = peaks()
     rows = res if not (banded and world > 1) else band[1] - band[0]
-    alg = 108 * T + 28 * rows * res       # per GPU: every rank reads all triangles, writes its own rows
+    bpp = 3 if (image is not None or u8_local is not None) else 28       # image-only frames write 3 bytes per pixel
+    alg = 108 * T + bpp * rows * res      # per GPU: every rank reads all triangles, writes its own rows
     k_avg = k_ms / max(k_launches, 1)
 
     cpu = e2e = None
@@ -957,6 +981,8 @@ def measure_workload(args, workload, world, rank, local, dev, cpu_threads=None, 
     del f
     if frame is not None:
         frame.close()
+    if image is not None:
+        image.close()
     return line
 
 
@@ -1006,7 +1032,7 @@ def main():
                     help="sphere_8192_bands only: rows per rank equal (uniform) or cut where the estimated cost balances")
     ap.add_argument("--res", type=int, default=0, help="sphere_8192_bands only: override the resolution (scaled sphere)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the C2 / C3 / C4 lines measured after the headline")
-    ap.add_argument("--gather", default="auto", choices=["auto", "none", "bands", "u8", "z", "exchange", "exchange_nccl", "u8_peer", "all", "peer"],
+    ap.add_argument("--gather", default="auto", choices=["auto", "none", "bands", "u8", "z", "exchange", "exchange_nccl", "u8_peer", "u8_local", "all", "peer"],
                     help="also time the final NCCL gather (reported beside, never inside, the headline value); "
                          "peer (sphere_8192_bands only): no gather at all -- every rank's filler renders its band straight into "
                          "rank 0's frame over NVLink (sharding.PeerFrame), and the value is frames/s complete on rank 0")

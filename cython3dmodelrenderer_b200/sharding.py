@@ -366,3 +366,59 @@ class RowExchange:
         if self.own:
             self._check(self._L.crb_shared_free(self.device, self.own))
             self.own = 0
+
+
+class PeerImage:
+    """One h x w run.py:26 image (uint8, rows flipped) in the memory of rank `dst`, assembled by band-sharded fillers (config
+    C4): rank r renders its row band with `render_views(..., want=(), u8_exchange=img.plan(band))` and k_raster stores the
+    band's image rows straight into rank `dst`'s memory over NVLink (crb_set_u8_exchange with one band).  3 bytes per pixel
+    instead of the 28 of a PeerFrame: 201 MB for 8192^2, far below one GPU's NVLink ingress per frame time, so -- unlike the
+    float32 frame -- the complete image on ONE rank scales with the number of GPUs.  Collective constructor / close."""
+
+    def __init__(self, h, w, dst=0, local_device=None):
+        import ctypes
+        from . import _lib
+        self._L = _lib.load_library()
+        self._check = _lib.check
+        self.h, self.w, self.dst = int(h), int(w), int(dst)
+        self.world = _world()
+        self.rank = dist.get_rank() if self.world > 1 else 0
+        self.device = torch.cuda.current_device() if local_device is None else int(local_device)
+        self.owner = self.rank == self.dst
+        ptr = ctypes.c_void_p()
+        box = [None]
+        if self.owner:
+            handle = ctypes.create_string_buffer(64)
+            self._check(self._L.crb_shared_alloc(self.device, max(self.h * self.w * 3, 256), ctypes.byref(ptr), handle))
+            box = [handle.raw]
+        if self.world > 1:
+            dist.broadcast_object_list(box, src=self.dst)
+        if not self.owner:
+            self._check(self._L.crb_shared_open(self.device, ctypes.create_string_buffer(box[0], 64), ctypes.byref(ptr)))
+        self.base = int(ptr.value)
+
+    def plan(self, band):
+        """`u8_exchange` argument for the filler that owns image rows [row0, row1) (unflipped): its flipped rows are the
+        image's rows [h - row1, h - row0)."""
+        row0, row1 = int(band[0]), int(band[1])
+        return row1 - row0, [self.base + (self.h - row1) * self.w * 3]
+
+    def tensor(self):
+        """The image as a torch uint8 tensor [h, w, 3] (on other ranks than `dst` it reads over NVLink)."""
+        from .pixel_buffer_filler import wrap_device_pointer
+        return wrap_device_pointer(torch, self.base, (self.h, self.w, 3), torch.device("cuda", self.device), dtype=torch.uint8)
+
+    def complete(self):
+        torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            dist.barrier()
+
+    def close(self):
+        if self.base:
+            if not self.owner:
+                self._check(self._L.crb_shared_close(self.device, self.base))
+            if self.world > 1:
+                dist.barrier()
+            if self.owner:
+                self._check(self._L.crb_shared_free(self.device, self.base))
+            self.base = 0

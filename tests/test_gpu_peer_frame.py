@@ -112,3 +112,41 @@ def test_row_exchange_from_inside_the_rasterizer(world, gather_to, tmp_path):
         for s in range(world):
             assert np.array_equal(got[s], refs[s])
         assert not (tmp_path / f"got{1 - gather_to}.npy").exists()
+
+
+def _image_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from cython3dmodelrenderer_b200 import AdvancedPixelBufferFiller, sharding, views as VW
+        dev = rank % torch.cuda.device_count()
+        torch.cuda.set_device(dev)
+        h, w = 320, 256
+        m = load_indexed("bunny")
+        dv, dc, dn = (torch.from_numpy(a).cuda() for a in (m._vertices_by_triangles, m._colors_by_triangles, m._normals_by_triangles))
+        ident = torch.from_numpy(VW.view_matrix()[None, :]).cuda()
+        bands = sharding.balanced_bands([1.0, 1.0, 6.0, 6.0, 2.0, 1.0, 1.0, 1.0, 1.0, 1.0], world, h)
+        img = sharding.PeerImage(h, w, dst=0, local_device=dev)
+        f = AdvancedPixelBufferFiller(h, w, fov=45.0, device=dev, band=bands[rank])
+        f.render_views(dv, dc, dn, ident, want=(), chunk=1, guro_light=[0, 0, 1], u8_exchange=img.plan(bands[rank]))
+        img.complete()
+        if rank == 0:
+            np.save(os.path.join(out_dir, "img.npy"), img.tensor().cpu().numpy())
+            full = AdvancedPixelBufferFiller(h, w, fov=45.0, device=dev)
+            ref = full.render_views(dv, dc, dn, ident, want=(), chunk=1, guro_light=[0, 0, 1], color_u8_out=True)["color_u8"][0]
+            np.save(os.path.join(out_dir, "ref.npy"), ref.cpu().numpy())
+        dist.barrier()
+        del f
+        img.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_band_fillers_assemble_the_uint8_image_on_rank0(world, tmp_path):
+    """sharding.PeerImage: band-sharded fillers store their rows of run.py's (lit, flipped, uint8) image straight into rank 0's
+    memory from inside the rasterizer; the assembled image equals a single filler's."""
+    mp.spawn(_image_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    got, ref = np.load(tmp_path / "img.npy"), np.load(tmp_path / "ref.npy")
+    assert int((ref.sum(axis=-1) > 0).sum()) > 5000
+    assert np.array_equal(got, ref)
