@@ -271,9 +271,8 @@ __device__ __forceinline__ bool fdiv_ok(float n1, float n2, float n3)
 // pyx:215-242 for the pixel's winning triangle: barycentrics (mu:5-34), depth, colour, normal (left-associated sums).
 // Returns false if the fragment would not have been drawn (some barycentric < 0, NaN depth) -- cannot happen for a key
 // that won, kept as a guard.  All operands come from the triangle's 128-byte shade record.
-__device__ __forceinline__ bool shade_fragment(const Frame &F, long long ridx, float px, float py, float &z, float c[3], float n[3])
+__device__ __forceinline__ bool shade_fragment(const Frame &F, const float4 *R, float px, float py, float &z, float c[3], float n[3])
 {
-    const float4 *R = F.shrec + (DBG(F, FLAG_DBG_ONEREC) ? 0ll : ridx) * SREC;
     const float4 A = R[S_A], B = R[S_B], C = R[S_C];
     // x0=A.x y0=A.y x1=A.z y1=A.w x2=B.x y2=B.y z0=B.z z1=B.w z2=C.x  l03=C.y l13=C.z l23=C.w
     const float n1 = (A.z - B.x) * (py - B.y) - (A.w - B.y) * (px - B.x);
@@ -1036,9 +1035,20 @@ constexpr unsigned PK_FAST = 16u;    // FL_SPAN and FL_FDIV: div_rn_by() applies
 constexpr int PK_XA = 8, PK_XB = 14, PK_YT = 20;   // tile-relative rectangle: first x (6 bits), end x (6 bits), first row (5 bits)
 
 // Visibility + deferred shading of one busy tile (n triangles staged at list offset off).
-__device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, TileSmem &S, const bool clear, const int view,
+__device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, TileSmem &S_, const bool clear, const int view,
                                             const int tx, const int ty, const unsigned n, const unsigned off, const int rowLo, const int rowHi)
 {
+#ifndef CRB_NO_OPAQUE_SMEM
+    // The address of the CTA's shared memory goes through an empty asm: under the 40-register cap the compiler otherwise re-derives
+    // the shared-window base (S2R SR_CgaCtaId + LEA) inside the exact and the shading loops instead of keeping it; an opaque
+    // value cannot be rematerialised, and __isShared keeps the accesses LDS / STS / ATOMS.
+    TileSmem *Sp = &S_;
+    asm volatile("" : "+l"(Sp));
+    __builtin_assume(__isShared(Sp));
+    TileSmem &S = *Sp;
+#else
+    TileSmem &S = S_;
+#endif
     const int x0 = tx * TW, yl0 = ty * TH;       // yl0: row inside the band's buffers
     const int y0 = F.row0 + yl0;                  // absolute image row
     const int tw = min(TW, F.W - x0), th = min(min(TH, F.row1 - y0), rowHi);   // this CTA's rows of the tile: [rowLo, th)
@@ -1119,7 +1129,14 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
         // the warp's last.  qn: entries in the queue (warp-uniform).
         unsigned qn = 0, trip = 0;
         bool finished = false;
-        unsigned short *fq = S.u.st.fq[wid];
+#ifdef CRB_PIN_WARP_OFFS
+        unsigned woff = wid;                             // (an opaque copy: fq / slotw below cost one add from it instead of a re-derivation from tid)
+        asm volatile("" : "+r"(woff));
+#else
+        const unsigned woff = wid;
+#endif
+        unsigned short *fq = S.u.st.fq[woff];
+        float4 *slotw = &S.u.st.slot[woff][0][0];        // this warp's two slot arrays (trip parity 0 / 1)
         for (unsigned tb = 0; !finished; tb += NT) {
             const unsigned rem = tb < totalRows ? totalRows - tb : 0u;
             const unsigned share = (rem >= (unsigned)NT || !deal) ? 32u : (rem + NT / 32 - 1u) / (NT / 32);
@@ -1141,7 +1158,7 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
                 const float A1 = E0.x * (py - E0.y), A2 = E1.x * (py - E1.y), A3 = E2.x * (py - E2.y);
                 xa = (int)((pk >> PK_XA) & 63u);
                 int xb = (int)((pk >> PK_XB) & 63u);
-                S.u.st.slot[wid][par][lane] = make_float4(A1, A2, A3, __uint_as_float(o | (yl << 8)));
+                slotw[par * 32u + lane] = make_float4(A1, A2, A3, __uint_as_float(o | (yl << 8)));
                 // pass 1: which pixels of the row need the exact path.  A pixel is certainly outside (bar_k < 0) when a
                 // numerator is below its threshold; each numerator is a monotone function of x (every rounding in
                 // A - l2*(px - b) is monotone), so the pixels that survive all three tests form ONE interval.
@@ -1207,7 +1224,7 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
                     if (b + lane < qn) {
                         const unsigned e = fq[b + lane];
                         const unsigned src = e & 31u, bit = (e >> 5) & 31u;
-                        const float4 q = S.u.st.slot[wid][e >> 10][src];
+                        const float4 q = slotw[(e >> 10) * 32u + src];
                         const unsigned info = __float_as_uint(q.w), o2 = info & 255u;
                         const float2 h0 = *reinterpret_cast<const float2 *>(&S.u.st.e0[o2].z);
                         const float2 h1 = *reinterpret_cast<const float2 *>(&S.u.st.e1[o2].z);
@@ -1266,6 +1283,10 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
     const long long tilebase = slab + (long long)yl0 * F.W + x0;          // first pixel of the tile in its slab
     const unsigned rowStep = (unsigned)(NT / TW) * (unsigned)F.W;
     long long pix = tilebase + (unsigned)((int)wid * F.W + (int)lane);    // this thread's pixels: column lane, rows wid, wid + 8, ...
+    const float4 *recv = F.shrec + (long long)view * F.T * SREC;          // the view's shade records
+#ifdef CRB_PIN_RECV
+    asm volatile("" : "+l"(recv));       // (kept in registers: re-derived from view and T per pixel otherwise)
+#endif
     for (int p = tid; p < TH * TW; p += NT, pix += rowStep) {
         const int yy = p / TW, xx = (int)lane;
         if (yy < rowLo || yy >= th || xx >= tw) continue;
@@ -1274,9 +1295,8 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
         bool write = clear;
         if (key != KEY_EMPTY && !DBG(F, FLAG_DBG_NOSHADE)) {
             const unsigned tri = ~(unsigned)(key & 0xFFFFFFFFull);
-            const long long ridx = (long long)view * F.T + tri;
             float fz, fc[3], fn[3];
-            if (shade_fragment(F, ridx, (float)(x0 + xx), (float)(y0 + yy), fz, fc, fn)) {
+            if (shade_fragment(F, recv + (size_t)(DBG(F, FLAG_DBG_ONEREC) ? 0u : tri) * SREC, (float)(x0 + xx), (float)(y0 + yy), fz, fc, fn)) {
                 const float zold = clear ? Z_INIT : F.z[pix];
                 if (!(fz > zold)) {  // pyx:223: drawn unless new_z > z_buffer (equal depth overwrites)
                     z = fz; c[0] = fc[0]; c[1] = fc[1]; c[2] = fc[2]; nn[0] = fn[0]; nn[1] = fn[1]; nn[2] = fn[2];
@@ -1489,7 +1509,7 @@ __global__ void __launch_bounds__(NT) k_shade_atomic(const Frame F, unsigned lon
         const unsigned tri = ~(unsigned)(key & 0xFFFFFFFFull);
         const int y = F.row0 + (int)(pix / F.W), x = (int)(pix % F.W);
         float fz, fc[3], fn[3];
-        if (shade_fragment(F, tri, (float)x, (float)y, fz, fc, fn)) {
+        if (shade_fragment(F, F.shrec + (size_t)tri * SREC, (float)x, (float)y, fz, fc, fn)) {
             const float zold = clear ? Z_INIT : F.z[pix];
             if (!(fz > zold)) {
                 z = fz; c[0] = fc[0]; c[1] = fc[1]; c[2] = fc[2]; nn[0] = fn[0]; nn[1] = fn[1]; nn[2] = fn[2];
