@@ -1129,14 +1129,8 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
         // the warp's last.  qn: entries in the queue (warp-uniform).
         unsigned qn = 0, trip = 0;
         bool finished = false;
-#ifdef CRB_PIN_WARP_OFFS
-        unsigned woff = wid;                             // (an opaque copy: fq / slotw below cost one add from it instead of a re-derivation from tid)
-        asm volatile("" : "+r"(woff));
-#else
-        const unsigned woff = wid;
-#endif
-        unsigned short *fq = S.u.st.fq[woff];
-        float4 *slotw = &S.u.st.slot[woff][0][0];        // this warp's two slot arrays (trip parity 0 / 1)
+        unsigned short *fq = S.u.st.fq[wid];
+        float4 *slotw = &S.u.st.slot[wid][0][0];        // this warp's two slot arrays (trip parity 0 / 1)
         for (unsigned tb = 0; !finished; tb += NT) {
             const unsigned rem = tb < totalRows ? totalRows - tb : 0u;
             const unsigned share = (rem >= (unsigned)NT || !deal) ? 32u : (rem + NT / 32 - 1u) / (NT / 32);
@@ -1284,9 +1278,6 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
     const unsigned rowStep = (unsigned)(NT / TW) * (unsigned)F.W;
     long long pix = tilebase + (unsigned)((int)wid * F.W + (int)lane);    // this thread's pixels: column lane, rows wid, wid + 8, ...
     const float4 *recv = F.shrec + (long long)view * F.T * SREC;          // the view's shade records
-#ifdef CRB_PIN_RECV
-    asm volatile("" : "+l"(recv));       // (kept in registers: re-derived from view and T per pixel otherwise)
-#endif
     for (int p = tid; p < TH * TW; p += NT, pix += rowStep) {
         const int yy = p / TW, xx = (int)lane;
         if (yy < rowLo || yy >= th || xx >= tw) continue;
