@@ -407,7 +407,13 @@ def run_gpu_arm(args):
                 both = timed(both_fn)
                 only = timed(only_fn)
                 t = xch.tensor()
-                check_px = int((t[world - 1, 0].sum(dim=-1) > 0).sum().item()) if t is not None else None
+                # lit pixels of view 0 of the LAST rank as far as this rank received it (all of it on the gather destination, this
+                # rank's row band after the exchange -- summed over the ranks below)
+                check_px = int((t[world - 1, 0].sum(dim=-1) > 0).sum().item()) if t is not None else 0
+                if mode == "exchange":
+                    cp = torch.tensor([check_px], dtype=torch.int64, device=dev)
+                    dist.all_reduce(cp)
+                    check_px = int(cp.item())
                 same = None
                 if t is not None:      # the delivered bytes are the ones a local render of the same views holds
                     band = u8[0, :xch.hb] if mode == "exchange" and rank == 0 else (u8[0] if rank == 0 else None)

@@ -580,6 +580,8 @@ __device__ __forceinline__ void setup_chunk(const Frame &F, const int view, cons
     if (drawn) tile_span(F, bx, by, tx0, tx1, ty0, ty1);
     unsigned *cnt_view = F.count + (long long)view * F.nTiles;
     const int nt = drawn ? (tx1 - tx0 + 1) * (ty1 - ty0 + 1) : 0;
+    // (counted with one fire-and-forget atomicAdd per (triangle, tile): aggregating the lanes of a warp that hit the same tile --
+    // what k_fill does for its slot-returning atomics -- costs more in MATCH than the reductions it saves: 86 -> 96 us)
     if (nt <= WIDE_TILES)
         for (int ty = ty0; ty <= ty1; ++ty)
             for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(cnt_view + ty * F.tilesX + tx, 1u);
@@ -818,14 +820,28 @@ __device__ __forceinline__ void fill_chunk(const Frame &F, const int view, const
     }
     const long long vb = (long long)view * F.nTiles;
     const int nt = drawn ? (tx1 - tx0 + 1) * (ty1 - ty0 + 1) : 0;
-    if (nt <= WIDE_TILES)
-        for (int ty = ty0; ty <= ty1; ++ty)
-            for (int tx = tx0; tx <= tx1; ++tx) {
-                const long long t = vb + ty * F.tilesX + tx;
-                const unsigned at = F.offset[t] + atomicAdd(F.cursor + t, 1u);
-                float4 *o = F.ls + (size_t)at * 4;     // one 64-byte entry = two whole sectors
+    {   // lanes of the warp that append to the same tile in the same turn take their slots with ONE atomicAdd (mesh neighbours
+        // fall into the same tile: a warp's 32 triangles usually touch two or three tiles)
+        const unsigned lane = tix & 31u;
+        const int small = nt <= WIDE_TILES ? nt : 0;
+        const int turns = __reduce_max_sync(0xFFFFFFFFu, small);
+        int cx = tx0, cy = ty0;
+        for (int k = 0; k < turns; ++k) {
+            const bool act = k < small;
+            const long long t = vb + cy * F.tilesX + cx;
+            const unsigned tag = act ? (unsigned)t : 0xFFFFFFE0u + lane;      // inactive lanes match nobody
+            const unsigned grp = __match_any_sync(0xFFFFFFFFu, tag);
+            const int leader = __ffs(grp) - 1;
+            unsigned base = 0;
+            if (act && (int)lane == leader) base = F.offset[t] + atomicAdd(F.cursor + t, (unsigned)__popc(grp));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (act) {
+                float4 *o = F.ls + (size_t)(base + __popc(grp & ((1u << lane) - 1u))) * 4;     // one 64-byte entry = two whole sectors
                 o[0] = a; o[1] = b; o[2] = s2; o[3] = s3;
+                if (++cx > tx1) { cx = tx0; ++cy; }
             }
+        }
+    }
     // triangles that span many tiles: the whole warp scatters them, a tile per lane (see setup_chunk)
     for (unsigned wide = __ballot_sync(0xFFFFFFFFu, nt > WIDE_TILES); wide; wide &= wide - 1u) {
         const int src = __ffs(wide) - 1;
