@@ -463,7 +463,7 @@ __device__ __forceinline__ void setup_chunk(const Frame &F, const int view, cons
     const int mi = valid ? me : 0;
     const long long tri = first + mi;
     const long long ridx = (long long)view * F.T + tri;
-    float x[3], y[3], z[3], nx[3], ny[3], nz[3];
+    float x[3], y[3], z[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         if (!valid) { x[k] = y[k] = z[k] = 1.0f; continue; }
@@ -498,17 +498,19 @@ __device__ __forceinline__ void setup_chunk(const Frame &F, const int view, cons
             __syncthreads();
         }
     }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        if (!valid) { nx[k] = ny[k] = nz[k] = 1.0f; continue; }
-        nx[k] = sn[mi * 9 + k * 3 + 0];
-        ny[k] = sn[mi * 9 + k * 3 + 1];
-        nz[k] = sn[mi * 9 + k * 3 + 2];
-        if (F.views) view_normal(sM, nx[k], ny[k], nz[k]);
+    // pyx:202-204: (n0z + n1z + n2z)/3 >= 0 in double -- only the sign of the float sum matters (NaN: not culled).  A full-frame
+    // filler has culled already (every triangle that got this far faces the camera); the full view-space normals are formed
+    // only where the record is written, so that their nine registers are not live across the projection and the denominators.
+    if (banded && valid) {
+        const float *q = sn + mi * 9;
+        float z0 = q[2], z1 = q[5], z2 = q[8];
+        if (F.views) {
+            z0 = (sM[6] * q[0] + sM[7] * q[1]) + sM[8] * q[2];
+            z1 = (sM[6] * q[3] + sM[7] * q[4]) + sM[8] * q[5];
+            z2 = (sM[6] * q[6] + sM[7] * q[7]) + sM[8] * q[8];
+        }
+        drawn = drawn && !(((z0 + z1) + z2) >= 0.0f);
     }
-    // pyx:202-204: (n0z + n1z + n2z)/3 >= 0 in double -- only the sign of the float sum matters (NaN: not culled)
-    const float nsum = (nz[0] + nz[1]) + nz[2];
-    drawn = drawn && !(nsum >= 0.0f);
     const unsigned bx = drawn ? ((unsigned)xl | ((unsigned)xr << 16)) : 0u;
     const unsigned by = drawn ? ((unsigned)yt | ((unsigned)yb << 16)) : 0u;
 
@@ -565,6 +567,14 @@ __device__ __forceinline__ void setup_chunk(const Frame &F, const int view, cons
     R[S_A] = make_float4(x[0], y[0], x[1], y[1]);
     R[S_B] = make_float4(x[2], y[2], z[0], z[1]);
     R[S_C] = make_float4(z[2], l03, l13, l23);
+    float nx[3], ny[3], nz[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        nx[k] = sn[mi * 9 + k * 3 + 0];
+        ny[k] = sn[mi * 9 + k * 3 + 1];
+        nz[k] = sn[mi * 9 + k * 3 + 2];
+        if (F.views) view_normal(sM, nx[k], ny[k], nz[k]);
+    }
     R[S_N0] = make_float4(nx[0], ny[0], nz[0], nx[1]);
     R[S_N1] = make_float4(ny[1], nz[1], nx[2], ny[2]);
     R[S_X] = make_float4(nz[2], q[0], q[1], q[2]);
