@@ -135,6 +135,9 @@ struct Frame {
                                 // by one thread) per (triangle, tile) pair: (x0 y0 x1 y1) (x2 y2 z0 z1) (z2 d1 d2 d3) (bbox x, bbox y,
                                 // triangle index, flags) -- d = sign-normalised denominators; their reciprocals are formed when a tile
                                 // stages the entry (rcp.rn: three instructions' worth per entry instead of 16 more bytes per pair)
+    uint4 *wide;                // [wideCap] triangles that span more than WIDE_TILES tiles, handed by k_fill to k_fill_wide: (view, triangle,
+                                // bbox x, bbox y); their number in total[5].  wideCap == 0: k_fill scatters them itself (no k_fill_wide launch)
+    unsigned wideCap;
     unsigned long long *total;  // [0] pairs of this frame, [1] sticky max of overflowing totals, [2] busy tiles, [3] empty tiles
     unsigned long long *hstats; // mapped host word: (tiles of the launch << 32 | busy tiles), posted by k_raster for the next launch's grid size
     long long pairCap;
@@ -623,7 +626,7 @@ __global__ void __launch_bounds__(NT, CRB_SETUP_MIN_CTAS) k_setup(const Frame F)
     __shared__ unsigned char slist[NT];
     __shared__ unsigned wsum[NT / 32];
     if (blockIdx.x == 0 && threadIdx.x == 0) {  // k_alloc (next launch) accumulates
-        F.total[0] = 0ull; F.total[2] = 0ull; F.total[3] = 0ull; F.total[4] = 0ull;
+        F.total[0] = 0ull; F.total[2] = 0ull; F.total[3] = 0ull; F.total[4] = 0ull; F.total[5] = 0ull;
     }
     const long long chunksPerView = (F.T + NT - 1) / NT;
     const long long nItems = F.chunks ? (long long)F.chunks[0] : chunksPerView * F.nViews;
@@ -852,8 +855,22 @@ __device__ __forceinline__ void fill_chunk(const Frame &F, const int view, const
             }
         }
     }
-    // triangles that span many tiles: the whole warp scatters them, a tile per lane (see setup_chunk)
-    for (unsigned wide = __ballot_sync(0xFFFFFFFFu, nt > WIDE_TILES); wide; wide &= wide - 1u) {
+    // Triangles that span many tiles (a quad of the 2048^2 basketball covers hundreds).  With a k_fill_wide launch behind this
+    // kernel they are only listed here and scattered there, a warp per triangle: done in place, one after the other by the warp
+    // that owns them, a chunk of 256 such triangles kept two warps busy for the length of the whole kernel (basketball: 76 us of
+    // k_fill on 128 warps).  Without that launch (or with the list full): in place, a tile per lane (see setup_chunk).
+    unsigned widem = __ballot_sync(0xFFFFFFFFu, nt > WIDE_TILES);
+    if (F.wideCap && widem) {
+        const unsigned lane = tix & 31u;
+        unsigned long long first = 0ull;
+        if ((int)lane == __ffs(widem) - 1) first = atomicAdd(F.total + 5, (unsigned long long)__popc(widem));
+        first = __shfl_sync(0xFFFFFFFFu, first, __ffs(widem) - 1);
+        const unsigned long long at = first + __popc(widem & ((1u << lane) - 1u));
+        const bool listed = nt > WIDE_TILES && at < (unsigned long long)F.wideCap;
+        if (listed) F.wide[at] = make_uint4((unsigned)view, (unsigned)tri, bx, by);
+        widem = __ballot_sync(0xFFFFFFFFu, nt > WIDE_TILES && !listed);
+    }
+    for (unsigned wide = widem; wide; wide &= wide - 1u) {
         const int src = __ffs(wide) - 1;
         auto bc = [src](float4 v) {
             return make_float4(__shfl_sync(0xFFFFFFFFu, v.x, src), __shfl_sync(0xFFFFFFFFu, v.y, src), __shfl_sync(0xFFFFFFFFu, v.z, src),
@@ -887,6 +904,47 @@ __global__ void __launch_bounds__(FT, CRB_FILL_MIN_CTAS) k_fill(const Frame F)
     if (*F.total > (unsigned long long)F.pairCap) return;
     const unsigned n = F.chunks[0];
     for (unsigned i = blockIdx.x / (NT / FT); i < n; i += gridDim.x / (NT / FT)) fill_chunk(F, 0, F.chunks[1 + i], chunksPerView, false, tix);
+}
+
+// The triangles k_fill listed as spanning many tiles: a CTA per triangle (a screen-filling one covers thousands of tiles), a tile
+// per thread and turn, four turns' slot atomics in flight before the first entry is stored.
+constexpr int FWT = 256;
+__global__ void __launch_bounds__(FWT) k_fill_wide(const Frame F)
+{
+    if (*F.total > (unsigned long long)F.pairCap) return;
+    const unsigned long long listed = F.total[5];
+    const unsigned n = (unsigned)(listed < (unsigned long long)F.wideCap ? listed : (unsigned long long)F.wideCap);
+    for (unsigned e = blockIdx.x; e < n; e += gridDim.x) {
+        const uint4 w = F.wide[e];
+        const long long ridx = (long long)w.x * F.T + w.y;
+        const float4 *R = F.shrec + ridx * SREC;
+        const float4 a = R[S_A], b = R[S_B], c = R[S_C];
+        const unsigned fl = __float_as_uint(R[S_C2].z);
+        const float4 s2 = make_float4(c.x, (fl & (FL_NEG << 0)) ? -c.y : c.y, (fl & (FL_NEG << 1)) ? -c.z : c.z, (fl & (FL_NEG << 2)) ? -c.w : c.w);
+        const float4 s3 = make_float4(__uint_as_float(w.z), __uint_as_float(w.w), __uint_as_float(w.y), __uint_as_float(fl));
+        int tx0, tx1, ty0, ty1;
+        tile_span(F, w.z, w.w, tx0, tx1, ty0, ty1);
+        const int wx = tx1 - tx0 + 1, nt = wx * (ty1 - ty0 + 1);
+        const long long vb = (long long)w.x * F.nTiles;
+        for (int i0 = (int)threadIdx.x; i0 < nt; i0 += 4 * FWT) {
+            unsigned at[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = i0 + FWT * j;
+                at[j] = 0u;
+                if (i < nt) {
+                    const long long t = vb + (ty0 + i / wx) * F.tilesX + tx0 + i % wx;
+                    at[j] = F.offset[t] + atomicAdd(F.cursor + t, 1u);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (i0 + FWT * j < nt) {
+                    float4 *o = F.ls + (size_t)at[j] * 4;
+                    o[0] = a; o[1] = b; o[2] = s2; o[3] = s3;
+                }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1457,7 +1515,7 @@ __global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame 
     if (bidx == 0 && threadIdx.x == 0 && F.hstats) {
         volatile unsigned long long *hs = reinterpret_cast<volatile unsigned long long *>(F.hstats);
         hs[0] = ((unsigned long long)nAll << 32) | nLight;
-        hs[1] = nHeavy;
+        hs[1] = (unsigned long long)nHeavy | ((F.total[5] > 0xFFFFFFFFull ? 0xFFFFFFFFull : F.total[5]) << 32);     // + triangles that span many tiles
     }
     if (clear && !split && !DBG(F, FLAG_DBG_NOCLEAR)) {
         const unsigned ne = (unsigned)F.total[3];
@@ -1784,6 +1842,8 @@ struct crb_filler {
     unsigned *count, *offset, *cursor, *empty;
     uint4 *busy, *busyH;
     float4 *ls;
+    uint4 *wide;
+    long long wideCap;
     unsigned long long *total;
     float *stage_v, *stage_c, *stage_n;  // device staging for host-pointer calls
     // differential path scratch (library-owned, lazily allocated)
@@ -1816,6 +1876,7 @@ struct crb_filler {
     bool prof_on;
     int prof_n;
     cudaEvent_t *prof_ev;  // 2 * PROF_MAX events, created on first use
+    int wide_kernel;       // triangles that span many tiles are scattered by k_fill_wide (CRB_OPT_WIDE_KERNEL = 0: by k_fill itself)
     unsigned char *u8x[CRB_MAX_EXCHANGE];   // crb_set_u8_exchange: receive buffer of every row band (u8x_n == 0: off)
     int u8x_n, u8x_rows;
 };
@@ -1823,7 +1884,7 @@ struct crb_filler {
 namespace {
 
 struct WsLayout {
-    size_t shrec, recE, alive, chunks, count, offset, cursor, busy, busyH, empty, ls, total, set_bytes, sv, sc, sn, bytes;
+    size_t shrec, recE, alive, chunks, count, offset, cursor, busy, busyH, empty, ls, wide, total, set_bytes, sv, sc, sn, bytes;
 };
 
 long long default_pair_cap(const crb_filler *f, long long T, int views)
@@ -1832,6 +1893,8 @@ long long default_pair_cap(const crb_filler *f, long long T, int views)
     long long cap = 4 * T * views + tiles * views + 65536;
     return cap;
 }
+
+long long wide_capacity(long long T, int views) { return (T > 0 ? T : 1) * views / 8 + 1024; }
 
 WsLayout ws_layout(const crb_filler *f, long long T, int views, long long pairCap)
 {
@@ -1851,6 +1914,7 @@ WsLayout ws_layout(const crb_filler *f, long long T, int views, long long pairCa
     L.busyH = take((size_t)tiles * views * 16 * SPLIT_BANDS);
     L.empty = take((size_t)tiles * views * 4);
     L.ls = take((size_t)pairCap * 64);
+    L.wide = take((size_t)wide_capacity(T, views) * 16);
     L.total = take(64);
     L.set_bytes = o;            // everything above exists twice (two launches of a batch in flight, see crb_render_views)
     o = 2 * L.set_bytes;
@@ -1916,6 +1980,8 @@ void fill_frame(const crb_filler *f, Frame *F, int set = 0)
     F->count = at(f->count); F->offset = at(f->offset); F->cursor = at(f->cursor);
     F->busy = at(f->busy); F->busyH = at(f->busyH); F->empty = at(f->empty);
     F->ls = at(f->ls);
+    F->wide = at(f->wide);
+    F->wideCap = 0;          // run_prep decides per launch whether k_fill_wide follows k_fill
     F->total = at(f->total);
     F->hstats = f->hstats_dev;
     F->pairCap = f->pairCap;
@@ -1986,9 +2052,19 @@ int setup_smem_attr(int device)
 }
 
 // project/setup/count -> alloc -> fill for up to maxViews views
-int run_prep(crb_filler *f, Frame &F, cudaStream_t st)
+int run_prep(crb_filler *f, Frame &F, cudaStream_t st, int slot = 0)
 {
     int rc;
+    // Triangles that span many tiles get a kernel of their own (k_fill_wide) -- but only where there are any: the launch is
+    // issued when the previous frame at this position of the batch posted some (k_raster reports their number with the
+    // busy-tile statistics) or has not reported yet; otherwise k_fill scatters the odd one itself, as it does when the list is full.
+    bool wide_kernel = false;
+    if (f->hstats && f->wide_kernel) {
+        const unsigned long long hs = *reinterpret_cast<volatile unsigned long long *>(f->hstats + 2 * (slot & 7));
+        const unsigned long long hw = *reinterpret_cast<volatile unsigned long long *>(f->hstats + 2 * (slot & 7) + 1) >> 32;
+        wide_kernel = hs == 0ull || hw != 0ull;
+    }
+    F.wideCap = wide_kernel && !(F.flags & CRB_PATH_ATOMIC) ? (unsigned)(f->wideCap > 0xFFFFFFF0ll ? 0xFFFFFFF0ll : f->wideCap) : 0u;
     unsigned gT = (unsigned)((F.T + NT - 1) / NT);
     // band-sharded single view: list the chunks that can reach the band first, then walk only those (persistent grids)
     const bool banded = F.row0 > 0 || F.row1 < F.H;
@@ -2024,6 +2100,10 @@ int run_prep(crb_filler *f, Frame &F, cudaStream_t st)
     if (F.T > 0) {
         k_fill<<<dim3(gT * (NT / FT), F.nViews), FT, 0, st>>>(F);
         if ((rc = launch_check(f, "k_fill"))) return rc;
+        if (F.wideCap) {
+            k_fill_wide<<<(unsigned)f->sm_count * 6, FWT, 0, st>>>(F);
+            if ((rc = launch_check(f, "k_fill_wide"))) return rc;
+        }
     }
     return CRB_OK;
 }
@@ -2050,7 +2130,7 @@ int run_raster(crb_filler *f, Frame &F, cudaStream_t st, int slot)
     if (f->raster_ctas > 0) { gL = f->raster_ctas; gH = f->raster_ctas / 8 + 1; }
     else if (f->hstats && f->raster_ctas == 0) {
         const unsigned long long hs = *reinterpret_cast<volatile unsigned long long *>(f->hstats + 2 * slot);
-        const unsigned long long hh = *reinterpret_cast<volatile unsigned long long *>(f->hstats + 2 * slot + 1);
+        const unsigned long long hh = *reinterpret_cast<volatile unsigned long long *>(f->hstats + 2 * slot + 1) & 0xFFFFFFFFull;
         const double tiles = (double)(hs >> 32), light = (double)(hs & 0xFFFFFFFFull), heavy = (double)hh;
         if (tiles > 0) {
             gL = (long long)(light / tiles * 1.125 * (double)nAllTiles / (double)f->tiles_per_cta) + 56;
@@ -2078,7 +2158,7 @@ int run_raster(crb_filler *f, Frame &F, cudaStream_t st, int slot)
 
 int run_tiled(crb_filler *f, Frame &F, cudaStream_t st, int slot = 0)
 {
-    int rc = run_prep(f, F, st);
+    int rc = run_prep(f, F, st, slot);
     return rc ? rc : run_raster(f, F, st, slot);
 }
 
@@ -2135,6 +2215,8 @@ int bind_ws_pointers(crb_filler *f, void *ws, size_t bytes, long long T, int vie
     f->count = (unsigned *)(b + L.count); f->offset = (unsigned *)(b + L.offset); f->cursor = (unsigned *)(b + L.cursor);
     f->busy = (uint4 *)(b + L.busy); f->busyH = (uint4 *)(b + L.busyH); f->empty = (unsigned *)(b + L.empty);
     f->ls = (float4 *)(b + L.ls);
+    f->wide = (uint4 *)(b + L.wide);
+    f->wideCap = wide_capacity(T, views);
     f->total = (unsigned long long *)(b + L.total);
     f->stage_v = (float *)(b + L.sv); f->stage_c = (float *)(b + L.sc); f->stage_n = (float *)(b + L.sn);
     f->set_bytes = L.set_bytes;
@@ -2326,6 +2408,7 @@ int crb_create(int h, int w, float fov, float z_near, float z_far, int device, c
         f->split_heavy = 1;
         f->band_prepass = 1;
         f->chunk_pipeline = 1;
+        f->wide_kernel = 1;
         {
             Shell sh;
             int src = shell_acquire(device, &sh);
@@ -2760,7 +2843,7 @@ int crb_render_views(crb_filler *f, const float *v, const float *c, const float 
             continue;
         }
         if (f->set_used[set]) CU(cudaStreamWaitEvent(f->s_prep, f->ev_raster[set], 0));   // the set's previous frame has been rasterized
-        if ((rc = run_prep(f, F, f->s_prep))) return rc;
+        if ((rc = run_prep(f, F, f->s_prep, i))) return rc;
         CU(cudaEventRecord(f->ev_fill[set], f->s_prep));
         CU(cudaStreamWaitEvent(f->s_raster, f->ev_fill[set], 0));
         if ((rc = run_raster(f, F, f->s_raster, i))) return rc;
@@ -2933,6 +3016,7 @@ int crb_set_option(crb_filler *f, int option, int value)
     case CRB_OPT_TMA_ROWS: f->out_tma = (value == 2) ? 2 : (value ? 1 : 0); return CRB_OK;
     case CRB_OPT_RASTER_CTAS: f->raster_ctas = value > 0 ? value : 0; return CRB_OK;
     case CRB_OPT_SPLIT_HEAVY: f->split_heavy = value ? 1 : 0; return CRB_OK;
+    case CRB_OPT_WIDE_KERNEL: f->wide_kernel = value ? 1 : 0; return CRB_OK;
     case CRB_OPT_BAND_PREPASS: f->band_prepass = value ? 1 : 0; return CRB_OK;
     default: return fail(CRB_ERR_INVALID, "unknown option %d", option);
     }

@@ -163,6 +163,9 @@ int crb_render_host(crb_filler *f, const float *v, const float *c, const float *
                                     0 (default): sized from the busy-tile count the previous launch reported */
 #define CRB_OPT_SPLIT_HEAVY 6    /* single-view launches cut tiles with many triangles into four row bands rasterized by
                                     different CTAs (default 1) */
+#define CRB_OPT_WIDE_KERNEL 7    /* triangles that span more than 12 tiles are listed by k_fill and scattered by a kernel of their own
+                                    (k_fill_wide, a warp per triangle; launched only while frames contain such triangles); 0: k_fill
+                                    scatters them itself (default 1) */
 int crb_set_option(crb_filler *f, int option, int value);
 
 /* Orders `stream` behind rasterizer work left in flight by CRB_DEFER_JOIN (no host synchronisation). */

@@ -843,9 +843,11 @@ def test_degenerate_image_sizes(size, Filler, O):
         assert_same(buffers(g), buffers(o), f"{h}x{w} seed {seed}")
 
 
-def test_screen_filling_triangles_and_one_crowded_tile(Filler, O):
-    """Two extremes of the binning: triangles that cover every tile of a 1536x1024 frame (thousands of tiles per triangle),
-    and 30 000 small triangles inside a single tile (one list far longer than a staging batch, heavy-tile bands)."""
+@pytest.mark.parametrize("wide_kernel", [1, 0])
+def test_screen_filling_triangles_and_one_crowded_tile(wide_kernel, Filler, O):
+    """Two extremes of the binning: triangles that cover every tile of a 1536x1024 frame (thousands of tiles per triangle;
+    scattered by k_fill_wide, or -- option off, and in the second frame of the first case's filler if that frame had none -- by
+    k_fill itself), and 30 000 small triangles inside a single tile (one list far longer than a staging batch, heavy-tile bands)."""
     rng = np.random.default_rng(5)
     big = np.array([[[-30, -30, 2.0], [30, -30, 2.0], [0, 40, 2.0]],
                     [[-25, 25, 1.5], [0, -35, 1.5], [25, 25, 1.5]],
@@ -859,12 +861,23 @@ def test_screen_filling_triangles_and_one_crowded_tile(Filler, O):
     cs = (rng.random((T, 3, 3)) * 255).astype(np.float32)
     m = TriModel(np.concatenate([big, small]), np.concatenate([cb, cs]), np.concatenate([nb, ns]))
     h, w = 1024, 1536
+    from cython3dmodelrenderer_b200 import _lib
     g, o = Filler(h, w, fov=45.0), O.OracleFiller(h, w, fov=45.0)
+    g.set_option(_lib.CRB_OPT_WIDE_KERNEL, wide_kernel)
     g.clear()
     g.render_model(m)
     o.render_model(m)
     assert int((o.get_z_buffer() < 1e5).sum()) > h * w // 2
     assert_same(buffers(g), buffers(o), "big + crowded")
+    # a frame without wide triangles, then the wide ones again: the launch decision follows the previous frame's report, the
+    # result must not
+    ms = TriModel(small, cs, ns)
+    for model in (ms, m):
+        g.clear()
+        g.render_model(model)
+        o = O.OracleFiller(h, w, fov=45.0)
+        o.render_model(model)
+        assert_same(buffers(g), buffers(o), "after a frame without wide triangles")
 
 
 def test_render_host_overflow_is_never_silent(O, trex):

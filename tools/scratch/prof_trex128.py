@@ -17,6 +17,8 @@ if wl == "trex":
 else:
     if wl == "sphere":
         m = synthetic.uv_sphere(3200, 1564); res = 8192
+    elif wl == "basketball":
+        m = load_indexed("basketball"); res = 2048
     else:
         m = load_indexed("bunny"); res = 4096
     dv, dc, dn = (torch.from_numpy(a).cuda() for a in (m._vertices_by_triangles, m._colors_by_triangles, m._normals_by_triangles))
