@@ -497,12 +497,15 @@ def run_gpu_arm(args):
                         "lengthens each k_raster launch; frac_kernel_alone is k_raster with that overlap switched off",
                 "frac_kernel_alone": (alg_bytes_frame * views_per_launch / (a_ms / max(a_launches, 1) / 1000.0) / 1e9 / peak) if a_ms > 0 else None,
                 "avg_launch_ms_alone": a_ms / max(a_launches, 1)}
-    prof = os.path.join(ROOT, "profiles", "r01_k_raster_traffic.json")   # from the ncu --set full capture of the same launch
-    if os.path.exists(prof):
-        try:
-            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
-        except Exception:
-            pass
+    for name in ("r02_k_raster_traffic.json", "r01_k_raster_traffic.json"):    # from the ncu --set full capture of the same launch
+        prof = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(prof):
+            try:
+                roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+                roofline["traffic_source"] = "profiles/" + name
+                break
+            except Exception:
+                pass
 
     # ---- e2e: host buffers through the C ABI, H2D + render + D2H of all three buffers per frame -------------------
     e2e_frames = args.e2e_frames

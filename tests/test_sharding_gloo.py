@@ -161,3 +161,35 @@ def test_sharded_results_equal_unsharded(world, tmp_path):
     for r in range(1, world):
         rr = np.load(tmp_path / f"r{r}.npz")
         assert bits_equal(rr["z_all"], r0["z_all"]) and bits_equal(rr["z_band"], r0["z_full"])
+
+
+def test_row_exchange_plan_addresses_match_the_kernel_formula():
+    """sharding.RowExchange.plan / PeerImage.plan hand crb_set_u8_exchange one base address per row band; k_raster stores image
+    row r (after the flip) of the call's view k at base[d] + ((k * hb + r - d * hb) * w + x) * 3 with d = r // hb
+    (csrc/crender_b200.cu u8_pixel).  Emulated here on a flat byte array for every (source rank, view, row): each byte of every
+    receive buffer is written exactly once, at the [source][view][row][x][c] position `tensor()` exposes.  No GPU needed."""
+    import numpy as np
+    from cython3dmodelrenderer_b200 import sharding
+    world, V, h, w = 4, 3, 16, 5
+    hb = h // world
+    view_bytes = hb * w * 3
+    bufs = [np.zeros(world * V * view_bytes, np.int64) for _ in range(world)]      # receive buffer of rank d, as write counters
+    for s in range(world):
+        xch = sharding.RowExchange.__new__(sharding.RowExchange)           # the arithmetic only: no allocation, no process group
+        xch.rank, xch.V, xch.view_bytes, xch.hb = s, V, view_bytes, hb
+        xch.base = [d * 10 ** 9 for d in range(world)]                     # fake device addresses, one per destination rank
+        for first in (0, 2):                                               # two calls: views [0, 2) and [2, 3)
+            rows_per_band, bases = xch.plan(first)
+            assert rows_per_band == hb
+            for k in range(V - first if first else 2):
+                for r in range(h):
+                    d = r // hb
+                    off = bases[d] + ((k * hb + (r - d * hb)) * w) * 3 - d * 10 ** 9
+                    bufs[d][off:off + w * 3] += 1
+                    # the position tensor() gives this row: [source s][view first + k][row r - d * hb]
+                    assert off == ((s * V + first + k) * hb + (r - d * hb)) * w * 3
+    assert all((b == 1).all() for b in bufs)
+    img = sharding.PeerImage.__new__(sharding.PeerImage)
+    img.base, img.h, img.w = 4096, 64, 8
+    rows, bases = img.plan((32, 48))                                        # unflipped rows [32, 48) are image rows [16, 32) after the flip
+    assert rows == 16 and bases == [4096 + 16 * 8 * 3]
