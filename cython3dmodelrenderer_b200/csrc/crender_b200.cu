@@ -2056,13 +2056,13 @@ int run_prep(crb_filler *f, Frame &F, cudaStream_t st, int slot = 0)
 {
     int rc;
     // Triangles that span many tiles get a kernel of their own (k_fill_wide) -- but only where there are any: the launch is
-    // issued when the previous frame at this position of the batch posted some (k_raster reports their number with the
-    // busy-tile statistics) or has not reported yet; otherwise k_fill scatters the odd one itself, as it does when the list is full.
+    // issued when the previous frame at this position of the batch posted two dozen or more per view (k_raster reports their
+    // number with the busy-tile statistics) or has not reported yet; otherwise k_fill scatters the odd one itself, as it does when the list is full.
     bool wide_kernel = false;
     if (f->hstats && f->wide_kernel) {
         const unsigned long long hs = *reinterpret_cast<volatile unsigned long long *>(f->hstats + 2 * (slot & 7));
         const unsigned long long hw = *reinterpret_cast<volatile unsigned long long *>(f->hstats + 2 * (slot & 7) + 1) >> 32;
-        wide_kernel = hs == 0ull || hw != 0ull;
+        wide_kernel = hs == 0ull || hw >= 24ull * (unsigned long long)F.nViews;      // (a handful per view is quicker done in place than launched for)
     }
     F.wideCap = wide_kernel && !(F.flags & CRB_PATH_ATOMIC) ? (unsigned)(f->wideCap > 0xFFFFFFF0ll ? 0xFFFFFFF0ll : f->wideCap) : 0u;
     unsigned gT = (unsigned)((F.T + NT - 1) / NT);
