@@ -18,7 +18,7 @@ SOURCES = [os.path.join(CSRC, "crender_b200.cu"), os.path.join(CSRC, "ingest_b20
 CRB_OK = 0
 CRB_ERR_INVALID, CRB_ERR_CUDA, CRB_ERR_ZERODIV, CRB_ERR_STATE, CRB_ERR_OVERFLOW = -1, -2, -3, -4, -5
 CRB_ERR_SYNTAX, CRB_ERR_RANGE = -6, -7
-CRB_CLEAR_FIRST, CRB_PATH_ATOMIC, CRB_GURO, CRB_NO_SYNC, CRB_DL_SPARSE, CRB_DEFER_JOIN, CRB_HOST_PAGEABLE = 1, 2, 4, 8, 16, 32, 64
+CRB_CLEAR_FIRST, CRB_PATH_ATOMIC, CRB_GURO, CRB_NO_SYNC, CRB_DL_SPARSE, CRB_DEFER_JOIN, CRB_HOST_PAGEABLE, CRB_SYNC_UPLOAD = 1, 2, 4, 8, 16, 32, 64, 128
 CRB_OPT_CHUNK_PIPELINE, CRB_OPT_TMA, CRB_OPT_TMA_ROWS, CRB_OPT_BAND_PREPASS, CRB_OPT_RASTER_CTAS, CRB_OPT_SPLIT_HEAVY, CRB_OPT_WIDE_KERNEL = 1, 2, 3, 4, 5, 6, 7
 CRB_BUF_Z, CRB_BUF_COLOR, CRB_BUF_NORMALS, CRB_BUF_ALL = 1, 2, 4, 7
 
@@ -67,6 +67,8 @@ SIGNATURES = {
     "crb_trace_dump": (_i, [ctypes.c_char_p]),
     "crb_status_async": (_i, [_vp, _vp, _vp]),
     "crb_render_image_host": (_i, [_vp, _vp, _vp, _vp, _i64, _u, _fp, _vp, _vp, _vp, _vp]),
+    "crb_host_register": (_i, [_vp, _sz]),
+    "crb_host_unregister": (_i, [_vp]),
     "crb_shared_alloc": (_i, [_i, _sz, ctypes.POINTER(_vp), ctypes.c_char_p]),
     "crb_shared_open": (_i, [_i, ctypes.c_char_p, ctypes.POINTER(_vp)]),
     "crb_shared_close": (_i, [_i, _vp]),

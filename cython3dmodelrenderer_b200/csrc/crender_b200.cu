@@ -2696,8 +2696,10 @@ static int render_host_once(crb_filler *f, const float *v, const float *c, const
     trec.who = f;
     trace_mark(tr, 0, st);
     { int urc = (flags & CRB_HOST_PAGEABLE) ? upload_pageable(f, v, c, n, T, st) : upload_inputs(f, v, c, n, T, st); if (urc) return urc; }
+    const bool sync_upload = (flags & CRB_SYNC_UPLOAD) && (flags & CRB_NO_SYNC) && !(flags & CRB_HOST_PAGEABLE) && T > 0;
+    if (sync_upload) CU(cudaEventRecord(f->ev_start, st));      // (ev_start: free between crb_render_views calls)
     trace_mark(tr, 1, st);
-    int rc = crb_render(f, f->stage_v, f->stage_c, f->stage_n, T, flags & ~CRB_HOST_PAGEABLE, stream);
+    int rc = crb_render(f, f->stage_v, f->stage_c, f->stage_n, T, flags & ~(CRB_HOST_PAGEABLE | CRB_SYNC_UPLOAD), stream);
     if (rc) return rc;
     trace_mark(tr, 2, st);
     const bool sparse = (flags & CRB_DL_SPARSE) && (flags & CRB_CLEAR_FIRST) && !(flags & CRB_PATH_ATOMIC);
@@ -2746,6 +2748,29 @@ static int render_host_once(crb_filler *f, const float *v, const float *c, const
     trace_mark(tr, 3, st);
     if (tr) g_trace.push_back(trec);
     if (!(flags & CRB_NO_SYNC)) CU(cudaStreamSynchronize(st));
+    else if (sync_upload) CU(cudaEventSynchronize(f->ev_start));      // the inputs have left host memory; the frame is still in flight
+    return CRB_OK;
+}
+
+int crb_host_register(void *ptr, size_t bytes)
+{
+    if (!ptr || !bytes) return fail(CRB_ERR_INVALID, "NULL argument or zero size");
+    const cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(CRB_ERR_CUDA, "cudaHostRegister failed: %s", cudaGetErrorString(e));
+    }
+    return CRB_OK;
+}
+
+int crb_host_unregister(void *ptr)
+{
+    if (!ptr) return CRB_OK;
+    const cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(CRB_ERR_CUDA, "cudaHostUnregister failed: %s", cudaGetErrorString(e));
+    }
     return CRB_OK;
 }
 

@@ -39,6 +39,49 @@ def _check_tri_array(a, name):
     return a
 
 
+class _HostArrays:
+    """Host arrays a caller renders again and again (the reference idiom: one Model, a new filler per frame) are page-locked in
+    place on their second sighting (crb_host_register) and then read by the GPU directly, instead of being copied into a pinned
+    staging buffer every frame (0.15 ms of a 0.9 ms T-Rex frame).  Arrays that are new every frame (a model that is rotated
+    between frames) are never registered -- page-locking costs more than one copy.  A weakref finalizer releases the
+    registration with the array."""
+    MAX_SEEN, MIN_BYTES = 256, 64 << 10
+    seen = {}            # (address, nbytes) -> sightings
+    registered = {}      # address -> nbytes
+
+    @classmethod
+    def pinned(cls, L, a):
+        """True if `a` (C-contiguous float32 ndarray) is page-locked by an earlier call; counts the sighting otherwise."""
+        import weakref
+        ptr, nb = a.ctypes.data, a.nbytes
+        if cls.registered.get(ptr) == nb:
+            return True
+        if nb < cls.MIN_BYTES or not a.flags.writeable:
+            return False
+        key = (ptr, nb)
+        n = cls.seen.get(key, 0) + 1
+        if len(cls.seen) > cls.MAX_SEEN:
+            cls.seen.clear()
+        cls.seen[key] = n
+        if n >= 2 and ptr not in cls.registered:
+            if L.crb_host_register(ctypes.c_void_p(ptr), ctypes.c_size_t(nb)) == _lib.CRB_OK:
+                cls.registered[ptr] = nb
+                try:
+                    weakref.finalize(a, cls._release, L, ptr)
+                except TypeError:          # an object that cannot be weakly referenced: do not keep its memory locked
+                    cls._release(L, ptr)
+            cls.seen.pop(key, None)
+        return False      # (this call still copies: the registration serves the next one)
+
+    @classmethod
+    def _release(cls, L, ptr):
+        if cls.registered.pop(ptr, None) is not None:
+            try:
+                L.crb_host_unregister(ctypes.c_void_p(ptr))
+            except Exception:
+                pass
+
+
 class _DevicePointer:
     """CUDA array interface over a raw device address (memory owned elsewhere, e.g. a frame mapped from another rank)."""
 
@@ -67,6 +110,11 @@ class AdvancedPixelBufferFiller:
     """
 
     PAGEABLE_MIN_BYTES = 8 << 20      # host arrays of at least this size go up through the library's threaded staging ring
+    # Download prefetch: the buffers the caller fetched after the previous frame (of this filler, or -- a new filler per frame is
+    # the reference's idiom, run.py:21 -- of the filler before this one) start travelling to their host mirrors as soon as the
+    # frame is rendered, back to back, instead of one by one when get_*_buffer() asks for them.
+    _fetched_by_previous = frozenset()
+    _fetched_by_current = set()
 
     def __init__(self, h, w, fov=90.0, z_near=0.1, z_far=1000.0, n_threads=1, device=None, band=None, out_ptrs=None):
         torch = _require_cuda()
@@ -112,6 +160,10 @@ class AdvancedPixelBufferFiller:
         self._status = None           # pinned status words of the last frame (crb_status_async)
         self._unchecked = None        # the last render, until its status words have been looked at (see _validate)
         self._deferred_keep = None    # inputs of a batch issued with defer_join (see render_views)
+        self._prefetched = set()      # mirrors whose download is already queued behind the last render
+        self._fetched = None          # names fetched since this filler's last render (None: nothing rendered yet)
+        cls = type(self)
+        cls._fetched_by_previous, cls._fetched_by_current = frozenset(cls._fetched_by_current), set()
 
     # ------------------------------------------------------------------------------------------------ plumbing
     def __del__(self):
@@ -186,12 +238,26 @@ class AdvancedPixelBufferFiller:
                 check(rc)
                 break
             self._ensure_workspace(u[4], self._ws_views, int(need.value * 1.25) + 1024)
+            self._prefetched.clear()      # (downloads queued behind the skipped frame fetched nothing new)
             self._queue_render(*u)
             self._torch.cuda.current_stream(self._dev).synchronize()
 
     def _get(self, name, bit):
         t = self._mirror(name)
         self._materialize_clear()
+        type(self)._fetched_by_current.add(name)
+        if self._fetched is not None:
+            self._fetched.add(name)
+        if self._stale[name] and name in self._prefetched:
+            # the download was queued right behind the render: wait for it (and, first read of the frame, for its status words)
+            self._prefetched.discard(name)
+            cap = self._pair_cap
+            if self._unchecked is not None:
+                self._validate()
+            else:
+                self._torch.cuda.current_stream(self._dev).synchronize()
+            if self._pair_cap == cap:
+                self._stale[name] = False
         if self._stale[name]:
             args = {"z": None, "color": None, "normals": None}
             args[name] = t.data_ptr()
@@ -242,6 +308,7 @@ class AdvancedPixelBufferFiller:
         """Fresh-filler state (pyx:65-67).  The reference has no reset (a new filler per frame is its idiom,
         run.py:21); here the clear is fused into the next frame's tile pass instead of a separate memset."""
         self._pending_clear = True
+        self._prefetched.clear()
         self._unchecked = None    # whatever the last frame was, nothing of it remains
         for name in self._stale:
             self._stale[name] = True
@@ -276,6 +343,11 @@ class AdvancedPixelBufferFiller:
             # (CRB_HOST_PAGEABLE) -- a single-threaded NumPy copy into pinned memory was 75 ms of the 10 M-triangle frame
             v, c, n = (np.ascontiguousarray(a) for a in (v, c, n))
             flags |= _lib.CRB_HOST_PAGEABLE
+        elif not on_device and T > 0 and all(a.flags.c_contiguous and a.dtype == np.float32 for a in (v, c, n)) and \
+                all([_HostArrays.pinned(self._L, a) for a in (v, c, n)]):
+            # the caller's own arrays, page-locked in place by an earlier frame: the GPU reads them directly, and the call
+            # returns once they have been read (CRB_SYNC_UPLOAD) -- the caller may change them afterwards, as upstream
+            flags |= _lib.CRB_SYNC_UPLOAD
         elif not on_device:
             if self._stage is None or self._stage.shape[1] < T:
                 self._stage = torch.empty((3, max(T, 1), 3, 3), dtype=torch.float32, pin_memory=True)
@@ -287,8 +359,22 @@ class AdvancedPixelBufferFiller:
             v = c = n = None
         args = (on_device, v, c, n, T, flags)
         self._queue_render(*args)
+        self._prefetched.clear()
+        want = self._fetched if self._fetched is not None else type(self)._fetched_by_previous
+        self._fetched = set()
+        if check_status and self.row0 == 0 and self.row1 == self.h:
+            for name, bit in (("color", _lib.CRB_BUF_COLOR), ("normals", _lib.CRB_BUF_NORMALS), ("z", _lib.CRB_BUF_Z)):
+                if name in want and name not in self._exposed:
+                    dst = {"z": None, "color": None, "normals": None}
+                    dst[name] = self._mirror(name).data_ptr()
+                    check(self._L.crb_download(self._handle, bit, dst["z"], dst["color"], dst["normals"], self._stream()))
+                    self._prefetched.add(name)
         if check_status:
             self._unchecked = args       # (device inputs stay referenced until the frame is known to have been drawn)
+            if flags & (_lib.CRB_HOST_PAGEABLE | _lib.CRB_SYNC_UPLOAD):
+                # the frame was read from the caller's own arrays: should it have to be drawn again (pair list overflow), that
+                # must happen before the caller gets a chance to change them
+                self._validate()
         elif not on_device:
             torch.cuda.current_stream(self._dev).synchronize()     # the pinned staging is reused by the next call
         self._pending_clear = False
@@ -303,7 +389,7 @@ class AdvancedPixelBufferFiller:
         """Queues one frame (upload of the staged host arrays if any, kernels, status words) on the current stream."""
         if on_device:
             check(self._L.crb_render(self._handle, v.data_ptr(), c.data_ptr(), n.data_ptr(), T, flags, self._stream()))
-        elif flags & _lib.CRB_HOST_PAGEABLE:
+        elif flags & (_lib.CRB_HOST_PAGEABLE | _lib.CRB_SYNC_UPLOAD):
             check(self._L.crb_render_host(self._handle, v.ctypes.data, c.ctypes.data, n.ctypes.data, T,
                                           flags | _lib.CRB_NO_SYNC, 0, None, None, None, self._stream()))
         else:
@@ -324,6 +410,7 @@ class AdvancedPixelBufferFiller:
         self._validate()
         self._materialize_clear()
         self._push_exposed()
+        self._prefetched.clear()         # the caller may change the device buffers: what get_*_buffer() returns is read afterwards
         return self._z, self._color, self._normals
 
     def illuminate_guro(self, light_direction):
@@ -334,6 +421,7 @@ class AdvancedPixelBufferFiller:
         arr = (ctypes.c_float * 3)(*[float(x) for x in light_direction])
         check(self._L.crb_guro(self._handle, arr, self._stream()))
         self._stale["color"] = True
+        self._prefetched.discard("color")
 
     def color_u8_flipped(self):
         """run.py:26 `image[::-1].astype('uint8')` computed on device; returns a torch CUDA uint8 tensor."""

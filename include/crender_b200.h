@@ -59,6 +59,9 @@ extern "C" {
                                   threads, chunk by chunk, each chunk's host-to-device copy in flight while the next is being
                                   staged; the arrays have been read completely when the call returns (CRB_NO_SYNC included).
                                   Without the flag the three pointers must be page-locked (they are handed to cudaMemcpyAsync). */
+#define CRB_SYNC_UPLOAD 128u    /* crb_render_host + CRB_NO_SYNC: return once v / c / n have left host memory (the caller may then reuse
+                                  or free them), with the frame itself still in flight.  For page-locked inputs that are not a
+                                  private staging copy -- e.g. a Model's own arrays registered with crb_host_register */
 #define CRB_DL_SPARSE 16u      /* crb_render_host + CRB_CLEAR_FIRST only: sparse read-back.  The caller promises that the host
                                   output arrays still hold what the previous CRB_DL_SPARSE call of this filler left in them
                                   (fresh-filler values -- z 1e6, colour 0, normals 0 -- before the first call, or after
@@ -93,6 +96,13 @@ int crb_shared_alloc(int device, size_t bytes, void **ptr, unsigned char handle[
 int crb_shared_open(int device, const unsigned char handle[CRB_SHARED_HANDLE_BYTES], void **ptr);
 int crb_shared_close(int device, void *ptr);
 int crb_shared_free(int device, void *ptr);
+
+/* Page-locks (cudaHostRegister) / releases an existing host allocation, so that crb_render_host can read it in place instead of
+ * through a staging copy -- for callers that render the same host arrays again and again (a reference Model's
+ * _vertices_by_triangles / _colors_by_triangles / _normals_by_triangles are ordinary NumPy memory).  crb_host_register fails
+ * with CRB_ERR_CUDA for memory that cannot be registered (already registered, read-only mappings, ...): fall back to copying. */
+int crb_host_register(void *ptr, size_t bytes);
+int crb_host_unregister(void *ptr);
 
 /* ---- constructor pieces: pyx:39-77 (__cinit__) and pyx:83-90 (_init_projection_matrix) ------------------- */
 

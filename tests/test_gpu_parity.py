@@ -399,6 +399,40 @@ def test_pageable_host_arrays_through_the_staging_ring(Filler, O, trex, monkeypa
     assert_same(buffers(f), buffers(o), "pageable host arrays")
 
 
+def test_recurring_host_arrays_are_read_in_place(Filler, O, trex):
+    """The reference idiom renders the same Model with a new filler per frame: from the third frame on its arrays are page-locked
+    in place and read by the GPU directly (crb_host_register, CRB_SYNC_UPLOAD).  Results must not depend on which path ran, and a
+    change the caller makes right after render_model returns must show in the next frame, not in this one."""
+    from cython3dmodelrenderer_b200 import pixel_buffer_filler as P
+    v, c, n = (a.copy() for a in (trex._vertices_by_triangles, trex._colors_by_triangles, trex._normals_by_triangles))
+    m = TriModel(v, c, n)
+    o = O.OracleFiller(200, 256, fov=45.0)
+    o.render_model(m)
+    want = buffers(o)
+    for frame in range(4):
+        f = Filler(200, 256, fov=45.0)
+        f.render_model(m)
+        if frame == 3:
+            assert P._HostArrays.registered.get(v.ctypes.data) == v.nbytes        # frames 2.. read the arrays in place
+            keep = c.copy()
+            c[:] = 0.0                                                             # after the call returned: not in this frame
+            assert_same(buffers(f), want, "frame 3, colours zeroed after render_model")
+            c[:] = keep
+        else:
+            assert_same(buffers(f), want, f"frame {frame}")
+    c[:] = c * np.float32(0.5)                                                     # an in-place change is seen by the next frame
+    o2 = O.OracleFiller(200, 256, fov=45.0)
+    o2.render_model(m)
+    f = Filler(200, 256, fov=45.0)
+    f.render_model(m)
+    assert_same(buffers(f), buffers(o2), "after an in-place change")
+    ptr = v.ctypes.data
+    del m, v, f
+    import gc
+    gc.collect()
+    assert ptr not in P._HostArrays.registered                                     # released with the array
+
+
 def test_full_size_sphere_properties(Filler):
     """Config C4 at full size (10 003 200 triangles, 8192^2): too big for a CPU compare in seconds, so size-independent
     properties: band-sharded == unsharded (exact), tiled path == atomic path (exact), re-rendering is idempotent, the
