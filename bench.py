@@ -819,9 +819,31 @@ def measure_workload(args, workload, world, rank, local, dev, cpu_threads=None, 
     if banded and world > 1 and args.bands == "balanced":
         # cut the frame where the estimated cost (triangles per 32-row strip) balances, not into equal row counts: the
         # sphere's poles hold far more triangles per row than its equator.  Rank 0 decides, everybody follows.
-        box = [sharding.balanced_bands(sharding.tile_row_costs(dv, dn, res, res, FOV), world, res) if rank == 0 else None]
+        costs = [float(x) for x in sharding.tile_row_costs(dv, dn, res, res, FOV)] if rank == 0 else None
+        box = [sharding.balanced_bands(costs, world, res) if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         bands = box[0]
+        # ... and the estimate is corrected by what the bands really cost: three rounds of (render a few frames, compare the
+        # ranks' times, cut again) -- load balancing before the timed region, like the choice of the bands itself
+        for _ in range(3):
+            fcal = AdvancedPixelBufferFiller(res, res, fov=FOV, device=local, band=bands[rank])
+            for _w in range(2):
+                fcal.clear(); fcal.render_arrays(dv, dc, dn)
+            torch.cuda.synchronize(); dist.barrier()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _w in range(4):
+                fcal.clear(); fcal.render_arrays(dv, dc, dn, check_status=False)
+            c1.record(); torch.cuda.synchronize()
+            mine = torch.tensor([c0.elapsed_time(c1) / 4], dtype=torch.float64, device=dev)
+            every = [torch.zeros_like(mine) for _r in range(world)]
+            dist.all_gather(every, mine)
+            del fcal
+            if rank == 0:
+                new_bands, costs = sharding.rebalance_bands(costs, bands, [float(t.item()) for t in every], world, res)
+                box = [new_bands]
+            dist.broadcast_object_list(box, src=0)
+            bands = box[0]
         band = bands[rank]
     gather_mode = args.gather if banded and (world > 1 or args.gather == "u8_local") else "none"
     if gather_mode == "auto":

@@ -96,6 +96,22 @@ def balanced_bands(costs, world, h, align=TILE_ROWS):
     return [(min(a * align, h), min(b * align, h)) for a, b in zip(starts, ends)]
 
 
+def rebalance_bands(costs, bands, measured, world, h, align=TILE_ROWS):
+    """One step of measured load balancing: the estimated cost of every strip inside band b is scaled by measured[b] /
+    estimated(b) (what the band's frame really took against what the strips were thought to cost), and the frame is cut again.
+    Returns (new bands, scaled strip costs -- the input of the next step).  Two or three steps settle the bands where the
+    heuristic of tile_row_costs is off (its coefficients were fitted to one build of the kernels)."""
+    costs = [float(c) for c in costs]
+    scaled = list(costs)
+    for (r0, r1), t in zip(bands, measured):
+        s0, s1 = r0 // align, (r1 + align - 1) // align
+        est = sum(costs[s0:s1])
+        if est > 0 and t > 0 and s1 > s0:
+            for i in range(s0, s1):
+                scaled[i] = costs[i] * float(t) / est
+    return balanced_bands(scaled, world, h, align), scaled
+
+
 def _world():
     return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 

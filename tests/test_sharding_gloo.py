@@ -193,3 +193,23 @@ def test_row_exchange_plan_addresses_match_the_kernel_formula():
     img.base, img.h, img.w = 4096, 64, 8
     rows, bases = img.plan((32, 48))                                        # unflipped rows [32, 48) are image rows [16, 32) after the flip
     assert rows == 16 and bases == [4096 + 16 * 8 * 3]
+
+
+def test_rebalance_bands_moves_rows_away_from_the_slow_rank():
+    """sharding.rebalance_bands: a band that took longer than its estimate gets fewer strips in the next cut; bands stay a
+    partition of the frame on strip boundaries, and equal measurements leave a balanced cut alone."""
+    from cython3dmodelrenderer_b200 import sharding
+    h, world = 32 * 16, 4
+    costs = [1.0] * 16
+    bands = sharding.balanced_bands(costs, world, h)
+    assert bands == [(0, 128), (128, 256), (256, 384), (384, 512)]
+    same, _ = sharding.rebalance_bands(costs, bands, [1.0, 1.0, 1.0, 1.0], world, h)
+    assert same == bands
+    new, scaled = sharding.rebalance_bands(costs, bands, [1.0, 3.0, 1.0, 1.0], world, h)
+    assert new[0][0] == 0 and new[-1][1] == h and all(a[1] == b[0] for a, b in zip(new, new[1:]))
+    assert all(r0 % 32 == 0 and r1 % 32 == 0 for r0, r1 in new)
+    rows = [r1 - r0 for r0, r1 in new]
+    assert scaled[4:8] == [0.75] * 4 and scaled[:4] == [0.25] * 4          # cost x measured / estimated, band by band
+    # the slow band's old rows [128, 256) are now shared by more ranks: no new band contains all of them
+    assert not any(r0 <= 128 and r1 >= 256 for r0, r1 in new)
+    assert sum(rows) == h
