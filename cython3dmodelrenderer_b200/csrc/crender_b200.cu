@@ -1354,9 +1354,19 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
 #ifdef CRB_NO_OUT_STAGE
     const bool vec = false;
 #else
-    const bool vec = clear && !tma && (tw == TW) && ((F.W & 3) == 0) && !(F.flags & FLAG_OUT_DIRECT);   // ... or as 16-byte vector stores
+    const bool vec = clear && !tma && (tw == TW) && ((F.W & 3) == 0) && !(F.flags & FLAG_OUT_DIRECT) &&
+                     (F.color || F.normals);                                                            // ... or as 16-byte vector stores
 #endif
     const bool stage = tma || vec;
+    // The uint8 image of a fresh frame whose float32 rows need no staging (image-only frames: HostImagePipeline, the row exchange,
+    // PeerImage) is staged instead: the shading loop writes its three bytes per pixel into shared memory and the tile's rows leave
+    // as 16-byte vector stores, six per 96-byte row = three whole sectors -- what a row exchange sends over NVLink is sectors, and
+    // three byte stores per pixel touch each of them partially (N = 8: 0.77 of the rendering rate delivered).
+#ifdef CRB_NO_OUT_STAGE
+    const bool u8stage = false;
+#else
+    const bool u8stage = !stage && clear && F.color_u8 && tw == TW && !(F.W & 15) && (!F.u8xN || F.u8xRows % TH == 0);
+#endif
     const float bg = background_color(F);
     const long long tilebase = slab + (long long)yl0 * F.W + x0;          // first pixel of the tile in its slab
     const unsigned rowStep = (unsigned)(NT / TW) * (unsigned)F.W;
@@ -1391,12 +1401,26 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
             if (F.color) { F.color[pix * 3] = c[0]; F.color[pix * 3 + 1] = c[1]; F.color[pix * 3 + 2] = c[2]; }
             if (F.normals) { F.normals[pix * 3] = nn[0]; F.normals[pix * 3 + 1] = nn[1]; F.normals[pix * 3 + 2] = nn[2]; }
         }
-        if (F.color_u8 && write) {
+        if (F.color_u8 && write) {       // (one test on the float32-only path, as before the staging)
+#ifndef CRB_NO_OUT_STAGE
+            unsigned char *o = u8stage ? reinterpret_cast<unsigned char *>(S.u.out.col) + p * 3 : u8_pixel(F, view, yl0 + yy, x0 + xx);
+#else
             unsigned char *o = u8_pixel(F, view, yl0 + yy, x0 + xx);
+#endif
             o[0] = to_u8(c[0]); o[1] = to_u8(c[1]); o[2] = to_u8(c[2]);
         }
     }
     PH(7);
+#ifndef CRB_NO_OUT_STAGE
+    if (u8stage) {
+        __syncthreads();
+        const unsigned char *sb = reinterpret_cast<const unsigned char *>(S.u.out.col);
+        for (int i = tid; i < (th - rowLo) * 6; i += NT) {
+            const int r = rowLo + i / 6, q = i - (i / 6) * 6;
+            reinterpret_cast<uint4 *>(u8_pixel(F, view, yl0 + r, x0))[q] = reinterpret_cast<const uint4 *>(sb + r * (TW * 3))[q];
+        }
+    }
+#endif
     if (DBG(F, FLAG_DBG_NOOUT)) return;
 #ifndef CRB_NO_OUT_STAGE
     if (tma) {
