@@ -1004,7 +1004,12 @@ def measure_workload(args, workload, world, rank, local, dev, cpu_threads=None, 
                        "l2": "frame buffers %.2f GB per GPU vs 126 MB L2" % (28 * rows * res / 1e9)},
             "gtri_per_s": fps * T / 1e9, "clocks": clocks.summary(), "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "k_raster", "achieved": alg / (k_avg / 1000.0) / 1e9 if k_avg else None,
-                         "peak": peak, "unit": "GB/s", "frac": (alg / (k_avg / 1000.0) / 1e9 / peak) if k_avg else None,
+                         "peak": peak, "unit": "GB/s",
+                         # (a band-sharded rank rasterizes only the triangles its pre-pass listed: 108 T bytes per rank would
+                         # overstate what rank 0's small pole band reads, so the fraction is given for whole frames only)
+                         "frac": (alg / (k_avg / 1000.0) / 1e9 / peak) if (k_avg and not (banded and world > 1)) else None,
+                         "band_note": ("rank 0's k_raster on its own band; `achieved` counts 108 B for every triangle of the frame "
+                                       "although the band pre-pass hands k_raster only the chunks that reach the band") if (banded and world > 1) else None,
                          "traffic": None, "peak_source": peak_src, "avg_launch_ms": k_avg,
                          "algorithmic_bytes_per_launch": alg, "share_of_step": k_ms / ms_own if ms_own else None},
             "cpu_baseline": cpu, "e2e": e2e, "gather": gather, "checks": {"covered_pixels": int(cov.item())},
