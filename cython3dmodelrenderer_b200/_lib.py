@@ -20,6 +20,7 @@ CRB_ERR_INVALID, CRB_ERR_CUDA, CRB_ERR_ZERODIV, CRB_ERR_STATE, CRB_ERR_OVERFLOW 
 CRB_ERR_SYNTAX, CRB_ERR_RANGE = -6, -7
 CRB_CLEAR_FIRST, CRB_PATH_ATOMIC, CRB_GURO, CRB_NO_SYNC, CRB_DL_SPARSE, CRB_DEFER_JOIN, CRB_HOST_PAGEABLE, CRB_SYNC_UPLOAD = 1, 2, 4, 8, 16, 32, 64, 128
 CRB_OPT_CHUNK_PIPELINE, CRB_OPT_TMA, CRB_OPT_TMA_ROWS, CRB_OPT_BAND_PREPASS, CRB_OPT_RASTER_CTAS, CRB_OPT_SPLIT_HEAVY, CRB_OPT_WIDE_KERNEL = 1, 2, 3, 4, 5, 6, 7
+CRB_OPT_RASTER_SHAPE = 8
 CRB_BUF_Z, CRB_BUF_COLOR, CRB_BUF_NORMALS, CRB_BUF_ALL = 1, 2, 4, 7
 
 _vp, _i, _i64, _u, _f, _sz = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint, ctypes.c_float,

@@ -42,7 +42,12 @@ namespace {
 
 constexpr int TW = 32;          // tile width in pixels  (one 128-byte line of z, three of colour / normals)
 constexpr int TH = 32;          // tile height in pixels
-constexpr int NT = 256;         // threads per CTA in every kernel
+constexpr int NT = 256;         // threads per CTA in every kernel but the tile rasterizer
+// The tile rasterizer is instantiated in two CTA shapes (RasterShape / RasterLarge / RasterSmall, further down); the macros below
+// are the large shape's parameters, the CRB_SMALL_* ones the small shape's.
+#ifndef CRB_RT
+#define CRB_RT 256              // threads per CTA of k_raster (a multiple of 32)
+#endif
 #ifdef CRB_ABLATION
 #define DBG(F, bit) (((F).flags & (bit)) != 0u)
 #else
@@ -53,9 +58,8 @@ constexpr unsigned FLAG_DBG_NOCLEAR = 0x10000u, FLAG_DBG_NOSHADE = 0x20000u, FLA
 constexpr unsigned FLAG_OUT_DIRECT = 0x200u;   // experiment: shaded pixels stored straight from registers (12-byte strided stores)
 constexpr unsigned FLAG_OUT_TMA = 0x100u;   // internal Frame.flags bit: shaded colour / normal rows leave through TMA boxes
 #ifndef CRB_CH
-#define CRB_CH 128
+#define CRB_CH 128              // triangles staged in shared memory per pass of the tile rasterizer
 #endif
-constexpr int CH = CRB_CH;         // triangles staged in shared memory per pass of the tile rasterizer
 constexpr unsigned SPLIT_N = 48;  // single-view launches: tiles with more triangles than this are rasterized by SPLIT_BANDS CTAs, 8 rows each
 constexpr int SPLIT_BANDS = 4;
 #ifndef CRB_CLEAR_EVERY
@@ -65,9 +69,8 @@ constexpr unsigned CE = CRB_CLEAR_EVERY;  // every CE-th CTA of k_raster is a cl
 constexpr int WIDE_TILES = 12;    // a triangle whose pixel rectangle touches more tiles than this is binned by its whole warp
 constexpr unsigned HEAVY_N = 64;  // tiles with more triangles than this are rasterized first (longest first: shorter kernel tail)
 #ifndef CRB_FQ
-#define CRB_FQ 256
+#define CRB_FQ 256              // fragments a warp compacts per round (8 per row)
 #endif
-constexpr int FQ = CRB_FQ;          // fragments a warp compacts per round (8 per row)
 #ifndef CRB_KEY_STRIDE
 #define CRB_KEY_STRIDE 35
 #endif
@@ -81,13 +84,13 @@ constexpr float REJ_EPS = 1e-6f;      // fast-reject guard band on barycentric n
 constexpr float L3_MIN = 1e-30f, L3_MAX = 1e30f;
 constexpr int MAX_DIM = 65535;  // bbox corners are packed in 16 bits
 #ifndef CRB_CLEAR_ROWS
-#define CRB_CLEAR_ROWS 32
+#define CRB_CLEAR_ROWS 32       // rows per TMA box of the fused clear (TH: one box per array and tile)
 #endif
-constexpr int CLEAR_ROWS = CRB_CLEAR_ROWS;   // rows per TMA box of the fused clear (TH: one box per array and tile)
 constexpr int BOX_ROWS = 8;       // rows per TMA box (clear pattern and shaded rows go out 8 tile rows at a time)
+constexpr int HSTAT_WORDS = 4;    // 64-bit words of busy-tile statistics k_raster posts per position in a batch of launches (8 positions)
+constexpr size_t HSTAT_BYTES = 8 * HSTAT_WORDS * 8;
 constexpr int PROF_MAX = 8192;  // k_raster launches that can be timed between two crb_profile_read calls
 
-static_assert(CH <= NT && CH <= 256, "one staged triangle per thread, 8-bit owner index");
 static_assert(TW == 32, "a tile row is one warp wide");
 
 // Per-(view,triangle) records written by k_setup.
@@ -736,6 +739,7 @@ __global__ void __launch_bounds__(NT) k_band_chunks(const Frame F)
 // K2b: list space for every tile.  Block-wide exclusive scan (warp shuffles) of the tile counts, one bump
 // allocation per CTA.  List order in memory is irrelevant: the packed key makes the result order-independent.
 // ------------------------------------------------------------------------------------------------------------
+template <int NTH = NT>
 __device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned *warp_sums, unsigned &block_total)
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -749,7 +753,7 @@ __device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned *w
     __syncthreads();
     unsigned base = 0, tot = 0;
 #pragma unroll
-    for (int w = 0; w < NT / 32; ++w) {
+    for (int w = 0; w < NTH / 32; ++w) {
         const unsigned s = warp_sums[w];
         if (w < wid) base += s;
         tot += s;
@@ -1004,7 +1008,20 @@ __device__ unsigned long long g_phase[16];
 #define PH(k) do { } while (0)
 #endif
 
+// Shape of the tile rasterizer: threads per CTA, triangles staged per pass, fragment queue per warp, rows per clear box, resident CTAs
+// per SM the launch bounds ask for, and whether shaded colour / normal rows are staged in shared memory (TMA boxes / vector stores)
+// or stored straight from registers.  Two shapes are instantiated, see RasterLarge / RasterSmall below.
+template <int RT_, int CH_, int FQ_, int CLEAR_ROWS_, int MIN_CTAS_, bool OUT_STAGE_>
+struct RasterShape {
+    static constexpr int RT = RT_, CH = CH_, FQ = FQ_, CLEAR_ROWS = CLEAR_ROWS_, MIN_CTAS = MIN_CTAS_;
+    static constexpr bool OUT_STAGE = OUT_STAGE_;
+    static_assert(CH_ <= RT_ && CH_ <= 256 && RT_ % 32 == 0 && RT_ <= NT, "one staged triangle per thread, 8-bit owner index");
+    static_assert(FQ_ % 32 == 0 && FQ_ >= 64 && TH % CLEAR_ROWS_ == 0, "queue rounds of FQ/32 - 1 pixels per row; whole clear boxes per tile");
+};
+
+template <class C>
 struct __align__(128) TileSmem {
+    static constexpr int RT = C::RT, CH = C::CH, FQ = C::FQ, CLEAR_ROWS = C::CLEAR_ROWS;
     // TMA source first (128-byte aligned): shaded colour / normal rows of the tile
     union {
         struct {
@@ -1017,15 +1034,13 @@ struct __align__(128) TileSmem {
             float4 td[CH];  // d1 d2 d3 (denominators, > 0 where sane) | PK_* flags and the tile-relative pixel rectangle
             float4 tr[CH];  // 1/d1 1/d2 1/d3 (correctly rounded) | first row work item of the triangle
             unsigned char owner[CH * TH];  // row work item -> staged triangle
-            float4 slot[NT / 32][2][32];   // per warp, per trip parity: the trip's 32 rows (A1 A2 A3 | staged triangle, tile row)
-            unsigned short fq[NT / 32][FQ];  // per warp: queue of fragments (row lane | x << 5 | trip parity << 10)
+            float4 slot[RT / 32][2][32];   // per warp, per trip parity: the trip's 32 rows (A1 A2 A3 | staged triangle, tile row)
+            unsigned short fq[RT / 32][FQ];  // per warp: queue of fragments (row lane | x << 5 | trip parity << 10)
         } st;
-#ifndef CRB_NO_OUT_STAGE
-        struct {
-            float col[TH * TW * 3];
-            float nrm[TH * TW * 3];
+        struct {                              // (without row staging: only the 3 KB the staged uint8 image of a tile needs)
+            float col[C::OUT_STAGE ? TH * TW * 3 : TH * TW * 3 / 4];
+            float nrm[C::OUT_STAGE ? TH * TW * 3 : 4];
         } out;
-#endif
         struct {                              // clear CTAs only: the constant pattern their TMA boxes are stored from
             float z[CLEAR_ROWS * TW];         //   Z_INIT
             float c[CLEAR_ROWS * TW * 3];     //   background colour
@@ -1033,7 +1048,7 @@ struct __align__(128) TileSmem {
         } pat;
     } u;
     unsigned long long keys[TH * KEY_STRIDE];
-    unsigned warp_sums[NT / 32];
+    unsigned warp_sums[RT / 32];
 };
 
 // Writes one tile of cleared pixels (fresh-filler values) with plain stores -- the path for images whose rows are not
@@ -1119,19 +1134,23 @@ constexpr unsigned PK_FAST = 16u;    // FL_SPAN and FL_FDIV: div_rn_by() applies
 constexpr int PK_XA = 8, PK_XB = 14, PK_YT = 20;   // tile-relative rectangle: first x (6 bits), end x (6 bits), first row (5 bits)
 
 // Visibility + deferred shading of one busy tile (n triangles staged at list offset off).
-__device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, TileSmem &S_, const bool clear, const int view,
+template <class C>
+__device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, TileSmem<C> &S_, const bool clear, const int view,
                                             const int tx, const int ty, const unsigned n, const unsigned off, const int rowLo, const int rowHi)
 {
+    constexpr int RT = C::RT, CH = C::CH, FQ = C::FQ;      // (shadow the defaults of the same names)
+    constexpr bool OUT_STAGE = C::OUT_STAGE;
+    typedef TileSmem<C> TS;
 #ifndef CRB_NO_OPAQUE_SMEM
     // The address of the CTA's shared memory goes through an empty asm: under the 40-register cap the compiler otherwise re-derives
     // the shared-window base (S2R SR_CgaCtaId + LEA) inside the exact and the shading loops instead of keeping it; an opaque
     // value cannot be rematerialised, and __isShared keeps the accesses LDS / STS / ATOMS.
-    TileSmem *Sp = &S_;
+    TS *Sp = &S_;
     asm volatile("" : "+l"(Sp));
     __builtin_assume(__isShared(Sp));
-    TileSmem &S = *Sp;
+    TS &S = *Sp;
 #else
-    TileSmem &S = S_;
+    TS &S = S_;
 #endif
     const int x0 = tx * TW, yl0 = ty * TH;       // yl0: row inside the band's buffers
     const int y0 = F.row0 + yl0;                  // absolute image row
@@ -1142,7 +1161,7 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
     asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
     const unsigned lane = tid & 31u, wid = tid >> 5;
     PH_DECL
-    for (int i = tid; i < TH * KEY_STRIDE / 2; i += NT) reinterpret_cast<ulonglong2 *>(S.keys)[i] = make_ulonglong2(KEY_EMPTY, KEY_EMPTY);
+    for (int i = tid; i < TH * KEY_STRIDE / 2; i += RT) reinterpret_cast<ulonglong2 *>(S.keys)[i] = make_ulonglong2(KEY_EMPTY, KEY_EMPTY);
 
     // ---- visibility: every (triangle,row) of the tile is one work item -------------------------------------
     for (unsigned base = 0; base < n; base += CH) {
@@ -1184,7 +1203,7 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
             S.u.st.td[tid] = make_float4(c.y, c.z, c.w, __uint_as_float(pk));
         }
         unsigned totalRows;
-        const unsigned start = block_exclusive_scan(rows, S.warp_sums, totalRows);
+        const unsigned start = block_exclusive_scan<RT>(rows, S.warp_sums, totalRows);
         if (tid < m) {
             S.u.st.tr[tid] = make_float4(tr3.x, tr3.y, tr3.z, __uint_as_float(start));
             for (unsigned j = 0; j < rows; ++j) S.u.st.owner[start + j] = (unsigned char)tid;
@@ -1215,9 +1234,9 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
         bool finished = false;
         unsigned short *fq = S.u.st.fq[wid];
         float4 *slotw = &S.u.st.slot[wid][0][0];        // this warp's two slot arrays (trip parity 0 / 1)
-        for (unsigned tb = 0; !finished; tb += NT) {
+        for (unsigned tb = 0; !finished; tb += RT) {
             const unsigned rem = tb < totalRows ? totalRows - tb : 0u;
-            const unsigned share = (rem >= (unsigned)NT || !deal) ? 32u : (rem + NT / 32 - 1u) / (NT / 32);
+            const unsigned share = (rem >= (unsigned)RT || !deal) ? 32u : (rem + RT / 32 - 1u) / (RT / 32);
             if (wid * share >= rem) {                        // no rows left for this warp (warp-uniform) ...
                 if (qn == 0u) break;
                 finished = true;                             // ... but fragments of its last trip: one more turn evaluates them
@@ -1346,33 +1365,21 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
 
     // ---- deferred shading of the winners, staged so that colour / normals leave as whole rows ---------------
     const long long slab = (long long)view * F.slabPixels;
-#ifdef CRB_NO_OUT_STAGE
-    const bool tma = false;
-#else
-    const bool tma = clear && M.use != 0u && (F.flags & FLAG_OUT_TMA);     // colour / normal rows leave through TMA boxes
-#endif
-#ifdef CRB_NO_OUT_STAGE
-    const bool vec = false;
-#else
-    const bool vec = clear && !tma && (tw == TW) && ((F.W & 3) == 0) && !(F.flags & FLAG_OUT_DIRECT) &&
+    const bool tma = OUT_STAGE && clear && M.use != 0u && (F.flags & FLAG_OUT_TMA);     // colour / normal rows leave through TMA boxes
+    const bool vec = OUT_STAGE && clear && !tma && (tw == TW) && ((F.W & 3) == 0) && !(F.flags & FLAG_OUT_DIRECT) &&
                      (F.color || F.normals);                                                            // ... or as 16-byte vector stores
-#endif
     const bool stage = tma || vec;
     // The uint8 image of a fresh frame whose float32 rows need no staging (image-only frames: HostImagePipeline, the row exchange,
     // PeerImage) is staged instead: the shading loop writes its three bytes per pixel into shared memory and the tile's rows leave
     // as 16-byte vector stores, six per 96-byte row = three whole sectors -- what a row exchange sends over NVLink is sectors, and
     // three byte stores per pixel touch each of them partially (N = 8: 0.77 of the rendering rate delivered).
-#ifdef CRB_NO_OUT_STAGE
-    const bool u8stage = false;
-#else
     const bool u8stage = !stage && clear && F.color_u8 && tw == TW && !(F.W & 15) && (!F.u8xN || F.u8xRows % TH == 0);
-#endif
     const float bg = background_color(F);
     const long long tilebase = slab + (long long)yl0 * F.W + x0;          // first pixel of the tile in its slab
-    const unsigned rowStep = (unsigned)(NT / TW) * (unsigned)F.W;
+    const unsigned rowStep = (unsigned)(RT / TW) * (unsigned)F.W;
     long long pix = tilebase + (unsigned)((int)wid * F.W + (int)lane);    // this thread's pixels: column lane, rows wid, wid + 8, ...
     const float4 *recv = F.shrec + (long long)view * F.T * SREC;          // the view's shade records
-    for (int p = tid; p < TH * TW; p += NT, pix += rowStep) {
+    for (int p = tid; p < TH * TW; p += RT, pix += rowStep) {
         const int yy = p / TW, xx = (int)lane;
         if (yy < rowLo || yy >= th || xx >= tw) continue;
         const unsigned long long key = S.keys[yy * KEY_STRIDE + xx];
@@ -1389,56 +1396,48 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
                 }
             }
         }
-#ifndef CRB_NO_OUT_STAGE
-        if (stage) {
+        if (OUT_STAGE && stage) {
             S.u.out.col[p * 3] = c[0]; S.u.out.col[p * 3 + 1] = c[1]; S.u.out.col[p * 3 + 2] = c[2];
             S.u.out.nrm[p * 3] = nn[0]; S.u.out.nrm[p * 3 + 1] = nn[1]; S.u.out.nrm[p * 3 + 2] = nn[2];
             if (F.z && !DBG(F, FLAG_DBG_NOOUT)) F.z[pix] = z;
-        } else
-#endif
-        if (write) {
+        } else if (write) {
             if (F.z) F.z[pix] = z;
             if (F.color) { F.color[pix * 3] = c[0]; F.color[pix * 3 + 1] = c[1]; F.color[pix * 3 + 2] = c[2]; }
             if (F.normals) { F.normals[pix * 3] = nn[0]; F.normals[pix * 3 + 1] = nn[1]; F.normals[pix * 3 + 2] = nn[2]; }
         }
         if (F.color_u8 && write) {       // (one test on the float32-only path, as before the staging)
-#ifndef CRB_NO_OUT_STAGE
             unsigned char *o = u8stage ? reinterpret_cast<unsigned char *>(S.u.out.col) + p * 3 : u8_pixel(F, view, yl0 + yy, x0 + xx);
-#else
-            unsigned char *o = u8_pixel(F, view, yl0 + yy, x0 + xx);
-#endif
             o[0] = to_u8(c[0]); o[1] = to_u8(c[1]); o[2] = to_u8(c[2]);
         }
     }
     PH(7);
-#ifndef CRB_NO_OUT_STAGE
     if (u8stage) {
         __syncthreads();
         const unsigned char *sb = reinterpret_cast<const unsigned char *>(S.u.out.col);
-        for (int i = tid; i < (th - rowLo) * 6; i += NT) {
+        for (int i = tid; i < (th - rowLo) * 6; i += RT) {
             const int r = rowLo + i / 6, q = i - (i / 6) * 6;
             reinterpret_cast<uint4 *>(u8_pixel(F, view, yl0 + r, x0))[q] = reinterpret_cast<const uint4 *>(sb + r * (TW * 3))[q];
         }
     }
-#endif
     if (DBG(F, FLAG_DBG_NOOUT)) return;
-#ifndef CRB_NO_OUT_STAGE
-    if (tma) {
+    if (OUT_STAGE && tma) {
         fence_async_smem();
         __syncthreads();
         PH(8);
-        if (lane == 0) {   // warp w: array w/4 (colour, normals), row block w%4
-            const int r = (int)(wid & 3u) * BOX_ROWS;
-            if (r >= rowLo && r < th) {       // row bands are multiples of BOX_ROWS
-                if (wid < 4) { if (M.use & CRB_BUF_COLOR) tma_store_box(&M.c, S.u.out.col + r * TW * 3, x0 * 3, yl0 + r, view); }
-                else if (M.use & CRB_BUF_NORMALS) tma_store_box(&M.n, S.u.out.nrm + r * TW * 3, x0 * 3, yl0 + r, view);
+        if (lane == 0) {   // box job j: array j/4 (colour, normals), row block j%4; one job per warp with eight warps
+            for (unsigned job = wid; job < 8u; job += RT / 32) {
+                const int r = (int)(job & 3u) * BOX_ROWS;
+                if (r >= rowLo && r < th) {       // row bands are multiples of BOX_ROWS
+                    if (job < 4u) { if (M.use & CRB_BUF_COLOR) tma_store_box(&M.c, S.u.out.col + r * TW * 3, x0 * 3, yl0 + r, view); }
+                    else if (M.use & CRB_BUF_NORMALS) tma_store_box(&M.n, S.u.out.nrm + r * TW * 3, x0 * 3, yl0 + r, view);
+                }
             }
             tma_commit();
         }
-    } else if (vec) {
+    } else if (OUT_STAGE && vec) {
         __syncthreads();
         const int q = tid & 7;
-        for (int r = rowLo + (tid >> 3); r < th; r += NT / 8) {
+        for (int r = rowLo + (tid >> 3); r < th; r += RT / 8) {
             const long long o = (slab + (long long)(yl0 + r) * F.W + x0) * 3;
             if (F.color) {
                 float4 *g = reinterpret_cast<float4 *>(F.color + o);
@@ -1452,14 +1451,15 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
             }
         }
     }
-#endif
     PH(9);
 }
 
 // The fused clear through TMA: one tile = three whole-tile boxes (z, colour, normals) stored from the constant pattern in
 // shared memory; the hardware clips boxes at the image edge.  Called by one lane.
-__device__ __forceinline__ void tma_clear_tile(const TMaps &M, const TileSmem &S, unsigned t)
+template <class C>
+__device__ __forceinline__ void tma_clear_tile(const TMaps &M, const TileSmem<C> &S, unsigned t)
 {
+    constexpr int CLEAR_ROWS = C::CLEAR_ROWS;
     const int view = (int)(t >> 22), yl0 = (int)((t >> 11) & 2047u) * TH, x0 = (int)(t & 2047u) * TW;
 #pragma unroll
     for (int r = 0; r < TH; r += CLEAR_ROWS) {
@@ -1480,10 +1480,12 @@ __device__ __forceinline__ void tma_clear_tile(const TMaps &M, const TileSmem &S
 #ifndef CRB_RASTER_MIN_CTAS
 #define CRB_RASTER_MIN_CTAS 6
 #endif
-static_assert(sizeof(TileSmem) + 1024 <= 233472 / CRB_RASTER_MIN_CTAS, "k_raster: shared memory per CTA exceeds the residency its launch bounds assume");
-__global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame F, const __grid_constant__ TMaps M)
+template <class C>
+__global__ void __launch_bounds__(C::RT, C::MIN_CTAS) k_raster(const Frame F, const __grid_constant__ TMaps M)
 {
-    __shared__ TileSmem S;
+    constexpr int RT = C::RT, CLEAR_ROWS = C::CLEAR_ROWS;
+    static_assert(sizeof(TileSmem<C>) + 1024 <= 233472 / C::MIN_CTAS, "k_raster: shared memory per CTA exceeds the residency its launch bounds assume");
+    __shared__ TileSmem<C> S;
     PH_DECL
     const bool clear = (F.flags & CRB_CLEAR_FIRST) != 0;
     const bool split = clear && M.use != 0u;
@@ -1494,14 +1496,14 @@ __global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame 
         Gb = gridDim.x - Gc;
         if ((blockIdx.x & (CE - 1u)) == CE - 1u) {
             // ---- clear CTA: warp w issues the tiles e = ci + (w + 8k) * Gc
-            const unsigned stride = Gc * (NT / 32);
+            const unsigned stride = Gc * (RT / 32);
             unsigned e = ci + (threadIdx.x >> 5) * Gc;
             unsigned t = e < nAll ? F.empty[e] : 0u;              // speculative: flies with the totals
             const unsigned long long pairs = F.total[0];
             const unsigned ne = (unsigned)F.total[3];
             if (pairs > (unsigned long long)F.pairCap || DBG(F, FLAG_DBG_NOCLEAR)) return;     // frame skipped: buffers stay untouched
             const float bg = background_color(F);
-            for (int i = threadIdx.x; i < CLEAR_ROWS * TW * 3 / 4; i += NT) {
+            for (int i = threadIdx.x; i < CLEAR_ROWS * TW * 3 / 4; i += RT) {
                 reinterpret_cast<float4 *>(S.u.pat.c)[i] = make_float4(bg, bg, bg, bg);
                 reinterpret_cast<float4 *>(S.u.pat.n)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (i < CLEAR_ROWS * TW / 4) reinterpret_cast<float4 *>(S.u.pat.z)[i] = make_float4(Z_INIT, Z_INIT, Z_INIT, Z_INIT);
@@ -1540,13 +1542,14 @@ __global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame 
         volatile unsigned long long *hs = reinterpret_cast<volatile unsigned long long *>(F.hstats);
         hs[0] = ((unsigned long long)nAll << 32) | nLight;
         hs[1] = (unsigned long long)nHeavy | ((F.total[5] > 0xFFFFFFFFull ? 0xFFFFFFFFull : F.total[5]) << 32);     // + triangles that span many tiles
+        hs[2] = pairs;                                                                                                  // (triangle, tile) pairs: the next launch's shape
     }
     if (clear && !split && !DBG(F, FLAG_DBG_NOCLEAR)) {
         const unsigned ne = (unsigned)F.total[3];
         for (unsigned e = bidx; e < ne; e += Gb) {
             const unsigned t = F.empty[e];
             const int view = (int)(t >> 22), ty = (int)((t >> 11) & 2047u), tx = (int)(t & 2047u);
-            write_clear_tile<NT>(F, 0u, view, tx * TW, ty * TH, min(TW, F.W - tx * TW), min(TH, F.row1 - F.row0 - ty * TH));
+            write_clear_tile<RT>(F, 0u, view, tx * TW, ty * TH, min(TW, F.W - tx * TW), min(TH, F.row1 - F.row0 - ty * TH));
         }
     }
     PH(0);
@@ -1566,6 +1569,40 @@ __global__ void __launch_bounds__(NT, CRB_RASTER_MIN_CTAS) k_raster(const Frame 
     if ((threadIdx.x & 31) == 0) tma_wait_read();           // shared memory must outlive the bulk reads
     PH(10);
 }
+
+// The two shapes of the tile rasterizer.  RasterLarge -- 256 threads, 128 triangles staged per pass, shaded rows staged for TMA
+// boxes, 6 CTAs per SM -- is the shape for tiles of many triangles (the 10 M-triangle sphere: ~150 per tile).  RasterSmall -- 128
+// threads, 32 triangles per pass, rows stored straight from registers, 12 CTAs per SM, the same 48 warps and 40 registers -- is
+// the shape for everything else: the eight warps of a large CTA wait for each other at the barrier before shading (28 % of all
+// stall samples, ncu) while most tiles hold 20-40 triangles, i.e. fewer (triangle, row) items than eight warps take 32 at a
+// time; four warps per tile idle less, execute the per-warp prologue half as often and leave twice as many tiles in flight
+// (T-Rex x128: k_raster 1003 -> 883 us, bunny 4096^2 286 -> 244 us; the sphere would lose 25 %: 1193 -> 1492 us).
+// run_raster picks the shape per launch from the triangles per busy tile the previous launch posted.
+#ifdef CRB_NO_OUT_STAGE
+constexpr bool LARGE_OUT_STAGE = false;
+#else
+constexpr bool LARGE_OUT_STAGE = true;
+#endif
+typedef RasterShape<CRB_RT, CRB_CH, CRB_FQ, CRB_CLEAR_ROWS, CRB_RASTER_MIN_CTAS, LARGE_OUT_STAGE> RasterLarge;
+#ifndef CRB_SMALL_RT
+#define CRB_SMALL_RT 128
+#endif
+#ifndef CRB_SMALL_CH
+#define CRB_SMALL_CH 32
+#endif
+#ifndef CRB_SMALL_FQ
+#define CRB_SMALL_FQ 128
+#endif
+#ifndef CRB_SMALL_CLEAR_ROWS
+#define CRB_SMALL_CLEAR_ROWS 8
+#endif
+#ifndef CRB_SMALL_MIN_CTAS
+#define CRB_SMALL_MIN_CTAS 12
+#endif
+typedef RasterShape<CRB_SMALL_RT, CRB_SMALL_CH, CRB_SMALL_FQ, CRB_SMALL_CLEAR_ROWS, CRB_SMALL_MIN_CTAS, false> RasterSmall;
+#ifndef CRB_SHAPE_LARGE_FROM
+#define CRB_SHAPE_LARGE_FROM 64      // triangles per busy tile from which the large shape is launched
+#endif
 
 // ------------------------------------------------------------------------------------------------------------
 // Differential path (CRB_PATH_ATOMIC): one warp per triangle, global 64-bit atomicMin, then a per-pixel shade.
@@ -1876,6 +1913,7 @@ struct crb_filler {
     long long launches;
     // optional timing of the dominant kernel (k_raster) with CUDA events on the launching stream
     int raster_ctas;       // experiments: fixed k_raster grid (0 = automatic)
+    int raster_shape;      // CRB_OPT_RASTER_SHAPE: 0 = per launch from the posted statistics, 1 = RasterLarge, 2 = RasterSmall
     int sm_count;
     int use_tma;           // tensor maps are built where the layout allows (CRB_NO_TMA=1 disables): k_clear stores TMA boxes
     unsigned *shown_busy;        // sparse read-back: per tile, mask of the 32 rows that hold something in the frame the caller's host arrays show
@@ -2055,12 +2093,12 @@ bool encode_map(CUtensorMap *m, float *base, int comps, const Frame &F, int box_
 }
 
 // All or nothing: every non-NULL output array gets a map, or the launch uses plain stores.
-unsigned encode_maps(TMaps *M, const Frame &F)
+unsigned encode_maps(TMaps *M, const Frame &F, int clear_rows)
 {
     unsigned use = 0;
-    if (F.z) { if (!encode_map(&M->z, F.z, 1, F, BOX_ROWS) || !encode_map(&M->zt, F.z, 1, F, CLEAR_ROWS)) return 0u; use |= CRB_BUF_Z; }
-    if (F.color) { if (!encode_map(&M->c, F.color, 3, F, BOX_ROWS) || !encode_map(&M->ct, F.color, 3, F, CLEAR_ROWS)) return 0u; use |= CRB_BUF_COLOR; }
-    if (F.normals) { if (!encode_map(&M->n, F.normals, 3, F, BOX_ROWS) || !encode_map(&M->nt, F.normals, 3, F, CLEAR_ROWS)) return 0u; use |= CRB_BUF_NORMALS; }
+    if (F.z) { if (!encode_map(&M->z, F.z, 1, F, BOX_ROWS) || !encode_map(&M->zt, F.z, 1, F, clear_rows)) return 0u; use |= CRB_BUF_Z; }
+    if (F.color) { if (!encode_map(&M->c, F.color, 3, F, BOX_ROWS) || !encode_map(&M->ct, F.color, 3, F, clear_rows)) return 0u; use |= CRB_BUF_COLOR; }
+    if (F.normals) { if (!encode_map(&M->n, F.normals, 3, F, BOX_ROWS) || !encode_map(&M->nt, F.normals, 3, F, clear_rows)) return 0u; use |= CRB_BUF_NORMALS; }
     return use;
 }
 
@@ -2087,8 +2125,8 @@ int run_prep(crb_filler *f, Frame &F, cudaStream_t st, int slot = 0)
     // number with the busy-tile statistics) or has not reported yet; otherwise k_fill scatters the odd one itself, as it does when the list is full.
     bool wide_kernel = false;
     if (f->hstats && f->wide_kernel) {
-        const unsigned long long hs = *reinterpret_cast<volatile unsigned long long *>(f->hstats + 2 * (slot & 7));
-        const unsigned long long hw = *reinterpret_cast<volatile unsigned long long *>(f->hstats + 2 * (slot & 7) + 1) >> 32;
+        const unsigned long long hs = *reinterpret_cast<volatile unsigned long long *>(f->hstats + HSTAT_WORDS * (slot & 7));
+        const unsigned long long hw = *reinterpret_cast<volatile unsigned long long *>(f->hstats + HSTAT_WORDS * (slot & 7) + 1) >> 32;
         wide_kernel = hs == 0ull || hw >= 24ull * (unsigned long long)F.nViews;      // (a handful per view is quicker done in place than launched for)
     }
     F.wideCap = wide_kernel && !(F.flags & CRB_PATH_ATOMIC) ? (unsigned)(f->wideCap > 0xFFFFFFF0ll ? 0xFFFFFFF0ll : f->wideCap) : 0u;
@@ -2141,13 +2179,26 @@ int run_raster(crb_filler *f, Frame &F, cudaStream_t st, int slot)
 {
     int rc;
     slot &= 7;                                   // busy-tile statistics are kept per position in a batch of launches
-    if (F.hstats) F.hstats += 2 * slot;
+    if (F.hstats) F.hstats += HSTAT_WORDS * slot;
     const long long nAllTiles = (long long)F.nViews * F.nTiles;
     const bool prof = f->prof_on && f->prof_n < PROF_MAX;
+    // Shape of the rasterizer's CTAs (RasterLarge / RasterSmall): from the triangles per busy tile of the previous launch at this
+    // position of the batch; before any launch has reported, from the triangles per tile of the frame.
+    bool small = f->raster_shape == 2;
+    if (f->raster_shape == 0) {
+        small = F.T < (long long)(CRB_SHAPE_LARGE_FROM / 2) * F.nTiles;
+        if (f->hstats) {
+            const unsigned long long hs = *reinterpret_cast<volatile unsigned long long *>(f->hstats + HSTAT_WORDS * slot);
+            const unsigned long long hh = *reinterpret_cast<volatile unsigned long long *>(f->hstats + HSTAT_WORDS * slot + 1) & 0xFFFFFFFFull;
+            const unsigned long long hp = *reinterpret_cast<volatile unsigned long long *>(f->hstats + HSTAT_WORDS * slot + 2);
+            const unsigned long long busy = (hs & 0xFFFFFFFFull) + hh;
+            if ((hs >> 32) > 0 && busy > 0) small = hp < (unsigned long long)CRB_SHAPE_LARGE_FROM * busy;
+        }
+    }
     TMaps M;
     memset(&M, 0, sizeof(M));
     const bool clear = (F.flags & CRB_CLEAR_FIRST) != 0;
-    if (f->use_tma && clear && !(F.W & 3) && !F.color_u8) M.use = encode_maps(&M, F);
+    if (f->use_tma && clear && !(F.W & 3) && !F.color_u8) M.use = encode_maps(&M, F, small ? RasterSmall::CLEAR_ROWS : RasterLarge::CLEAR_ROWS);
     if (M.use && f->out_tma == 1) F.flags |= FLAG_OUT_TMA;
     if (f->out_tma == 2) F.flags |= FLAG_OUT_DIRECT;
     F.flags |= f->dbg_flags;
@@ -2157,13 +2208,13 @@ int run_raster(crb_filler *f, Frame &F, cudaStream_t st, int slot)
     long long gL = nAllTiles, gH = nAllTiles / 16 + 1;     // light / heavy rasterizing roles
     if (f->raster_ctas > 0) { gL = f->raster_ctas; gH = f->raster_ctas / 8 + 1; }
     else if (f->hstats && f->raster_ctas == 0) {
-        const unsigned long long hs = *reinterpret_cast<volatile unsigned long long *>(f->hstats + 2 * slot);
-        const unsigned long long hh = *reinterpret_cast<volatile unsigned long long *>(f->hstats + 2 * slot + 1) & 0xFFFFFFFFull;
+        const unsigned long long hs = *reinterpret_cast<volatile unsigned long long *>(f->hstats + HSTAT_WORDS * slot);
+        const unsigned long long hh = *reinterpret_cast<volatile unsigned long long *>(f->hstats + HSTAT_WORDS * slot + 1) & 0xFFFFFFFFull;
         const double tiles = (double)(hs >> 32), light = (double)(hs & 0xFFFFFFFFull), heavy = (double)hh;
         if (tiles > 0) {
             gL = (long long)(light / tiles * 1.125 * (double)nAllTiles / (double)f->tiles_per_cta) + 56;
             gH = (long long)(heavy / tiles * 1.125 * (double)nAllTiles) + 8;
-            const long long wave = (long long)f->sm_count * CRB_RASTER_MIN_CTAS;
+            const long long wave = (long long)f->sm_count * (small ? RasterSmall::MIN_CTAS : RasterLarge::MIN_CTAS);
             if (gL + gH < wave) gL = wave - gH;
         }
     }
@@ -2175,7 +2226,8 @@ int run_raster(crb_filler *f, Frame &F, cudaStream_t st, int slot)
     long long gR = gL + gH;
     if (M.use) gR = (long long)CE * ((gR + CE - 2) / (CE - 1));     // CE - 1 rasterizing CTAs + one clear CTA per group of CE (see k_raster)
     if (prof) CU(cudaEventRecord(f->prof_ev[2 * f->prof_n], st));
-    k_raster<<<(unsigned)gR, NT, 0, st>>>(F, M);
+    if (small) k_raster<RasterSmall><<<(unsigned)gR, RasterSmall::RT, 0, st>>>(F, M);
+    else k_raster<RasterLarge><<<(unsigned)gR, RasterLarge::RT, 0, st>>>(F, M);
     if ((rc = launch_check(f, "k_raster"))) return rc;
     if (prof) {
         CU(cudaEventRecord(f->prof_ev[2 * f->prof_n + 1], st));
@@ -2282,7 +2334,7 @@ int shell_acquire(int device, Shell *out)
             if (g_shells[i].device == device) {
                 *out = g_shells[i];
                 g_shells.erase(g_shells.begin() + (long)i);
-                if (out->hstats) memset(out->hstats, 0, 128);
+                if (out->hstats) memset(out->hstats, 0, HSTAT_BYTES);
                 return CRB_OK;
             }
     }
@@ -2300,8 +2352,8 @@ int shell_acquire(int device, Shell *out)
         CU(cudaEventCreateWithFlags(&sh.ev_raster[k], cudaEventDisableTiming));
     }
     void *hp = nullptr, *dp = nullptr;
-    if (cudaHostAlloc(&hp, 128, cudaHostAllocMapped) == cudaSuccess && cudaHostGetDevicePointer(&dp, hp, 0) == cudaSuccess) {
-        memset(hp, 0, 128);
+    if (cudaHostAlloc(&hp, HSTAT_BYTES, cudaHostAllocMapped) == cudaSuccess && cudaHostGetDevicePointer(&dp, hp, 0) == cudaSuccess) {
+        memset(hp, 0, HSTAT_BYTES);
         sh.hstats = (unsigned long long *)hp;
         sh.hstats_dev = (unsigned long long *)dp;
     } else {
@@ -2432,6 +2484,7 @@ int crb_create(int h, int w, float fov, float z_near, float z_far, int device, c
         CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
         f->sm_count = sms > 0 ? sms : 148;
         f->raster_ctas = 0;
+        f->raster_shape = 0;
         f->use_tma = 1;
         f->split_heavy = 1;
         f->band_prepass = 1;
@@ -3071,6 +3124,7 @@ int crb_set_option(crb_filler *f, int option, int value)
     case CRB_OPT_SPLIT_HEAVY: f->split_heavy = value ? 1 : 0; return CRB_OK;
     case CRB_OPT_WIDE_KERNEL: f->wide_kernel = value ? 1 : 0; return CRB_OK;
     case CRB_OPT_BAND_PREPASS: f->band_prepass = value ? 1 : 0; return CRB_OK;
+    case CRB_OPT_RASTER_SHAPE: f->raster_shape = (value == 1 || value == 2) ? value : 0; return CRB_OK;
     default: return fail(CRB_ERR_INVALID, "unknown option %d", option);
     }
 }

@@ -951,3 +951,61 @@ def test_render_host_overflow_is_never_silent(O, trex):
         assert float(bz.min()) == 7.0 and float(bc.max()) == 7.0       # frame not drawn, not even cleared
     finally:
         L.crb_destroy(g)
+
+
+@pytest.mark.parametrize("shape", [1, 2], ids=["large", "small"])
+def test_both_rasterizer_shapes_bit_exact(shape, Filler, O, trex):
+    """The tile rasterizer exists in two CTA shapes (CRB_OPT_RASTER_SHAPE: 256 threads / 128 staged triangles / TMA rows, and
+    128 threads / 32 staged triangles / direct stores), picked per launch from the posted statistics; forced here, each must
+    give the oracle's bits on every kind of frame: fresh and compositing, light and crowded tiles (several staging passes),
+    heavy tiles cut into row bands, known-answer cases, partial tiles, batched views with every output kind."""
+    from cython3dmodelrenderer_b200 import _lib, views as VW
+    import torch
+
+    def filler(h, w, fov):
+        g = Filler(h, w, fov=fov)
+        g.set_option(_lib.CRB_OPT_RASTER_SHAPE, shape)
+        return g
+    for seed in range(8):
+        rng = np.random.default_rng(4000 + seed)
+        h, w, fov = int(rng.integers(8, 200)), int(rng.integers(8, 200)), float(rng.uniform(20, 120))
+        m = random_scene(seed)
+        g, o = filler(h, w, fov), O.OracleFiller(h, w, fov=fov)
+        for _ in range(2 if seed % 3 == 0 else 1):
+            g.render_model(m)
+            o.render_model(m)
+        assert_same(buffers(g), buffers(o), f"shape {shape} seed {seed} {h}x{w}")
+    for (h, w), seed in (((257, 391), 100), ((96, 128), 221)):      # dense: hundreds of triangles per tile, split heavy tiles
+        m = random_scene(seed, T=5000, span=0.55)
+        g, o = filler(h, w, 70.0), O.OracleFiller(h, w, fov=70.0)
+        g.clear(); g.render_model(m); o.render_model(m)
+        assert_same(buffers(g), buffers(o), f"shape {shape} dense {h}x{w}")
+        m2 = random_scene(300 + seed, T=2000, span=0.7)
+        g.render_model(m2); o.render_model(m2)
+        assert_same(buffers(g), buffers(o), f"shape {shape} dense composite {h}x{w}")
+    for name in sorted(KATS):
+        v, c, n = KATS[name]
+        g, o = filler(50, 70, 90.0), O.OracleFiller(50, 70, fov=90.0)
+        g.render_arrays(v, c, n); o.render_arrays(v, c, n)
+        assert_same(buffers(g), buffers(o), f"shape {shape} {name}")
+    info = CHECKS["cases"]["trex_1024x1024_fov45"]
+    g = filler(1024, 1024, 45.0)
+    g.render_model(trex)
+    assert (sha(g.get_z_buffer()), sha(g.get_color_buffer()), sha(g.get_normals_buffer())) == (info["z"], info["color"], info["normals"])
+    # batched views: float32 slabs, the flipped uint8 image, fused Guro -- against the other shape's bits and the oracle's first view
+    dv, dc, dn = (torch.from_numpy(a).cuda() for a in (trex._vertices_by_triangles, trex._colors_by_triangles, trex._normals_by_triangles))
+    vw = VW.orbit_views(12, first=0, count=5)
+    outs = {}
+    for sh in (shape, 3 - shape):
+        g = Filler(160, 192, fov=45.0)
+        g.set_option(_lib.CRB_OPT_RASTER_SHAPE, sh)
+        r = g.render_views(dv, dc, dn, vw, color_u8_out=True, chunk=2)
+        lit = g.render_views(dv, dc, dn, vw, want=("color",), guro_light=[0.3, -0.2, 1.0], color_u8_out=True, chunk=5)
+        torch.cuda.synchronize()
+        outs[sh] = [r[k].cpu().numpy() for k in ("z", "color", "normals", "color_u8")] + [lit["color"].cpu().numpy(), lit["color_u8"].cpu().numpy()]
+    for a, b in zip(outs[1], outs[2]):
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+    vk, nk = VW.transform_arrays_host(vw[0], trex._vertices_by_triangles, trex._normals_by_triangles)
+    o = O.OracleFiller(160, 192, fov=45.0)
+    o.render_arrays(vk, trex._colors_by_triangles, nk)
+    assert_same(tuple(outs[shape][k][0] for k in range(3)), buffers(o), f"shape {shape} view 0")

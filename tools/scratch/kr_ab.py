@@ -6,12 +6,14 @@ import torch
 from conftest import load_indexed
 from cython3dmodelrenderer_b200 import AdvancedPixelBufferFiller, views as VW, synthetic
 tag = sys.argv[1] if len(sys.argv) > 1 else "cur"
+SHAPE = int(os.environ.get("KR_SHAPE", "0"))      # CRB_OPT_RASTER_SHAPE: 0 auto, 1 large, 2 small
+from cython3dmodelrenderer_b200 import _lib
 out = []
 m = load_indexed("trex"); res, V = 1024, 128
 dv, dc, dn = (torch.from_numpy(a).cuda() for a in (m._vertices_by_triangles, m._colors_by_triangles, m._normals_by_triangles))
 views = torch.from_numpy(VW.orbit_views(V)).cuda()
 z = torch.empty((V, res, res), device="cuda"); c = torch.empty((V, res, res, 3), device="cuda"); n = torch.empty((V, res, res, 3), device="cuda")
-f = AdvancedPixelBufferFiller(res, res, fov=45.0)
+f = AdvancedPixelBufferFiller(res, res, fov=45.0); SHAPE and f.set_option(_lib.CRB_OPT_RASTER_SHAPE, SHAPE)
 for _ in range(3):
     f.render_views(dv, dc, dn, views, z_out=z, color_out=c, normals_out=n, chunk=V)
 torch.cuda.synchronize(); f.profile(True)
@@ -26,7 +28,7 @@ del z, c, n, f
 for name, res in (("bunny", 4096), ("sphere", 8192)):
     mm = synthetic.uv_sphere(3200, 1564) if name == "sphere" else load_indexed(name)
     dv, dc, dn = (torch.from_numpy(a).cuda() for a in (mm._vertices_by_triangles, mm._colors_by_triangles, mm._normals_by_triangles))
-    f = AdvancedPixelBufferFiller(res, res, fov=45.0)
+    f = AdvancedPixelBufferFiller(res, res, fov=45.0); SHAPE and f.set_option(_lib.CRB_OPT_RASTER_SHAPE, SHAPE)
     for _ in range(3):
         f.clear(); f.render_arrays(dv, dc, dn)
     torch.cuda.synchronize(); f.profile(True)
@@ -37,4 +39,4 @@ for name, res in (("bunny", 4096), ("sphere", 8192)):
     k, ms = f.profile_read(); f.profile(False)
     out.append(f"{name} k_raster {ms / k * 1000:.1f} us step {e0.elapsed_time(e1) / 20 * 1000:.1f} us")
     del f
-print(tag, " | ".join(out))
+print(tag, f"shape={SHAPE}", " | ".join(out))
