@@ -46,7 +46,7 @@ constexpr int NT = 256;         // threads per CTA in every kernel but the tile 
 // The tile rasterizer is instantiated in two CTA shapes (RasterShape / RasterLarge / RasterSmall, further down); the macros below
 // are the large shape's parameters, the CRB_SMALL_* ones the small shape's.
 #ifndef CRB_RT
-#define CRB_RT 256              // threads per CTA of k_raster (a multiple of 32)
+#define CRB_RT 128              // threads per CTA of k_raster (a multiple of 32)
 #endif
 #ifdef CRB_ABLATION
 #define DBG(F, bit) (((F).flags & (bit)) != 0u)
@@ -58,7 +58,7 @@ constexpr unsigned FLAG_DBG_NOCLEAR = 0x10000u, FLAG_DBG_NOSHADE = 0x20000u, FLA
 constexpr unsigned FLAG_OUT_DIRECT = 0x200u;   // experiment: shaded pixels stored straight from registers (12-byte strided stores)
 constexpr unsigned FLAG_OUT_TMA = 0x100u;   // internal Frame.flags bit: shaded colour / normal rows leave through TMA boxes
 #ifndef CRB_CH
-#define CRB_CH 128              // triangles staged in shared memory per pass of the tile rasterizer
+#define CRB_CH 96               // triangles staged in shared memory per pass of the tile rasterizer
 #endif
 constexpr unsigned SPLIT_N = 48;  // single-view launches: tiles with more triangles than this are rasterized by SPLIT_BANDS CTAs, 8 rows each
 constexpr int SPLIT_BANDS = 4;
@@ -84,7 +84,7 @@ constexpr float REJ_EPS = 1e-6f;      // fast-reject guard band on barycentric n
 constexpr float L3_MIN = 1e-30f, L3_MAX = 1e30f;
 constexpr int MAX_DIM = 65535;  // bbox corners are packed in 16 bits
 #ifndef CRB_CLEAR_ROWS
-#define CRB_CLEAR_ROWS 32       // rows per TMA box of the fused clear (TH: one box per array and tile)
+#define CRB_CLEAR_ROWS 16       // rows per TMA box of the fused clear (the constant pattern must fit the staging area it shares)
 #endif
 constexpr int BOX_ROWS = 8;       // rows per TMA box (clear pattern and shaded rows go out 8 tile rows at a time)
 constexpr int HSTAT_WORDS = 4;    // 64-bit words of busy-tile statistics k_raster posts per position in a batch of launches (8 positions)
@@ -1478,7 +1478,7 @@ __device__ __forceinline__ void tma_clear_tile(const TMaps &M, const TileSmem<C>
 // 6 resident CTAs per SM (40 registers, 36.9 KB shared memory each -- 0.7 KB below the limit): 5 with 48 registers measured
 // 8.7 % slower (profiles/history/r02_probe_variants.json)
 #ifndef CRB_RASTER_MIN_CTAS
-#define CRB_RASTER_MIN_CTAS 6
+#define CRB_RASTER_MIN_CTAS 8
 #endif
 template <class C>
 __global__ void __launch_bounds__(C::RT, C::MIN_CTAS) k_raster(const Frame F, const __grid_constant__ TMaps M)
@@ -1570,28 +1570,35 @@ __global__ void __launch_bounds__(C::RT, C::MIN_CTAS) k_raster(const Frame F, co
     PH(10);
 }
 
-// The two shapes of the tile rasterizer.  RasterLarge -- 256 threads, 128 triangles staged per pass, shaded rows staged for TMA
-// boxes, 6 CTAs per SM -- is the shape for tiles of many triangles (the 10 M-triangle sphere: ~150 per tile).  RasterSmall -- 128
-// threads, 32 triangles per pass, rows stored straight from registers, 12 CTAs per SM, the same 48 warps and 40 registers -- is
-// the shape for everything else: the eight warps of a large CTA wait for each other at the barrier before shading (28 % of all
-// stall samples, ncu) while most tiles hold 20-40 triangles, i.e. fewer (triangle, row) items than eight warps take 32 at a
-// time; four warps per tile idle less, execute the per-warp prologue half as often and leave twice as many tiles in flight
-// (T-Rex x128: k_raster 1003 -> 883 us, bunny 4096^2 286 -> 244 us; the sphere would lose 25 %: 1193 -> 1492 us).
-// run_raster picks the shape per launch from the triangles per busy tile the previous launch posted.
-#ifdef CRB_NO_OUT_STAGE
-constexpr bool LARGE_OUT_STAGE = false;
-#else
+// The two shapes of the tile rasterizer, both CTAs of 128 threads that store shaded pixels straight from registers.
+// Round 1 / early round 2 ran ONE shape: 256 threads, 128 triangles staged per pass, shaded rows staged in shared memory for TMA
+// boxes, 6 CTAs per SM at 40 registers.  ncu showed 28 % of all stall samples at block barriers -- the eight warps of a CTA waiting
+// for each other before shading, while most tiles hold 20-40 triangles, i.e. fewer (triangle, row) items than eight warps take
+// 32 at a time.  Four warps per tile idle less, run the per-warp prologue half as often, and without the 24 KB of row staging
+// twice as many tiles are in flight per SM (measured, k_raster per 128 T-Rex views / bunny 4096^2 / 10 M-triangle sphere 8192^2):
+//     256 threads, CH 128, rows staged, 6 CTAs/SM, 40 registers      1003 / 286 / 1193 us
+//     192 threads, CH  64,              8 CTAs/SM, 40 registers       929 / 265 / 1193
+//     160 threads, CH  56,              9 CTAs/SM, 40 registers       895 / 253 / 1239
+//     128 threads, CH  32, FQ 128,     12 CTAs/SM, 40 registers       883 / 246 / 1492
+//     128 threads, CH  24, FQ 256,     12 CTAs/SM, 40 registers       868 / 232 / 1680    <- RasterSmall
+//     128 threads, CH  96, FQ 256,      8 CTAs/SM, 62 registers       911 / 252 / 1107    <- RasterLarge
+//     128 threads, CH 128, FQ 256,      7 CTAs/SM, 66 registers       965 / 270 / 1133
+// Tiles of ~150 triangles (the sphere) want many triangles per staging pass and registers instead of warps; ordinary frames want
+// many small CTAs.  run_raster picks the shape per launch from the triangles per busy tile the previous launch posted.
+#ifdef CRB_LARGE_OUT_STAGE       // (shaded rows staged for TMA boxes: 24 KB more shared memory per CTA, needs CRB_RASTER_MIN_CTAS <= 6)
 constexpr bool LARGE_OUT_STAGE = true;
+#else
+constexpr bool LARGE_OUT_STAGE = false;
 #endif
 typedef RasterShape<CRB_RT, CRB_CH, CRB_FQ, CRB_CLEAR_ROWS, CRB_RASTER_MIN_CTAS, LARGE_OUT_STAGE> RasterLarge;
 #ifndef CRB_SMALL_RT
 #define CRB_SMALL_RT 128
 #endif
 #ifndef CRB_SMALL_CH
-#define CRB_SMALL_CH 32
+#define CRB_SMALL_CH 24
 #endif
 #ifndef CRB_SMALL_FQ
-#define CRB_SMALL_FQ 128
+#define CRB_SMALL_FQ 256
 #endif
 #ifndef CRB_SMALL_CLEAR_ROWS
 #define CRB_SMALL_CLEAR_ROWS 8
@@ -2159,7 +2166,7 @@ int run_prep(crb_filler *f, Frame &F, cudaStream_t st, int slot = 0)
     }
     // cutting heavy tiles only pays while the frame is latency-bound, i.e. while its tiles do not fill the machine several
     // times over (T-Rex 1024^2: 56 -> 38 us; the 8192^2 sphere with 75 triangles in every tile would lose 25 %)
-    F.splitHeavy = (F.nViews == 1 && f->split_heavy && F.nTiles <= 4 * f->sm_count * CRB_RASTER_MIN_CTAS) ? 1u : 0u;
+    F.splitHeavy = (F.nViews == 1 && f->split_heavy && F.nTiles <= 4 * f->sm_count * 6) ? 1u : 0u;
     const long long nAllTiles = (long long)F.nViews * F.nTiles;
     k_alloc<<<(unsigned)((nAllTiles + NT - 1) / NT), NT, 0, st>>>(F);
     if ((rc = launch_check(f, "k_alloc"))) return rc;
