@@ -1043,8 +1043,7 @@ struct __align__(128) TileSmem {
         } out;
         struct {                              // clear CTAs only: the constant pattern their TMA boxes are stored from
             float z[CLEAR_ROWS * TW];         //   Z_INIT
-            float c[CLEAR_ROWS * TW * 3];     //   background colour
-            float n[CLEAR_ROWS * TW * 3];     //   0
+            float c[CLEAR_ROWS * TW * 3];     //   background colour = 0 (background_color) = the cleared normals: one pattern serves both
         } pat;
     } u;
     unsigned long long keys[TH * KEY_STRIDE];
@@ -1178,13 +1177,16 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
             // correctly rounded reciprocals of the (sign-normalised) denominators, for div_rn_by: RN(1/-x) = -RN(1/x), so these are
             // the bits k_setup's rcp.rn of the signed denominators would give after the same sign flip
             tr3 = make_float4(__frcp_rn(c.y), __frcp_rn(c.z), __frcp_rn(c.w), 0.0f);
-            {   // the shading pass will want this triangle's 128-byte record: start pulling it into L1 now
+#ifndef CRB_NO_REC_PREFETCH
+            if (CH < 64) {   // the shading pass will want this triangle's 128-byte record: start pulling it into L1 now (T-Rex x128
+                             // -2.6 %; tiles of ~150 triangles evict them again before they are shaded: the large shape goes without)
                 const char *sr = reinterpret_cast<const char *>(F.shrec + ((long long)view * F.T + d.z) * SREC);
                 asm volatile("prefetch.global.L1 [%0];" :: "l"(sr));
                 asm volatile("prefetch.global.L1 [%0];" :: "l"(sr + 32));
                 asm volatile("prefetch.global.L1 [%0];" :: "l"(sr + 64));
                 asm volatile("prefetch.global.L1 [%0];" :: "l"(sr + 96));
             }
+#endif
             // edge vectors, sign-normalised (exact negation: flip the sign bit)
             const unsigned s1 = (d.w & 1u) << 31, s2 = (d.w & 2u) << 30, s3 = (d.w & 4u) << 29;
             S.u.st.e0[tid] = make_float4(__uint_as_float(__float_as_uint(a.z - b.x) ^ s1), b.y,
@@ -1201,6 +1203,11 @@ __device__ __forceinline__ void raster_tile(const Frame &F, const TMaps &M, Tile
                                 ((d.w & (FL_SPAN | FL_FDIV)) == (FL_SPAN | FL_FDIV) ? PK_FAST : 0u) |
                                 ((unsigned)xa << PK_XA) | ((unsigned)max(xb, xa) << PK_XB) | ((unsigned)((yt - y0) & 31) << PK_YT);
             S.u.st.td[tid] = make_float4(c.y, c.z, c.w, __uint_as_float(pk));
+        }
+        if (base + CH < n) {     // the next pass's list entries (64 B each, contiguous): start pulling their lines in now (T-Rex x128: -1.3 %)
+            const unsigned nm = min((unsigned)CH, n - base - CH);
+            for (unsigned i = tid; i < (nm + 1u) / 2u; i += RT)
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(F.ls + (size_t)(off + base + CH + 2u * i) * 4));
         }
         unsigned totalRows;
         const unsigned start = block_exclusive_scan<RT>(rows, S.warp_sums, totalRows);
@@ -1465,7 +1472,7 @@ __device__ __forceinline__ void tma_clear_tile(const TMaps &M, const TileSmem<C>
     for (int r = 0; r < TH; r += CLEAR_ROWS) {
         if (M.use & CRB_BUF_Z) tma_store_box(&M.zt, S.u.pat.z, x0, yl0 + r, view);
         if (M.use & CRB_BUF_COLOR) tma_store_box(&M.ct, S.u.pat.c, x0 * 3, yl0 + r, view);
-        if (M.use & CRB_BUF_NORMALS) tma_store_box(&M.nt, S.u.pat.n, x0 * 3, yl0 + r, view);
+        if (M.use & CRB_BUF_NORMALS) tma_store_box(&M.nt, S.u.pat.c, x0 * 3, yl0 + r, view);
     }
 }
 
@@ -1495,7 +1502,7 @@ __global__ void __launch_bounds__(C::RT, C::MIN_CTAS) k_raster(const Frame F, co
         const unsigned Gc = gridDim.x / CE, ci = blockIdx.x / CE;
         Gb = gridDim.x - Gc;
         if ((blockIdx.x & (CE - 1u)) == CE - 1u) {
-            // ---- clear CTA: warp w issues the tiles e = ci + (w + 8k) * Gc
+            // ---- clear CTA: warp w issues the tiles e = ci + (w + k * warps) * Gc
             const unsigned stride = Gc * (RT / 32);
             unsigned e = ci + (threadIdx.x >> 5) * Gc;
             unsigned t = e < nAll ? F.empty[e] : 0u;              // speculative: flies with the totals
@@ -1504,8 +1511,7 @@ __global__ void __launch_bounds__(C::RT, C::MIN_CTAS) k_raster(const Frame F, co
             if (pairs > (unsigned long long)F.pairCap || DBG(F, FLAG_DBG_NOCLEAR)) return;     // frame skipped: buffers stay untouched
             const float bg = background_color(F);
             for (int i = threadIdx.x; i < CLEAR_ROWS * TW * 3 / 4; i += RT) {
-                reinterpret_cast<float4 *>(S.u.pat.c)[i] = make_float4(bg, bg, bg, bg);
-                reinterpret_cast<float4 *>(S.u.pat.n)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                reinterpret_cast<float4 *>(S.u.pat.c)[i] = make_float4(bg, bg, bg, bg);       // (bg is 0.0f: also the normals' pattern)
                 if (i < CLEAR_ROWS * TW / 4) reinterpret_cast<float4 *>(S.u.pat.z)[i] = make_float4(Z_INIT, Z_INIT, Z_INIT, Z_INIT);
             }
             fence_async_smem();

@@ -28,8 +28,8 @@ def phase_ranges():
     shade = find(r"---- deferred shading", left)
     out = find(r"if \(DBG\(F, FLAG_DBG_NOOUT\)\) return;", shade)
     end = find(r"^// The fused clear through TMA", out)
-    kr = find(r"^__global__ void __launch_bounds__\(NT, CRB_RASTER_MIN_CTAS\) k_raster")
-    kend = find(r"^// Differential path", kr)
+    kr = find(r"^__global__ void __launch_bounds__\(C::RT, C::MIN_CTAS\) k_raster")
+    kend = find(r"^// The two shapes of the tile rasterizer", kr)
     sf = find(r"bool shade_fragment\("); sfe = find(r"^// Colour of a pixel no triangle covers", sf)
     dv = find(r"float div_rn_by\("); dve = find(r"^// pyx:215-242", dv)
     km = find(r"void smem_key_min\("); kme = find(r"^// Tensor maps", km)
