@@ -1613,6 +1613,9 @@ typedef RasterShape<CRB_RT, CRB_CH, CRB_FQ, CRB_CLEAR_ROWS, CRB_RASTER_MIN_CTAS,
 #define CRB_SMALL_MIN_CTAS 12
 #endif
 typedef RasterShape<CRB_SMALL_RT, CRB_SMALL_CH, CRB_SMALL_FQ, CRB_SMALL_CLEAR_ROWS, CRB_SMALL_MIN_CTAS, false> RasterSmall;
+// ... and a third for frames of so few busy tiles that they do not fill the machine once (a single 1024^2 frame): eight warps per
+// tile, 128 triangles per pass -- such a frame takes as long as its slowest CTA, and idle warps cost nothing there
+typedef RasterShape<256, 128, 256, 16, 6, false> RasterWide;
 #ifndef CRB_SHAPE_LARGE_FROM
 #define CRB_SHAPE_LARGE_FROM 64      // triangles per busy tile from which the large shape is launched
 #endif
@@ -1926,7 +1929,7 @@ struct crb_filler {
     long long launches;
     // optional timing of the dominant kernel (k_raster) with CUDA events on the launching stream
     int raster_ctas;       // experiments: fixed k_raster grid (0 = automatic)
-    int raster_shape;      // CRB_OPT_RASTER_SHAPE: 0 = per launch from the posted statistics, 1 = RasterLarge, 2 = RasterSmall
+    int raster_shape;      // CRB_OPT_RASTER_SHAPE: 0 = per launch from the posted statistics, 1 = RasterLarge, 2 = RasterSmall, 3 = RasterWide
     int sm_count;
     int use_tma;           // tensor maps are built where the layout allows (CRB_NO_TMA=1 disables): k_clear stores TMA boxes
     unsigned *shown_busy;        // sparse read-back: per tile, mask of the 32 rows that hold something in the frame the caller's host arrays show
@@ -2195,23 +2198,33 @@ int run_raster(crb_filler *f, Frame &F, cudaStream_t st, int slot)
     if (F.hstats) F.hstats += HSTAT_WORDS * slot;
     const long long nAllTiles = (long long)F.nViews * F.nTiles;
     const bool prof = f->prof_on && f->prof_n < PROF_MAX;
-    // Shape of the rasterizer's CTAs (RasterLarge / RasterSmall): from the triangles per busy tile of the previous launch at this
-    // position of the batch; before any launch has reported, from the triangles per tile of the frame.
-    bool small = f->raster_shape == 2;
-    if (f->raster_shape == 0) {
-        small = F.T < (long long)(CRB_SHAPE_LARGE_FROM / 2) * F.nTiles;
+    // Shape of the rasterizer's CTAs (RasterSmall / RasterLarge / RasterWide, see there).  A frame whose busy tiles do not even
+    // fill the machine once is as slow as its slowest CTA: the most threads per tile win (single T-Rex frame 1024^2: wide 36 us,
+    // large 41, small 60); up to a few waves the large shape (T-Rex 2048^2: 67 vs 80 us); beyond that throughput counts and the
+    // triangles per busy tile decide (bunny 4096^2, one frame: small 262 us, large 286, wide 315).  Busy tiles and pairs are those
+    // the previous launch at this position of the batch posted; before any launch has reported, the frame's tiles and triangles.
+    int shape = f->raster_shape;
+    if (shape == 0) {
+        const long long wave = (long long)f->sm_count * RasterWide::MIN_CTAS;
+        double busy = (double)nAllTiles, per_tile = (double)F.T * 2.0 / (double)F.nTiles;
         if (f->hstats) {
             const unsigned long long hs = *reinterpret_cast<volatile unsigned long long *>(f->hstats + HSTAT_WORDS * slot);
             const unsigned long long hh = *reinterpret_cast<volatile unsigned long long *>(f->hstats + HSTAT_WORDS * slot + 1) & 0xFFFFFFFFull;
             const unsigned long long hp = *reinterpret_cast<volatile unsigned long long *>(f->hstats + HSTAT_WORDS * slot + 2);
-            const unsigned long long busy = (hs & 0xFFFFFFFFull) + hh;
-            if ((hs >> 32) > 0 && busy > 0) small = hp < (unsigned long long)CRB_SHAPE_LARGE_FROM * busy;
+            const double records = (double)((hs & 0xFFFFFFFFull) + hh);
+            if ((hs >> 32) > 0 && records > 0) {
+                busy = records * (double)nAllTiles / (double)(hs >> 32);
+                per_tile = (double)hp / records;
+            }
         }
+        shape = busy <= (double)wave ? 3 : (busy <= 4.0 * (double)wave || per_tile >= (double)CRB_SHAPE_LARGE_FROM) ? 1 : 2;
     }
+    const int clear_rows = shape == 2 ? RasterSmall::CLEAR_ROWS : shape == 3 ? RasterWide::CLEAR_ROWS : RasterLarge::CLEAR_ROWS;
+    const int min_ctas = shape == 2 ? RasterSmall::MIN_CTAS : shape == 3 ? RasterWide::MIN_CTAS : RasterLarge::MIN_CTAS;
     TMaps M;
     memset(&M, 0, sizeof(M));
     const bool clear = (F.flags & CRB_CLEAR_FIRST) != 0;
-    if (f->use_tma && clear && !(F.W & 3) && !F.color_u8) M.use = encode_maps(&M, F, small ? RasterSmall::CLEAR_ROWS : RasterLarge::CLEAR_ROWS);
+    if (f->use_tma && clear && !(F.W & 3) && !F.color_u8) M.use = encode_maps(&M, F, clear_rows);
     if (M.use && f->out_tma == 1) F.flags |= FLAG_OUT_TMA;
     if (f->out_tma == 2) F.flags |= FLAG_OUT_DIRECT;
     F.flags |= f->dbg_flags;
@@ -2227,7 +2240,7 @@ int run_raster(crb_filler *f, Frame &F, cudaStream_t st, int slot)
         if (tiles > 0) {
             gL = (long long)(light / tiles * 1.125 * (double)nAllTiles / (double)f->tiles_per_cta) + 56;
             gH = (long long)(heavy / tiles * 1.125 * (double)nAllTiles) + 8;
-            const long long wave = (long long)f->sm_count * (small ? RasterSmall::MIN_CTAS : RasterLarge::MIN_CTAS);
+            const long long wave = (long long)f->sm_count * min_ctas;
             if (gL + gH < wave) gL = wave - gH;
         }
     }
@@ -2239,7 +2252,8 @@ int run_raster(crb_filler *f, Frame &F, cudaStream_t st, int slot)
     long long gR = gL + gH;
     if (M.use) gR = (long long)CE * ((gR + CE - 2) / (CE - 1));     // CE - 1 rasterizing CTAs + one clear CTA per group of CE (see k_raster)
     if (prof) CU(cudaEventRecord(f->prof_ev[2 * f->prof_n], st));
-    if (small) k_raster<RasterSmall><<<(unsigned)gR, RasterSmall::RT, 0, st>>>(F, M);
+    if (shape == 2) k_raster<RasterSmall><<<(unsigned)gR, RasterSmall::RT, 0, st>>>(F, M);
+    else if (shape == 3) k_raster<RasterWide><<<(unsigned)gR, RasterWide::RT, 0, st>>>(F, M);
     else k_raster<RasterLarge><<<(unsigned)gR, RasterLarge::RT, 0, st>>>(F, M);
     if ((rc = launch_check(f, "k_raster"))) return rc;
     if (prof) {
@@ -3137,7 +3151,7 @@ int crb_set_option(crb_filler *f, int option, int value)
     case CRB_OPT_SPLIT_HEAVY: f->split_heavy = value ? 1 : 0; return CRB_OK;
     case CRB_OPT_WIDE_KERNEL: f->wide_kernel = value ? 1 : 0; return CRB_OK;
     case CRB_OPT_BAND_PREPASS: f->band_prepass = value ? 1 : 0; return CRB_OK;
-    case CRB_OPT_RASTER_SHAPE: f->raster_shape = (value == 1 || value == 2) ? value : 0; return CRB_OK;
+    case CRB_OPT_RASTER_SHAPE: f->raster_shape = (value >= 1 && value <= 3) ? value : 0; return CRB_OK;
     default: return fail(CRB_ERR_INVALID, "unknown option %d", option);
     }
 }

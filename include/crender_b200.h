@@ -176,9 +176,11 @@ int crb_render_host(crb_filler *f, const float *v, const float *c, const float *
 #define CRB_OPT_WIDE_KERNEL 7    /* triangles that span more than 12 tiles are listed by k_fill and scattered by a kernel of their own
                                     (k_fill_wide, a warp per triangle; launched only while frames contain such triangles); 0: k_fill
                                     scatters them itself (default 1) */
-#define CRB_OPT_RASTER_SHAPE 8   /* CTA shape of the tile rasterizer: 0 (default) chosen per launch from the triangles per busy tile
-                                    the previous launch posted; 1: 256 threads, 128 triangles staged per pass, 6 CTAs per SM (tiles
-                                    of many triangles); 2: 128 threads, 32 triangles per pass, 12 CTAs per SM */
+#define CRB_OPT_RASTER_SHAPE 8   /* CTA shape of the tile rasterizer: 0 (default) chosen per launch from the busy tiles and the triangles
+                                    per busy tile the previous launch posted; 1: 128 threads, 96 triangles staged per pass, 8 CTAs per
+                                    SM (tiles of many triangles, frames of a few waves); 2: 128 threads, 24 triangles per pass, 12 CTAs
+                                    per SM (large batches of ordinary tiles); 3: 256 threads, 128 triangles per pass, 6 CTAs per SM
+                                    (frames that do not fill the machine once).  Results do not depend on it. */
 int crb_set_option(crb_filler *f, int option, int value);
 
 /* Orders `stream` behind rasterizer work left in flight by CRB_DEFER_JOIN (no host synchronisation). */

@@ -953,10 +953,10 @@ def test_render_host_overflow_is_never_silent(O, trex):
         L.crb_destroy(g)
 
 
-@pytest.mark.parametrize("shape", [1, 2], ids=["large", "small"])
+@pytest.mark.parametrize("shape", [1, 2, 3], ids=["large", "small", "wide"])
 def test_both_rasterizer_shapes_bit_exact(shape, Filler, O, trex):
-    """The tile rasterizer exists in two CTA shapes (CRB_OPT_RASTER_SHAPE: 256 threads / 128 staged triangles / TMA rows, and
-    128 threads / 32 staged triangles / direct stores), picked per launch from the posted statistics; forced here, each must
+    """The tile rasterizer exists in three CTA shapes (CRB_OPT_RASTER_SHAPE: 128 threads / 96 staged triangles, 128 threads / 24
+    staged triangles, 256 threads / 128 staged triangles), picked per launch from the posted statistics; forced here, each must
     give the oracle's bits on every kind of frame: fresh and compositing, light and crowded tiles (several staging passes),
     heavy tiles cut into row bands, known-answer cases, partial tiles, batched views with every output kind."""
     from cython3dmodelrenderer_b200 import _lib, views as VW
@@ -996,15 +996,16 @@ def test_both_rasterizer_shapes_bit_exact(shape, Filler, O, trex):
     dv, dc, dn = (torch.from_numpy(a).cuda() for a in (trex._vertices_by_triangles, trex._colors_by_triangles, trex._normals_by_triangles))
     vw = VW.orbit_views(12, first=0, count=5)
     outs = {}
-    for sh in (shape, 3 - shape):
+    for sh in (1, 2, 3):
         g = Filler(160, 192, fov=45.0)
         g.set_option(_lib.CRB_OPT_RASTER_SHAPE, sh)
         r = g.render_views(dv, dc, dn, vw, color_u8_out=True, chunk=2)
         lit = g.render_views(dv, dc, dn, vw, want=("color",), guro_light=[0.3, -0.2, 1.0], color_u8_out=True, chunk=5)
         torch.cuda.synchronize()
         outs[sh] = [r[k].cpu().numpy() for k in ("z", "color", "normals", "color_u8")] + [lit["color"].cpu().numpy(), lit["color_u8"].cpu().numpy()]
-    for a, b in zip(outs[1], outs[2]):
-        assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+    for other in (1, 2, 3):
+        for a, b in zip(outs[shape], outs[other]):
+            assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
     vk, nk = VW.transform_arrays_host(vw[0], trex._vertices_by_triangles, trex._normals_by_triangles)
     o = O.OracleFiller(160, 192, fov=45.0)
     o.render_arrays(vk, trex._colors_by_triangles, nk)
