@@ -14,6 +14,7 @@ dv, dc, dn = (torch.from_numpy(a).cuda() for a in (m._vertices_by_triangles, m._
 views = torch.from_numpy(VW.orbit_views(V)).cuda()
 z = torch.empty((V, res, res), device="cuda"); c = torch.empty((V, res, res, 3), device="cuda"); n = torch.empty((V, res, res, 3), device="cuda")
 f = AdvancedPixelBufferFiller(res, res, fov=45.0); SHAPE and f.set_option(_lib.CRB_OPT_RASTER_SHAPE, SHAPE)
+if os.environ.get('KR_CTAS'): f.set_option(_lib.CRB_OPT_RASTER_CTAS, int(os.environ['KR_CTAS']))
 for _ in range(3):
     f.render_views(dv, dc, dn, views, z_out=z, color_out=c, normals_out=n, chunk=V)
 torch.cuda.synchronize(); f.profile(True)
@@ -29,6 +30,7 @@ for name, res in (("bunny", 4096), ("sphere", 8192)):
     mm = synthetic.uv_sphere(3200, 1564) if name == "sphere" else load_indexed(name)
     dv, dc, dn = (torch.from_numpy(a).cuda() for a in (mm._vertices_by_triangles, mm._colors_by_triangles, mm._normals_by_triangles))
     f = AdvancedPixelBufferFiller(res, res, fov=45.0); SHAPE and f.set_option(_lib.CRB_OPT_RASTER_SHAPE, SHAPE)
+    if os.environ.get('KR_CTAS'): f.set_option(_lib.CRB_OPT_RASTER_CTAS, int(os.environ['KR_CTAS']))
     for _ in range(3):
         f.clear(); f.render_arrays(dv, dc, dn)
     torch.cuda.synchronize(); f.profile(True)
