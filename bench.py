@@ -825,7 +825,9 @@ def measure_workload(args, workload, world, rank, local, dev, cpu_threads=None, 
         bands = box[0]
         # ... and the estimate is corrected by what the bands really cost: three rounds of (render a few frames, compare the
         # ranks' times, cut again) -- load balancing before the timed region, like the choice of the bands itself
-        for _ in range(3):
+        # (the cut that measured best is kept: a re-cut can also land on the wrong side of a threshold, e.g. of the band pre-pass)
+        tried = []
+        for rnd in range(4):
             fcal = AdvancedPixelBufferFiller(res, res, fov=FOV, device=local, band=bands[rank])
             for _w in range(2):
                 fcal.clear(); fcal.render_arrays(dv, dc, dn)
@@ -840,7 +842,12 @@ def measure_workload(args, workload, world, rank, local, dev, cpu_threads=None, 
             dist.all_gather(every, mine)
             del fcal
             if rank == 0:
-                new_bands, costs = sharding.rebalance_bands(costs, bands, [float(t.item()) for t in every], world, res)
+                times = [float(t.item()) for t in every]
+                tried.append((max(times), bands))
+                if rnd < 3:
+                    new_bands, costs = sharding.rebalance_bands(costs, bands, times, world, res)
+                else:
+                    new_bands = min(tried, key=lambda tb: tb[0])[1]
                 box = [new_bands]
             dist.broadcast_object_list(box, src=0)
             bands = box[0]

@@ -2129,8 +2129,9 @@ int setup_smem_attr(int device)
     return CRB_OK;
 }
 
-#ifndef CRB_PREPASS_DEN
-#define CRB_PREPASS_DEN 2      // the band pre-pass runs for bands of at most 1 / CRB_PREPASS_DEN of the frame
+#ifndef CRB_PREPASS_EIGHTHS
+#define CRB_PREPASS_EIGHTHS 5  // the band pre-pass runs for bands of at most this many eighths of the frame (half-frame bands gain
+                               // 7 %; a cut balanced by measurement lands a few strips off the middle, which must not switch it off)
 #endif
 // project/setup/count -> alloc -> fill for up to maxViews views
 int run_prep(crb_filler *f, Frame &F, cudaStream_t st, int slot = 0)
@@ -2153,7 +2154,7 @@ int run_prep(crb_filler *f, Frame &F, cudaStream_t st, int slot = 0)
     // (it reads the vertex array once more than k_setup alone would: it pays when many chunks miss the band -- measured on the
     // 10 M-triangle sphere with the persistent k_setup that walks the listed chunks through its bulk-copy ring: half-frame bands
     // 1.14 -> 1.06 ms; round 1, with one-chunk CTAs: half 1.16 -> 1.22 ms, quarter 0.84 -> 0.82, eighth 0.59 -> 0.51)
-    if (banded && f->band_prepass && (long long)CRB_PREPASS_DEN * (F.row1 - F.row0) <= F.H && F.nViews == 1 && !F.views && F.T >= 8 * NT && !(F.flags & CRB_PATH_ATOMIC) &&
+    if (banded && f->band_prepass && 8ll * (F.row1 - F.row0) <= (long long)CRB_PREPASS_EIGHTHS * F.H && F.nViews == 1 && !F.views && F.T >= 8 * NT && !(F.flags & CRB_PATH_ATOMIC) &&
         !(reinterpret_cast<uintptr_t>(F.v) & 15u)) {
         const size_t so = (size_t)(reinterpret_cast<const char *>(F.alive) - reinterpret_cast<const char *>(f->alive));   // workspace set in use
         F.chunks = reinterpret_cast<unsigned *>(reinterpret_cast<char *>(f->chunks) + so);
