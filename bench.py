@@ -205,6 +205,14 @@ def best_cpu_threads(arrays, colors):
     return best[1]
 
 
+def headline_config(T, V, n_total, chunk):
+    """`config` of the headline line -- one function, because both arms must print the same dict."""
+    return {"workload": "trex_1024_orbit", "res": RES, "fov": FOV, "triangles": int(T), "views_per_gpu_per_step": int(V),
+            "orbit_views_total": int(n_total), "view_to_rank": "k mod N", "views_per_launch": int(chunk), "illumination": False,
+            "buffers": "z+color+normals f32, fresh per view", "l2": "outputs %.2f GB/step per GPU >> 126 MB L2; "
+            "the 1.5 MB mesh is re-read per view by design" % (V * 28 * RES * RES / 1e9)}
+
+
 def sample_view_indices(n_total, count=8):
     """Views k * n_total / count: an evenly spread sample of the orbit (frames of different view angles cost differently)."""
     return [(k * n_total) // count for k in range(count)]
@@ -256,9 +264,9 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic orbit of the T-Rex fixture (tests/golden/trex_fit.npz)",
-        "config": {"workload": "trex_1024_orbit", "res": RES, "fov": FOV, "triangles": int(T), "illumination": False,
-                   "sample_frames_per_step": sample, "orbit_views_total": n_total,
-                   "sample_views": sample_view_indices(n_total, 8)},
+        # the same config as the GPU arm's line (the driver compares the two dicts); what this arm sampled of it is said beside it
+        "config": headline_config(int(T), args.views, n_total, args.chunk),
+        "reference_sample": {"frames_per_step": sample, "views": sample_view_indices(n_total, 8)},
         "gtri_per_s": fps * T / 1e9,
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "host_cores": os.cpu_count(), "kind": kind,
                          "sample": f"{sample} frames per step x {args.steps} steps cycling through 8 evenly spread views "
@@ -714,10 +722,7 @@ def run_gpu_arm(args):
             "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic orbit of the T-Rex fixture (tests/golden/trex_fit.npz = README fit_model flow)",
-            "config": {"workload": "trex_1024_orbit", "res": RES, "fov": FOV, "triangles": T, "views_per_gpu_per_step": V,
-                       "orbit_views_total": n_total, "view_to_rank": "k mod N", "views_per_launch": args.chunk, "illumination": False,
-                       "buffers": "z+color+normals f32, fresh per view", "l2": "outputs %.2f GB/step per GPU >> 126 MB L2; "
-                       "the 1.5 MB mesh is re-read per view by design" % (V * 28 * RES * RES / 1e9)},
+            "config": headline_config(T, V, n_total, args.chunk),
             "gtri_per_s": fps * T / 1e9, "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cpu, "single_frame": single, "drop_in": drop_in, "gather": gather, "secondary": secondary,
             "checks": {"covered_pixels_view0": covered0, "e2e_covered_pixels": e2e_cov, "e2e_image_u8_lit_pixels": img_cov, "e2e_dense_covered_pixels": dense_cov, "e2e_sync_covered_pixels": sync_cov, "pairs_last_launch": int(need.value),
