@@ -1010,7 +1010,7 @@ __device__ unsigned long long g_phase[16];
 
 // Shape of the tile rasterizer: threads per CTA, triangles staged per pass, fragment queue per warp, rows per clear box, resident CTAs
 // per SM the launch bounds ask for, and whether shaded colour / normal rows are staged in shared memory (TMA boxes / vector stores)
-// or stored straight from registers.  Two shapes are instantiated, see RasterLarge / RasterSmall below.
+// or stored straight from registers.  Three shapes are instantiated, see RasterLarge / RasterSmall / RasterWide below.
 template <int RT_, int CH_, int FQ_, int CLEAR_ROWS_, int MIN_CTAS_, bool OUT_STAGE_>
 struct RasterShape {
     static constexpr int RT = RT_, CH = CH_, FQ = FQ_, CLEAR_ROWS = CLEAR_ROWS_, MIN_CTAS = MIN_CTAS_;
@@ -1482,8 +1482,8 @@ __device__ __forceinline__ void tma_clear_tile(const TMaps &M, const TileSmem<C>
 // frame) -- a few thousand cycles of queueing, no arithmetic -- so those stores drain beside the rasterizing CTAs that
 // share its SM for the whole length of the kernel.  Launches without tensor maps clear with plain stores up front,
 // every CTA adopting its share of the empty tiles.
-// 6 resident CTAs per SM (40 registers, 36.9 KB shared memory each -- 0.7 KB below the limit): 5 with 48 registers measured
-// 8.7 % slower (profiles/history/r02_probe_variants.json)
+// Resident CTAs per SM follow the shape (RasterSmall 12 at 40 registers, RasterLarge 8 at 62, RasterWide 6 at 40); the
+// static_assert in k_raster ties each shape's shared memory to the residency its launch bounds ask for.
 #ifndef CRB_RASTER_MIN_CTAS
 #define CRB_RASTER_MIN_CTAS 8
 #endif
@@ -1576,7 +1576,8 @@ __global__ void __launch_bounds__(C::RT, C::MIN_CTAS) k_raster(const Frame F, co
     PH(10);
 }
 
-// The two shapes of the tile rasterizer, both CTAs of 128 threads that store shaded pixels straight from registers.
+// The two throughput shapes of the tile rasterizer, both CTAs of 128 threads that store shaded pixels straight from registers
+// (the third, RasterWide, follows them).
 // Round 1 / early round 2 ran ONE shape: 256 threads, 128 triangles staged per pass, shaded rows staged in shared memory for TMA
 // boxes, 6 CTAs per SM at 40 registers.  ncu showed 28 % of all stall samples at block barriers -- the eight warps of a CTA waiting
 // for each other before shading, while most tiles hold 20-40 triangles, i.e. fewer (triangle, row) items than eight warps take

@@ -101,3 +101,14 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["cpu_baseline"]["kind"] in ("reference", "port")
+    # both arms print the same `config` (the driver compares the dicts): the GPU arm's line is built from the same function
+    sys.path.insert(0, ROOT)
+    import bench as B
+    assert d["config"] == json.loads(json.dumps(B.headline_config(13814, 128, 128, 128)))
+    assert d["metric"] == B.METRIC and d["higher_is_better"] is True
+    assert inspect_uses_headline_config(B.run_gpu_arm)
+
+
+def inspect_uses_headline_config(fn):
+    import inspect
+    return '"config": headline_config(' in inspect.getsource(fn)
