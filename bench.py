@@ -1046,11 +1046,13 @@ def run_extra_workload(args):
 
 
 _REAL_STDOUT = None
+_T_START = time.time()
 
 
 def emit(line):
     """The JSON line goes to the process's original stdout; everything else (NCCL banners, library chatter) was sent to
     stderr by main()."""
+    line.setdefault("wall_s", round(time.time() - _T_START, 1))    # process start -> this line (imports, fixtures, every leg)
     data = (json.dumps(line) + "\n").encode()
     if _REAL_STDOUT is None:
         sys.stdout.write(data.decode()); sys.stdout.flush()
