@@ -342,6 +342,13 @@ def run_gpu_arm(args):
         ms = float(t.item())
     frames = world * V * args.steps
     fps = frames / (ms / 1000.0)
+    if rank == 0:      # what the watchdog prints should a later leg (deliveries, secondary configs) hang: the headline, measured above
+        _PARTIAL.update({
+            "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic orbit of the T-Rex fixture (tests/golden/trex_fit.npz = README fit_model flow)",
+            "config": headline_config(T, V, n_total, args.chunk), "gtri_per_s": fps * T / 1e9, "clocks": clocks.summary(),
+            "gpu_launches": launches})
 
     # the rasterizer timed alone: the same steps without the front end of the next launch running beside it
     _lib.check(f._L.crb_set_option(f._handle, _lib.CRB_OPT_CHUNK_PIPELINE, 0))
@@ -1047,12 +1054,33 @@ def run_extra_workload(args):
 
 _REAL_STDOUT = None
 _T_START = time.time()
+_PARTIAL = {}          # rank 0: the headline fields, as soon as they are measured (see start_watchdog)
+_EMITTED = False
+
+
+def start_watchdog(budget_s):
+    """Last resort, never reached by a healthy run (the default run takes a minute or two): the legs after the headline exchange
+    data between ranks (NCCL, peer mappings), and a rank that fails inside one leaves the others waiting in a collective until the
+    driver's limit kills the job with nothing printed.  After `budget_s` seconds of process time every rank leaves; rank 0 first
+    prints the headline it has already measured, marked "truncated"."""
+    def fire():
+        if not _EMITTED and int(os.environ.get("RANK", "0")) == 0 and _PARTIAL:
+            line = dict(_PARTIAL)
+            line["truncated"] = f"watchdog: a leg after the headline did not finish within {budget_s:.0f} s of process time"
+            emit(line)
+        os._exit(0 if (_EMITTED or int(os.environ.get("RANK", "0")) != 0) else 3)
+    t = threading.Timer(budget_s, fire)
+    t.daemon = True
+    t.start()
+    return t
 
 
 def emit(line):
     """The JSON line goes to the process's original stdout; everything else (NCCL banners, library chatter) was sent to
     stderr by main()."""
+    global _EMITTED
     line.setdefault("wall_s", round(time.time() - _T_START, 1))    # process start -> this line (imports, fixtures, every leg)
+    _EMITTED = True
     data = (json.dumps(line) + "\n").encode()
     if _REAL_STDOUT is None:
         sys.stdout.write(data.decode()); sys.stdout.flush()
@@ -1086,7 +1114,11 @@ def main():
                     help="also time the final NCCL gather (reported beside, never inside, the headline value); "
                          "peer (sphere_8192_bands only): no gather at all -- every rank's filler renders its band straight into "
                          "rank 0's frame over NVLink (sharding.PeerFrame), and the value is frames/s complete on rank 0")
+    ap.add_argument("--budget-s", type=float, default=float(os.environ.get("CRB_BENCH_BUDGET_S", "720")),
+                    help="watchdog: leave (rank 0 printing the headline it has) after this many seconds; 0 = off")
     args = ap.parse_args()
+    if args.budget_s > 0:
+        start_watchdog(args.budget_s)
     if args.impl == "reference":
         run_reference_arm(args)
     elif args.workload != "trex_1024_orbit":

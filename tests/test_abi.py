@@ -112,3 +112,28 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
 def inspect_uses_headline_config(fn):
     import inspect
     return '"config": headline_config(' in inspect.getsource(fn)
+
+
+def test_bench_watchdog_prints_the_headline_it_has():
+    """bench.py's last resort: should a leg after the headline hang (a rank lost inside a collective), rank 0 prints the headline
+    fields already measured, marked truncated, and every rank leaves with 0; with nothing measured rank 0 leaves with 3."""
+    import json
+    import subprocess
+    import textwrap
+    code = textwrap.dedent(f'''
+        import sys, time
+        sys.argv = ["bench.py"]
+        sys.path.insert(0, {ROOT!r})
+        import bench as B
+        PARTIAL
+        B.start_watchdog(0.2)
+        time.sleep(20)
+        print("not reached")
+    ''')
+    r = subprocess.run([sys.executable, "-c", code.replace("PARTIAL", 'B._PARTIAL.update({"metric": "m", "value": 1.0})')],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "not reached" not in r.stdout
+    d = json.loads(r.stdout.strip())
+    assert d["value"] == 1.0 and "truncated" in d
+    r = subprocess.run([sys.executable, "-c", code.replace("PARTIAL", "pass")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 3 and r.stdout.strip() == ""
