@@ -240,6 +240,35 @@ def cpu_frames(model, n_total, frames, warm=2):
     return kind, cores, times
 
 
+def reference_renderer_flow_ms(model, cores, frames=5):
+    """The whole run.py:20-25 flow of the reference on the host: its Renderer, GuroIllumination([0, 0, 1]) (NumPy over the whole
+    frame) and Version C filler, a new filler per frame; median milliseconds per frame.  None without oracle/_ref."""
+    from conftest import TriModel
+    from oracle import build_ref
+    if not build_ref.built():
+        return None
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(1)
+    sys.stdout.flush()
+    os.dup2(devnull, 1)          # (the reference printf()s per OpenMP thread)
+    try:
+        from crender.cy import Renderer
+        from crender.cy.illumination import GuroIllumination
+        from crender.cy.pixel_buffer_filler import AdvancedPixelBufferFiller as Ref
+        m = TriModel(model._vertices_by_triangles, model._colors_by_triangles, model._normals_by_triangles)
+        ts = []
+        for _ in range(frames + 1):
+            t0 = time.perf_counter()
+            Renderer(Ref(RES, RES, fov=FOV, n_threads=cores), GuroIllumination([0, 0, 1]), None, RES, RES).render(m)
+            ts.append(time.perf_counter() - t0)
+    finally:
+        os.dup2(saved, 1)
+        os.close(devnull)
+        os.close(saved)
+    return 1000.0 * statistics.median(ts[1:])
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -683,8 +712,20 @@ def run_gpu_arm(args):
             ff = AdvancedPixelBufferFiller(RES, RES, fov=FOV, n_threads=8, device=local)
             ff.render_model(mk)
             return ff.get_color_buffer()
+        def renderer_flow():     # run.py:20-25 with this package's Renderer + GuroIllumination: the light on the device buffers
+            from cython3dmodelrenderer_b200 import GuroIllumination, Renderer
+            ff = AdvancedPixelBufferFiller(RES, RES, fov=FOV, n_threads=8, device=local)
+            return Renderer(ff, GuroIllumination([0, 0, 1]), None, RES, RES).render(mk)
+        try:
+            renderer_ms = per_frame(renderer_flow)
+        except Exception as ex:      # (must never take the headline line down)
+            renderer_ms = repr(ex)[:200]
         drop_in = {"new_filler_per_frame_ms": per_frame(new_filler), "one_filler_clear_render_get3_ms": per_frame(reused),
                    "new_filler_color_only_ms": per_frame(new_filler_color_only),
+                   "renderer_guro_new_filler_ms": renderer_ms,
+                   "renderer_guro_what": "Renderer(filler, GuroIllumination([0, 0, 1]), ...).render(model) of this package, a new filler "
+                                         "per frame: rasterizer + crb_guro on the device, the lit colour buffer (12.6 MB) downloaded; "
+                                         "cpu_baseline.renderer_guro_ms is the reference's own three classes on the host",
                    "pcie_floor_ms": {"three_buffers": 28 * RES * RES / 55e6, "color_only": 12 * RES * RES / 55e6,
                                      "note": "dense float32 download at the ~55 GB/s this link sustains"},
                    "what": "AdvancedPixelBufferFiller(...).render_model(model) + the three get_*_buffer() calls on host NumPy data, "
@@ -699,6 +740,10 @@ def run_gpu_arm(args):
                          f"render_model only, fresh filler per frame, n_threads={cores} (the fastest of 8/16/32/nproc/2/nproc on this "
                          f"host, nproc={os.cpu_count()})", "median_ms": 1000 * statistics.median(times)}
         cpu_threads = cores
+        try:
+            cpu["renderer_guro_ms"] = reference_renderer_flow_ms(model, cores)
+        except Exception as ex:
+            cpu["renderer_guro_ms"] = repr(ex)[:200]
 
     # ---- the other BASELINE.json configs, measured in the same run (C2, C3: one GPU; C4: row bands over the N ranks) ----------
     secondary = None

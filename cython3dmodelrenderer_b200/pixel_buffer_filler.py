@@ -115,6 +115,7 @@ class AdvancedPixelBufferFiller:
     # frame is rendered, back to back, instead of one by one when get_*_buffer() asks for them.
     _fetched_by_previous = frozenset()
     _fetched_by_current = set()
+    _view_owner = {}      # address of a host mirror handed out by get_*_buffer() -> weak reference to its filler (owner_of_views)
 
     def __init__(self, h, w, fov=90.0, z_near=0.1, z_far=1000.0, n_threads=1, device=None, band=None, out_ptrs=None):
         torch = _require_cuda()
@@ -168,6 +169,13 @@ class AdvancedPixelBufferFiller:
     # ------------------------------------------------------------------------------------------------ plumbing
     def __del__(self):
         try:
+            for t in getattr(self, "_host", {}).values():       # (pinned memory is recycled: drop this filler's addresses)
+                r = type(self)._view_owner.get(t.data_ptr())
+                if r is not None and r() in (None, self):
+                    type(self)._view_owner.pop(t.data_ptr(), None)
+        except Exception:
+            pass
+        try:
             if getattr(self, "_handle", None):
                 self._L.crb_destroy(self._handle)
                 self._handle = None
@@ -201,7 +209,22 @@ class AdvancedPixelBufferFiller:
             t = self._torch.empty(src.shape, dtype=self._torch.float32, pin_memory=True)
             self._host[name] = t
             self._host_np[name] = t.numpy()
+            import weakref
+            type(self)._view_owner[t.data_ptr()] = weakref.ref(self)
         return self._host[name]
+
+    @classmethod
+    def owner_of_views(cls, color_buffer, n_buffer):
+        """The filler whose live views the two arrays are -- the very objects its get_color_buffer() and get_normals_buffer()
+        return -- or None.  (illumination.GuroIllumination uses it to light the device buffers behind the views.)"""
+        try:
+            ref = cls._view_owner.get(int(color_buffer.__array_interface__["data"][0]))
+        except (AttributeError, KeyError, TypeError):
+            return None
+        f = ref() if ref is not None else None
+        if f is None or f._host_np.get("color") is not color_buffer or f._host_np.get("normals") is not n_buffer:
+            return None
+        return f
 
     def _push_exposed(self):
         """Live-view contract (pyx:246-253 return views of the filler's own memory): whatever the caller wrote
@@ -281,15 +304,17 @@ class AdvancedPixelBufferFiller:
         """pyx:80-81"""
         return self.h, self.w
 
-    def render_model(self, model):
+    def render_model(self, model, prefetch=True):
         """pyx:92-104.  Reads model._vertices_by_triangles / _colors_by_triangles / _normals_by_triangles
-        ([T,3,3] float32), never mutates them, composites into the persistent buffers."""
+        ([T,3,3] float32), never mutates them, composites into the persistent buffers.  (`prefetch=False`, not in the
+        reference: do not start downloading the buffers the previous frame's caller fetched -- renderer.Renderer lights the
+        colour buffer on the device first.)"""
         v = _check_tri_array(getattr(model, "_vertices_by_triangles"), "vertices")
         c = _check_tri_array(getattr(model, "_colors_by_triangles"), "colors")
         n = _check_tri_array(getattr(model, "_normals_by_triangles"), "normals")
         if not (v.shape[0] == c.shape[0] == n.shape[0]):
             raise IndexError("Out of bounds on buffer access (axis 0)")   # what the bounds-checked memoryviews raise
-        self.render_arrays(v, c, n)
+        self.render_arrays(v, c, n, prefetch=prefetch)
 
     def get_normals_buffer(self):
         """pyx:246-247 -- live float32 [h,w,3] view (same array object on every call)."""
@@ -314,7 +339,7 @@ class AdvancedPixelBufferFiller:
             self._stale[name] = True
         self._exposed.clear()   # arrays handed out earlier are detached until fetched again
 
-    def render_arrays(self, v, c, n, path="tiled", check_status=True):
+    def render_arrays(self, v, c, n, path="tiled", check_status=True, prefetch=True):
         """Render [T,3,3] float32 arrays.  numpy inputs are staged through pinned memory and copied H2D;
         torch CUDA tensors are used in place (device-resident inputs)."""
         torch = self._torch
@@ -362,7 +387,7 @@ class AdvancedPixelBufferFiller:
         self._prefetched.clear()
         want = self._fetched if self._fetched is not None else type(self)._fetched_by_previous
         self._fetched = set()
-        if check_status and self.row0 == 0 and self.row1 == self.h:
+        if check_status and prefetch and self.row0 == 0 and self.row1 == self.h:
             for name, bit in (("color", _lib.CRB_BUF_COLOR), ("normals", _lib.CRB_BUF_NORMALS), ("z", _lib.CRB_BUF_Z)):
                 if name in want and name not in self._exposed:
                     dst = {"z": None, "color": None, "normals": None}

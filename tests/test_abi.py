@@ -137,3 +137,66 @@ def test_bench_watchdog_prints_the_headline_it_has():
     assert d["value"] == 1.0 and "truncated" in d
     r = subprocess.run([sys.executable, "-c", code.replace("PARTIAL", "pass")], capture_output=True, text=True, timeout=120)
     assert r.returncode == 3 and r.stdout.strip() == ""
+
+
+def test_drop_in_renderer_and_illumination_host_logic():
+    """renderer.py / illumination.py without a GPU: the constructor keeps upstream's attributes (guro_illumination.py:17-18:
+    negated, normalised, float32), foreign arrays are refused (no NumPy path), and Renderer.render takes upstream's own
+    sequence (renderer.py:47-49) for a filler / illumination pair that is not this package's."""
+    import cython3dmodelrenderer_b200 as P
+    g = P.GuroIllumination([0, 0, 1])
+    assert g.light_direction.dtype == np.float32 and g.light_direction.tobytes() == np.array([-0.0, -0.0, -1.0], np.float32).tobytes()
+    g = P.GuroIllumination([1, 2, -2])
+    want = -np.asarray([1, 2, -2], dtype="float32")
+    assert g.light_direction.tobytes() == (want / np.linalg.norm(want)).tobytes()
+    with pytest.raises(TypeError, match="no NumPy path"):
+        g.draw_illumination(np.zeros((2, 2, 3), np.float32), np.zeros((2, 2, 3), np.float32))
+    assert P.AdvancedPixelBufferFiller.owner_of_views(np.zeros(3), None) is None
+    assert P.AdvancedPixelBufferFiller.owner_of_views(object(), object()) is None
+    assert P.NoIllumination().draw_illumination(None, None) is None and issubclass(P.GuroIllumination, P.IlluminationDrawer)
+
+    calls = []
+
+    class FakeFiller:
+        color, normals = np.ones((2, 2, 3), np.float32), np.ones((2, 2, 3), np.float32)
+
+        def render_model(self, m):
+            calls.append(("render_model", m))
+
+        def get_color_buffer(self):
+            calls.append("get_color")
+            return self.color
+
+        def get_normals_buffer(self):
+            calls.append("get_normals")
+            return self.normals
+
+    class FakeLight(P.IlluminationDrawer):
+        def draw_illumination(self, c, n):
+            calls.append(("draw", c is FakeFiller.color, n is FakeFiller.normals))
+            c *= 0.5
+
+    class FakeModel:
+        def __init__(self):
+            self.ops = []
+
+        def get_max_span(self):
+            return 4.0
+
+        def get_mean_vertex(self):
+            return np.array([1.0, 2.0, 3.0])
+
+        def scale(self, s):
+            self.ops.append(("scale", s))
+
+        def shift(self, v):
+            self.ops.append(("shift", tuple(np.asarray(v, dtype=float))))
+
+    r = P.Renderer(FakeFiller(), FakeLight(), None, 100, 60)
+    assert (r.im_h, r.im_w, r.use_tqdm, r.triangle_iterator_type) == (100, 60, True, None) and r.reset_buffers() is None
+    m = FakeModel()
+    image = r.render(m)
+    assert image is FakeFiller.color and float(image[0, 0, 0]) == 0.5 and m.ops == []
+    assert calls == [("render_model", m), "get_color", "get_normals", ("draw", True, True), "get_color"]
+    r.render(m, normalize_model=True)        # renderer.py:41-46: span = min(h // 2, w // 2) = 30
+    assert m.ops == [("scale", 30 / 4.0), ("shift", (-1.0 + 50, -2.0 + 30, -3.0 - 30))]

@@ -815,6 +815,54 @@ def test_reference_renderer_flow_with_the_drop_in_filler(Filler, trex, capfd):
     assert np.array_equal(gu8, ru8)
 
 
+def test_drop_in_renderer_and_illumination_match_the_reference_flow(Filler, trex, bunny, capfd):
+    """run.py:20-26 three ways -- the reference's own classes on its own Cython filler; the reference's Renderer driving this
+    package's filler AND GuroIllumination (draw_illumination recognises the filler's live views and lights the device buffers);
+    this package's Renderer + GuroIllumination + filler -- over two render() calls on the same filler (the second composites
+    onto the lit frame and lights the whole buffer again, renderer.py:47-49): bit-identical images, normals and depth."""
+    from oracle import build_ref
+    if not build_ref.built():
+        pytest.skip("oracle/_ref (reference Cython build) not present")
+    import sys
+    from conftest import ROOT
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    import cython3dmodelrenderer_b200 as P
+    from crender.cy import Renderer as RefRenderer
+    from crender.cy.illumination import GuroIllumination as RefGuro, NoIllumination as RefNone
+    from crender.cy.pixel_buffer_filler import AdvancedPixelBufferFiller as RefFiller
+    from crender.cy.triangle_iterator import SimpleIterator
+    h, w = 320, 256
+    light = [0.3, -0.2, 1.0]
+    for ref_ill, our_ill in ((lambda: RefGuro(light), lambda: P.GuroIllumination(light)), (RefNone, P.NoIllumination)):
+        results = []
+        for fcls, rcls, ill in ((RefFiller, RefRenderer, ref_ill), (Filler, RefRenderer, our_ill), (Filler, P.Renderer, our_ill)):
+            filler = fcls(h, w, fov=45, n_threads=1)
+            renderer = rcls(filler, ill(), SimpleIterator, h, w)
+            frames = []
+            for m in (trex, bunny):
+                image = renderer.render(m)
+                if fcls is Filler:
+                    assert image is filler.get_color_buffer()      # the live view, the same object every time
+                frames.append((image.copy(), image[::-1].astype("uint8"), filler.get_normals_buffer().copy(), filler.get_z_buffer().copy()))
+            results.append(frames)
+        capfd.readouterr()
+        for other in results[1:]:
+            for (ri, ru8, rn, rz), (gi, gu8, gn, gz) in zip(results[0], other):
+                assert int((rz < 1e5).sum()) > 5000
+                assert bits_equal(gz, rz) and bits_equal(gn, rn)
+                assert bits_equal(gi, ri), "lit colour buffer differs from the reference flow"
+                assert np.array_equal(gu8, ru8)
+    # arrays that are not the live views of a filler of this package: no NumPy path here
+    with pytest.raises(TypeError):
+        P.GuroIllumination(light).draw_illumination(np.zeros((h, w, 3), np.float32), np.zeros((h, w, 3), np.float32))
+    f = Filler(h, w, fov=45)
+    f.render_model(trex)
+    with pytest.raises(TypeError):      # (a copy is not the view)
+        P.GuroIllumination(light).draw_illumination(f.get_color_buffer().copy(), f.get_normals_buffer())
+
+
 @pytest.mark.parametrize("case", sorted(k for k in CHECKS["cases"] if k.endswith("_guro")))
 def test_reference_golden_lit_colour(case, Filler, trex, bunny, basketball):
     """The reference's Renderer.render + GuroIllumination result (golden checksum of the lit colour buffer), three ways:
@@ -833,6 +881,12 @@ def test_reference_golden_lit_colour(case, Filler, trex, bunny, basketball):
     dv, dc, dn = (torch.from_numpy(a).cuda() for a in (m._vertices_by_triangles, m._colors_by_triangles, m._normals_by_triangles))
     out = f.render_views(dv, dc, dn, VW.view_matrix()[None, :], want=("color",), guro_light=info["light"])
     assert sha(out["color"][0].cpu().numpy()) == info["color_lit"]
+    # ... and a fourth: this package's Renderer + GuroIllumination (renderer.py / illumination.py: the run.py flow with the
+    # illumination on the device buffers, only the lit colour crossing PCIe)
+    from cython3dmodelrenderer_b200 import GuroIllumination, Renderer
+    f2 = Filler(info["h"], info["w"], fov=info["fov"])
+    image = Renderer(f2, GuroIllumination(info["light"]), None, info["h"], info["w"]).render(m)
+    assert image is f2.get_color_buffer() and sha(image) == info["color_lit"]
 
 
 def test_repeated_renders_are_bit_identical(Filler, trex):
