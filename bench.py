@@ -240,7 +240,7 @@ def cpu_frames(model, n_total, frames, warm=2):
     return kind, cores, times
 
 
-def reference_renderer_flow_ms(model, cores, frames=5):
+def reference_renderer_flow_ms(model, cores, frames=5, res=None):
     """The whole run.py:20-25 flow of the reference on the host: its Renderer, GuroIllumination([0, 0, 1]) (NumPy over the whole
     frame) and Version C filler, a new filler per frame; median milliseconds per frame.  None without oracle/_ref."""
     from conftest import TriModel
@@ -260,7 +260,7 @@ def reference_renderer_flow_ms(model, cores, frames=5):
         ts = []
         for _ in range(frames + 1):
             t0 = time.perf_counter()
-            Renderer(Ref(RES, RES, fov=FOV, n_threads=cores), GuroIllumination([0, 0, 1]), None, RES, RES).render(m)
+            Renderer(Ref(res or RES, res or RES, fov=FOV, n_threads=cores), GuroIllumination([0, 0, 1]), None, res or RES, res or RES).render(m)
             ts.append(time.perf_counter() - t0)
     finally:
         os.dup2(saved, 1)
@@ -1055,6 +1055,25 @@ def measure_workload(args, workload, world, rank, local, dev, cpu_threads=None, 
                       "; steady state of a render loop (frames 4.. of the process)", "first_frame_ms": first_ms, "frames_timed": nrep,
                "covered_pixels": int((out[2] < 1e5).sum())}
         del out
+        if guro:      # the reference's render() flow (renderer.py:47-49) with this package's Renderer + GuroIllumination: lit colour only
+            try:
+                from cython3dmodelrenderer_b200 import GuroIllumination, Renderer
+
+                def renderer_frame():
+                    ff = AdvancedPixelBufferFiller(res, res, fov=FOV, n_threads=8, device=local)
+                    return Renderer(ff, GuroIllumination([0, 0, 1]), None, res, res).render(m_host)
+                for _ in range(3):
+                    renderer_frame()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(nrep):
+                    renderer_frame()
+                torch.cuda.synchronize()
+                e2e["renderer_guro_value"] = nrep / (time.perf_counter() - t0)
+                e2e["renderer_guro_d2h_bytes_per_step"] = 12 * res * res
+                cpu["renderer_guro_ms"] = reference_renderer_flow_ms(model, cores, frames=2, res=res)
+            except Exception as ex:
+                e2e["renderer_guro_value"] = repr(ex)[:200]
 
     line = None
     if rank == 0:
